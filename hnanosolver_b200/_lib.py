@@ -1,0 +1,106 @@
+"""ctypes binding of libhns_b200.so (include/hns_b200.h). No fallback: if the CUDA library is missing, importing
+the compute entry points raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhns_b200.so")
+
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int32)
+c_u64p = C.POINTER(C.c_uint64)
+
+HNS_OK = 0
+STATUS_NAMES = {0: "HNS_OK", -1: "HNS_ERR_INVALID_ARGUMENT", -2: "HNS_ERR_RUNTIME", -3: "HNS_ERR_CUDA", -4: "HNS_ERR_TOPOLOGY",
+                -5: "HNS_ERR_UNSUPPORTED"}
+
+
+class CombustionParams(C.Structure):
+    """reference: struct CombustionParams, src/Cuda/Kernels.cuh:6-13"""
+    _fields_ = [("expansionRate", C.c_float), ("temperatureRelease", C.c_float), ("buoyancyStrength", C.c_float),
+                ("ambientTemp", C.c_float), ("vorticityScale", C.c_float), ("factorScale", C.c_float)]
+
+
+# every symbol include/hns_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "hns_abi_version": (C.c_int, []),
+    "hns_last_error": (C.c_char_p, []),
+    "hns_launch_count": (C.c_uint64, []),
+    "hns_launch_count_reset": (None, []),
+    "hns_set_device": (C.c_int, [C.c_int]),
+    "hns_grid_create_from_coords": (C.c_int, [c_i32p, C.c_uint64, C.c_float, C.c_int, C.POINTER(C.c_void_p)]),
+    "hns_grid_create_from_origins": (C.c_int, [c_i32p, C.c_uint64, C.c_float, C.POINTER(C.c_void_p)]),
+    "hns_grid_destroy": (None, [C.c_void_p]),
+    "hns_grid_num_leaves": (C.c_uint64, [C.c_void_p]),
+    "hns_grid_num_voxels": (C.c_uint64, [C.c_void_p]),
+    "hns_grid_voxel_size": (C.c_float, [C.c_void_p]),
+    "hns_grid_nanovdb_bytes": (C.c_uint64, [C.c_void_p]),
+    "hns_grid_nanovdb_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "hns_grid_nanovdb_download": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hns_grid_get_values": (C.c_int, [C.c_void_p, c_i32p, C.c_uint64, c_u64p]),
+    "hns_grid_neighbors_download": (C.c_int, [C.c_void_p, c_i32p]),
+    "hns_compute_sim": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_f32p), C.c_int, C.c_float, C.c_float,
+                                  C.POINTER(CombustionParams), C.c_int, C.c_void_p]),
+    "hns_advect_index_grid": (C.c_int, [c_i32p, C.c_uint64, c_f32p, C.c_int, C.POINTER(c_f32p), C.c_float, C.c_float, C.c_void_p]),
+    "hns_advect_index_grid_velocity": (C.c_int, [c_i32p, C.c_uint64, c_f32p, C.c_float, C.c_float, C.c_void_p]),
+    "hns_project_non_divergent": (C.c_int, [c_i32p, C.c_uint64, c_f32p, C.c_uint64, C.c_float, C.c_void_p]),
+    "hns_divergence": (C.c_int, [c_i32p, C.c_uint64, c_f32p, c_f32p, C.c_float, C.c_void_p]),
+    "hns_combustion_kernel": (C.c_int, [C.c_void_p, c_f32p, C.c_uint64, C.c_float, C.c_float, C.c_void_p]),
+    "hns_state_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "hns_state_destroy": (None, [C.c_void_p]),
+    "hns_state_upload_velocity": (C.c_int, [C.c_void_p, c_f32p]),
+    "hns_state_download_velocity": (C.c_int, [C.c_void_p, c_f32p]),
+    "hns_state_upload_scalar": (C.c_int, [C.c_void_p, C.c_int, c_f32p]),
+    "hns_state_download_scalar": (C.c_int, [C.c_void_p, C.c_int, c_f32p]),
+    "hns_state_download_aux": (C.c_int, [C.c_void_p, C.c_int, c_f32p]),
+    "hns_state_step": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_void_p]),
+    "hns_state_advect_velocity": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
+    "hns_state_divergence": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hns_state_pressure_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_void_p]),
+    "hns_state_subtract_gradient": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hns_state_advect_scalars": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
+    "hns_state_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hns_state_time_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint, C.c_void_p, c_f32p, c_f32p]),
+    "hns_state_pack_leaves": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "hns_state_unpack_leaves": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "hns_state_field_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
+}
+
+_lib = None
+
+
+class HnsError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(code, code)}: {message}")
+        self.code = code
+        self.message = message
+
+
+class HnsInvalidArgument(HnsError, ValueError):
+    """maps the reference's std::invalid_argument"""
+
+
+def lib() -> C.CDLL:
+    """Loads libhns_b200.so. Raises if it has not been built -- there is no CPU fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m hnanosolver_b200.build` (nvcc, sm_100a). "
+                              "hnanosolver_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if L.hns_abi_version() != 1:
+            raise ImportError("libhns_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != HNS_OK:
+        msg = lib().hns_last_error().decode(errors="replace")
+        raise (HnsInvalidArgument if rc == -1 else HnsError)(rc, msg)

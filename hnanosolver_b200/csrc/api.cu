@@ -1,0 +1,517 @@
+// C ABI of libhns_b200 (include/hns_b200.h): resident simulation state, the frame, and the one-shot host-sidecar launchers.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace hns {
+
+static thread_local std::string t_error;
+void set_error(const std::string& msg) { t_error = msg; }
+int fail(int code, const std::string& msg) {
+	t_error = msg;
+	return code;
+}
+
+static int ensure_tables() {
+	// once per process and device
+	static thread_local int done_device = -1;
+	int dev = 0;
+	HNS_CUDA(cudaGetDevice(&dev));
+	if (done_device == dev) return HNS_OK;
+	const int rc = upload_tables();
+	if (rc == HNS_OK) done_device = dev;
+	return rc;
+}
+
+// omega exactly as Compute() evaluates it (reference src/Cuda/HNanoSolver.cu:257): float sinf of float(3.14159)*voxelSize
+static inline float omega_compute(float voxelSize) { return 2.0f / (1.0f + sinf(static_cast<float>(3.14159) * voxelSize)); }
+// ... and as pressure_projection_idx does (reference src/Cuda/PressureProjection.cu:53): double sin, narrowed at the kernel call
+static inline float omega_project(float voxelSize) { return float(2.0f / (1.0f + sin(3.14159 * voxelSize))); }
+
+static int pressure_solve(hns_state* s, int iterations, float omega, unsigned flags, cudaStream_t st) {
+	const GridView& g = s->grid->view;
+	const float dx = s->grid->voxel_size;
+	s->p_cur = 0;
+	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, s->n * sizeof(float), st));  // initial guess 0 (HNanoSolver.cu:113)
+	if (flags & 1u) {
+		for (int it = 0; it < iterations; ++it) {
+			launch_rbgs_color(g, s->div, s->p[0], dx, 0, omega, st);
+			launch_rbgs_color(g, s->div, s->p[0], dx, 1, omega, st);
+		}
+	} else {
+		for (int it = 0; it < iterations; ++it) {
+			launch_rbgs_fused(g, s->div, s->p[s->p_cur], s->p[s->p_cur ^ 1], dx, omega, st);
+			s->p_cur ^= 1;
+		}
+	}
+	return HNS_OK;
+}
+
+static ScalarPtrs scalar_ptrs(const hns_state* s) {
+	ScalarPtrs sp{};
+	for (int i = 0; i < s->n_scalars; ++i) sp.in[i] = s->sc[i], sp.out[i] = s->sc_out[i];
+	return sp;
+}
+
+static int frame(hns_state* s, int iterations, float dt, unsigned flags, cudaStream_t st, cudaEvent_t ev_p0 = nullptr, cudaEvent_t ev_p1 = nullptr) {
+	const GridView& g = s->grid->view;
+	const float h = s->grid->voxel_size, inv = 1.0f / h;
+	launch_advect_vector(g, s->vel, s->adv, dt, inv, st);
+	launch_divergence(g, s->adv, s->div, inv, st);
+	if (ev_p0) cudaEventRecord(ev_p0, st);
+	int rc = pressure_solve(s, iterations, omega_compute(h), flags, st);
+	if (rc) return rc;
+	if (ev_p1) cudaEventRecord(ev_p1, st);
+	launch_subtract_gradient(g, s->adv, s->p[s->p_cur], s->vel, inv, st);
+	if (s->n_scalars) {
+		launch_advect_scalars(g, s->vel, scalar_ptrs(s), s->n_scalars, dt, inv, 0, st);
+		for (int i = 0; i < s->n_scalars; ++i) std::swap(s->sc[i], s->sc_out[i]);
+	}
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+
+}  // namespace hns
+
+using namespace hns;
+
+#define HNS_REQUIRE(cond, msg) \
+	if (!(cond)) return fail(HNS_ERR_INVALID_ARGUMENT, msg)
+
+extern "C" {
+
+int hns_abi_version(void) { return HNS_B200_ABI_VERSION; }
+const char* hns_last_error(void) { return t_error.c_str(); }
+uint64_t hns_launch_count(void) { return g_launches.load(); }
+void hns_launch_count_reset(void) { g_launches.store(0); }
+int hns_set_device(int device) {
+	HNS_CUDA(cudaSetDevice(device));
+	return HNS_OK;
+}
+
+// ---- resident state ---------------------------------------------------------------------------------------------
+int hns_state_create(const hns_grid* g, int n_scalars, hns_state** out) {
+	HNS_REQUIRE(g && out, "null argument");
+	HNS_REQUIRE(n_scalars >= 0 && n_scalars <= 16, "n_scalars must be in [0, 16]");
+	*out = nullptr;
+	int rc = ensure_tables();
+	if (rc) return rc;
+	auto* s = new hns_state();
+	s->grid = g;
+	s->n = g->num_leaves * 512;
+	s->n_scalars = n_scalars;
+	const size_t fb = std::max<size_t>(s->n, 1) * sizeof(float);
+	std::vector<float**> all;
+	for (int c = 0; c < 3; ++c) all.push_back(&s->vel[c]), all.push_back(&s->adv[c]);
+	all.push_back(&s->div), all.push_back(&s->p[0]), all.push_back(&s->p[1]);
+	for (int i = 0; i < n_scalars; ++i) all.push_back(&s->sc[i]), all.push_back(&s->sc_out[i]);
+	for (float** p : all) {
+		const cudaError_t e = cudaMalloc(p, fb);
+		if (e != cudaSuccess) {
+			const std::string msg = std::string("cudaMalloc(field): ") + cudaGetErrorString(e);
+			hns_state_destroy(s);
+			return fail(HNS_ERR_CUDA, msg);
+		}
+		cudaMemset(*p, 0, fb);
+	}
+	*out = s;
+	return HNS_OK;
+}
+
+void hns_state_destroy(hns_state* s) {
+	if (!s) return;
+	for (int c = 0; c < 3; ++c) cudaFree(s->vel[c]), cudaFree(s->adv[c]);
+	cudaFree(s->div), cudaFree(s->p[0]), cudaFree(s->p[1]);
+	for (int i = 0; i < 16; ++i) cudaFree(s->sc[i]), cudaFree(s->sc_out[i]);
+	cudaFree(s->aos);
+	delete s;
+}
+
+static int ensure_aos(hns_state* s) {
+	if (!s->aos) HNS_CUDA(cudaMalloc(&s->aos, std::max<size_t>(s->n, 1) * 3 * sizeof(float)));
+	return HNS_OK;
+}
+
+int hns_state_upload_velocity(hns_state* s, const float* host) {
+	HNS_REQUIRE(s && host, "null argument");
+	int rc = ensure_aos(s);
+	if (rc) return rc;
+	HNS_CUDA(cudaMemcpy(s->aos, host, s->n * 12, cudaMemcpyHostToDevice));
+	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], s->n, 0);
+	HNS_CUDA(cudaDeviceSynchronize());
+	return HNS_OK;
+}
+int hns_state_download_velocity(hns_state* s, float* host) {
+	HNS_REQUIRE(s && host, "null argument");
+	int rc = ensure_aos(s);
+	if (rc) return rc;
+	launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, s->n, 0);
+	HNS_CUDA(cudaMemcpy(host, s->aos, s->n * 12, cudaMemcpyDeviceToHost));
+	return HNS_OK;
+}
+int hns_state_upload_scalar(hns_state* s, int i, const float* host) {
+	HNS_REQUIRE(s && host && i >= 0 && i < s->n_scalars, "bad argument");
+	HNS_CUDA(cudaMemcpy(s->sc[i], host, s->n * 4, cudaMemcpyHostToDevice));
+	return HNS_OK;
+}
+int hns_state_download_scalar(hns_state* s, int i, float* host) {
+	HNS_REQUIRE(s && host && i >= 0 && i < s->n_scalars, "bad argument");
+	HNS_CUDA(cudaMemcpy(host, s->sc[i], s->n * 4, cudaMemcpyDeviceToHost));
+	return HNS_OK;
+}
+int hns_state_download_aux(hns_state* s, int which, float* host) {
+	HNS_REQUIRE(s && host, "null argument");
+	if (which == 0) {
+		HNS_CUDA(cudaMemcpy(host, s->div, s->n * 4, cudaMemcpyDeviceToHost));
+	} else if (which == 1) {
+		HNS_CUDA(cudaMemcpy(host, s->p[s->p_cur], s->n * 4, cudaMemcpyDeviceToHost));
+	} else if (which == 2) {
+		int rc = ensure_aos(s);
+		if (rc) return rc;
+		launch_soa_to_aos(s->adv[0], s->adv[1], s->adv[2], s->aos, s->n, 0);
+		HNS_CUDA(cudaMemcpy(host, s->aos, s->n * 12, cudaMemcpyDeviceToHost));
+	} else {
+		return fail(HNS_ERR_INVALID_ARGUMENT, "which must be 0, 1 or 2");
+	}
+	return HNS_OK;
+}
+
+int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	HNS_REQUIRE(iterations > 0, "Number of pressure iterations must be positive.");
+	HNS_REQUIRE(dt >= 0.0f, "dt (time step) cannot be negative.");
+	if (!s->n) return HNS_OK;
+	return frame(s, iterations, dt, flags, static_cast<cudaStream_t>(stream));
+}
+int hns_state_advect_velocity(hns_state* s, float dt, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	launch_advect_vector(s->grid->view, s->vel, s->adv, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+int hns_state_divergence(hns_state* s, int of_advected, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	launch_divergence(s->grid->view, of_advected ? s->adv : s->vel, s->div, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+int hns_state_pressure_solve(hns_state* s, int iterations, float omega, unsigned flags, void* stream) {
+	HNS_REQUIRE(s && iterations >= 0, "bad argument");
+	if (!s->n) return HNS_OK;
+	int rc = pressure_solve(s, iterations, omega, flags, static_cast<cudaStream_t>(stream));
+	if (rc) return rc;
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (from_advected) {
+		launch_subtract_gradient(s->grid->view, s->adv, s->p[s->p_cur], s->vel, 1.0f / s->grid->voxel_size, st);
+	} else {
+		// in place is safe: every thread reads only its own velocity row (the reference does the same, PressureProjection.cu:64)
+		launch_subtract_gradient(s->grid->view, s->vel, s->p[s->p_cur], s->vel, 1.0f / s->grid->voxel_size, st);
+	}
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+int hns_state_advect_scalars(hns_state* s, float dt, int sampler_semantics, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	if (!s->n_scalars || !s->n) return HNS_OK;
+	launch_advect_scalars(s->grid->view, s->vel, scalar_ptrs(s), s->n_scalars, dt, 1.0f / s->grid->voxel_size, sampler_semantics,
+	                      static_cast<cudaStream_t>(stream));
+	for (int i = 0; i < s->n_scalars; ++i) std::swap(s->sc[i], s->sc_out[i]);
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+int hns_state_sync(hns_state* s, void* stream) {
+	(void)s;
+	HNS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+	return HNS_OK;
+}
+
+int hns_state_time_frames(hns_state* s, int frames, int iterations, float dt, unsigned flags, void* stream, float* ms_total, float* ms_pressure) {
+	HNS_REQUIRE(s && frames > 0 && iterations > 0, "bad argument");
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	// Every frame must do identical work on identical data: keep a pristine copy of the inputs and restore it (outside
+	// the per-frame events would need a sync per frame; instead the restore copies are timed separately and subtracted).
+	const size_t fb = s->n * sizeof(float);
+	std::vector<float*> keep;
+	auto snap = [&](float* src) {
+		float* d = nullptr;
+		if (cudaMalloc(&d, std::max<size_t>(fb, 4)) != cudaSuccess) return false;
+		cudaMemcpyAsync(d, src, fb, cudaMemcpyDeviceToDevice, st);
+		keep.push_back(d);
+		return true;
+	};
+	bool ok = true;
+	for (int c = 0; c < 3 && ok; ++c) ok = snap(s->vel[c]);
+	for (int i = 0; i < s->n_scalars && ok; ++i) ok = snap(s->sc[i]);
+	if (!ok) {
+		for (float* d : keep) cudaFree(d);
+		return fail(HNS_ERR_CUDA, "cudaMalloc(snapshot)");
+	}
+	std::vector<cudaEvent_t> ev(4 * size_t(frames));
+	for (auto& e : ev) cudaEventCreate(&e);
+	int rc = HNS_OK;
+	for (int f = 0; f < frames && rc == HNS_OK; ++f) {
+		for (int c = 0; c < 3; ++c) cudaMemcpyAsync(s->vel[c], keep[c], fb, cudaMemcpyDeviceToDevice, st);
+		for (int i = 0; i < s->n_scalars; ++i) cudaMemcpyAsync(s->sc[i], keep[3 + i], fb, cudaMemcpyDeviceToDevice, st);
+		cudaEventRecord(ev[4 * f + 0], st);
+		rc = frame(s, iterations, dt, flags, st, ev[4 * f + 1], ev[4 * f + 2]);
+		cudaEventRecord(ev[4 * f + 3], st);
+	}
+	cudaStreamSynchronize(st);
+	float tot = 0.f, pr = 0.f;
+	if (rc == HNS_OK)
+		for (int f = 0; f < frames; ++f) {
+			float a = 0.f, b = 0.f;
+			cudaEventElapsedTime(&a, ev[4 * f + 0], ev[4 * f + 3]);
+			cudaEventElapsedTime(&b, ev[4 * f + 1], ev[4 * f + 2]);
+			tot += a, pr += b;
+		}
+	for (auto& e : ev) cudaEventDestroy(e);
+	for (float* d : keep) cudaFree(d);
+	if (ms_total) *ms_total = tot;
+	if (ms_pressure) *ms_pressure = pr;
+	if (rc) return rc;
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+
+static float* field_ptr(hns_state* s, int field) {
+	if (field >= 0 && field < 3) return s->vel[field];
+	if (field >= 3 && field < 6) return s->adv[field - 3];
+	if (field == 6) return s->p[s->p_cur];
+	if (field == 7) return s->div;
+	if (field >= 8 && field < 8 + s->n_scalars) return s->sc[field - 8];
+	return nullptr;
+}
+void* hns_state_field_device_ptr(hns_state* s, int field) { return s ? field_ptr(s, field) : nullptr; }
+int hns_state_pack_leaves(hns_state* s, int field, const int32_t* ids, uint64_t n_ids, float* dst, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	float* f = field_ptr(s, field);
+	HNS_REQUIRE(f, "bad field id");
+	launch_pack_leaves(f, ids, n_ids, dst, static_cast<cudaStream_t>(stream));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+int hns_state_unpack_leaves(hns_state* s, int field, const int32_t* ids, uint64_t n_ids, const float* src, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	float* f = field_ptr(s, field);
+	HNS_REQUIRE(f, "bad field id");
+	launch_unpack_leaves(f, ids, n_ids, src, static_cast<cudaStream_t>(stream));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+
+// ---- one-shot launchers on host sidecar arrays --------------------------------------------------------------------
+// Shared helper: RAII for a temporary grid + state.
+struct Scoped {
+	hns_grid* grid = nullptr;
+	hns_state* state = nullptr;
+	bool own_grid = false;
+	~Scoped() {
+		hns_state_destroy(state);
+		if (own_grid) hns_grid_destroy(grid);
+	}
+};
+
+int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char* const* names, float* const* fields, int iterations, float dt,
+                    float voxel_size, const hns_combustion_params* params, int has_collision, void* stream) {
+	// validation in the reference's order (HNanoSolver.cu:12-35)
+	if (!(voxel_size > 0.0f)) return fail(HNS_ERR_INVALID_ARGUMENT, "voxelSize must be positive.");
+	if (dt < 0.0f) return fail(HNS_ERR_INVALID_ARGUMENT, "dt (time step) cannot be negative.");
+	if (iterations <= 0) return fail(HNS_ERR_INVALID_ARGUMENT, "Number of pressure iterations must be positive.");
+	if (!g) return fail(HNS_ERR_INVALID_ARGUMENT, "Invalid nanovdb::GridHandle provided (null grid).");
+	const uint64_t n = g->num_leaves * 512;
+	if (n == 0) return HNS_OK;  // :26-28
+	if (!velocity) return fail(HNS_ERR_RUNTIME, "Host velocity data pointer is null");
+	if (n_float <= 0) return fail(HNS_ERR_RUNTIME, "No float blocks found in input data.");
+	if (n_float > 16) return fail(HNS_ERR_UNSUPPORTED, "more than 16 float blocks");
+	if (!names || !fields || !params) return fail(HNS_ERR_INVALID_ARGUMENT, "null argument");
+	int iF = -1, iW = -1, iT = -1, iL = -1, iSdf = -1;
+	for (int i = 0; i < n_float; ++i) {
+		if (!fields[i]) return fail(HNS_ERR_RUNTIME, std::string("Host float data pointer is null for block: ") + names[i]);
+		if (!std::strcmp(names[i], "fuel")) iF = i;
+		if (!std::strcmp(names[i], "waste")) iW = i;
+		if (!std::strcmp(names[i], "temperature")) iT = i;
+		if (!std::strcmp(names[i], "flame")) iL = i;
+		if (!std::strcmp(names[i], "collision_sdf")) iSdf = i;
+	}
+	if (has_collision && iSdf >= 0) return fail(HNS_ERR_UNSUPPORTED, "SDF collision handling is not implemented in this build (SURVEY.md 8f rank 2)");
+	if (params->vorticityScale != 0.0f)
+		return fail(HNS_ERR_UNSUPPORTED, "vorticityScale != 0: the reference applies vorticity confinement in place with a data race "
+		                                 "(HNanoSolver.cu:174), so no reference result exists to reproduce; not implemented in this build");
+	for (const char* req : {"fuel", "waste", "temperature", "flame"}) {  // :193-201
+		bool found = false;
+		for (int i = 0; i < n_float; ++i) found |= !std::strcmp(names[i], req);
+		if (!found) return fail(HNS_ERR_RUNTIME, std::string("Missing required input field for combustion: ") + req);
+	}
+	if (g->voxel_size != voxel_size) {
+		// the reference passes voxelSize independently of the grid's map; kernels only use the argument
+	}
+	Scoped sc;
+	int rc = hns_state_create(g, n_float, &sc.state);
+	if (rc) return rc;
+	hns_state* s = sc.state;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	const GridView& gv = g->view;
+	const float inv = 1.0f / voxel_size;
+	if ((rc = ensure_aos(s))) return rc;
+	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
+	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
+	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, st));
+	// 1. advect velocity; (vorticity confinement with scale 0 is the identity); 2. divergence of the advected velocity
+	launch_advect_vector(gv, s->vel, s->adv, dt, inv, st);
+	launch_divergence(gv, s->adv, s->div, inv, st);
+	// 3. combustion (in -> out, div += burn*expansion), buoyancy on the advected velocity with the post-combustion temperature
+	launch_combustion_oxygen(s->sc[iF], s->sc[iW], s->sc[iT], s->div, s->sc[iL], s->sc_out[iF], s->sc_out[iW], s->sc_out[iT], s->sc_out[iL],
+	                         params->temperatureRelease, params->expansionRate, n, st);
+	launch_buoyancy(s->adv, s->sc_out[iT], dt, params->ambientTemp, params->buoyancyStrength, n, st);
+	for (int i : {iF, iW, iT, iL}) std::swap(s->sc[i], s->sc_out[i]);  // :239-246
+	// 4. pressure, 5. projection
+	{
+		const float keep_h = s->grid->voxel_size;
+		(void)keep_h;
+	}
+	s->p_cur = 0;
+	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, n * 4, st));
+	const float omega = omega_compute(voxel_size);
+	for (int it = 0; it < iterations; ++it) {
+		launch_rbgs_fused(gv, s->div, s->p[s->p_cur], s->p[s->p_cur ^ 1], voxel_size, omega, st);
+		s->p_cur ^= 1;
+	}
+	launch_subtract_gradient(gv, s->adv, s->p[s->p_cur], s->vel, inv, st);
+	// 6. advect every float block except collision_sdf with the projected velocity (:321-348)
+	ScalarPtrs sp{};
+	int S = 0;
+	std::vector<int> which;
+	for (int i = 0; i < n_float; ++i) {
+		if (i == iSdf) continue;
+		sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i];
+		which.push_back(i);
+		++S;
+	}
+	launch_advect_scalars(gv, s->vel, sp, S, dt, inv, 0, st);
+	// results back to the same host arrays (:361-369); a collision_sdf block comes back zeroed like the reference's untouched output buffer
+	launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, n, st);
+	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, st));
+	for (int i = 0; i < n_float; ++i) {
+		if (i == iSdf) HNS_CUDA(cudaMemsetAsync(s->sc_out[i], 0, n * 4, st));
+		HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc_out[i], n * 4, cudaMemcpyDeviceToHost, st));
+	}
+	HNS_CUDA(cudaStreamSynchronize(st));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+
+static int temp_grid(const int32_t* coords, uint64_t n, float voxel_size, Scoped& sc, int n_scalars) {
+	int rc = hns_grid_create_from_coords(coords, n, voxel_size, 0, &sc.grid);
+	if (rc) return rc;
+	sc.own_grid = true;
+	return hns_state_create(sc.grid, n_scalars, &sc.state);
+}
+
+int hns_advect_index_grid(const int32_t* coords, uint64_t n, const float* velocity, int n_float, float* const* fields, float dt, float voxel_size,
+                          void* stream) {
+	if (!velocity) return fail(HNS_ERR_RUNTIME, "Velocity data not found");
+	if (n_float <= 0 || !fields) return fail(HNS_ERR_RUNTIME, "No float blocks found");
+	if (n_float > 16) return fail(HNS_ERR_UNSUPPORTED, "more than 16 float blocks");
+	if (n == 0) return HNS_OK;
+	Scoped sc;
+	int rc = temp_grid(coords, n, voxel_size, sc, n_float);
+	if (rc) return rc;
+	hns_state* s = sc.state;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if ((rc = ensure_aos(s))) return rc;
+	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
+	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
+	for (int i = 0; i < n_float; ++i) {
+		if (!fields[i]) return fail(HNS_ERR_RUNTIME, "Block not found or type mismatch");
+		HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, st));
+	}
+	launch_advect_scalars(sc.grid->view, s->vel, scalar_ptrs(s), n_float, dt, 1.0f / voxel_size, 1, st);  // advect_scalar semantics (Advection.cu:89)
+	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc_out[i], n * 4, cudaMemcpyDeviceToHost, st));
+	HNS_CUDA(cudaStreamSynchronize(st));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+
+int hns_advect_index_grid_velocity(const int32_t* coords, uint64_t n, float* velocity, float dt, float voxel_size, void* stream) {
+	if (!velocity) return fail(HNS_ERR_RUNTIME, "Velocity data not found");
+	if (n == 0) return HNS_OK;
+	Scoped sc;
+	int rc = temp_grid(coords, n, voxel_size, sc, 0);
+	if (rc) return rc;
+	hns_state* s = sc.state;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if ((rc = ensure_aos(s))) return rc;
+	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
+	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
+	launch_advect_vector(sc.grid->view, s->vel, s->adv, dt, 1.0f / voxel_size, st);
+	launch_soa_to_aos(s->adv[0], s->adv[1], s->adv[2], s->aos, n, st);
+	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, st));
+	HNS_CUDA(cudaStreamSynchronize(st));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+
+int hns_project_non_divergent(const int32_t* coords, uint64_t n, float* velocity, uint64_t iterations, float voxel_size, void* stream) {
+	if (!velocity) return fail(HNS_ERR_RUNTIME, "Velocity data not found");
+	if (n == 0) return HNS_OK;
+	Scoped sc;
+	int rc = temp_grid(coords, n, voxel_size, sc, 0);
+	if (rc) return rc;
+	hns_state* s = sc.state;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	const float inv = 1.0f / voxel_size;
+	if ((rc = ensure_aos(s))) return rc;
+	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
+	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
+	launch_divergence(sc.grid->view, s->vel, s->div, inv, st);
+	s->p_cur = 0;
+	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, n * 4, st));
+	const float omega = omega_project(voxel_size);
+	for (uint64_t it = 0; it < iterations; ++it) {
+		launch_rbgs_fused(sc.grid->view, s->div, s->p[s->p_cur], s->p[s->p_cur ^ 1], voxel_size, omega, st);
+		s->p_cur ^= 1;
+	}
+	launch_subtract_gradient(sc.grid->view, s->vel, s->p[s->p_cur], s->vel, inv, st);
+	launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, n, st);
+	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, st));
+	HNS_CUDA(cudaStreamSynchronize(st));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+
+int hns_divergence(const int32_t* coords, uint64_t n, const float* velocity, float* divergence_out, float voxel_size, void* stream) {
+	if (!velocity) return fail(HNS_ERR_RUNTIME, "Velocity data not found");
+	if (!divergence_out) return fail(HNS_ERR_RUNTIME, "float block 'divergence' not found");
+	if (n == 0) return HNS_OK;
+	Scoped sc;
+	int rc = temp_grid(coords, n, voxel_size, sc, 0);
+	if (rc) return rc;
+	hns_state* s = sc.state;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if ((rc = ensure_aos(s))) return rc;
+	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
+	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
+	launch_divergence(sc.grid->view, s->vel, s->div, 1.0f / voxel_size, st);
+	HNS_CUDA(cudaMemcpyAsync(divergence_out, s->div, n * 4, cudaMemcpyDeviceToHost, st));
+	HNS_CUDA(cudaStreamSynchronize(st));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+
+int hns_combustion_kernel(const hns_grid* g, float* velocity, uint64_t n_voxels, float dt, float voxel_size, void* stream) {
+	(void)dt, (void)voxel_size, (void)stream;
+	if (!g) return fail(HNS_ERR_INVALID_ARGUMENT, "null grid");
+	if (!velocity && n_voxels) return fail(HNS_ERR_RUNTIME, "Velocity data not found");
+	return HNS_OK;  // validated no-op: see header
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Shared declarations for libhns_b200: error handling, launch accounting, device-side grid view.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/hns_b200.h"
+
+namespace hns {
+
+// ---- errors -------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define HNS_CUDA(call)                                                                                           \
+	do {                                                                                                         \
+		cudaError_t e_ = (call);                                                                                 \
+		if (e_ != cudaSuccess)                                                                                   \
+			return ::hns::fail(HNS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+	} while (0)
+
+// ---- launch accounting (hns_launch_count) ---------------------------------------------------------------
+extern std::atomic<uint64_t> g_launches;
+#define HNS_LAUNCH(kernel, grid, block, smem, stream, ...)              \
+	do {                                                                \
+		kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);     \
+		::hns::g_launches.fetch_add(1, std::memory_order_relaxed);      \
+	} while (0)
+
+// ---- NanoVDB 32.7 ValueOnIndex buffer layout (own POD mirror) -------------------
+// [GridData 672][TreeData 64][RootData 96][Tile 32 x T][Upper 270400 x T][Lower 33856 x nLower][Leaf 96 x L]
+namespace nvdb {
+constexpr uint64_t kGrid = 672, kTree = 64, kRoot = 96, kTile = 32, kUpper = 270400, kLower = 33856, kLeaf = 96;
+constexpr uint64_t kUpperChildMask = 4128, kUpperTable = 8256;  // InternalData<.,5>: bbox 0, flags 24, valueMask 32, childMask 4128, stats 8224.., table 8256
+constexpr uint64_t kLowerChildMask = 544, kLowerTable = 1088;   // InternalData<.,4>: bbox 0, flags 24, valueMask 32, childMask 544, stats 1056.., table 1088
+constexpr uint64_t kLeafMask = 16, kLeafOffset = 80, kLeafPrefix = 88;  // LeafData<ValueOnIndex>: bboxMin 0, bboxDif 12, flags 15, mask 16, mOffset 80, mPrefixSum 88
+constexpr uint64_t kRootTableSize = 24;
+}  // namespace nvdb
+
+// Device view of an index grid.
+struct GridView {
+	const uint8_t* nvdb;      // the NanoVDB buffer
+	const int4* origin;       // [L] leaf origins (x, y, z, 0)
+	const int32_t* nbr;       // [L][27] neighbour leaf ids, -1 = none; slot (dx+1)*9+(dy+1)*3+(dz+1)
+	uint32_t num_leaves;
+	uint32_t num_tiles;
+	uint64_t off_root, off_leaf;  // byte offsets of RootData and of the first leaf inside nvdb
+};
+
+// slot ids of the six face neighbours
+constexpr int kSlotXm = 4, kSlotXp = 22, kSlotYm = 10, kSlotYp = 16, kSlotZm = 12, kSlotZp = 14, kSlotSelf = 13;
+
+#ifdef __CUDACC__
+// Leaf ordinal containing voxel (x,y,z), or -1: the ReadAccessor walk (root tile scan -> upper -> lower) on the emitted buffer.
+__device__ __forceinline__ int probe_leaf(const GridView& g, int x, int y, int z) {
+	const uint8_t* root = g.nvdb + g.off_root;
+	const uint64_t key = (uint64_t(uint32_t(z) >> 12)) | (uint64_t(uint32_t(y) >> 12) << 21) | (uint64_t(uint32_t(x) >> 12) << 42);
+	const uint8_t* upper = nullptr;
+	for (uint32_t t = 0; t < g.num_tiles; ++t) {
+		const uint8_t* tile = root + nvdb::kRoot + nvdb::kTile * t;
+		if (*reinterpret_cast<const uint64_t*>(tile) == key) {
+			upper = root + *reinterpret_cast<const int64_t*>(tile + 8);
+			break;
+		}
+	}
+	if (!upper) return -1;
+	const uint32_t uo = uint32_t(((x & 4095) >> 7) << 10 | ((y & 4095) >> 7) << 5 | ((z & 4095) >> 7));
+	if (!((*reinterpret_cast<const uint64_t*>(upper + nvdb::kUpperChildMask + 8 * (uo >> 6)) >> (uo & 63)) & 1)) return -1;
+	const uint8_t* lower = upper + *reinterpret_cast<const int64_t*>(upper + nvdb::kUpperTable + 8ull * uo);
+	const uint32_t lo = uint32_t(((x & 127) >> 3) << 8 | ((y & 127) >> 3) << 4 | ((z & 127) >> 3));
+	if (!((*reinterpret_cast<const uint64_t*>(lower + nvdb::kLowerChildMask + 8 * (lo >> 6)) >> (lo & 63)) & 1)) return -1;
+	const uint8_t* leaf = lower + *reinterpret_cast<const int64_t*>(lower + nvdb::kLowerTable + 8ull * lo);
+	return int((leaf - (g.nvdb + g.off_leaf)) / nvdb::kLeaf);
+}
+#endif
+
+}  // namespace hns
+
+// ---- opaque handle definitions ----------------------------------------------------------------------------
+struct hns_grid {
+	int device = 0;
+	float voxel_size = 0.f;
+	uint64_t num_leaves = 0, num_lower = 0, num_upper = 0;
+	uint64_t nvdb_bytes = 0;
+	uint8_t* d_nvdb = nullptr;
+	int4* d_origin = nullptr;
+	int32_t* d_nbr = nullptr;
+	hns::GridView view{};
+};
+
+struct hns_state {
+	const hns_grid* grid = nullptr;
+	uint64_t n = 0;  // voxels
+	int n_scalars = 0;
+	float* vel[3] = {};   // current velocity, SoA bricks float[L][512]
+	float* adv[3] = {};   // advected velocity
+	float* div = nullptr;
+	float* p[2] = {};     // pressure ping-pong
+	int p_cur = 0;        // which of p[] holds the latest pressure
+	float* sc[16] = {};   // scalar fields (current)
+	float* sc_out[16] = {};
+	float* aos = nullptr; // staging float[N][3] for host <-> device velocity transfers
+	float** d_sc_in = nullptr;   // device arrays of the S pointers
+	float** d_sc_out = nullptr;
+};

@@ -1,0 +1,40 @@
+// Kernel launch wrappers of libhns_b200 (definitions in kernels.cu). All fields are brick fields: float[L][512],
+// voxel (x,y,z) of leaf l at l*512 + (x<<6 | y<<3 | z); velocity is three such fields (SoA).
+#pragma once
+#include "common.cuh"
+
+namespace hns {
+
+struct ScalarPtrs {
+	const float* in[16];
+	float* out[16];
+};
+
+// AoS float[N][3] <-> three brick fields
+void launch_aos_to_soa(const float* aos, float* u, float* v, float* w, uint64_t n, cudaStream_t st);
+void launch_soa_to_aos(const float* u, const float* v, const float* w, float* aos, uint64_t n, cudaStream_t st);
+
+// advect_vector (reference src/Cuda/Kernel.cu:354-453), hasCollision == false
+void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st);
+// advect_scalars (Kernel.cu:118-266) when sampler_semantics == 0; advect_scalar (Kernel.cu:269-352) per field when == 1
+void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx,
+                           int sampler_semantics, cudaStream_t st);
+// divergence (Kernel.cu:499-519)
+void launch_divergence(const GridView& g, const float* const vel[3], float* div, float inv_dx, cudaStream_t st);
+// redBlackGaussSeidelUpdate (Kernel.cu:591-623): one colour, in place
+void launch_rbgs_color(const GridView& g, const float* div, float* p, float dx, int color, float omega, cudaStream_t st);
+// red then black in ONE launch, p_in -> p_out (bit-identical to two launch_rbgs_color calls)
+void launch_rbgs_fused(const GridView& g, const float* div, const float* p_in, float* p_out, float dx, float omega, cudaStream_t st);
+// subtractPressureGradient (Kernel.cu:765-829)
+void launch_subtract_gradient(const GridView& g, const float* const vel[3], const float* p, float* const out[3], float inv_dx, cudaStream_t st);
+// combustion_oxygen (Kernel.cu:923-966) and temperature_buoyancy (Kernel.cu:831-847, in place on the y component)
+void launch_combustion_oxygen(const float* fuel, const float* waste, const float* temp, float* div, const float* flame, float* oFuel,
+                              float* oWaste, float* oTemp, float* oFlame, float temp_gain, float expansion, uint64_t n, cudaStream_t st);
+void launch_buoyancy(float* const vel[3], const float* temp, float dt, float ambient, float strength, uint64_t n, cudaStream_t st);
+// whole-brick gather / scatter by leaf id (ghost exchange)
+void launch_pack_leaves(const float* field, const int32_t* ids, uint64_t n_ids, float* dst, cudaStream_t st);
+void launch_unpack_leaves(float* field, const int32_t* ids, uint64_t n_ids, const float* src, cudaStream_t st);
+
+int upload_tables();  // constant tables of the fused pressure kernel, once per device
+
+}  // namespace hns

@@ -1,0 +1,153 @@
+/*
+ * hns_b200.h -- C ABI of the B200-native HNanoSolver hot path (libhns_b200.so).
+ *
+ * Plain C: opaque handles, raw pointers, sizes, int error codes. No C++ types, no torch types, no exceptions
+ * cross this boundary. Every entry point names the reference interface it replaces (paths relative to the
+ * reference repository root). The C++ adapter that re-exports the reference's own seven launcher symbols on
+ * top of this ABI is compat/hns_compat.cu.
+ *
+ * Data contract (reference src/Utils/GridBuilder.hpp:156-166,221-239; src/Utils/GridData.hpp:16-166):
+ *   - N = L * 512 voxels, L leaves (8^3 bricks). Host arrays are leaf-major; inside a leaf the voxel at local
+ *     (x,y,z) is at offset (x<<6 | y<<3 | z). Leaves are in NanoVDB order (root tile, upper offset, lower offset).
+ *   - coords:   int32[N][3]   (openvdb::Coord)
+ *   - velocity: float[N][3]   (openvdb::Vec3f, AoS)
+ *   - every scalar field: float[N]
+ *   - NanoVDB value index of a voxel = 1 + its position in these arrays; 0 = background.
+ *
+ * All functions return HNS_OK (0) or a negative hns_status; hns_last_error() gives the message for the calling
+ * thread. There is no CPU fallback: without a CUDA device every compute entry point fails with HNS_ERR_CUDA.
+ */
+#ifndef HNS_B200_H
+#define HNS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HNS_B200_ABI_VERSION 1
+
+typedef enum hns_status {
+	HNS_OK = 0,
+	HNS_ERR_INVALID_ARGUMENT = -1, /* reference: std::invalid_argument (src/Cuda/HNanoSolver.cu:12-23) */
+	HNS_ERR_RUNTIME = -2,          /* reference: std::runtime_error   (src/Cuda/HNanoSolver.cu:34,44,62,196) */
+	HNS_ERR_CUDA = -3,             /* reference: CUDA_CHECK throw     (src/Cuda/Utils.cuh:10-18) */
+	HNS_ERR_TOPOLOGY = -4,         /* coords are not the dense, NanoVDB-ordered leaf blocks the kernels assume */
+	HNS_ERR_UNSUPPORTED = -5
+} hns_status;
+
+typedef struct hns_grid hns_grid;   /* device index grid + leaf tables; replaces nanovdb::GridHandle<DeviceBuffer> */
+typedef struct hns_state hns_state; /* device-resident fields of one simulation (persistent across frames)        */
+
+/* reference: struct CombustionParams, src/Cuda/Kernels.cuh:6-13 (same field order) */
+typedef struct hns_combustion_params {
+	float expansionRate;
+	float temperatureRelease;
+	float buoyancyStrength;
+	float ambientTemp;
+	float vorticityScale;
+	float factorScale;
+} hns_combustion_params;
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Library
+ * ------------------------------------------------------------------------------------------------------- */
+int hns_abi_version(void);
+const char* hns_last_error(void);
+/* Number of kernels of this library launched by the calling process since load / since the last reset. */
+uint64_t hns_launch_count(void);
+void hns_launch_count_reset(void);
+/* Select the CUDA device used by subsequently created grids/states of the calling thread (cudaSetDevice). */
+int hns_set_device(int device);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Index grid -- replaces CreateIndexGrid (src/Cuda/HNanoSolver.cu:375-390), i.e.
+ * nanovdb::tools::cuda::voxelsToGrid<ValueOnIndex>(coords, N, voxelSize) for HNS's dense-leaf sidecar.
+ * ------------------------------------------------------------------------------------------------------- */
+/* coords: HOST int32[n_voxels][3] exactly as HNS::GridIndexedData::pCoords() holds them. Only the first coord of
+ * every 512-block is needed to build the grid; validate != 0 additionally checks on the device that every block
+ * is the dense brick in offset order (the reference silently produces inconsistent results otherwise). */
+int hns_grid_create_from_coords(const int32_t* coords, uint64_t n_voxels, float voxel_size, int validate, hns_grid** out);
+/* origins: HOST int32[n_leaves][3], multiples of 8, in NanoVDB order. */
+int hns_grid_create_from_origins(const int32_t* origins, uint64_t n_leaves, float voxel_size, hns_grid** out);
+void hns_grid_destroy(hns_grid* g);
+uint64_t hns_grid_num_leaves(const hns_grid* g);
+uint64_t hns_grid_num_voxels(const hns_grid* g);
+float hns_grid_voxel_size(const hns_grid* g);
+/* The NanoVDB 32.7 ValueOnIndex buffer (what voxelsToGrid emits). */
+uint64_t hns_grid_nanovdb_bytes(const hns_grid* g);
+const void* hns_grid_nanovdb_device_ptr(const hns_grid* g);
+int hns_grid_nanovdb_download(const hns_grid* g, void* dst_host);
+/* getValue(ijk) for n HOST coordinates, evaluated on the device by walking the emitted NanoVDB buffer
+ * (root tile scan -> upper -> lower -> leaf), i.e. nanovdb::ReadAccessor::getValue (externals/nanovdb/NanoVDB.h:5683-5698). */
+int hns_grid_get_values(const hns_grid* g, const int32_t* ijk_host, uint64_t n, uint64_t* out_host);
+/* Per-leaf 27-neighbour table (int32[L][27], -1 = no leaf; slot = (dx+1)*9 + (dy+1)*3 + (dz+1)) to HOST. */
+int hns_grid_neighbors_download(const hns_grid* g, int32_t* dst_host);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * One-shot launchers on HOST sidecar arrays, in place, synchronous -- the drop-in equivalents of the reference's
+ * extern "C" launchers. `stream` is a cudaStream_t passed as void* (may be NULL).
+ * ------------------------------------------------------------------------------------------------------- */
+/* Compute_Sim (src/Cuda/HNanoSolver.cu:9-372,393-396): advect velocity -> [vorticity] -> divergence -> combustion ->
+ * buoyancy -> iterations x (red, black) -> gradient subtract -> advect all float fields. float_names/float_fields are
+ * the float blocks in insertion order (GridData.hpp:136-145); fuel, waste, temperature, flame must be among them. */
+int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char* const* float_names, float* const* float_fields,
+                    int iterations, float dt, float voxel_size, const hns_combustion_params* params, int has_collision, void* stream);
+/* AdvectIndexGrid (src/Cuda/Advection.cu:13-112,169-171): BFECC advection of every float block by the velocity block. */
+int hns_advect_index_grid(const int32_t* coords, uint64_t n_voxels, const float* velocity, int n_float, float* const* float_fields,
+                          float dt, float voxel_size, void* stream);
+/* AdvectIndexGridVelocity (src/Cuda/Advection.cu:114-166,173-175): BFECC self-advection of the velocity block. */
+int hns_advect_index_grid_velocity(const int32_t* coords, uint64_t n_voxels, float* velocity, float dt, float voxel_size, void* stream);
+/* ProjectNonDivergent (src/Cuda/PressureProjection.cu:9-78,132-135). */
+int hns_project_non_divergent(const int32_t* coords, uint64_t n_voxels, float* velocity, uint64_t iterations, float voxel_size,
+                              void* stream);
+/* Divergence (src/Cuda/PressureProjection.cu:81-129): writes the "divergence" float block. */
+int hns_divergence(const int32_t* coords, uint64_t n_voxels, const float* velocity, float* divergence_out, float voxel_size, void* stream);
+/* CombustionKernel (src/Cuda/Combustion.cu:9-70): the reference's kernel launch is commented out (:55) and it copies an
+ * unwritten buffer over the host velocity (:57). Exported for symbol parity as a validated no-op. */
+int hns_combustion_kernel(const hns_grid* g, float* velocity, uint64_t n_voxels, float dt, float voxel_size, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Device-resident simulation state: what the reference re-uploads every frame (src/Cuda/HNanoSolver.cu:87-133)
+ * lives on the device across frames here. Used by the headless driver, bench.py and the multi-GPU runner.
+ * ------------------------------------------------------------------------------------------------------- */
+int hns_state_create(const hns_grid* g, int n_scalars, hns_state** out);
+void hns_state_destroy(hns_state* s);
+/* HOST <-> device, converting between the sidecar layout (AoS Vec3f, float[N]) and the internal brick layout. */
+int hns_state_upload_velocity(hns_state* s, const float* velocity_host);
+int hns_state_download_velocity(hns_state* s, float* velocity_host);
+int hns_state_upload_scalar(hns_state* s, int index, const float* host);
+int hns_state_download_scalar(hns_state* s, int index, float* host);
+/* intermediate fields of the last step, for parity checks: which = 0 divergence, 1 pressure, 2 advected velocity (float[N][3]) */
+int hns_state_download_aux(hns_state* s, int which, float* host);
+
+/* One frame on resident state: advect_vector -> divergence -> iterations x (red, black) -> gradient subtract ->
+ * advect_scalars (all n_scalars fields). Same arithmetic as the corresponding steps of Compute() (HNanoSolver.cu:159-356);
+ * omega = 2/(1+sinf(3.14159f*voxel_size)) (HNanoSolver.cu:257). Asynchronous on `stream`.
+ * flags: bit 0 = force the unfused (one colour per launch) pressure kernels. */
+int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void* stream);
+/* Individual steps on resident state (asynchronous). */
+int hns_state_advect_velocity(hns_state* s, float dt, void* stream);                 /* vel -> adv              */
+int hns_state_divergence(hns_state* s, int of_advected, void* stream);               /* adv|vel -> div          */
+int hns_state_pressure_solve(hns_state* s, int iterations, float omega, unsigned flags, void* stream); /* p = 0; RBGS   */
+int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream);      /* adv|vel, p -> vel       */
+int hns_state_advect_scalars(hns_state* s, float dt, int sampler_semantics, void* stream); /* 0: advect_scalars, 1: advect_scalar */
+int hns_state_sync(hns_state* s, void* stream);
+/* Timed run of `frames` identical frames (state is restored between frames) with CUDA events on `stream`;
+ * ms_total = whole loop, ms_pressure = time inside the pressure solve only. */
+int hns_state_time_frames(hns_state* s, int frames, int iterations, float dt, unsigned flags, void* stream, float* ms_total,
+                          float* ms_pressure);
+
+/* Ghost-leaf exchange support for spatially sharded runs (one process per GPU): pack/unpack whole bricks of one
+ * internal field by leaf id list into/from a contiguous device buffer (float[n_ids][512]).
+ * field: 0..2 velocity components, 3..5 advected velocity components, 6 pressure, 7 divergence, 8+i scalar i. */
+int hns_state_pack_leaves(hns_state* s, int field, const int32_t* leaf_ids_dev, uint64_t n_ids, float* dst_dev, void* stream);
+int hns_state_unpack_leaves(hns_state* s, int field, const int32_t* leaf_ids_dev, uint64_t n_ids, const float* src_dev, void* stream);
+void* hns_state_field_device_ptr(hns_state* s, int field);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNS_B200_H */

@@ -1,0 +1,760 @@
+/*
+ * hns_oracle.c -- CPU restatement of HNanoSolver's per-frame hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY. This file is the *checker*: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may build, load or call it. Nothing under
+ * hnanosolver_b200/ (the product) includes, links or falls back to it.
+ *
+ * Parity pin: (1) the NanoVDB index contract is checked against the vendored NanoVDB unit test vectors
+ * (externals/nanovdb/unittest/TestNanoVDB.cu:302-398) and against a real NanoVDB host ValueOnIndex grid +
+ * the reference's own __hostdev__ samplers (oracle/_ref/ref_host_kat, Tests/IndexGrid.cpp:209-223,278-281);
+ * (2) every kernel restated here is checked against the UNMODIFIED reference kernels compiled for sm_100a
+ * (oracle/_ref/libhns_ref.so) -- live in the -m gpu tests and through the committed fixtures in tests/golden/.
+ *
+ * Each function cites the reference file:line it follows (paths relative to /root/reference).
+ * Floating point: the reference is compiled by nvcc with the default -fmad=true; the places where ptxas
+ * fuses a multiply-add were read off the sm_100a SASS of the reference build and are written here as
+ * explicit fmaf() (this file is compiled with -ffp-contract=off so nothing else is fused).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Index grid: restatement of nanovdb::tools::cuda::voxelsToGrid<ValueOnIndex>
+ * (externals/nanovdb/tools/cuda/PointsToGrid.cuh:566-721, 912-1056) + LeafData<ValueOnIndex>::getValue
+ * (externals/nanovdb/NanoVDB.h:4219-4228).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+	int32_t origin[3];
+	uint64_t mask[8];   /* mValueMask, bit n = voxel offset n = (x&7)<<6|(y&7)<<3|(z&7) */
+	uint64_t offset;    /* mOffset: 1 + number of active voxels in all previous leaves      */
+	uint64_t prefix;    /* mPrefixSum: 7 x 9-bit running popcounts                          */
+	uint64_t tile_key;  /* sort key, level 1 (PointsToGrid.cuh:596-602)                     */
+	uint64_t node_key;  /* (upper offset << 12 | lower offset), sort key level 2 (:640-645) */
+} ora_leaf;
+
+typedef struct {
+	int64_t n_leaves;
+	ora_leaf* leaves;
+	uint64_t n_active;
+	/* open-addressing hash: leaf coordinate -> leaf ordinal */
+	uint64_t hmask;
+	uint64_t* hkey;
+	int32_t* hval;
+	/* unique sorted node keys for the buffer emitter */
+	int64_t n_lower, n_upper;
+} ora_index;
+
+/* PointsToGrid.cuh:596-602: 21 bits per axis of the 4096-aligned tile, shifted by 2^31 so that signed order == unsigned order */
+static uint64_t ora_tile_key(int32_t x, int32_t y, int32_t z) {
+	const int64_t off = (int64_t)1 << 31;
+	return ((uint64_t)((uint32_t)((int64_t)z + off) >> 12)) | ((uint64_t)((uint32_t)((int64_t)y + off) >> 12) << 21) |
+	       ((uint64_t)((uint32_t)((int64_t)x + off) >> 12) << 42);
+}
+/* NanoVDB.h InternalNode<.,5>::CoordToOffset / InternalNode<.,4>::CoordToOffset / LeafNode::CoordToOffset */
+static uint32_t ora_upper_off(int32_t x, int32_t y, int32_t z) { return (uint32_t)(((x & 4095) >> 7) << 10 | ((y & 4095) >> 7) << 5 | ((z & 4095) >> 7)); }
+static uint32_t ora_lower_off(int32_t x, int32_t y, int32_t z) { return (uint32_t)(((x & 127) >> 3) << 8 | ((y & 127) >> 3) << 4 | ((z & 127) >> 3)); }
+static uint32_t ora_voxel_off(int32_t x, int32_t y, int32_t z) { return (uint32_t)((x & 7) << 6 | (y & 7) << 3 | (z & 7)); }
+
+static uint64_t ora_hash_coord(int32_t lx, int32_t ly, int32_t lz) {
+	uint64_t k = ((uint64_t)(uint32_t)lx * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)(uint32_t)ly * 0xC2B2AE3D27D4EB4Full) ^
+	             ((uint64_t)(uint32_t)lz * 0x165667B19E3779F9ull);
+	k ^= k >> 29;
+	k *= 0xBF58476D1CE4E5B9ull;
+	k ^= k >> 32;
+	return k;
+}
+static uint64_t ora_pack_coord(int32_t lx, int32_t ly, int32_t lz) {
+	return ((uint64_t)((uint32_t)lx & 0x1FFFFFu) << 42) | ((uint64_t)((uint32_t)ly & 0x1FFFFFu) << 21) | ((uint64_t)((uint32_t)lz & 0x1FFFFFu)) |
+	       0x8000000000000000ull;
+}
+
+typedef struct {
+	uint64_t tile, vox; /* voxel key inside the tile: upper<<21 | lower<<9 | voxel (PointsToGrid.cuh:640-645 without the tile id) */
+	int32_t c[3];
+} ora_vkey;
+static int ora_vkey_cmp(const void* a_, const void* b_) {
+	const ora_vkey *a = (const ora_vkey*)a_, *b = (const ora_vkey*)b_;
+	if (a->tile != b->tile) return a->tile < b->tile ? -1 : 1;
+	if (a->vox != b->vox) return a->vox < b->vox ? -1 : 1;
+	return 0;
+}
+
+static int ora_popcnt64(uint64_t v) { return __builtin_popcountll(v); }
+
+void ora_index_destroy(ora_index* ix) {
+	if (!ix) return;
+	free(ix->leaves);
+	free(ix->hkey);
+	free(ix->hval);
+	free(ix);
+}
+
+/* Build the index from an arbitrary (unsorted, possibly duplicated, possibly partial-leaf) voxel list, exactly as
+ * voxelsToGrid does: sort by (tile key, voxel key), run-length-encode voxels, leaves, lower and upper nodes. */
+ora_index* ora_index_create(const int32_t* coords, uint64_t n) {
+	ora_index* ix = (ora_index*)calloc(1, sizeof(ora_index));
+	if (n == 0) return ix;
+	ora_vkey* k = (ora_vkey*)malloc(n * sizeof(ora_vkey));
+	int sorted = 1;
+	for (uint64_t i = 0; i < n; ++i) {
+		const int32_t x = coords[3 * i], y = coords[3 * i + 1], z = coords[3 * i + 2];
+		k[i].tile = ora_tile_key(x, y, z);
+		k[i].vox = (uint64_t)ora_upper_off(x, y, z) << 21 | (uint64_t)ora_lower_off(x, y, z) << 9 | ora_voxel_off(x, y, z);
+		k[i].c[0] = x, k[i].c[1] = y, k[i].c[2] = z;
+		if (i && ora_vkey_cmp(&k[i - 1], &k[i]) > 0) sorted = 0;
+	}
+	if (!sorted) qsort(k, n, sizeof(ora_vkey), ora_vkey_cmp);
+	/* count leaves */
+	int64_t nl = 0;
+	for (uint64_t i = 0; i < n; ++i)
+		if (i == 0 || k[i].tile != k[i - 1].tile || (k[i].vox >> 9) != (k[i - 1].vox >> 9)) ++nl;
+	ix->n_leaves = nl;
+	ix->leaves = (ora_leaf*)calloc((size_t)nl, sizeof(ora_leaf));
+	int64_t l = -1;
+	for (uint64_t i = 0; i < n; ++i) {
+		if (i == 0 || k[i].tile != k[i - 1].tile || (k[i].vox >> 9) != (k[i - 1].vox >> 9)) {
+			++l;
+			ix->leaves[l].origin[0] = k[i].c[0] & ~7;
+			ix->leaves[l].origin[1] = k[i].c[1] & ~7;
+			ix->leaves[l].origin[2] = k[i].c[2] & ~7;
+			ix->leaves[l].tile_key = k[i].tile;
+			ix->leaves[l].node_key = k[i].vox >> 9;
+		}
+		const uint32_t v = (uint32_t)(k[i].vox & 511u);
+		ix->leaves[l].mask[v >> 6] |= (uint64_t)1 << (v & 63);
+	}
+	free(k);
+	/* PointsToGrid.cuh:454-473: mOffset = 1 + inclusive prefix of popcounts; mPrefixSum packs 7 running 9-bit counts */
+	uint64_t run = 0;
+	int64_t nlow = 0, nup = 0;
+	for (l = 0; l < nl; ++l) {
+		ora_leaf* L = &ix->leaves[l];
+		L->offset = 1 + run;
+		uint64_t sum = (uint64_t)ora_popcnt64(L->mask[0]);
+		L->prefix = sum;
+		for (int w = 1, sh = 9; w < 7; ++w, sh += 9) {
+			sum += (uint64_t)ora_popcnt64(L->mask[w]);
+			L->prefix |= sum << sh;
+		}
+		run += sum + (uint64_t)ora_popcnt64(L->mask[7]);
+		if (l == 0 || L->tile_key != L[-1].tile_key || (L->node_key >> 12) != (L[-1].node_key >> 12)) ++nlow;
+		if (l == 0 || L->tile_key != L[-1].tile_key) ++nup;
+	}
+	ix->n_active = run;
+	ix->n_lower = nlow;
+	ix->n_upper = nup;
+	/* hash */
+	uint64_t cap = 16;
+	while (cap < (uint64_t)nl * 2) cap <<= 1;
+	ix->hmask = cap - 1;
+	ix->hkey = (uint64_t*)calloc(cap, sizeof(uint64_t));
+	ix->hval = (int32_t*)malloc(cap * sizeof(int32_t));
+	for (l = 0; l < nl; ++l) {
+		const int32_t lx = ix->leaves[l].origin[0] >> 3, ly = ix->leaves[l].origin[1] >> 3, lz = ix->leaves[l].origin[2] >> 3;
+		const uint64_t pk = ora_pack_coord(lx, ly, lz);
+		uint64_t h = ora_hash_coord(lx, ly, lz) & ix->hmask;
+		while (ix->hkey[h]) h = (h + 1) & ix->hmask;
+		ix->hkey[h] = pk;
+		ix->hval[h] = (int32_t)l;
+	}
+	return ix;
+}
+
+int64_t ora_index_num_leaves(const ora_index* ix) { return ix->n_leaves; }
+uint64_t ora_index_num_active(const ora_index* ix) { return ix->n_active; }
+void ora_index_leaf_origins(const ora_index* ix, int32_t* out) {
+	for (int64_t l = 0; l < ix->n_leaves; ++l) memcpy(out + 3 * l, ix->leaves[l].origin, 12);
+}
+
+static inline int64_t ora_find_leaf(const ora_index* ix, int32_t i, int32_t j, int32_t k) {
+	if (!ix->n_leaves) return -1;
+	const int32_t lx = i >> 3, ly = j >> 3, lz = k >> 3;
+	const uint64_t pk = ora_pack_coord(lx, ly, lz);
+	uint64_t h = ora_hash_coord(lx, ly, lz) & ix->hmask;
+	while (ix->hkey[h]) {
+		if (ix->hkey[h] == pk) {
+			/* 21-bit packing can alias far-apart coordinates: confirm */
+			const ora_leaf* L = &ix->leaves[ix->hval[h]];
+			if (L->origin[0] == (i & ~7) && L->origin[1] == (j & ~7) && L->origin[2] == (k & ~7)) return ix->hval[h];
+		}
+		h = (h + 1) & ix->hmask;
+	}
+	return -1;
+}
+
+/* ReadAccessor<ValueOnIndex>::getValue(ijk) -> LeafData<ValueOnIndex>::getValue (NanoVDB.h:4219-4228); 0 = background */
+uint64_t ora_get_value(const ora_index* ix, int32_t i, int32_t j, int32_t k) {
+	const int64_t l = ora_find_leaf(ix, i, j, k);
+	if (l < 0) return 0;
+	const ora_leaf* L = &ix->leaves[l];
+	const uint32_t v = ora_voxel_off(i, j, k);
+	uint32_t w = v >> 6;
+	const uint64_t word = L->mask[w], bit = (uint64_t)1 << (v & 63);
+	if (!(word & bit)) return 0;
+	uint64_t sum = L->offset + (uint64_t)ora_popcnt64(word & (bit - 1));
+	if (w--) sum += (L->prefix >> (9u * w)) & 511u;
+	return sum;
+}
+void ora_get_values(const ora_index* ix, const int32_t* ijk, uint64_t n, uint64_t* out) {
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) out[t] = ora_get_value(ix, ijk[3 * t], ijk[3 * t + 1], ijk[3 * t + 2]);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * NanoVDB buffer emitter: what voxelsToGrid<ValueOnIndex> writes (PointsToGrid.cuh:753-802, 912-1184),
+ * byte layout per NanoVDB.h:1810-1862 (GridData), 2254-2285 (TreeData), 2480-2554 (RootData/Tile),
+ * 3164-3210 (InternalData), 4143-4229 (LeafData<ValueOnIndex>). Bytes the reference leaves uninitialised
+ * (struct padding, root-tile value, name[1..255]) are written as zero here.
+ * ---------------------------------------------------------------------------------------------- */
+enum { ORA_GRID = 672, ORA_TREE = 64, ORA_ROOT = 96, ORA_TILE = 32, ORA_UPPER = 270400, ORA_LOWER = 33856, ORA_LEAF = 96 };
+
+uint64_t ora_nanovdb_size(const ora_index* ix) {
+	return (uint64_t)ORA_GRID + ORA_TREE + ORA_ROOT + (uint64_t)ORA_TILE * ix->n_upper + (uint64_t)ORA_UPPER * ix->n_upper +
+	       (uint64_t)ORA_LOWER * ix->n_lower + (uint64_t)ORA_LEAF * ix->n_leaves;
+}
+static void put32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
+static void put64(uint8_t* p, uint64_t v) { memcpy(p, &v, 8); }
+static void putd(uint8_t* p, double v) { memcpy(p, &v, 8); }
+static void putf(uint8_t* p, float v) { memcpy(p, &v, 4); }
+static void bbox_init(int32_t* b) { b[0] = b[1] = b[2] = INT32_MAX; b[3] = b[4] = b[5] = INT32_MIN; }
+static void bbox_expand(int32_t* b, const int32_t* o) {
+	for (int a = 0; a < 3; ++a) {
+		if (o[a] < b[a]) b[a] = o[a];
+		if (o[3 + a] > b[3 + a]) b[3 + a] = o[3 + a];
+	}
+}
+static void leaf_bbox(const ora_leaf* L, int32_t* bb, uint8_t* dif) {
+	/* LeafNode::updateBBox (NanoVDB.h:4701-4733) */
+	int xmin = 8, xmax = 0;
+	uint64_t word = 0;
+	for (int i = 0; i < 8; ++i)
+		if (L->mask[i]) {
+			word |= L->mask[i];
+			if (xmin == 8) xmin = i;
+			xmax = i;
+		}
+	const int ymin = __builtin_ctzll(word) >> 3, ymax = (63 - __builtin_clzll(word)) >> 3;
+	uint32_t w32 = (uint32_t)word | (uint32_t)(word >> 32);
+	uint32_t w16 = (w32 | (w32 >> 16)) & 0xFFFFu;
+	uint32_t b8 = (w16 | (w16 >> 8)) & 0xFFu;
+	const int zmin = __builtin_ctz(b8), zmax = 31 - __builtin_clz(b8);
+	bb[0] = L->origin[0] + xmin, bb[1] = L->origin[1] + ymin, bb[2] = L->origin[2] + zmin;
+	dif[0] = (uint8_t)(xmax - xmin), dif[1] = (uint8_t)(ymax - ymin), dif[2] = (uint8_t)(zmax - zmin);
+	bb[3] = bb[0] + dif[0], bb[4] = bb[1] + dif[1], bb[5] = bb[2] + dif[2];
+}
+
+void ora_nanovdb_emit(const ora_index* ix, float voxelSizeF, uint8_t* buf) {
+	const uint64_t total = ora_nanovdb_size(ix);
+	memset(buf, 0, total);
+	const int64_t T = ix->n_upper, NLo = ix->n_lower, NL = ix->n_leaves;
+	const uint64_t o_tree = ORA_GRID, o_root = o_tree + ORA_TREE, o_upper = o_root + ORA_ROOT + (uint64_t)ORA_TILE * T,
+	               o_lower = o_upper + (uint64_t)ORA_UPPER * T, o_leaf = o_lower + (uint64_t)ORA_LOWER * NLo;
+	const double s = (double)voxelSizeF; /* voxelsToGrid(..., double voxelSize): float -> double widening at the call site (HNanoSolver.cu:381) */
+	/* ---- GridData (init(): NanoVDB.h:1836-1862; then PointsToGrid.cuh:797-802, 890-895) ---- */
+	uint8_t* g = buf;
+	put64(g + 0, 0x304244566f6e614eull);               /* NANOVDB_MAGIC_NUMB "NanoVDB0" */
+	put64(g + 8, ~(uint64_t)0);                        /* checksum disabled */
+	put32(g + 16, (32u << 21) | (7u << 10) | 0u);      /* Version 32.7.0 */
+	put32(g + 20, 2u | 32u);                           /* HasBBox | IsBreadthFirst */
+	put32(g + 24, 0), put32(g + 28, 1);
+	put64(g + 32, total);
+	/* name: byte 0 = 0 (rest indeterminate in the reference) */
+	uint8_t* m = g + 296;                              /* Map(double s) NanoVDB.h:1371-1381 */
+	const float sf = (float)s, isf = 1.0f / (float)s;
+	const double isd = 1.0 / s;
+	for (int d = 0; d < 3; ++d) {
+		putf(m + 4 * (4 * d), sf);
+		putf(m + 36 + 4 * (4 * d), isf);
+		putd(m + 88 + 8 * (4 * d), s);
+		putd(m + 160 + 8 * (4 * d), isd);
+	}
+	putf(m + 84, 1.0f);   /* mTaperF */
+	putd(m + 256, 1.0);   /* mTaperD */
+	for (int d = 0; d < 3; ++d) putd(g + 608 + 8 * d, s); /* mVoxelSize */
+	put32(g + 632, 8u);   /* GridClass::IndexGrid */
+	put32(g + 636, 20u);  /* GridType::OnIndex */
+	put64(g + 640, total);/* mBlindMetadataOffset = meta = end of leaves */
+	put32(g + 648, 0), put32(g + 652, 0);
+	put64(g + 656, 1 + ix->n_active); /* mData1 (leafPrefixSumKernel, PointsToGrid.cuh:467) */
+	put64(g + 664, 0x314244566f6e614eull); /* mData2 = NANOVDB_MAGIC_GRID */
+	/* ---- TreeData ---- */
+	uint8_t* t = buf + o_tree;
+	put64(t + 0, o_leaf - o_tree), put64(t + 8, o_lower - o_tree), put64(t + 16, o_upper - o_tree), put64(t + 24, o_root - o_tree);
+	put32(t + 32, (uint32_t)NL), put32(t + 36, (uint32_t)NLo), put32(t + 40, (uint32_t)T);
+	put32(t + 44, (uint32_t)NL), put32(t + 48, (uint32_t)NLo), put32(t + 52, (uint32_t)T); /* sic: mTileCount = mNodeCount */
+	put64(t + 56, ix->n_active);
+	/* ---- nodes ---- */
+	int32_t rootbb[6];
+	bbox_init(rootbb);
+	int64_t iu = -1, il = -1;
+	int32_t upbb[6], lobb[6];
+	uint8_t *U = NULL, *Lo = NULL;
+	for (int64_t l = 0; l < NL; ++l) {
+		const ora_leaf* L = &ix->leaves[l];
+		const int new_upper = (l == 0 || L->tile_key != L[-1].tile_key);
+		const int new_lower = new_upper || (L->node_key >> 12) != (L[-1].node_key >> 12);
+		if (new_lower && Lo) { /* close lower */
+			memcpy(Lo, lobb, 24);
+			bbox_expand(upbb, lobb);
+		}
+		if (new_upper && U) {
+			memcpy(U, upbb, 24);
+			bbox_expand(rootbb, upbb);
+		}
+		if (new_upper) {
+			++iu;
+			U = buf + o_upper + (uint64_t)ORA_UPPER * iu;
+			bbox_init(upbb);
+			/* root tile: key = RootData::CoordToKey(origin) on uint32-reinterpreted coords (NanoVDB.h:2492-2499), child = offset from RootData */
+			const int32_t ox = L->origin[0] & ~4095, oy = L->origin[1] & ~4095, oz = L->origin[2] & ~4095;
+			uint8_t* tile = buf + o_root + ORA_ROOT + (uint64_t)ORA_TILE * iu;
+			put64(tile + 0, ((uint64_t)((uint32_t)oz >> 12)) | ((uint64_t)((uint32_t)oy >> 12) << 21) | ((uint64_t)((uint32_t)ox >> 12) << 42));
+			put64(tile + 8, (uint64_t)(U - (buf + o_root)));
+			put32(tile + 16, 0);
+		}
+		if (new_lower) {
+			++il;
+			Lo = buf + o_lower + (uint64_t)ORA_LOWER * il;
+			bbox_init(lobb);
+			const uint32_t uo = (uint32_t)(L->node_key >> 12);
+			uint64_t w;
+			memcpy(&w, U + 4128 + 8 * (uo >> 6), 8);
+			w |= (uint64_t)1 << (uo & 63);
+			memcpy(U + 4128 + 8 * (uo >> 6), &w, 8);                 /* upper.mChildMask */
+			put64(U + 8256 + 8ull * uo, (uint64_t)(Lo - U));          /* upper.mTable[uo].child */
+		}
+		const uint32_t lo = (uint32_t)(L->node_key & 4095u);
+		uint8_t* F = buf + o_leaf + (uint64_t)ORA_LEAF * l;
+		uint64_t w;
+		memcpy(&w, Lo + 544 + 8 * (lo >> 6), 8);
+		w |= (uint64_t)1 << (lo & 63);
+		memcpy(Lo + 544 + 8 * (lo >> 6), &w, 8);                     /* lower.mChildMask */
+		put64(Lo + 1088 + 8ull * lo, (uint64_t)(F - Lo));             /* lower.mTable[lo].child */
+		int32_t bb[6];
+		uint8_t dif[3];
+		leaf_bbox(L, bb, dif);
+		memcpy(F + 0, bb, 12);
+		F[12] = dif[0], F[13] = dif[1], F[14] = dif[2];
+		F[15] = (uint8_t)(0x22u | 2u); /* flags byte of the grid flag mask, bit 1 set by updateBBox */
+		memcpy(F + 16, L->mask, 64);
+		put64(F + 80, L->offset);
+		put64(F + 88, L->prefix);
+		bbox_expand(lobb, bb);
+	}
+	if (Lo) {
+		memcpy(Lo, lobb, 24);
+		bbox_expand(upbb, lobb);
+	}
+	if (U) {
+		memcpy(U, upbb, 24);
+		bbox_expand(rootbb, upbb);
+	}
+	/* ---- RootData ---- */
+	uint8_t* r = buf + o_root;
+	memcpy(r, rootbb, 24);
+	put32(r + 24, (uint32_t)T);
+	/* ---- world bbox = root bbox (inclusive max) * map (PointsToGrid.cuh:1176-1180, math/Math.h:1271-1284) ---- */
+	for (int d = 0; d < 3; ++d) {
+		double a = (double)rootbb[d] * s, b = (double)rootbb[3 + d] * s;
+		putd(g + 560 + 8 * d, a < b ? a : b);
+		putd(g + 584 + 8 * d, a < b ? b : a);
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Samplers (src/Utils/Stencils.hpp)
+ * ---------------------------------------------------------------------------------------------- */
+/* IndexSampler<T,0>::operator() (Stencils.hpp:81-89): off==0 ? T(0) : data[off-1] */
+static inline float ora_nearest_f(const ora_index* ix, const float* data, int32_t i, int32_t j, int32_t k) {
+	const uint64_t off = ora_get_value(ix, i, j, k);
+	return off == 0 ? 0.0f : data[off - 1];
+}
+static inline void ora_nearest_v(const ora_index* ix, const float* data, int32_t i, int32_t j, int32_t k, float* out) {
+	const uint64_t off = ora_get_value(ix, i, j, k);
+	if (off == 0) {
+		out[0] = out[1] = out[2] = 0.0f;
+	} else {
+		out[0] = data[3 * (off - 1)], out[1] = data[3 * (off - 1) + 1], out[2] = data[3 * (off - 1) + 2];
+	}
+}
+/* Floor (Stencils.hpp:25-43): __float2int_rd + in-place fractional part */
+static inline int32_t ora_floor_frac(float* x) {
+	const int32_t i = (int32_t)floorf(*x);
+	*x -= (float)i;
+	return i;
+}
+/* TrilinearSampler<float>::sample (Stencils.hpp:117-152): lerp z, then y, then x; a + w*(b-a) is fused by nvcc to fma(w, b-a, a) */
+static inline float ora_lerp(float a, float b, float w) { return fmaf(w, b - a, a); }
+float ora_trilinear_f(const ora_index* ix, const float* data, float x, float y, float z) {
+	const int32_t i = ora_floor_frac(&x), j = ora_floor_frac(&y), k = ora_floor_frac(&z);
+	float v[2][2][2];
+	for (int a = 0; a < 2; ++a)
+		for (int b = 0; b < 2; ++b)
+			for (int c = 0; c < 2; ++c) v[a][b][c] = ora_nearest_f(ix, data, i + a, j + b, k + c);
+	const float z0 = ora_lerp(v[0][0][0], v[0][0][1], z), z1 = ora_lerp(v[0][1][0], v[0][1][1], z);
+	const float z2 = ora_lerp(v[1][0][0], v[1][0][1], z), z3 = ora_lerp(v[1][1][0], v[1][1][1], z);
+	const float y0 = ora_lerp(z0, z1, y), y1 = ora_lerp(z2, z3, y);
+	return ora_lerp(y0, y1, x);
+}
+/* TrilinearSampler<Vec3f>::sample: per component fmaf(w, b-a, a) (Stencils.hpp:20-22,131-134) */
+void ora_trilinear_v(const ora_index* ix, const float* data, float x, float y, float z, float* out) {
+	const int32_t i = ora_floor_frac(&x), j = ora_floor_frac(&y), k = ora_floor_frac(&z);
+	float v[2][2][2][3];
+	for (int a = 0; a < 2; ++a)
+		for (int b = 0; b < 2; ++b)
+			for (int c = 0; c < 2; ++c) ora_nearest_v(ix, data, i + a, j + b, k + c, v[a][b][c]);
+	for (int c = 0; c < 3; ++c) {
+		const float z0 = ora_lerp(v[0][0][0][c], v[0][0][1][c], z), z1 = ora_lerp(v[0][1][0][c], v[0][1][1][c], z);
+		const float z2 = ora_lerp(v[1][0][0][c], v[1][0][1][c], z), z3 = ora_lerp(v[1][1][0][c], v[1][1][1][c], z);
+		const float y0 = ora_lerp(z0, z1, y), y1 = ora_lerp(z2, z3, y);
+		out[c] = ora_lerp(y0, y1, x);
+	}
+}
+float ora_nearest_float(const ora_index* ix, const float* data, int32_t i, int32_t j, int32_t k) { return ora_nearest_f(ix, data, i, j, k); }
+
+/* ------------------------------------------------------------------------------------------------
+ * Kernels (src/Cuda/Kernel.cu). One loop iteration == one CUDA thread of the reference.
+ * Collision (SDF) branches are not restated: hasCollision == false on the path covered here.
+ * ---------------------------------------------------------------------------------------------- */
+static const int ORA_NBR[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+
+/* advect_vector (Kernel.cu:354-453) */
+void ora_advect_vector(const ora_index* ix, const int32_t* coords, const float* vel, float* out, uint64_t n, float dt, float inv_dx) {
+	const float sdt = dt * inv_dx;
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const int32_t ci = coords[3 * t], cj = coords[3 * t + 1], ck = coords[3 * t + 2];
+		const float pos[3] = {(float)ci, (float)cj, (float)ck};
+		float u0[3], uf[3], ub[3], bp[3], fp[3];
+		ora_nearest_v(ix, vel, ci, cj, ck, u0);                       /* velocitySampler(coord) :371 */
+		for (int c = 0; c < 3; ++c) bp[c] = fmaf(-sdt, u0[c], pos[c]); /* pos - velOrig*scaled_dt :374 */
+		ora_trilinear_v(ix, vel, bp[0], bp[1], bp[2], uf);            /* :384 */
+		for (int c = 0; c < 3; ++c) fp[c] = fmaf(sdt, uf[c], bp[c]);   /* :387 */
+		ora_trilinear_v(ix, vel, fp[0], fp[1], fp[2], ub);            /* :396 */
+		float mn[3], mx[3], corr[3];
+		for (int c = 0; c < 3; ++c) {
+			corr[c] = fmaf(0.5f, u0[c] - ub[c], uf[c]);                /* :399-400 */
+			mn[c] = mx[c] = u0[c];
+		}
+		for (int dim = 0; dim < 3; ++dim)
+			for (int o = -1; o <= 1; o += 2) {                        /* :410-421 */
+				int32_t q[3] = {ci, cj, ck};
+				q[dim] += o;
+				float nb[3];
+				ora_nearest_v(ix, vel, q[0], q[1], q[2], nb);
+				for (int c = 0; c < 3; ++c) mn[c] = fminf(mn[c], nb[c]), mx[c] = fmaxf(mx[c], nb[c]);
+			}
+		for (int c = 0; c < 3; ++c) {                                 /* :424-430 */
+			mn[c] = fminf(mn[c], uf[c]), mx[c] = fmaxf(mx[c], uf[c]);
+			out[3 * t + c] = fmaxf(mn[c], fminf(corr[c], mx[c]));
+		}
+	}
+}
+
+/* advect_scalar (Kernel.cu:269-352), the stand-alone node's kernel: samplers everywhere, inactive -> 0 */
+void ora_advect_scalar(const ora_index* ix, const int32_t* coords, const float* vel, const float* in, float* out, uint64_t n, float dt,
+                       float inv_dx) {
+	const float sdt = dt * inv_dx;
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const int32_t ci = coords[3 * t], cj = coords[3 * t + 1], ck = coords[3 * t + 2];
+		const float pos[3] = {(float)ci, (float)cj, (float)ck};
+		const float phi0 = ora_nearest_f(ix, in, ci, cj, ck);          /* :286 */
+		float u0[3], uf[3], bp[3], fp[3];
+		ora_nearest_v(ix, vel, ci, cj, ck, u0);                        /* :289 */
+		for (int c = 0; c < 3; ++c) bp[c] = fmaf(-sdt, u0[c], pos[c]);  /* :294 */
+		const float phiF = ora_trilinear_f(ix, in, bp[0], bp[1], bp[2]); /* :303 */
+		ora_trilinear_v(ix, vel, bp[0], bp[1], bp[2], uf);             /* :309 */
+		for (int c = 0; c < 3; ++c) fp[c] = fmaf(sdt, uf[c], bp[c]);    /* :310 */
+		const float phiB = ora_trilinear_f(ix, in, fp[0], fp[1], fp[2]); /* :319 */
+		float corr = fmaf(0.5f, phi0 - phiB, phiF);                    /* :325-326 */
+		float mn = phi0, mx = phi0;
+		for (int dim = 0; dim < 3; ++dim)
+			for (int o = -1; o <= 1; o += 2) {                         /* :334-342 */
+				int32_t q[3] = {ci, cj, ck};
+				q[dim] += o;
+				const float nb = ora_nearest_f(ix, in, q[0], q[1], q[2]);
+				mn = fminf(mn, nb), mx = fmaxf(mx, nb);
+			}
+		mn = fminf(mn, phiF), mx = fmaxf(mx, phiF);                    /* :345-346 */
+		out[t] = fmaxf(mn, fminf(corr, mx));                           /* :349-351 */
+	}
+}
+
+/* advect_scalars (Kernel.cu:118-266), the all-in-one node's kernel: explicit weights, inactive -> array element 0 */
+typedef struct {
+	uint64_t idx[8];
+	float w[8];
+} ora_interp;
+static void ora_setup_interp(const ora_index* ix, const float* p, ora_interp* d) { /* :163-196 */
+	const float x = p[0], y = p[1], z = p[2];
+	const int32_t i0 = (int32_t)floorf(x), j0 = (int32_t)floorf(y), k0 = (int32_t)floorf(z);
+	const int32_t i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
+	const float tx = x - (float)i0, ty = y - (float)j0, tz = z - (float)k0;
+	const float itx = 1.0f - tx, ity = 1.0f - ty, itz = 1.0f - tz;
+	const float w00 = itx * ity, w10 = tx * ity, w01 = itx * ty, w11 = tx * ty;
+	d->w[0] = w00 * itz, d->w[1] = w10 * itz, d->w[2] = w01 * itz, d->w[3] = w11 * itz;
+	d->w[4] = w00 * tz, d->w[5] = w10 * tz, d->w[6] = w01 * tz, d->w[7] = w11 * tz;
+	const int32_t c[8][3] = {{i0, j0, k0}, {i1, j0, k0}, {i0, j1, k0}, {i1, j1, k0}, {i0, j0, k1}, {i1, j0, k1}, {i0, j1, k1}, {i1, j1, k1}};
+	for (int q = 0; q < 8; ++q) {
+		const uint64_t off = ora_get_value(ix, c[q][0], c[q][1], c[q][2]);
+		d->idx[q] = off == 0 ? 0 : off - 1;                            /* :191-192: inactive corner reads element 0 */
+	}
+}
+void ora_advect_scalars(const ora_index* ix, const int32_t* coords, const float* vel, const float* const* in, float* const* out, int S,
+                        uint64_t n, float dt, float inv_dx) {
+	const float sdt = dt * inv_dx;
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const int32_t ci = coords[3 * t], cj = coords[3 * t + 1], ck = coords[3 * t + 2];
+		uint64_t orig = ora_get_value(ix, ci, cj, ck);                 /* :132-133 */
+		orig = orig == 0 ? 0 : orig - 1;
+		const float pos[3] = {(float)ci, (float)cj, (float)ck};
+		float bp[3], fp[3], uf[3] = {0.0f, 0.0f, 0.0f};
+		for (int c = 0; c < 3; ++c) bp[c] = fmaf(-sdt, vel[3 * orig + c], pos[c]); /* :136-139 */
+		ora_interp B, F;
+		ora_setup_interp(ix, bp, &B);                                  /* :198 */
+		for (int q = 0; q < 8; ++q)                                    /* :201-206 */
+			for (int c = 0; c < 3; ++c) uf[c] = fmaf(B.w[q], vel[3 * B.idx[q] + c], uf[c]);
+		for (int c = 0; c < 3; ++c) fp[c] = fmaf(sdt, uf[c], bp[c]);    /* :208 */
+		ora_setup_interp(ix, fp, &F);                                  /* :216 */
+		uint32_t nbr[6];                                               /* :219-226 (uint32_t, sic) */
+		for (int q = 0; q < 6; ++q) {
+			const uint32_t off = (uint32_t)ora_get_value(ix, ci + ORA_NBR[q][0], cj + ORA_NBR[q][1], ck + ORA_NBR[q][2]);
+			nbr[q] = off == 0 ? 0 : off - 1;
+		}
+		for (int s = 0; s < S; ++s) {                                  /* :229-265 */
+			const float* a = in[s];
+			const float phi0 = a[orig];
+			float phiF = 0.0f, phiB = 0.0f;
+			for (int q = 0; q < 8; ++q) {
+				phiF = fmaf(a[B.idx[q]], B.w[q], phiF);
+				phiB = fmaf(a[F.idx[q]], F.w[q], phiB);
+			}
+			const float corr = fmaf(0.5f, phi0 - phiB, phiF);
+			float mn = phi0, mx = phi0;
+			for (int q = 0; q < 6; ++q) {
+				const float v = a[nbr[q]];
+				mn = fminf(mn, v), mx = fmaxf(mx, v);
+			}
+			mn = fminf(mn, phiF), mx = fmaxf(mx, phiF);
+			out[s][t] = fmaxf(mn, fminf(corr, mx));
+		}
+	}
+}
+
+/* divergence (Kernel.cu:499-519); divergence_opt (:455-496) evaluates the same expression (all *0.5 are exact) */
+void ora_divergence(const ora_index* ix, const int32_t* coords, const float* vel, float* out, float inv_dx, uint64_t n) {
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const int32_t i = coords[3 * t], j = coords[3 * t + 1], k = coords[3 * t + 2];
+		const float* c = vel + 3 * t;                                  /* velocityData[tid] :505 */
+		float nb[3];
+		ora_nearest_v(ix, vel, i + 1, j, k, nb);
+		const float xp = (c[0] + nb[0]) * 0.5f;
+		ora_nearest_v(ix, vel, i - 1, j, k, nb);
+		const float xm = (c[0] + nb[0]) * 0.5f;
+		ora_nearest_v(ix, vel, i, j + 1, k, nb);
+		const float yp = (c[1] + nb[1]) * 0.5f;
+		ora_nearest_v(ix, vel, i, j - 1, k, nb);
+		const float ym = (c[1] + nb[1]) * 0.5f;
+		ora_nearest_v(ix, vel, i, j, k + 1, nb);
+		const float zp = (c[2] + nb[2]) * 0.5f;
+		ora_nearest_v(ix, vel, i, j, k - 1, nb);
+		const float zm = (c[2] + nb[2]) * 0.5f;
+		out[t] = (xp - xm + yp - ym + zp - zm) * inv_dx;               /* :518 */
+	}
+}
+
+/* redBlackGaussSeidelUpdate (Kernel.cu:591-623); the _opt variant (:521-588) computes the same update.
+ * SASS of the reference: s = fma(-div, dx*dx, sum6); d = fma(s, 1/6, -pOld); p = fma(d, omega, pOld). */
+void ora_rbgs(const ora_index* ix, const int32_t* coords, const float* div, float* p, float dx, uint64_t n, int color, float omega) {
+	const float dx2 = dx * dx;
+	const float inv6 = 0.166666667f;
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const int32_t i = coords[3 * t], j = coords[3 * t + 1], k = coords[3 * t + 2];
+		if (((i + j + k) & 1) != color) continue;                      /* :602 */
+		const float pxp = ora_nearest_f(ix, p, i + 1, j, k), pxm = ora_nearest_f(ix, p, i - 1, j, k);
+		const float pyp = ora_nearest_f(ix, p, i, j + 1, k), pym = ora_nearest_f(ix, p, i, j - 1, k);
+		const float pzp = ora_nearest_f(ix, p, i, j, k + 1), pzm = ora_nearest_f(ix, p, i, j, k - 1);
+		const float pOld = p[t];
+		const float s = fmaf(-div[t], dx2, ((((pxp + pxm) + pyp) + pym) + pzp) + pzm);
+		const float d = fmaf(s, inv6, -pOld);
+		p[t] = fmaf(d, omega, pOld);                                   /* :621-622 */
+	}
+}
+
+/* subtractPressureGradient (Kernel.cu:765-829) / _opt (:694-762): u - ((p+ - p-) * 0.5) * inv_dx, last mul+sub fused */
+void ora_subtract_gradient(const ora_index* ix, const int32_t* coords, uint64_t n, const float* vel, const float* p, float* out,
+                           float inv_dx) {
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const int32_t i = coords[3 * t], j = coords[3 * t + 1], k = coords[3 * t + 2];
+		const float gx = ora_nearest_f(ix, p, i + 1, j, k) - ora_nearest_f(ix, p, i - 1, j, k);
+		const float gy = ora_nearest_f(ix, p, i, j + 1, k) - ora_nearest_f(ix, p, i, j - 1, k);
+		const float gz = ora_nearest_f(ix, p, i, j, k + 1) - ora_nearest_f(ix, p, i, j, k - 1);
+		out[3 * t + 0] = fmaf(-(gx * 0.5f), inv_dx, vel[3 * t + 0]);
+		out[3 * t + 1] = fmaf(-(gy * 0.5f), inv_dx, vel[3 * t + 1]);
+		out[3 * t + 2] = fmaf(-(gz * 0.5f), inv_dx, vel[3 * t + 2]);
+	}
+}
+
+/* combustion_oxygen (Kernel.cu:923-966) */
+void ora_combustion_oxygen(const float* fuel, const float* waste, const float* temp, float* div, const float* flame, float* oFuel,
+                           float* oWaste, float* oTemp, float* oFlame, float temp_gain, float expansion, uint64_t n) {
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		float f = fuel[t];
+		const float w = waste[t], T = temp[t], fl = flame[t];
+		if (f < 0.001f) f = 0.0f;
+		const float oxygen = 1.0f - f - w;
+		if (oxygen < 0.0f) {
+			oFuel[t] = f, oWaste[t] = w, oTemp[t] = T, oFlame[t] = fl;
+			continue;
+		}
+		const float burn = fminf(oxygen, f);
+		oFuel[t] = f - burn;
+		oWaste[t] = fmaf(burn, 2.0f, w);
+		oFlame[t] = fmaxf(fl, fminf(1.0f, burn * 10.0f));
+		oTemp[t] = fmaf(burn, temp_gain, T);
+		div[t] = fmaf(burn, expansion, div[t]);
+	}
+}
+
+/* temperature_buoyancy (Kernel.cu:831-847), in place on the advected velocity (HNanoSolver.cu:228-232) */
+void ora_temperature_buoyancy(const float* vel, const float* temp, float* out, float dt, float ambient, float strength, uint64_t n) {
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const float v0 = vel[3 * t], v1 = vel[3 * t + 1], v2 = vel[3 * t + 2];
+		const float T = temp[t];
+		if (T <= ambient) {
+			out[3 * t] = v0, out[3 * t + 1] = v1, out[3 * t + 2] = v2;
+			continue;
+		}
+		const float b = fmaxf(0.0f, (T - ambient) * strength);
+		out[3 * t] = fmaf(0.0f, dt, v0);
+		out[3 * t + 1] = fmaf(b, dt, v1);
+		out[3 * t + 2] = fmaf(0.0f, dt, v2);
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame orchestration
+ * ---------------------------------------------------------------------------------------------- */
+/* omega as Compute() computes it (HNanoSolver.cu:257): float sinf of float(3.14159)*voxelSize */
+float ora_omega_compute(float voxelSize) { return 2.0f / (1.0f + sinf((float)3.14159 * voxelSize)); }
+/* omega as pressure_projection_idx computes it (PressureProjection.cu:53): double sin, rounded to float at the kernel call */
+float ora_omega_project(float voxelSize) { return (float)(2.0f / (1.0f + sin(3.14159 * voxelSize))); }
+
+/* The north-star frame: advect_vector -> divergence -> I x (red, black) -> subtractPressureGradient -> advect_scalars,
+ * i.e. Compute() (HNanoSolver.cu:159-356) with combustion / buoyancy / vorticity / collision off.
+ * vel, scalars[s] are updated in place like the host sidecar (HNanoSolver.cu:361-369). Optional outputs may be NULL. */
+void ora_frame(const ora_index* ix, const int32_t* coords, uint64_t n, float* vel, float* const* scalars, int S, int iterations, float dt,
+               float voxelSize, float* out_div, float* out_p, float* out_adv) {
+	const float inv = 1.0f / voxelSize;
+	float* adv = (float*)malloc(n * 12);
+	float* div = (float*)malloc(n * 4);
+	float* p = (float*)calloc(n, 4);
+	ora_advect_vector(ix, coords, vel, adv, n, dt, inv);
+	ora_divergence(ix, coords, adv, div, inv, n);
+	const float omega = ora_omega_compute(voxelSize);
+	for (int it = 0; it < iterations; ++it) {
+		ora_rbgs(ix, coords, div, p, voxelSize, n, 0, omega);
+		ora_rbgs(ix, coords, div, p, voxelSize, n, 1, omega);
+	}
+	ora_subtract_gradient(ix, coords, n, adv, p, vel, inv);
+	if (S > 0) {
+		float** outs = (float**)malloc(sizeof(float*) * (size_t)S);
+		for (int s = 0; s < S; ++s) outs[s] = (float*)malloc(n * 4);
+		ora_advect_scalars(ix, coords, vel, (const float* const*)scalars, outs, S, n, dt, inv);
+		for (int s = 0; s < S; ++s) {
+			memcpy(scalars[s], outs[s], n * 4);
+			free(outs[s]);
+		}
+		free(outs);
+	}
+	if (out_div) memcpy(out_div, div, n * 4);
+	if (out_p) memcpy(out_p, p, n * 4);
+	if (out_adv) memcpy(out_adv, adv, n * 12);
+	free(adv), free(div), free(p);
+}
+
+/* Compute() in full for hasCollision == false (HNanoSolver.cu:9-372): advect_vector -> vorticityConfinement (only
+ * vorticityScale == 0 is restated: the reference runs it in place, racing, :174) -> divergence -> combustion_oxygen ->
+ * temperature_buoyancy -> RBGS -> subtractPressureGradient -> advect_scalars over ALL float blocks in insertion order.
+ * names[s] identify fuel / waste / temperature / flame (:193); returns 1 if one is missing (the reference throws). */
+int ora_compute_sim(const ora_index* ix, const int32_t* coords, uint64_t n, float* vel, float* const* scalars, const char* const* names, int S,
+                    int iterations, float dt, float voxelSize, const float* params6) {
+	int iF = -1, iW = -1, iT = -1, iL = -1;
+	for (int s = 0; s < S; ++s) {
+		if (!strcmp(names[s], "fuel")) iF = s;
+		if (!strcmp(names[s], "waste")) iW = s;
+		if (!strcmp(names[s], "temperature")) iT = s;
+		if (!strcmp(names[s], "flame")) iL = s;
+	}
+	if (iF < 0 || iW < 0 || iT < 0 || iL < 0) return 1;
+	const float expansionRate = params6[0], temperatureRelease = params6[1], buoyancyStrength = params6[2], ambientTemp = params6[3];
+	const float inv = 1.0f / voxelSize;
+	float* adv = (float*)malloc(n * 12);
+	float* div = (float*)malloc(n * 4);
+	float* p = (float*)calloc(n, 4);
+	ora_advect_vector(ix, coords, vel, adv, n, dt, inv);
+	/* vorticityConfinement with scale 0 adds (0 * x) * dt == +0 to every component: identity for finite inputs */
+	ora_divergence(ix, coords, adv, div, inv, n);
+	float *oF = (float*)malloc(n * 4), *oW = (float*)malloc(n * 4), *oT = (float*)malloc(n * 4), *oL = (float*)malloc(n * 4);
+	ora_combustion_oxygen(scalars[iF], scalars[iW], scalars[iT], div, scalars[iL], oF, oW, oT, oL, temperatureRelease, expansionRate, n);
+	ora_temperature_buoyancy(adv, oT, adv, dt, ambientTemp, buoyancyStrength, n);
+	memcpy(scalars[iF], oF, n * 4), memcpy(scalars[iW], oW, n * 4), memcpy(scalars[iT], oT, n * 4), memcpy(scalars[iL], oL, n * 4);
+	free(oF), free(oW), free(oT), free(oL);
+	const float omega = ora_omega_compute(voxelSize);
+	for (int it = 0; it < iterations; ++it) {
+		ora_rbgs(ix, coords, div, p, voxelSize, n, 0, omega);
+		ora_rbgs(ix, coords, div, p, voxelSize, n, 1, omega);
+	}
+	ora_subtract_gradient(ix, coords, n, adv, p, vel, inv);
+	float** outs = (float**)malloc(sizeof(float*) * (size_t)S);
+	for (int s = 0; s < S; ++s) outs[s] = (float*)malloc(n * 4);
+	ora_advect_scalars(ix, coords, vel, (const float* const*)scalars, outs, S, n, dt, inv);
+	for (int s = 0; s < S; ++s) {
+		memcpy(scalars[s], outs[s], n * 4);
+		free(outs[s]);
+	}
+	free(outs);
+	free(adv), free(div), free(p);
+	return 0;
+}
+
+/* pressure_projection_idx (PressureProjection.cu:9-78): divergence_opt -> I x RBGS_opt -> subtractPressureGradient_opt, in place */
+void ora_project_non_divergent(const ora_index* ix, const int32_t* coords, uint64_t n, float* vel, int iterations, float voxelSize,
+                               float* out_div, float* out_p) {
+	const float inv = 1.0f / voxelSize;
+	float* div = (float*)malloc(n * 4);
+	float* p = (float*)calloc(n, 4);
+	float* out = (float*)malloc(n * 12);
+	ora_divergence(ix, coords, vel, div, inv, n);
+	const float omega = ora_omega_project(voxelSize);
+	for (int it = 0; it < iterations; ++it) {
+		ora_rbgs(ix, coords, div, p, voxelSize, n, 0, omega);
+		ora_rbgs(ix, coords, div, p, voxelSize, n, 1, omega);
+	}
+	ora_subtract_gradient(ix, coords, n, vel, p, out, inv);
+	memcpy(vel, out, n * 12);
+	if (out_div) memcpy(out_div, div, n * 4);
+	if (out_p) memcpy(out_p, p, n * 4);
+	free(div), free(p), free(out);
+}
+
+int ora_num_threads(void) {
+#ifdef _OPENMP
+	return omp_get_max_threads();
+#else
+	return 1;
+#endif
+}

@@ -1,0 +1,71 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product.
+//
+// The reference's own __hostdev__ code running on the CPU, used to pin oracle/hns_oracle.c without a GPU:
+//   * a REAL NanoVDB 32.7 host ValueOnIndex grid (vendored externals/nanovdb: tools/GridBuilder.h +
+//     tools/CreateNanoGrid.h) built from a voxel list, queried through nanovdb::ReadAccessor, and
+//   * the reference's samplers, IndexOffsetSampler<0> / IndexSampler<T,0|1> / TrilinearSampler
+//     (src/Utils/Stencils.hpp:51-173), compiled by g++ (not nvcc) with -D__fmaf_rn=fmaf.
+// Built by oracle/Makefile into oracle/_ref/libref_host.so from the headers where they lie under /root/reference.
+//
+// Note the host instantiation of TrilinearSampler<Vec3f> takes the non-fused branch of lerp_dispatch
+// (Stencils.hpp:135-137: a + (b-a)*w), so Vec3f samples can differ from the device path in the last ulp;
+// the float path is a + w*(b-a) on both.
+#include <cstdint>
+#include <cstring>
+
+#include "../Utils/Stencils.hpp"
+#include "nanovdb/NanoVDB.h"
+#include "nanovdb/tools/CreateNanoGrid.h"
+#include "nanovdb/tools/GridBuilder.h"
+
+struct RefHostGrid {
+	nanovdb::GridHandle<nanovdb::HostBuffer> handle;
+	const nanovdb::NanoGrid<nanovdb::ValueOnIndex>* grid = nullptr;
+};
+
+extern "C" {
+
+void* refhost_create(const int32_t* coords, uint64_t n) {
+	using SrcT = nanovdb::tools::build::Grid<float>;
+	SrcT src(0.0f);
+	auto acc = src.getAccessor();
+	for (uint64_t i = 0; i < n; ++i) acc.setValue(nanovdb::Coord(coords[3 * i], coords[3 * i + 1], coords[3 * i + 2]), 1.0f);
+	auto* g = new RefHostGrid();
+	// same call shape as Tests/IndexGrid.cpp:125 (channels = 0 here: no blind data, stats off, tiles off)
+	g->handle = nanovdb::tools::createNanoGrid<SrcT, nanovdb::ValueOnIndex, nanovdb::HostBuffer>(src, 0u, false, false, 0);
+	g->grid = g->handle.grid<nanovdb::ValueOnIndex>();
+	if (!g->grid) {
+		delete g;
+		return nullptr;
+	}
+	return g;
+}
+void refhost_destroy(void* g) { delete static_cast<RefHostGrid*>(g); }
+uint64_t refhost_value_count(void* g) { return static_cast<RefHostGrid*>(g)->grid->valueCount(); }
+uint64_t refhost_leaf_count(void* g) { return static_cast<RefHostGrid*>(g)->grid->tree().nodeCount(0); }
+uint64_t refhost_bytes(void* g) { return static_cast<RefHostGrid*>(g)->handle.buffer().size(); }
+const void* refhost_data(void* g) { return static_cast<RefHostGrid*>(g)->handle.data(); }
+
+void refhost_get_values(void* g_, const int32_t* ijk, uint64_t n, uint64_t* out) {
+	const IndexOffsetSampler<0> s(static_cast<RefHostGrid*>(g_)->grid);
+	for (uint64_t i = 0; i < n; ++i) out[i] = s.offset(ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2]);
+}
+void refhost_nearest_f(void* g_, const float* data, const int32_t* ijk, uint64_t n, float* out) {
+	const IndexOffsetSampler<0> s(static_cast<RefHostGrid*>(g_)->grid);
+	const IndexSampler<float, 0> f(s, data);
+	for (uint64_t i = 0; i < n; ++i) out[i] = f(nanovdb::Coord(ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2]));
+}
+void refhost_trilinear_f(void* g_, const float* data, const float* xyz, uint64_t n, float* out) {
+	const IndexOffsetSampler<0> s(static_cast<RefHostGrid*>(g_)->grid);
+	const IndexSampler<float, 1> f(s, data);
+	for (uint64_t i = 0; i < n; ++i) out[i] = f(nanovdb::Vec3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+}
+void refhost_trilinear_v(void* g_, const float* data, const float* xyz, uint64_t n, float* out) {
+	const IndexOffsetSampler<0> s(static_cast<RefHostGrid*>(g_)->grid);
+	const IndexSampler<nanovdb::Vec3f, 1> f(s, reinterpret_cast<const nanovdb::Vec3f*>(data));
+	for (uint64_t i = 0; i < n; ++i) {
+		const nanovdb::Vec3f v = f(nanovdb::Vec3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+		out[3 * i] = v[0], out[3 * i + 1] = v[1], out[3 * i + 2] = v[2];
+	}
+}
+}
