@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- one advect+project frame of the HNanoSolver hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4] [--impl reference]
+
+Prints ONE JSON line (rank 0). A "step" is one full frame over one synthetic sparse smoke domain:
+  metric  : active voxel-updates/s  (N_voxels / frame time), BASELINE.json's metric
+  value   : device-resident frame (inputs in HBM when the timed region starts), CUDA events on the launch stream
+  e2e     : the same frame through the drop-in launcher calls (CreateIndexGrid + Compute_Sim) on pinned HOST buffers,
+            host<->device copies inside the timed region
+  roofline: the dominant kernel (fused red+black pressure sweep): algorithmic bytes per launch / measured launch time
+  cpu_baseline: the CPU oracle port on the box's host cores, bounded sample
+--impl reference runs the UNMODIFIED reference (its own src/Cuda kernels compiled for sm_100a, oracle/_ref) through its own
+launchers CreateIndexGrid + Compute_Sim on the same workload (the reference has no CPU implementation of this path: its
+implementation IS CUDA).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ITERATIONS = 40
+PARAMS6 = [0.5, 2.0, 1.5, 0.1, 0.0, 1.0]  # expansionRate, temperatureRelease, buoyancyStrength, ambientTemp, vorticityScale (off), factorScale
+FULL_FRAME_FIELDS = ["density", "fuel", "waste", "temperature", "flame"]
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------------------
+def build_workload(name: str, rank: int, world: int):
+    """Returns (workload, field_names, fields, frame_kind). N > 1: weak scaling, the bounding box grows with N
+    (512^3 -> 1024x512x512 -> 1024x1024x512 -> 1024^3) and each rank generates and owns one contiguous leaf range."""
+    from hnanosolver_b200 import synth
+
+    if world > 1:
+        from hnanosolver_b200 import dist
+
+        return dist.build_sharded_workload(name, rank, world)
+    w = synth.WORKLOADS[name](with_coords=False)
+    if name in ("c4", "c5"):
+        fields = dict(density=w.scalars[0], **synth.combustion_fields(w))
+        return w, list(fields), list(fields.values()), "full"
+    return w, list(w.scalar_names), list(w.scalars), "north_star"
+
+
+def algorithmic_bytes_per_voxel(S: int, I: int, full: bool) -> int:
+    b = 80 + 16 * I + 8 * S
+    if full:
+        b += 40 + 12                             # combustion_oxygen (4 R + 4 W + div RW) + temperature_buoyancy (T R, v.y RW)
+    return b
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) on a bounded sample
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_baseline(w, names, fields, full: bool, sample_leaves: int = 12288, budget_s: float = 20.0) -> dict:
+    from hnanosolver_b200 import synth
+    from oracle import oracle as O
+
+    L = min(sample_leaves, w.num_leaves)
+    n = L * 512
+    coords = synth.dense_coords(w.origins[:L])
+    ix = O.OracleIndex(coords)
+    vel = w.velocity[:n]
+    fl = {k: a[:n] for k, a in zip(names, fields)}
+    frames, t_used = 0, 0.0
+    while frames < 1 or (t_used < budget_s / 2 and frames < 3):
+        t = time.perf_counter()
+        if full:
+            ix.compute_sim(vel, fl, ITERATIONS, w.dt, w.voxel_size, PARAMS6)
+        else:
+            ix.frame(vel, list(fl.values()), ITERATIONS, w.dt, w.voxel_size)
+        t_used += time.perf_counter() - t
+        frames += 1
+    return {"value": n * frames / t_used, "unit": "voxel-updates/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"first {L} of {w.num_leaves} leaves ({n} voxels) of the same workload, {frames} full frame(s) at I={ITERATIONS}, "
+                      f"oracle/hns_oracle.c with OpenMP"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="pressure solve with one colour per launch (the reference's schedule)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: hnanosolver_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import hnanosolver_b200 as H
+    from hnanosolver_b200 import _lib, synth
+
+    _lib.lib().hns_set_device(local_rank)
+    t0 = time.time()
+    w, names, fields, kind = build_workload(args.workload, rank, world)
+    full = kind == "full"
+    S = len(fields)
+    log(f"[rank {rank}] workload {w.name}: {w.num_leaves} leaves, {w.num_voxels} voxels, S={S}, frame={kind}, generated in {time.time()-t0:.1f}s")
+    flags = H.Simulation.FLAG_UNFUSED_PRESSURE if args.unfused else 0
+
+    if world > 1:
+        from hnanosolver_b200 import dist as hdist
+
+        res = hdist.run_sharded_bench(w, names, fields, full, args, ITERATIONS, PARAMS6, rank, world, local_rank)
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+        return
+
+    # ---- device-resident frame -------------------------------------------------------------------------------
+    grid = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    sim = H.Simulation(grid, S)
+    sim.upload(w.velocity, fields)
+    if full:
+        sim.set_combustion(True, names.index("fuel"), names.index("waste"), names.index("temperature"), names.index("flame"),
+                           H.CombustionParams(*PARAMS6))
+    sim.time_frames(args.warmup, ITERATIONS, w.dt, flags)          # W untimed warm-up frames
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    _lib.lib().hns_launch_count_reset()
+    torch.cuda.synchronize()
+    tc0 = time.time()
+    ms_total, ms_pressure = sim.time_frames(args.steps, ITERATIONS, w.dt, flags)   # K timed frames, CUDA events on the launch stream
+    torch.cuda.synchronize()
+    tc1 = time.time()
+    launches = int(_lib.lib().hns_launch_count())
+    clocks = sampler.stop(tc0, tc1)
+    ms_step = ms_total / args.steps
+    N = w.num_voxels
+    value = N / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    n_sweeps = ITERATIONS * args.steps * (2 if args.unfused else 1)
+    sweep_ms = ms_pressure / n_sweeps
+    bytes_per_launch = 12 * N                                          # read p, read div, write p: each field once per launch
+    achieved = bytes_per_launch / (sweep_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "rbgs_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj["dram_bytes_per_voxel"] * N if tj.get("kernel") == ("k_rbgs_color" if args.unfused else "k_rbgs_fused") else None
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_rbgs_color (one colour)" if args.unfused else "k_rbgs_fused (red+black in one launch)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": sweep_ms, "launches_timed": n_sweeps,
+                "peak_source": peak_src,
+                "share_of_frame": ms_pressure / ms_total,
+                "frame_algorithmic_GBps": algorithmic_bytes_per_voxel(S, ITERATIONS, full) * N / (ms_step * 1e-3) / 1e9}
+
+    # ---- end to end through the drop-in launchers on pinned host buffers -------------------------------------------
+    del sim
+    data = H.GridIndexedData()
+    data.setAllocationType(H.AllocationType.CudaPinned)
+    data.allocateCoords(N)
+    for a in range(0, w.num_leaves, 8192):
+        b = min(w.num_leaves, a + 8192)
+        data.pCoords()[a * 512:b * 512] = synth.dense_coords(w.origins[a:b])
+    data.addValueBlock(H.VEC3F, "vel")
+    data.pValues(H.VEC3F, "vel")[:] = w.velocity
+    e2e_names = list(names)
+    for nm, a in zip(names, fields):
+        data.addValueBlock(H.FLOAT, nm)
+        data.pValues(H.FLOAT, nm)[:] = a
+    if not full:  # Compute_Sim needs the four combustion blocks (HNanoSolver.cu:193); add them so the same call can be made
+        extra = synth.combustion_fields(w)
+        for nm, a in extra.items():
+            if nm not in e2e_names:
+                data.addValueBlock(H.FLOAT, nm)
+                data.pValues(H.FLOAT, nm)[:] = a
+                e2e_names.append(nm)
+    params = H.CombustionParams(*PARAMS6)
+
+    def cook():
+        g = H.CreateIndexGrid(data, w.voxel_size)                      # per cook, like SOP_HNanoSolverVerb::cook (SOP_HNanoSolver.cpp:231)
+        H.Compute_Sim(data, g, ITERATIONS, w.dt, w.voxel_size, params, False)
+        g.reset()
+
+    for _ in range(2):
+        cook()
+    torch.cuda.synchronize()
+    te = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        cook()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - te) * 1e3 / args.e2e_steps
+    Se = len(e2e_names)
+    e2e = {"value": N / (e2e_ms * 1e-3), "unit": "voxel-updates/s", "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+           "h2d_bytes_per_step": int(N * (12 + 4 * Se) + grid.nanovdb_buffer().size + w.num_leaves * 16),
+           "d2h_bytes_per_step": int(N * (12 + 4 * Se)),
+           "call": "CreateIndexGrid + Compute_Sim on a pinned GridIndexedData (velocity + %d float blocks), in place, synchronous" % Se}
+
+    out = {"metric": "active voxel-updates/s per advect+project frame", "value": value, "unit": "voxel-updates/s", "n_gpus": 1,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {w.name}, {w.num_leaves} leaves = {N} active voxels, frame={kind}, I={ITERATIONS} red-black "
+                                  f"iterations, S={S} scalar fields, dt=1/24, voxel size 0.1, CFL<=2.5",
+                      "l2": "inputs larger than L2 (per-field %.0f MB, frame working set %.1f GB); no flush" % (4 * N / 1e6, (9 + 2 * S) * 4 * N / 1e9),
+                      "pressure": "unfused" if args.unfused else "fused red+black"},
+           "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(w, names, fields, full)
+    print(json.dumps(out), flush=True)
+
+
+def reference_arm(args, rank, world):
+    """The unmodified reference through its own launchers on the same workload (rank 0 only)."""
+    if rank != 0:
+        return
+    import torch
+
+    from hnanosolver_b200 import synth
+    from oracle import oracle as O
+
+    w, names, fields, kind = build_workload(args.workload, 0, 1)
+    full = kind == "full"
+    N = w.num_voxels
+    line = {"impl": "reference", "metric": "active voxel-updates/s per advect+project frame", "unit": "voxel-updates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w.name}, {w.num_leaves} leaves = {N} active voxels, frame={kind}, I={ITERATIONS}"}}
+    if O.ref_gpu_available():
+        rd = O.RefData(synth.dense_coords(w.origins), 2)  # AllocationType::CudaPinned
+        rd.add_vec3("vel", w.velocity)
+        fl = dict(zip(names, fields))
+        if not full:
+            for k, v in synth.combustion_fields(w).items():
+                fl.setdefault(k, v)
+        for k, v in fl.items():
+            rd.add_float(k, v)
+        for _ in range(args.warmup):
+            O.ref_cook_frame(rd, ITERATIONS, w.dt, w.voxel_size, PARAMS6)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            O.ref_cook_frame(rd, ITERATIONS, w.dt, w.voxel_size, PARAMS6)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t) * 1e3 / args.steps
+        Se = len(fl)
+        line.update(value=N / (ms * 1e-3), ms_per_step=ms,
+                    reference_kind="the reference's own CUDA kernels and launchers (src/Cuda/*.cu compiled unmodified for sm_100a), "
+                                   "CreateIndexGrid + Compute_Sim on a CudaPinned GridIndexedData, as SOP_HNanoSolverVerb::cook calls them",
+                    e2e={"value": N / (ms * 1e-3), "unit": "voxel-updates/s", "h2d_bytes_per_step": int(N * (12 + 24 + 4 * Se)),
+                         "d2h_bytes_per_step": int(N * (12 + 4 * Se)),
+                         "note": "the reference API is host-buffer-in / host-buffer-out by construction, so value == e2e"})
+    else:
+        line.update(value=None, ms_per_step=None, reference_kind="oracle/_ref/libhns_ref.so not present; CPU port only")
+    if not args.no_cpu_baseline:
+        cb = cpu_baseline(w, names, fields, full)
+        line["cpu_baseline"] = cb
+        if line.get("value") is None:
+            line["value"], line["ms_per_step"] = cb["value"], N / cb["value"] * 1e3
+            line["e2e"] = {"value": cb["value"], "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,7 @@ SIGNATURES = {
     "hns_state_upload_scalar": (C.c_int, [C.c_void_p, C.c_int, c_f32p]),
     "hns_state_download_scalar": (C.c_int, [C.c_void_p, C.c_int, c_f32p]),
     "hns_state_download_aux": (C.c_int, [C.c_void_p, C.c_int, c_f32p]),
+    "hns_state_set_combustion": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CombustionParams)]),
     "hns_state_step": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_void_p]),
     "hns_state_advect_velocity": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
     "hns_state_divergence": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

@@ -31,9 +31,8 @@ static inline float omega_compute(float voxelSize) { return 2.0f / (1.0f + sinf(
 // ... and as pressure_projection_idx does (reference src/Cuda/PressureProjection.cu:53): double sin, narrowed at the kernel call
 static inline float omega_project(float voxelSize) { return float(2.0f / (1.0f + sin(3.14159 * voxelSize))); }
 
-static int pressure_solve(hns_state* s, int iterations, float omega, unsigned flags, cudaStream_t st) {
+static int pressure_solve(hns_state* s, int iterations, float dx, float omega, unsigned flags, cudaStream_t st) {
 	const GridView& g = s->grid->view;
-	const float dx = s->grid->voxel_size;
 	s->p_cur = 0;
 	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, s->n * sizeof(float), st));  // initial guess 0 (HNanoSolver.cu:113)
 	if (flags & 1u) {
@@ -56,19 +55,39 @@ static ScalarPtrs scalar_ptrs(const hns_state* s) {
 	return sp;
 }
 
-static int frame(hns_state* s, int iterations, float dt, unsigned flags, cudaStream_t st, cudaEvent_t ev_p0 = nullptr, cudaEvent_t ev_p1 = nullptr) {
+// One frame on resident state = Compute() (reference src/Cuda/HNanoSolver.cu:159-356) without the host copies:
+//   advect_vector -> [vorticity: scale 0 == identity] -> divergence -> [combustion_oxygen -> temperature_buoyancy] ->
+//   iterations x (red, black) -> subtractPressureGradient -> advect_scalars over all scalar fields.
+// `voxel_size` is the launcher argument (the reference's kernels use it, not the grid's map).
+static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsigned flags, cudaStream_t st, cudaEvent_t ev_p0 = nullptr,
+                 cudaEvent_t ev_p1 = nullptr) {
 	const GridView& g = s->grid->view;
-	const float h = s->grid->voxel_size, inv = 1.0f / h;
+	const float h = voxel_size, inv = 1.0f / h;
 	launch_advect_vector(g, s->vel, s->adv, dt, inv, st);
 	launch_divergence(g, s->adv, s->div, inv, st);
+	if (s->comb_enabled) {
+		const int iF = s->comb_idx[0], iW = s->comb_idx[1], iT = s->comb_idx[2], iL = s->comb_idx[3];
+		launch_combustion_oxygen(s->sc[iF], s->sc[iW], s->sc[iT], s->div, s->sc[iL], s->sc_out[iF], s->sc_out[iW], s->sc_out[iT], s->sc_out[iL],
+		                         s->comb.temperatureRelease, s->comb.expansionRate, s->n, st);
+		launch_buoyancy(s->adv, s->sc_out[iT], dt, s->comb.ambientTemp, s->comb.buoyancyStrength, s->n, st);
+		for (int i : {iF, iW, iT, iL}) std::swap(s->sc[i], s->sc_out[i]);  // HNanoSolver.cu:239-246
+	}
 	if (ev_p0) cudaEventRecord(ev_p0, st);
-	int rc = pressure_solve(s, iterations, omega_compute(h), flags, st);
+	int rc = pressure_solve(s, iterations, h, omega_compute(h), flags, st);
 	if (rc) return rc;
 	if (ev_p1) cudaEventRecord(ev_p1, st);
 	launch_subtract_gradient(g, s->adv, s->p[s->p_cur], s->vel, inv, st);
 	if (s->n_scalars) {
-		launch_advect_scalars(g, s->vel, scalar_ptrs(s), s->n_scalars, dt, inv, 0, st);
-		for (int i = 0; i < s->n_scalars; ++i) std::swap(s->sc[i], s->sc_out[i]);
+		ScalarPtrs sp{};
+		int S = 0;
+		for (int i = 0; i < s->n_scalars; ++i) {
+			if (i == s->skip_scalar) continue;  // "collision_sdf" is not advected (HNanoSolver.cu:327)
+			sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i];
+			++S;
+		}
+		launch_advect_scalars(g, s->vel, sp, S, dt, inv, 0, st);
+		for (int i = 0; i < s->n_scalars; ++i)
+			if (i != s->skip_scalar) std::swap(s->sc[i], s->sc_out[i]);
 	}
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
@@ -179,12 +198,33 @@ int hns_state_download_aux(hns_state* s, int which, float* host) {
 	return HNS_OK;
 }
 
+int hns_state_set_combustion(hns_state* s, int enabled, int i_fuel, int i_waste, int i_temperature, int i_flame, const hns_combustion_params* params) {
+	HNS_REQUIRE(s, "null state");
+	if (!enabled) {
+		s->comb_enabled = false;
+		return HNS_OK;
+	}
+	HNS_REQUIRE(params, "null params");
+	const int idx[4] = {i_fuel, i_waste, i_temperature, i_flame};
+	for (int a = 0; a < 4; ++a) {
+		HNS_REQUIRE(idx[a] >= 0 && idx[a] < s->n_scalars, "combustion field index out of range");
+		for (int b = 0; b < a; ++b) HNS_REQUIRE(idx[a] != idx[b], "combustion field indices must be distinct");
+	}
+	if (params->vorticityScale != 0.0f)
+		return fail(HNS_ERR_UNSUPPORTED, "vorticityScale != 0: the reference applies vorticity confinement in place with a data race "
+		                                 "(HNanoSolver.cu:174), so no reference result exists to reproduce; not implemented in this build");
+	std::memcpy(s->comb_idx, idx, sizeof(idx));
+	s->comb = *params;
+	s->comb_enabled = true;
+	return HNS_OK;
+}
+
 int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void* stream) {
 	HNS_REQUIRE(s, "null state");
 	HNS_REQUIRE(iterations > 0, "Number of pressure iterations must be positive.");
 	HNS_REQUIRE(dt >= 0.0f, "dt (time step) cannot be negative.");
 	if (!s->n) return HNS_OK;
-	return frame(s, iterations, dt, flags, static_cast<cudaStream_t>(stream));
+	return frame(s, iterations, dt, s->grid->voxel_size, flags, static_cast<cudaStream_t>(stream));
 }
 int hns_state_advect_velocity(hns_state* s, float dt, void* stream) {
 	HNS_REQUIRE(s, "null state");
@@ -201,7 +241,7 @@ int hns_state_divergence(hns_state* s, int of_advected, void* stream) {
 int hns_state_pressure_solve(hns_state* s, int iterations, float omega, unsigned flags, void* stream) {
 	HNS_REQUIRE(s && iterations >= 0, "bad argument");
 	if (!s->n) return HNS_OK;
-	int rc = pressure_solve(s, iterations, omega, flags, static_cast<cudaStream_t>(stream));
+	int rc = pressure_solve(s, iterations, s->grid->voxel_size, omega, flags, static_cast<cudaStream_t>(stream));
 	if (rc) return rc;
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
@@ -261,7 +301,7 @@ int hns_state_time_frames(hns_state* s, int frames, int iterations, float dt, un
 		for (int c = 0; c < 3; ++c) cudaMemcpyAsync(s->vel[c], keep[c], fb, cudaMemcpyDeviceToDevice, st);
 		for (int i = 0; i < s->n_scalars; ++i) cudaMemcpyAsync(s->sc[i], keep[3 + i], fb, cudaMemcpyDeviceToDevice, st);
 		cudaEventRecord(ev[4 * f + 0], st);
-		rc = frame(s, iterations, dt, flags, st, ev[4 * f + 1], ev[4 * f + 2]);
+		rc = frame(s, iterations, dt, s->grid->voxel_size, flags, st, ev[4 * f + 1], ev[4 * f + 2]);
 		cudaEventRecord(ev[4 * f + 3], st);
 	}
 	cudaStreamSynchronize(st);
@@ -343,66 +383,31 @@ int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char*
 		if (!std::strcmp(names[i], "collision_sdf")) iSdf = i;
 	}
 	if (has_collision && iSdf >= 0) return fail(HNS_ERR_UNSUPPORTED, "SDF collision handling is not implemented in this build (SURVEY.md 8f rank 2)");
-	if (params->vorticityScale != 0.0f)
-		return fail(HNS_ERR_UNSUPPORTED, "vorticityScale != 0: the reference applies vorticity confinement in place with a data race "
-		                                 "(HNanoSolver.cu:174), so no reference result exists to reproduce; not implemented in this build");
 	for (const char* req : {"fuel", "waste", "temperature", "flame"}) {  // :193-201
 		bool found = false;
 		for (int i = 0; i < n_float; ++i) found |= !std::strcmp(names[i], req);
 		if (!found) return fail(HNS_ERR_RUNTIME, std::string("Missing required input field for combustion: ") + req);
-	}
-	if (g->voxel_size != voxel_size) {
-		// the reference passes voxelSize independently of the grid's map; kernels only use the argument
 	}
 	Scoped sc;
 	int rc = hns_state_create(g, n_float, &sc.state);
 	if (rc) return rc;
 	hns_state* s = sc.state;
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
-	const GridView& gv = g->view;
-	const float inv = 1.0f / voxel_size;
+	if ((rc = hns_state_set_combustion(s, 1, iF, iW, iT, iL, params))) return rc;
+	s->skip_scalar = iSdf;
 	if ((rc = ensure_aos(s))) return rc;
+	// H2D of the whole state (HNanoSolver.cu:120-133) -- the coords are not needed on the device here
 	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
 	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
 	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, st));
-	// 1. advect velocity; (vorticity confinement with scale 0 is the identity); 2. divergence of the advected velocity
-	launch_advect_vector(gv, s->vel, s->adv, dt, inv, st);
-	launch_divergence(gv, s->adv, s->div, inv, st);
-	// 3. combustion (in -> out, div += burn*expansion), buoyancy on the advected velocity with the post-combustion temperature
-	launch_combustion_oxygen(s->sc[iF], s->sc[iW], s->sc[iT], s->div, s->sc[iL], s->sc_out[iF], s->sc_out[iW], s->sc_out[iT], s->sc_out[iL],
-	                         params->temperatureRelease, params->expansionRate, n, st);
-	launch_buoyancy(s->adv, s->sc_out[iT], dt, params->ambientTemp, params->buoyancyStrength, n, st);
-	for (int i : {iF, iW, iT, iL}) std::swap(s->sc[i], s->sc_out[i]);  // :239-246
-	// 4. pressure, 5. projection
-	{
-		const float keep_h = s->grid->voxel_size;
-		(void)keep_h;
-	}
-	s->p_cur = 0;
-	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, n * 4, st));
-	const float omega = omega_compute(voxel_size);
-	for (int it = 0; it < iterations; ++it) {
-		launch_rbgs_fused(gv, s->div, s->p[s->p_cur], s->p[s->p_cur ^ 1], voxel_size, omega, st);
-		s->p_cur ^= 1;
-	}
-	launch_subtract_gradient(gv, s->adv, s->p[s->p_cur], s->vel, inv, st);
-	// 6. advect every float block except collision_sdf with the projected velocity (:321-348)
-	ScalarPtrs sp{};
-	int S = 0;
-	std::vector<int> which;
-	for (int i = 0; i < n_float; ++i) {
-		if (i == iSdf) continue;
-		sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i];
-		which.push_back(i);
-		++S;
-	}
-	launch_advect_scalars(gv, s->vel, sp, S, dt, inv, 0, st);
-	// results back to the same host arrays (:361-369); a collision_sdf block comes back zeroed like the reference's untouched output buffer
+	if ((rc = frame(s, iterations, dt, voxel_size, 0u, st))) return rc;
+	// results back into the same host arrays (HNanoSolver.cu:361-369); a collision_sdf block comes back zeroed like the
+	// reference's never-written output buffer
 	launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, n, st);
 	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, st));
 	for (int i = 0; i < n_float; ++i) {
-		if (i == iSdf) HNS_CUDA(cudaMemsetAsync(s->sc_out[i], 0, n * 4, st));
-		HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc_out[i], n * 4, cudaMemcpyDeviceToHost, st));
+		if (i == iSdf) HNS_CUDA(cudaMemsetAsync(s->sc[i], 0, n * 4, st));
+		HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc[i], n * 4, cudaMemcpyDeviceToHost, st));
 	}
 	HNS_CUDA(cudaStreamSynchronize(st));
 	HNS_CUDA(cudaGetLastError());

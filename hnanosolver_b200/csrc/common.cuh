@@ -103,6 +103,9 @@ struct hns_state {
 	float* sc[16] = {};   // scalar fields (current)
 	float* sc_out[16] = {};
 	float* aos = nullptr; // staging float[N][3] for host <-> device velocity transfers
-	float** d_sc_in = nullptr;   // device arrays of the S pointers
-	float** d_sc_out = nullptr;
+	// optional combustion + buoyancy stage of the all-in-one frame
+	bool comb_enabled = false;
+	int comb_idx[4] = {-1, -1, -1, -1};  // fuel, waste, temperature, flame
+	hns_combustion_params comb{};
+	int skip_scalar = -1;  // scalar that is carried but not advected ("collision_sdf")
 };

@@ -238,6 +238,10 @@ class Simulation:
         check(_lib.lib().hns_state_download_aux(self._h, which, _fp(out)))
         return out
 
+    def set_combustion(self, enabled: bool, fuel=0, waste=0, temperature=0, flame=0, params: CombustionParams | None = None):
+        check(_lib.lib().hns_state_set_combustion(self._h, int(enabled), fuel, waste, temperature, flame,
+                                                  C.byref(params) if params is not None else None))
+
     def step(self, iterations: int, dt: float, flags: int = 0, stream=None):
         check(_lib.lib().hns_state_step(self._h, iterations, dt, flags, _stream(stream)))
 

@@ -296,3 +296,22 @@ WORKLOADS = {
     "c4": lambda **kw: sparse_smoke(512, 0.30, 4, **kw),
     "c5": lambda **kw: narrow_band(1024, 2.0e8, 5, **kw),
 }
+
+
+def combustion_fields(w: Workload, seed: int = 123, chunk_leaves: int = 8192) -> dict:
+    """fuel / waste / temperature / flame for the all-in-one frame (reference src/Cuda/HNanoSolver.cu:193): hash noise,
+    fuel present in ~40 % of the voxels. Returned in the insertion order the frame uses."""
+    L, N = w.num_leaves, w.num_voxels
+    out = {k: np.empty(N, np.float32) for k in ("fuel", "waste", "temperature", "flame")}
+    for a in range(0, L, chunk_leaves):
+        b = min(L, a + chunk_leaves)
+        c = dense_coords(w.origins[a:b])
+        sl = slice(a * 512, b * 512)
+        out["fuel"][sl] = hash_noise(seed, c, 20) * (hash_noise(seed, c, 21) < 0.4)
+        out["waste"][sl] = 0.3 * hash_noise(seed, c, 22)
+        out["temperature"][sl] = hash_noise(seed, c, 23)
+        out["flame"][sl] = 0.2 * hash_noise(seed, c, 24)
+    for a in out.values():
+        if N:
+            a[0] = 0.0
+    return out

@@ -123,8 +123,14 @@ int hns_state_download_scalar(hns_state* s, int index, float* host);
 /* intermediate fields of the last step, for parity checks: which = 0 divergence, 1 pressure, 2 advected velocity (float[N][3]) */
 int hns_state_download_aux(hns_state* s, int which, float* host);
 
+/* Enables the combustion_oxygen + temperature_buoyancy stage of the all-in-one frame (src/Cuda/HNanoSolver.cu:190-250) on the
+ * scalar fields with the given indices; params->vorticityScale must be 0 (the reference's in-place vorticity pass races). */
+int hns_state_set_combustion(hns_state* s, int enabled, int i_fuel, int i_waste, int i_temperature, int i_flame,
+                             const hns_combustion_params* params);
+
 /* One frame on resident state: advect_vector -> divergence -> iterations x (red, black) -> gradient subtract ->
- * advect_scalars (all n_scalars fields). Same arithmetic as the corresponding steps of Compute() (HNanoSolver.cu:159-356);
+ * advect_scalars (all n_scalars fields); with hns_state_set_combustion the combustion + buoyancy stage runs after the divergence,
+ * exactly as in Compute(). Same arithmetic as the corresponding steps of Compute() (HNanoSolver.cu:159-356);
  * omega = 2/(1+sinf(3.14159f*voxel_size)) (HNanoSolver.cu:257). Asynchronous on `stream`.
  * flags: bit 0 = force the unfused (one colour per launch) pressure kernels. */
 int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void* stream);

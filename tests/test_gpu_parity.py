@@ -1,0 +1,420 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (hnanosolver_b200.launchers -> ctypes -> libhns_b200.so), against
+(1) the CPU oracle, (2) the committed golden fixtures, (3) the unmodified reference kernels / launchers running live on the
+same GPU (oracle/_ref/libhns_ref.so, when it travelled with the snapshot), and (4) size-independent properties at full size.
+
+Bar (north star): index topology bit-exact; fields within 1e-5 relative (helpers.REL_TOL) of the reference kernels.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import hnanosolver_b200 as H
+from helpers import REL_TOL, assert_close, nanovdb_compare_mask, rel_err
+from hnanosolver_b200 import synth
+from hnanosolver_b200.grid_data import FLOAT, VEC3F, GridIndexedData
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not O.ref_gpu_available(), reason="oracle/_ref/libhns_ref.so not present")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PARAMS6 = np.array([0.5, 2.0, 1.5, 0.1, 0.0, 1.0], np.float32)
+
+
+def small_cases():
+    return {
+        "soup_negative_multitile": synth.random_leaves(28, 4, 7, offset=(-24, 4096 - 16, -16), cfl=1.8, S=2),
+        "soup_dense": synth.random_leaves(60, 4, 9, cfl=1.2, S=3),
+        "single_leaf": synth.random_leaves(1, 1, 1, S=1),
+        "sphere32": synth.smoke_sphere(32, 1),
+    }
+
+
+@pytest.fixture(scope="module", params=list(small_cases()))
+def case(request):
+    return small_cases()[request.param]
+
+
+def run_product_frame(w, iterations, flags=0):
+    g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    sim = H.Simulation(g, len(w.scalars))
+    sim.upload(w.velocity, w.scalars)
+    sim.step(iterations, w.dt, flags)
+    sim.sync()
+    return dict(vel=sim.velocity(), div=sim.aux(0), p=sim.aux(1), adv=sim.aux(2), scalars=[sim.scalar(i) for i in range(len(w.scalars))])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# topology
+# ------------------------------------------------------------------------------------------------------------------
+def test_index_grid_matches_oracle_bit_exact(case):
+    w = case
+    data = GridIndexedData.from_arrays(w.coords)
+    g = H.CreateIndexGrid(data, w.voxel_size, validate=True)
+    ix = O.OracleIndex(w.coords)
+    assert g.num_leaves == ix.num_leaves == w.num_leaves
+    assert np.array_equal(g.nanovdb_buffer(), ix.nanovdb_buffer(w.voxel_size))
+    rng = np.random.default_rng(0)
+    q = np.concatenate([w.coords, w.coords[::3] + rng.integers(-17, 18, size=w.coords[::3].shape).astype(np.int32),
+                        rng.integers(-9000, 9000, size=(2000, 3)).astype(np.int32)])
+    assert np.array_equal(g.get_values(q), ix.get_values(q))
+    assert np.array_equal(g.get_values(w.coords), np.arange(1, w.num_voxels + 1, dtype=np.uint64))
+
+
+@needs_ref
+def test_index_grid_matches_reference_voxelsToGrid(case):
+    w = case
+    g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    rd = O.RefData(w.coords)
+    rg = O.RefGrid(rd, w.voxel_size)
+    ref, mine = rg.buffer(), g.nanovdb_buffer()
+    assert ref.size == mine.size
+    T = int(np.frombuffer(ref[672 + 40:672 + 44].tobytes(), np.uint32)[0])
+    bad = np.nonzero((ref != mine) & nanovdb_compare_mask(ref.size, T))[0]
+    assert bad.size == 0, f"NanoVDB buffer differs from voxelsToGrid at bytes {bad[:16]}"
+    rng = np.random.default_rng(1)
+    q = np.concatenate([w.coords[::2], w.coords[::3] + rng.integers(-12, 13, size=w.coords[::3].shape).astype(np.int32)])
+    assert np.array_equal(g.get_values(q), rg.get_values(q))
+
+
+def test_neighbor_table(case):
+    w = case
+    g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    nbr = g.neighbors()
+    lut = {tuple(o): i for i, o in enumerate(w.origins.tolist())}
+    for l, o in enumerate(w.origins.tolist()):
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    want = lut.get((o[0] + 8 * dx, o[1] + 8 * dy, o[2] + 8 * dz), -1)
+                    assert nbr[l, (dx + 1) * 9 + (dy + 1) * 3 + dz + 1] == want
+
+
+def test_topology_errors():
+    w = synth.random_leaves(10, 3, 2)
+    with pytest.raises(H.HnsError, match="NanoVDB order"):
+        H.create_index_grid_from_origins(w.origins[::-1].copy(), 0.1)
+    with pytest.raises(H.HnsError, match="multiple of 8"):
+        H.create_index_grid_from_origins(w.origins + 1, 0.1)
+    with pytest.raises(ValueError, match="voxelSize"):
+        H.create_index_grid_from_origins(w.origins, 0.0)
+    bad = GridIndexedData.from_arrays(w.coords[:-1])
+    with pytest.raises(H.HnsError, match="multiple of 512"):
+        H.CreateIndexGrid(bad, 0.1)
+    c = w.coords.copy()
+    c[700] += 1
+    with pytest.raises(H.HnsError, match="not a dense leaf"):
+        H.CreateIndexGrid(GridIndexedData.from_arrays(c), 0.1, validate=True)
+    empty = H.create_index_grid_from_origins(np.zeros((0, 3), np.int32), 0.1)
+    assert empty.num_leaves == 0 and empty.nanovdb_buffer().size == 672 + 64 + 96
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# kernels, stage by stage
+# ------------------------------------------------------------------------------------------------------------------
+def test_frame_stages_match_oracle(case):
+    w = case
+    I = 6
+    ix = O.OracleIndex(w.coords)
+    want = ix.frame(w.velocity, w.scalars, I, w.dt, w.voxel_size)
+    got = run_product_frame(w, I)
+    for k in ("adv", "div", "p", "vel"):
+        assert_close(got[k], want[k], k)
+    for i in range(len(w.scalars)):
+        assert_close(got["scalars"][i], want["scalars"][i], f"scalar {i}")
+
+
+def test_fused_pressure_sweep_is_bit_identical_to_two_colour_launches(case):
+    a = run_product_frame(case, 7, flags=0)
+    b = run_product_frame(case, 7, flags=H.Simulation.FLAG_UNFUSED_PRESSURE)
+    for k in ("p", "vel"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+@needs_ref
+def test_frame_stages_match_reference_kernels(case):
+    w = case
+    I = 9
+    rd = O.RefData(w.coords)
+    rd.add_vec3("vel", w.velocity)
+    for n, a in zip(w.scalar_names, w.scalars):
+        rd.add_float(n, a)
+    rg = O.RefGrid(rd, w.voxel_size)
+    rf = O.RefFrame(rd, rg, w.scalar_names)
+    rf.run(I, w.dt, w.voxel_size, 1)
+    want = rf.download()
+    got = run_product_frame(w, I)
+    for k in ("adv", "div", "p", "vel"):
+        assert_close(got[k], want[k], k)
+    for i in range(len(w.scalars)):
+        assert_close(got["scalars"][i], want["scalars"][i], f"scalar {i}")
+    # divergence L2 norm of the projected velocity agrees with the reference's (BASELINE.md parity gate)
+    ix = O.OracleIndex(w.coords)
+    n_got = np.sqrt(np.mean(ix.divergence(got["vel"], w.voxel_size).astype(np.float64) ** 2))
+    n_ref = np.sqrt(np.mean(ix.divergence(want["vel"], w.voxel_size).astype(np.float64) ** 2))
+    assert abs(n_got - n_ref) <= REL_TOL * n_ref
+
+
+def test_far_samples_take_the_tree_walk_path():
+    """CFL ~ 20: back-traced points land several leaves away, outside the 3x3x3 neighbour table."""
+    w = synth.random_leaves(50, 5, 4, cfl=20.0, S=1)
+    ix = O.OracleIndex(w.coords)
+    g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    sim = H.Simulation(g, 1)
+    sim.upload(w.velocity, w.scalars)
+    sim.advect_velocity(w.dt)
+    sim.advect_scalars(w.dt, 0)
+    sim.sync()
+    assert_close(sim.aux(2), ix.advect_vector(w.velocity, w.dt, w.voxel_size), "advect_vector, CFL 20")
+    assert_close(sim.scalar(0), ix.advect_scalars(w.velocity, w.scalars, w.dt, w.voxel_size)[0], "advect_scalars, CFL 20")
+    sim.upload(w.velocity, w.scalars)
+    sim.advect_scalars(w.dt, 1)
+    sim.sync()
+    assert_close(sim.scalar(0), ix.advect_scalar(w.velocity, w.scalars[0], w.dt, w.voxel_size), "advect_scalar, CFL 20")
+
+
+def test_inactive_corner_semantics_differ_between_the_two_scalar_kernels():
+    """advect_scalars reads array element 0 for inactive corners (Kernel.cu:192), advect_scalar reads 0 (Stencils.hpp:83)."""
+    w = synth.random_leaves(6, 3, 5, cfl=1.5, S=1)
+    w.scalars[0][0] = 100.0  # make element 0 stand out
+    ix = O.OracleIndex(w.coords)
+    g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    outs = []
+    for sem in (0, 1):
+        sim = H.Simulation(g, 1)
+        sim.upload(w.velocity, w.scalars)
+        sim.advect_scalars(w.dt, sem)
+        sim.sync()
+        outs.append(sim.scalar(0))
+    assert_close(outs[0], ix.advect_scalars(w.velocity, w.scalars, w.dt, w.voxel_size)[0], "advect_scalars semantics")
+    assert_close(outs[1], ix.advect_scalar(w.velocity, w.scalars[0], w.dt, w.voxel_size), "advect_scalar semantics")
+    assert not np.array_equal(outs[0], outs[1])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the drop-in launchers on host sidecars
+# ------------------------------------------------------------------------------------------------------------------
+def _sidecar(w, floats):
+    return GridIndexedData.from_arrays(w.coords, w.velocity, "vel", **floats)
+
+
+def test_launchers_match_oracle(case):
+    w = case
+    ix = O.OracleIndex(w.coords)
+    h, dt = w.voxel_size, w.dt
+    d = _sidecar(w, dict(zip(w.scalar_names, w.scalars)))
+    H.AdvectIndexGrid(d, dt, h)
+    for n, s in zip(w.scalar_names, w.scalars):
+        assert_close(d.pValues(FLOAT, n), ix.advect_scalar(w.velocity, s, dt, h), f"AdvectIndexGrid {n}")
+    d = _sidecar(w, {})
+    H.AdvectIndexGridVelocity(d, dt, h)
+    assert_close(d.pValues(VEC3F, "vel"), ix.advect_vector(w.velocity, dt, h), "AdvectIndexGridVelocity")
+    d = _sidecar(w, dict(divergence=np.zeros(w.num_voxels, np.float32)))
+    H.Divergence(d, h)
+    assert_close(d.pValues(FLOAT, "divergence"), ix.divergence(w.velocity, h), "Divergence")
+    d = _sidecar(w, {})
+    H.ProjectNonDivergent(d, 5, h)
+    assert_close(d.pValues(VEC3F, "vel"), ix.project_non_divergent(w.velocity, 5, h)[0], "ProjectNonDivergent")
+
+
+def _combustion_fields(n, seed=123):
+    rng = np.random.default_rng(seed)
+    f = dict(fuel=(rng.random(n) * (rng.random(n) < 0.4)).astype(np.float32), waste=(0.3 * rng.random(n)).astype(np.float32),
+             temperature=rng.random(n).astype(np.float32), flame=(0.2 * rng.random(n)).astype(np.float32))
+    for a in f.values():
+        a[0] = 0.0
+    return f
+
+
+def test_compute_sim_matches_oracle(case):
+    w = case
+    ix = O.OracleIndex(w.coords)
+    fields = dict(density=w.scalars[0], **_combustion_fields(w.num_voxels))
+    want_vel, want = ix.compute_sim(w.velocity, fields, 5, w.dt, w.voxel_size, PARAMS6)
+    d = _sidecar(w, fields)
+    g = H.CreateIndexGrid(d, w.voxel_size)
+    H.Compute_Sim(d, g, 5, w.dt, w.voxel_size, H.CombustionParams(*PARAMS6.tolist()), False)
+    assert_close(d.pValues(VEC3F, "vel"), want_vel, "Compute_Sim velocity")
+    for k, v in want.items():
+        assert_close(d.pValues(FLOAT, k), v, f"Compute_Sim {k}")
+
+
+@needs_ref
+def test_compute_sim_matches_reference_compute_sim(case):
+    w = case
+    fields = dict(density=w.scalars[0], **_combustion_fields(w.num_voxels))
+    rd = O.RefData(w.coords)
+    rd.add_vec3("vel", w.velocity)
+    for k, v in fields.items():
+        rd.add_float(k, v)
+    rg = O.RefGrid(rd, w.voxel_size)
+    O.ref_compute_sim(rd, rg, 8, w.dt, w.voxel_size, PARAMS6, False)
+    d = _sidecar(w, fields)
+    g = H.CreateIndexGrid(d, w.voxel_size)
+    H.Compute_Sim(d, g, 8, w.dt, w.voxel_size, H.CombustionParams(*PARAMS6.tolist()), False)
+    assert_close(d.pValues(VEC3F, "vel"), rd.blocks["vel"], "Compute_Sim velocity")
+    for k in fields:
+        assert_close(d.pValues(FLOAT, k), rd.blocks[k], f"Compute_Sim {k}")
+
+
+@needs_ref
+def test_standalone_launchers_match_reference_launchers(case):
+    w = case
+    h, dt = w.voxel_size, w.dt
+    rd = O.RefData(w.coords)
+    rd.add_vec3("vel", w.velocity)
+    for n, s in zip(w.scalar_names, w.scalars):
+        rd.add_float(n, s)
+    O.ref_advect_index_grid(rd, dt, h)
+    d = _sidecar(w, dict(zip(w.scalar_names, w.scalars)))
+    H.AdvectIndexGrid(d, dt, h)
+    for n in w.scalar_names:
+        assert_close(d.pValues(FLOAT, n), rd.blocks[n], f"AdvectIndexGrid {n}")
+    rd = O.RefData(w.coords)
+    rd.add_vec3("vel", w.velocity)
+    O.ref_project_non_divergent(rd, 10, h)
+    d = _sidecar(w, {})
+    H.ProjectNonDivergent(d, 10, h)
+    assert_close(d.pValues(VEC3F, "vel"), rd.blocks["vel"], "ProjectNonDivergent")
+
+
+def test_compute_sim_errors():
+    w = synth.random_leaves(4, 2, 1, S=1)
+    d = _sidecar(w, dict(density=w.scalars[0]))
+    g = H.CreateIndexGrid(d, w.voxel_size)
+    p = H.CombustionParams()
+    with pytest.raises(RuntimeError, match="Missing required input field for combustion: fuel"):
+        H.Compute_Sim(d, g, 4, w.dt, w.voxel_size, p, False)
+    two = _sidecar(w, dict(density=w.scalars[0]))
+    two.addValueBlock(VEC3F, "vel2")
+    with pytest.raises(RuntimeError, match="exactly one Vec3f block"):
+        H.Compute_Sim(two, g, 4, w.dt, w.voxel_size, p, False)
+    nof = _sidecar(w, {})
+    with pytest.raises(RuntimeError, match="No float blocks"):
+        H.Compute_Sim(nof, g, 4, w.dt, w.voxel_size, p, False)
+    empty = GridIndexedData()
+    H.Compute_Sim(empty, g, 4, w.dt, w.voxel_size, p, False)  # totalVoxels == 0 -> silent return (HNanoSolver.cu:26-28)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# golden fixtures (outputs of the reference itself, committed)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["soup", "sphere"])
+def test_against_golden_reference_outputs(name):
+    path = os.path.join(GOLDEN, f"ref_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not committed")
+    z = np.load(path)
+    h, dt, I = float(z["voxel_size"]), float(z["dt"]), int(z["iterations"])
+    g = H.create_index_grid_from_origins(z["origins"], h)
+    ref = z["nanovdb"]
+    T = int(np.frombuffer(ref[672 + 40:672 + 44].tobytes(), np.uint32)[0])
+    assert not ((g.nanovdb_buffer() != ref) & nanovdb_compare_mask(ref.size, T)).any()
+    assert np.array_equal(g.get_values(z["query_ijk"]), z["query_values"])
+    S = len(z["scalar_names"])
+    sim = H.Simulation(g, S)
+    sim.upload(z["velocity"], [z[f"scalar{i}"] for i in range(S)])
+    sim.step(I, dt)
+    sim.sync()
+    assert_close(sim.aux(2), z["frame_adv"], "advect_vector")
+    assert_close(sim.aux(0), z["frame_div"], "divergence")
+    assert_close(sim.aux(1), z["frame_p"], "pressure")
+    assert_close(sim.velocity(), z["frame_vel"], "projected velocity")
+    for i in range(S):
+        assert_close(sim.scalar(i), z[f"frame_scalar{i}"], f"scalar {i}")
+    fields = dict(density=z["scalar0"], fuel=z["comb_fuel"], waste=z["comb_waste"], temperature=z["comb_temperature"], flame=z["comb_flame"])
+    d = GridIndexedData.from_arrays(z["coords"], z["velocity"], "vel", **fields)
+    H.Compute_Sim(d, H.CreateIndexGrid(d, h), I, dt, h, H.CombustionParams(*z["params"].tolist()), False)
+    assert_close(d.pValues(VEC3F, "vel"), z["compute_sim_vel"], "Compute_Sim velocity")
+    for k in fields:
+        assert_close(d.pValues(FLOAT, k), z[f"compute_sim_{k}"], f"Compute_Sim {k}")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# full-size checks (BASELINE.json configs 2 and 4)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c4():
+    return synth.sparse_smoke(512, 0.30, 4, with_coords=False)
+
+
+def test_config2_full_frame_matches_oracle():
+    w = synth.smoke_plume(128, 2)
+    ix = O.OracleIndex(w.coords)
+    want = ix.frame(w.velocity, w.scalars, 40, w.dt, w.voxel_size)
+    got = run_product_frame(w, 40)
+    for k in ("adv", "div", "p", "vel"):
+        assert_close(got[k], want[k], k)
+    for i in range(2):
+        assert_close(got["scalars"][i], want["scalars"][i], f"scalar {i}")
+
+
+@needs_ref
+def test_config4_full_frame_matches_reference_kernels(c4):
+    w = c4
+    coords = synth.dense_coords(w.origins)
+    rd = O.RefData(coords)
+    rd.add_vec3("vel", w.velocity)
+    for n, a in zip(w.scalar_names, w.scalars):
+        rd.add_float(n, a)
+    rg = O.RefGrid(rd, w.voxel_size)
+    rf = O.RefFrame(rd, rg, w.scalar_names)
+    rf.run(40, w.dt, w.voxel_size, 1)
+    want = rf.download()
+    got = run_product_frame(w, 40)
+    for k in ("adv", "div", "p", "vel"):
+        assert_close(got[k], want[k], k)
+    for i in range(2):
+        assert_close(got["scalars"][i], want["scalars"][i], f"scalar {i}")
+
+
+def test_config4_size_independent_properties(c4):
+    w = c4
+    g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    sim = H.Simulation(g, 2)
+    # (1) fused and two-launch pressure schedules give the same bits at full size
+    sim.upload(w.velocity, w.scalars)
+    sim.step(10, w.dt, 0)
+    sim.sync()
+    p_f, v_f = sim.aux(1), sim.velocity()
+    sim.upload(w.velocity, w.scalars)
+    sim.step(10, w.dt, H.Simulation.FLAG_UNFUSED_PRESSURE)
+    sim.sync()
+    assert np.array_equal(p_f, sim.aux(1)) and np.array_equal(v_f, sim.velocity())
+    # (2) linearity of the pressure solve and projection in the velocity: scaling by 2 is exact in binary floating point
+    sim.upload(w.velocity, w.scalars)
+    sim.divergence(of_advected=False)
+    sim.pressure_solve(5, 1.5)
+    sim.sync()
+    p1 = sim.aux(1)
+    sim.upload(2 * w.velocity, w.scalars)
+    sim.divergence(of_advected=False)
+    sim.pressure_solve(5, 1.5)
+    sim.sync()
+    assert np.array_equal(sim.aux(1), 2 * p1)
+    # (3) zero velocity: BFECC advection is the identity (back-trace lands on the voxel, weights (1,0,..,0))
+    sim.upload(np.zeros_like(w.velocity), w.scalars)
+    sim.advect_scalars(w.dt, 0)
+    sim.sync()
+    assert np.array_equal(sim.scalar(0), w.scalars[0]) and np.array_equal(sim.scalar(1), w.scalars[1])
+    # (4) a constant velocity field has zero divergence wherever all six neighbours exist; host round trip is lossless
+    const = np.tile(np.array([0.3, -1.1, 0.7], np.float32), (w.num_voxels, 1))
+    sim.upload(const, w.scalars)
+    assert np.array_equal(sim.velocity(), const)
+    sim.divergence(of_advected=False)
+    sim.sync()
+    div = sim.aux(0).reshape(-1, 8, 8, 8)
+    assert np.abs(div[:, 1:7, 1:7, 1:7]).max() == 0.0
+
+
+def test_every_launch_is_counted():
+    from hnanosolver_b200 import _lib
+
+    w = synth.random_leaves(8, 3, 0, S=2)
+    g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    sim = H.Simulation(g, 2)
+    sim.upload(w.velocity, w.scalars)
+    _lib.lib().hns_launch_count_reset()
+    sim.step(10, w.dt)
+    sim.sync()
+    assert _lib.lib().hns_launch_count() == 1 + 1 + 10 + 1 + 1  # advect_vector, divergence, 10 fused sweeps, gradient, advect_scalars

@@ -1,0 +1,69 @@
+"""The oracle against outputs of the reference itself (fixtures made by tests/golden/make_golden.py on a B200 from
+oracle/_ref/libhns_ref.so = the unmodified reference kernels and launchers). Runs without a GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import REL_TOL, assert_close, nanovdb_compare_mask
+from oracle import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = [c for c in ("soup", "sphere") if os.path.exists(os.path.join(GOLDEN, f"ref_{c}.npz"))]
+pytestmark = pytest.mark.skipif(not CASES, reason="no golden fixtures committed yet")
+
+
+@pytest.fixture(scope="module", params=CASES)
+def gold(request):
+    z = np.load(os.path.join(GOLDEN, f"ref_{request.param}.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def _scalars(g):
+    return [g[f"scalar{i}"] for i in range(len(g["scalar_names"]))]
+
+
+def test_index_grid_bit_exact(gold):
+    ix = O.OracleIndex(gold["coords"])
+    assert np.array_equal(ix.get_values(gold["query_ijk"]), gold["query_values"])
+    buf = ix.nanovdb_buffer(float(gold["voxel_size"]))
+    ref = gold["nanovdb"]
+    assert buf.size == ref.size
+    T = int(np.frombuffer(ref[672 + 40:672 + 44].tobytes(), np.uint32)[0])
+    m = nanovdb_compare_mask(ref.size, T)
+    bad = np.nonzero((buf != ref) & m)[0]
+    assert bad.size == 0, f"oracle NanoVDB buffer differs from voxelsToGrid at bytes {bad[:16]}"
+
+
+def test_frame_stages(gold):
+    ix = O.OracleIndex(gold["coords"])
+    h, dt, I = float(gold["voxel_size"]), float(gold["dt"]), int(gold["iterations"])
+    r = ix.frame(gold["velocity"], _scalars(gold), I, dt, h)
+    assert_close(r["adv"], gold["frame_adv"], "advect_vector")
+    assert_close(r["div"], gold["frame_div"], "divergence")
+    assert_close(r["p"], gold["frame_p"], "pressure after RBGS")
+    assert_close(r["vel"], gold["frame_vel"], "projected velocity")
+    for i, s in enumerate(r["scalars"]):
+        assert_close(s, gold[f"frame_scalar{i}"], f"advect_scalars[{i}]")
+
+
+def test_standalone_launchers(gold):
+    ix = O.OracleIndex(gold["coords"])
+    h, dt, I = float(gold["voxel_size"]), float(gold["dt"]), int(gold["iterations"])
+    for i, s in enumerate(_scalars(gold)):
+        assert_close(ix.advect_scalar(gold["velocity"], s, dt, h), gold[f"advect_index_grid_{i}"], f"AdvectIndexGrid[{i}]")
+    assert_close(ix.advect_vector(gold["velocity"], dt, h), gold["advect_index_grid_velocity"], "AdvectIndexGridVelocity")
+    assert_close(ix.divergence(gold["velocity"], h), gold["divergence"], "Divergence")
+    vel, _, _ = ix.project_non_divergent(gold["velocity"], I, h)
+    assert_close(vel, gold["project_non_divergent"], "ProjectNonDivergent")
+
+
+def test_compute_sim(gold):
+    ix = O.OracleIndex(gold["coords"])
+    h, dt, I = float(gold["voxel_size"]), float(gold["dt"]), int(gold["iterations"])
+    fields = dict(density=gold["scalar0"], fuel=gold["comb_fuel"], waste=gold["comb_waste"], temperature=gold["comb_temperature"],
+                  flame=gold["comb_flame"])
+    vel, out = ix.compute_sim(gold["velocity"], fields, I, dt, h, gold["params"])
+    assert_close(vel, gold["compute_sim_vel"], "Compute_Sim velocity")
+    for k, v in out.items():
+        assert_close(v, gold[f"compute_sim_{k}"], f"Compute_Sim {k}")
