@@ -73,7 +73,7 @@ static void emit_nanovdb(const int32_t* origins, uint64_t L, const std::vector<L
 	put<float>(m + 84, 1.0f);
 	put<double>(m + 256, 1.0);
 	for (int d = 0; d < 3; ++d) put<double>(g + 608 + 8 * d, s);
-	put<uint32_t>(g + 632, 8u);                            // GridClass::IndexGrid
+	put<uint32_t>(g + 632, 0u);                            // GridClass::Unknown -- voxelsToGrid only tags off-index grids as IndexGrid
 	put<uint32_t>(g + 636, 20u);                           // GridType::OnIndex
 	put<int64_t>(g + 640, int64_t(bytes));                 // blind meta offset: end of leaves
 	put<uint64_t>(g + 656, 1u + 512u * L);                 // value count incl. background

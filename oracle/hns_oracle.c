@@ -277,7 +277,7 @@ void ora_nanovdb_emit(const ora_index* ix, float voxelSizeF, uint8_t* buf) {
 	putf(m + 84, 1.0f);   /* mTaperF */
 	putd(m + 256, 1.0);   /* mTaperD */
 	for (int d = 0; d < 3; ++d) putd(g + 608 + 8 * d, s); /* mVoxelSize */
-	put32(g + 632, 8u);   /* GridClass::IndexGrid */
+	put32(g + 632, 0u);   /* GridClass::Unknown: only the is_offindex branch sets IndexGrid (PointsToGrid.cuh:890-893), ValueOnIndex is not off-index */
 	put32(g + 636, 20u);  /* GridType::OnIndex */
 	put64(g + 640, total);/* mBlindMetadataOffset = meta = end of leaves */
 	put32(g + 648, 0), put32(g + 652, 0);
