@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--unfused", action="store_true", help="pressure solve with one colour per launch (the reference's schedule)")
+    ap.add_argument("--forward-only", action="store_true", help="no back-to-front black sweeps (disables the L2 reuse between launches)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -171,7 +171,7 @@ def main():
     full = kind == "full"
     S = len(fields)
     log(f"[rank {rank}] workload {w.name}: {w.num_leaves} leaves, {w.num_voxels} voxels, S={S}, frame={kind}, generated in {time.time()-t0:.1f}s")
-    flags = H.Simulation.FLAG_UNFUSED_PRESSURE if args.unfused else 0
+    flags = H.Simulation.FLAG_FORWARD_ONLY if args.forward_only else 0
 
     if world > 1:
         from hnanosolver_b200 import dist as hdist
@@ -210,19 +210,19 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    n_sweeps = ITERATIONS * args.steps * (2 if args.unfused else 1)
+    n_sweeps = ITERATIONS * args.steps * 2
     sweep_ms = ms_pressure / n_sweeps
-    bytes_per_launch = 12 * N                                          # read p, read div, write p: each field once per launch
+    bytes_per_launch = 8 * N                                           # one colour: read other-colour p, read+write this colour's p, read its div
     achieved = bytes_per_launch / (sweep_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "rbgs_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic = tj["dram_bytes_per_voxel"] * N if tj.get("kernel") == ("k_rbgs_color" if args.unfused else "k_rbgs_fused") else None
+            traffic = tj["dram_bytes_per_voxel"] * N if tj.get("kernel") == "k_rbgs_split" else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_rbgs_color (one colour)" if args.unfused else "k_rbgs_fused (red+black in one launch)",
+    roofline = {"bound": "hbm", "kernel": "k_rbgs_split (one red or black half-sweep on colour-split bricks)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": sweep_ms, "launches_timed": n_sweeps,
                 "peak_source": peak_src,
@@ -277,7 +277,7 @@ def main():
            "config": {"workload": f"{args.workload}: {w.name}, {w.num_leaves} leaves = {N} active voxels, frame={kind}, I={ITERATIONS} red-black "
                                   f"iterations, S={S} scalar fields, dt=1/24, voxel size 0.1, CFL<=2.5",
                       "l2": "inputs larger than L2 (per-field %.0f MB, frame working set %.1f GB); no flush" % (4 * N / 1e6, (9 + 2 * S) * 4 * N / 1e9),
-                      "pressure": "unfused" if args.unfused else "fused red+black"},
+                      "pressure": "red/black half-sweeps on colour-split bricks, " + ("forward only" if args.forward_only else "alternating direction")},
            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(w, names, fields, full)

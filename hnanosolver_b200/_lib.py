@@ -67,6 +67,7 @@ SIGNATURES = {
     "hns_state_pack_leaves": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "hns_state_unpack_leaves": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "hns_state_field_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "hns_state_field_floats_per_leaf": (C.c_int, [C.c_int]),
 }
 
 _lib = None

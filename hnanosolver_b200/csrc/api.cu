@@ -33,18 +33,12 @@ static inline float omega_project(float voxelSize) { return float(2.0f / (1.0f +
 
 static int pressure_solve(hns_state* s, int iterations, float dx, float omega, unsigned flags, cudaStream_t st) {
 	const GridView& g = s->grid->view;
-	s->p_cur = 0;
-	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, s->n * sizeof(float), st));  // initial guess 0 (HNanoSolver.cu:113)
-	if (flags & 1u) {
-		for (int it = 0; it < iterations; ++it) {
-			launch_rbgs_color(g, s->div, s->p[0], dx, 0, omega, st);
-			launch_rbgs_color(g, s->div, s->p[0], dx, 1, omega, st);
-		}
-	} else {
-		for (int it = 0; it < iterations; ++it) {
-			launch_rbgs_fused(g, s->div, s->p[s->p_cur], s->p[s->p_cur ^ 1], dx, omega, st);
-			s->p_cur ^= 1;
-		}
+	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, (s->n / 2) * sizeof(float), st));  // initial guess 0 (HNanoSolver.cu:113)
+	HNS_CUDA(cudaMemsetAsync(s->p[1], 0, (s->n / 2) * sizeof(float), st));
+	const bool alternate = !(flags & 2u);  // red sweeps walk the leaves front to back, black sweeps back to front (L2 reuse)
+	for (int it = 0; it < iterations; ++it) {
+		launch_rbgs_color(g, s->div, s->p, dx, 0, omega, 0, st);
+		launch_rbgs_color(g, s->div, s->p, dx, 1, omega, alternate ? 1 : 0, st);
 	}
 	return HNS_OK;
 }
@@ -76,7 +70,7 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 	int rc = pressure_solve(s, iterations, h, omega_compute(h), flags, st);
 	if (rc) return rc;
 	if (ev_p1) cudaEventRecord(ev_p1, st);
-	launch_subtract_gradient(g, s->adv, s->p[s->p_cur], s->vel, inv, st);
+	launch_subtract_gradient(g, s->adv, s->p, s->vel, inv, st);
 	if (s->n_scalars) {
 		ScalarPtrs sp{};
 		int S = 0;
@@ -125,17 +119,19 @@ int hns_state_create(const hns_grid* g, int n_scalars, hns_state** out) {
 	const size_t fb = std::max<size_t>(s->n, 1) * sizeof(float);
 	std::vector<float**> all;
 	for (int c = 0; c < 3; ++c) all.push_back(&s->vel[c]), all.push_back(&s->adv[c]);
-	all.push_back(&s->div), all.push_back(&s->p[0]), all.push_back(&s->p[1]);
+	std::vector<float**> halves = {&s->div[0], &s->div[1], &s->p[0], &s->p[1]};
 	for (int i = 0; i < n_scalars; ++i) all.push_back(&s->sc[i]), all.push_back(&s->sc_out[i]);
-	for (float** p : all) {
-		const cudaError_t e = cudaMalloc(p, fb);
-		if (e != cudaSuccess) {
-			const std::string msg = std::string("cudaMalloc(field): ") + cudaGetErrorString(e);
-			hns_state_destroy(s);
-			return fail(HNS_ERR_CUDA, msg);
+	for (int pass = 0; pass < 2; ++pass)
+		for (float** p : pass ? halves : all) {
+			const size_t bytes = pass ? std::max<size_t>(fb / 2, 4) : fb;
+			const cudaError_t e = cudaMalloc(p, bytes);
+			if (e != cudaSuccess) {
+				const std::string msg = std::string("cudaMalloc(field): ") + cudaGetErrorString(e);
+				hns_state_destroy(s);
+				return fail(HNS_ERR_CUDA, msg);
+			}
+			cudaMemset(*p, 0, bytes);
 		}
-		cudaMemset(*p, 0, fb);
-	}
 	*out = s;
 	return HNS_OK;
 }
@@ -143,7 +139,7 @@ int hns_state_create(const hns_grid* g, int n_scalars, hns_state** out) {
 void hns_state_destroy(hns_state* s) {
 	if (!s) return;
 	for (int c = 0; c < 3; ++c) cudaFree(s->vel[c]), cudaFree(s->adv[c]);
-	cudaFree(s->div), cudaFree(s->p[0]), cudaFree(s->p[1]);
+	cudaFree(s->div[0]), cudaFree(s->div[1]), cudaFree(s->p[0]), cudaFree(s->p[1]);
 	for (int i = 0; i < 16; ++i) cudaFree(s->sc[i]), cudaFree(s->sc_out[i]);
 	cudaFree(s->aos);
 	delete s;
@@ -183,10 +179,11 @@ int hns_state_download_scalar(hns_state* s, int i, float* host) {
 }
 int hns_state_download_aux(hns_state* s, int which, float* host) {
 	HNS_REQUIRE(s && host, "null argument");
-	if (which == 0) {
-		HNS_CUDA(cudaMemcpy(host, s->div, s->n * 4, cudaMemcpyDeviceToHost));
-	} else if (which == 1) {
-		HNS_CUDA(cudaMemcpy(host, s->p[s->p_cur], s->n * 4, cudaMemcpyDeviceToHost));
+	if (which == 0 || which == 1) {
+		int rc = ensure_aos(s);  // staging buffer doubles as scratch for the colour-split -> brick-order conversion
+		if (rc) return rc;
+		launch_split_to_brick(which == 0 ? s->div : s->p, s->aos, s->n, 0);
+		HNS_CUDA(cudaMemcpy(host, s->aos, s->n * 4, cudaMemcpyDeviceToHost));
 	} else if (which == 2) {
 		int rc = ensure_aos(s);
 		if (rc) return rc;
@@ -250,10 +247,10 @@ int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream) {
 	HNS_REQUIRE(s, "null state");
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if (from_advected) {
-		launch_subtract_gradient(s->grid->view, s->adv, s->p[s->p_cur], s->vel, 1.0f / s->grid->voxel_size, st);
+		launch_subtract_gradient(s->grid->view, s->adv, s->p, s->vel, 1.0f / s->grid->voxel_size, st);
 	} else {
 		// in place is safe: every thread reads only its own velocity row (the reference does the same, PressureProjection.cu:64)
-		launch_subtract_gradient(s->grid->view, s->vel, s->p[s->p_cur], s->vel, 1.0f / s->grid->voxel_size, st);
+		launch_subtract_gradient(s->grid->view, s->vel, s->p, s->vel, 1.0f / s->grid->voxel_size, st);
 	}
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
@@ -322,28 +319,37 @@ int hns_state_time_frames(hns_state* s, int frames, int iterations, float dt, un
 	return HNS_OK;
 }
 
-static float* field_ptr(hns_state* s, int field) {
+// field ids of the ghost-exchange interface: 0..2 velocity, 3..5 advected velocity, 6/7 pressure red/black, 8/9 divergence red/black,
+// 10+i scalar i. Pressure and divergence halves hold 256 floats per leaf, everything else 512.
+static float* field_ptr(hns_state* s, int field, int* floats_per_leaf) {
+	*floats_per_leaf = (field >= 6 && field <= 9) ? 256 : 512;
 	if (field >= 0 && field < 3) return s->vel[field];
 	if (field >= 3 && field < 6) return s->adv[field - 3];
-	if (field == 6) return s->p[s->p_cur];
-	if (field == 7) return s->div;
-	if (field >= 8 && field < 8 + s->n_scalars) return s->sc[field - 8];
+	if (field == 6 || field == 7) return s->p[field - 6];
+	if (field == 8 || field == 9) return s->div[field - 8];
+	if (field >= 10 && field < 10 + s->n_scalars) return s->sc[field - 10];
 	return nullptr;
 }
-void* hns_state_field_device_ptr(hns_state* s, int field) { return s ? field_ptr(s, field) : nullptr; }
+void* hns_state_field_device_ptr(hns_state* s, int field) {
+	int fpl;
+	return s ? field_ptr(s, field, &fpl) : nullptr;
+}
+int hns_state_field_floats_per_leaf(int field) { return (field >= 6 && field <= 9) ? 256 : 512; }
 int hns_state_pack_leaves(hns_state* s, int field, const int32_t* ids, uint64_t n_ids, float* dst, void* stream) {
 	HNS_REQUIRE(s, "null state");
-	float* f = field_ptr(s, field);
+	int fpl;
+	float* f = field_ptr(s, field, &fpl);
 	HNS_REQUIRE(f, "bad field id");
-	launch_pack_leaves(f, ids, n_ids, dst, static_cast<cudaStream_t>(stream));
+	launch_pack_leaves(f, ids, n_ids, dst, fpl, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
 int hns_state_unpack_leaves(hns_state* s, int field, const int32_t* ids, uint64_t n_ids, const float* src, void* stream) {
 	HNS_REQUIRE(s, "null state");
-	float* f = field_ptr(s, field);
+	int fpl;
+	float* f = field_ptr(s, field, &fpl);
 	HNS_REQUIRE(f, "bad field id");
-	launch_unpack_leaves(f, ids, n_ids, src, static_cast<cudaStream_t>(stream));
+	launch_unpack_leaves(f, ids, n_ids, src, fpl, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
@@ -478,14 +484,8 @@ int hns_project_non_divergent(const int32_t* coords, uint64_t n, float* velocity
 	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
 	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
 	launch_divergence(sc.grid->view, s->vel, s->div, inv, st);
-	s->p_cur = 0;
-	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, n * 4, st));
-	const float omega = omega_project(voxel_size);
-	for (uint64_t it = 0; it < iterations; ++it) {
-		launch_rbgs_fused(sc.grid->view, s->div, s->p[s->p_cur], s->p[s->p_cur ^ 1], voxel_size, omega, st);
-		s->p_cur ^= 1;
-	}
-	launch_subtract_gradient(sc.grid->view, s->vel, s->p[s->p_cur], s->vel, inv, st);
+	if ((rc = pressure_solve(s, int(iterations), voxel_size, omega_project(voxel_size), 0u, st))) return rc;
+	launch_subtract_gradient(sc.grid->view, s->vel, s->p, s->vel, inv, st);
 	launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, n, st);
 	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, st));
 	HNS_CUDA(cudaStreamSynchronize(st));
@@ -506,7 +506,8 @@ int hns_divergence(const int32_t* coords, uint64_t n, const float* velocity, flo
 	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
 	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
 	launch_divergence(sc.grid->view, s->vel, s->div, 1.0f / voxel_size, st);
-	HNS_CUDA(cudaMemcpyAsync(divergence_out, s->div, n * 4, cudaMemcpyDeviceToHost, st));
+	launch_split_to_brick(s->div, s->adv[0], n, st);  // adv[0] is free scratch here
+	HNS_CUDA(cudaMemcpyAsync(divergence_out, s->adv[0], n * 4, cudaMemcpyDeviceToHost, st));
 	HNS_CUDA(cudaStreamSynchronize(st));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;

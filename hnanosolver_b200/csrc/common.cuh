@@ -97,9 +97,8 @@ struct hns_state {
 	int n_scalars = 0;
 	float* vel[3] = {};   // current velocity, SoA bricks float[L][512]
 	float* adv[3] = {};   // advected velocity
-	float* div = nullptr;
-	float* p[2] = {};     // pressure ping-pong
-	int p_cur = 0;        // which of p[] holds the latest pressure
+	float* div[2] = {};   // divergence, colour-split: [0] red = (x+y+z) even, [1] black; float[L][256] each
+	float* p[2] = {};     // pressure, colour-split like div
 	float* sc[16] = {};   // scalar fields (current)
 	float* sc_out[16] = {};
 	float* aos = nullptr; // staging float[N][3] for host <-> device velocity transfers

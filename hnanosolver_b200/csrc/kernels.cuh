@@ -1,5 +1,6 @@
-// Kernel launch wrappers of libhns_b200 (definitions in kernels.cu). All fields are brick fields: float[L][512],
-// voxel (x,y,z) of leaf l at l*512 + (x<<6 | y<<3 | z); velocity is three such fields (SoA).
+// Kernel launch wrappers of libhns_b200 (definitions in kernels.cu). Velocity and the advected scalars are brick fields: float[L][512],
+// voxel (x,y,z) of leaf l at l*512 + (x<<6 | y<<3 | z), velocity as three such planes (SoA). Pressure and divergence are colour-split:
+// two half-brick fields float[L][256] (red = (x+y+z) even, black = odd), row (x,y) owning the quad j = z>>1.
 #pragma once
 #include "common.cuh"
 
@@ -20,20 +21,22 @@ void launch_advect_vector(const GridView& g, const float* const vel[3], float* c
 void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx,
                            int sampler_semantics, cudaStream_t st);
 // divergence (Kernel.cu:499-519)
-void launch_divergence(const GridView& g, const float* const vel[3], float* div, float inv_dx, cudaStream_t st);
-// redBlackGaussSeidelUpdate (Kernel.cu:591-623): one colour, in place
-void launch_rbgs_color(const GridView& g, const float* div, float* p, float dx, int color, float omega, cudaStream_t st);
-// red then black in ONE launch, p_in -> p_out (bit-identical to two launch_rbgs_color calls)
-void launch_rbgs_fused(const GridView& g, const float* div, const float* p_in, float* p_out, float dx, float omega, cudaStream_t st);
+void launch_divergence(const GridView& g, const float* const vel[3], float* const div[2], float inv_dx, cudaStream_t st);
+// redBlackGaussSeidelUpdate (Kernel.cu:591-623): one colour per launch, in place, on the colour-split layout (p[0] red, p[1] black)
+void launch_rbgs_color(const GridView& g, const float* const div[2], float* const p[2], float dx, int color, float omega, int reverse,
+                       cudaStream_t st);
 // subtractPressureGradient (Kernel.cu:765-829)
-void launch_subtract_gradient(const GridView& g, const float* const vel[3], const float* p, float* const out[3], float inv_dx, cudaStream_t st);
+void launch_subtract_gradient(const GridView& g, const float* const vel[3], const float* const p[2], float* const out[3], float inv_dx,
+                              cudaStream_t st);
 // combustion_oxygen (Kernel.cu:923-966) and temperature_buoyancy (Kernel.cu:831-847, in place on the y component)
-void launch_combustion_oxygen(const float* fuel, const float* waste, const float* temp, float* div, const float* flame, float* oFuel,
+void launch_combustion_oxygen(const float* fuel, const float* waste, const float* temp, float* const div[2], const float* flame, float* oFuel,
                               float* oWaste, float* oTemp, float* oFlame, float temp_gain, float expansion, uint64_t n, cudaStream_t st);
 void launch_buoyancy(float* const vel[3], const float* temp, float dt, float ambient, float strength, uint64_t n, cudaStream_t st);
 // whole-brick gather / scatter by leaf id (ghost exchange)
-void launch_pack_leaves(const float* field, const int32_t* ids, uint64_t n_ids, float* dst, cudaStream_t st);
-void launch_unpack_leaves(float* field, const int32_t* ids, uint64_t n_ids, const float* src, cudaStream_t st);
+void launch_pack_leaves(const float* field, const int32_t* ids, uint64_t n_ids, float* dst, int floats_per_leaf, cudaStream_t st);
+void launch_unpack_leaves(float* field, const int32_t* ids, uint64_t n_ids, const float* src, int floats_per_leaf, cudaStream_t st);
+// colour-split (red, black) -> brick order
+void launch_split_to_brick(const float* const f[2], float* out, uint64_t n, cudaStream_t st);
 
 int upload_tables();  // constant tables of the fused pressure kernel, once per device
 

@@ -192,7 +192,7 @@ class Simulation:
     """Device-resident state of one simulation: velocity + n_scalars float fields on an index grid."""
 
     AUX_DIVERGENCE, AUX_PRESSURE, AUX_ADVECTED = 0, 1, 2
-    FLAG_UNFUSED_PRESSURE = 1
+    FLAG_FORWARD_ONLY = 2  # every pressure half-sweep walks the leaves front to back (default: black sweeps run back to front)
 
     def __init__(self, grid: IndexGridHandle, n_scalars: int):
         self.grid = grid

@@ -132,7 +132,8 @@ int hns_state_set_combustion(hns_state* s, int enabled, int i_fuel, int i_waste,
  * advect_scalars (all n_scalars fields); with hns_state_set_combustion the combustion + buoyancy stage runs after the divergence,
  * exactly as in Compute(). Same arithmetic as the corresponding steps of Compute() (HNanoSolver.cu:159-356);
  * omega = 2/(1+sinf(3.14159f*voxel_size)) (HNanoSolver.cu:257). Asynchronous on `stream`.
- * flags: bit 0 = force the unfused (one colour per launch) pressure kernels. */
+ * flags: bit 1 = walk the leaves front to back in every pressure half-sweep (default: black sweeps run back to front so that each
+ * launch starts on the bricks still resident in L2). */
 int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void* stream);
 /* Individual steps on resident state (asynchronous). */
 int hns_state_advect_velocity(hns_state* s, float dt, void* stream);                 /* vel -> adv              */
@@ -148,7 +149,10 @@ int hns_state_time_frames(hns_state* s, int frames, int iterations, float dt, un
 
 /* Ghost-leaf exchange support for spatially sharded runs (one process per GPU): pack/unpack whole bricks of one
  * internal field by leaf id list into/from a contiguous device buffer (float[n_ids][512]).
- * field: 0..2 velocity components, 3..5 advected velocity components, 6 pressure, 7 divergence, 8+i scalar i. */
+ * field: 0..2 velocity components, 3..5 advected velocity components, 6/7 pressure red/black half, 8/9 divergence red/black half,
+ * 10+i scalar i. Pressure and divergence are stored colour-split (red = (x+y+z) even): 256 floats per leaf and half; every other
+ * field has 512 floats per leaf (hns_state_field_floats_per_leaf). */
+int hns_state_field_floats_per_leaf(int field);
 int hns_state_pack_leaves(hns_state* s, int field, const int32_t* leaf_ids_dev, uint64_t n_ids, float* dst_dev, void* stream);
 int hns_state_unpack_leaves(hns_state* s, int field, const int32_t* leaf_ids_dev, uint64_t n_ids, const float* src_dev, void* stream);
 void* hns_state_field_device_ptr(hns_state* s, int field);

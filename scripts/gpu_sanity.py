@@ -31,14 +31,14 @@ def run_case(w, iters):
         print("  bytes differing product vs reference voxelsToGrid:", diff.size, diff[:20])
     sim = H.Simulation(g, len(w.scalars)); sim.upload(w.velocity, w.scalars)
     t = time.time(); orc = ix.frame(w.velocity, w.scalars, iters, w.dt, w.voxel_size); t_or = time.time() - t
-    for flags, nm in ((0, "fused"), (1, "unfused")):
+    for flags, nm in ((0, "alternating"), (2, "forward")):
         sim.upload(w.velocity, w.scalars)
         sim.step(iters, w.dt, flags); sim.sync()
         out = dict(vel=sim.velocity(), div=sim.aux(0), p=sim.aux(1), adv=sim.aux(2), scalars=[sim.scalar(i) for i in range(len(w.scalars))])
         print(f"  [{nm}] vs oracle: adv {rel(out['adv'], orc['adv']):.2e} div {rel(out['div'], orc['div']):.2e} p {rel(out['p'], orc['p']):.2e} "
               f"vel {rel(out['vel'], orc['vel']):.2e} scal {[f'{rel(a, b):.2e}' for a, b in zip(out['scalars'], orc['scalars'])]}")
         if flags == 0: fused = out
-        else: print("  fused == unfused bitwise:", all(np.array_equal(fused[k], out[k]) for k in ("vel", "div", "p", "adv")))
+        else: print("  alternating == forward bitwise:", all(np.array_equal(fused[k], out[k]) for k in ("vel", "div", "p", "adv")))
     if have_ref:
         rf = O.RefFrame(rd, rg, w.scalar_names); rf.run(iters, w.dt, w.voxel_size, 1); r = rf.download()
         print(f"  product vs REFERENCE kernels: adv {rel(fused['adv'], r['adv']):.2e} div {rel(fused['div'], r['div']):.2e} p {rel(fused['p'], r['p']):.2e} "
@@ -54,7 +54,7 @@ def timing(name, iters=40, frames=5):
     t = time.time(); w = synth.WORKLOADS[name](with_coords=False); print(f"== timing {w.name}: L={w.num_leaves} N={w.num_voxels} gen {time.time()-t:.1f}s", flush=True)
     g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
     sim = H.Simulation(g, len(w.scalars)); sim.upload(w.velocity, w.scalars)
-    for flags, nm in ((0, "fused"), (1, "unfused")):
+    for flags, nm in ((0, "alternating"), (2, "forward")):
         sim.time_frames(2, iters, w.dt, flags)
         tot, pr = sim.time_frames(frames, iters, w.dt, flags)
         ms = tot / frames

@@ -1,4 +1,4 @@
-"""Minimal resident-frame driver for ncu: builds a workload, runs `frames` full frames. Usage: profile_frame.py [workload] [frames] [unfused]"""
+"""Minimal resident-frame driver for ncu: builds a workload, runs `frames` full frames. Usage: profile_frame.py [workload] [frames] [forward]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hnanosolver_b200 as H
@@ -6,7 +6,7 @@ from hnanosolver_b200 import synth
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c4"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-flags = 1 if len(sys.argv) > 3 and sys.argv[3] == "unfused" else 0
+flags = 2 if len(sys.argv) > 3 and sys.argv[3] == "forward" else 0
 w = synth.WORKLOADS[name](with_coords=False)
 fields = dict(density=w.scalars[0], **synth.combustion_fields(w))
 names = list(fields)

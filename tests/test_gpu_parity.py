@@ -124,9 +124,11 @@ def test_frame_stages_match_oracle(case):
         assert_close(got["scalars"][i], want["scalars"][i], f"scalar {i}")
 
 
-def test_fused_pressure_sweep_is_bit_identical_to_two_colour_launches(case):
+def test_sweep_direction_does_not_change_the_bits(case):
+    """Black half-sweeps walk the leaves back to front for L2 reuse; a half-sweep has no intra-colour dependencies, so the
+    traversal order must not change a single bit."""
     a = run_product_frame(case, 7, flags=0)
-    b = run_product_frame(case, 7, flags=H.Simulation.FLAG_UNFUSED_PRESSURE)
+    b = run_product_frame(case, 7, flags=H.Simulation.FLAG_FORWARD_ONLY)
     for k in ("p", "vel"):
         assert np.array_equal(a[k], b[k]), k
 
@@ -372,13 +374,13 @@ def test_config4_size_independent_properties(c4):
     w = c4
     g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
     sim = H.Simulation(g, 2)
-    # (1) fused and two-launch pressure schedules give the same bits at full size
+    # (1) alternating and forward-only sweep orders give the same bits at full size
     sim.upload(w.velocity, w.scalars)
     sim.step(10, w.dt, 0)
     sim.sync()
     p_f, v_f = sim.aux(1), sim.velocity()
     sim.upload(w.velocity, w.scalars)
-    sim.step(10, w.dt, H.Simulation.FLAG_UNFUSED_PRESSURE)
+    sim.step(10, w.dt, H.Simulation.FLAG_FORWARD_ONLY)
     sim.sync()
     assert np.array_equal(p_f, sim.aux(1)) and np.array_equal(v_f, sim.velocity())
     # (2) linearity of the pressure solve and projection in the velocity: scaling by 2 is exact in binary floating point
@@ -417,4 +419,4 @@ def test_every_launch_is_counted():
     _lib.lib().hns_launch_count_reset()
     sim.step(10, w.dt)
     sim.sync()
-    assert _lib.lib().hns_launch_count() == 1 + 1 + 10 + 1 + 1  # advect_vector, divergence, 10 fused sweeps, gradient, advect_scalars
+    assert _lib.lib().hns_launch_count() == 1 + 1 + 2 * 10 + 1 + 1  # advect_vector, divergence, 10 x (red, black), gradient, advect_scalars
