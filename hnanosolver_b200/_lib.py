@@ -61,6 +61,11 @@ SIGNATURES = {
     "hns_state_divergence": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "hns_state_pressure_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_void_p]),
     "hns_state_subtract_gradient": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hns_state_pressure_init": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hns_state_pressure_half_sweep": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]),
+    "hns_state_combustion_buoyancy": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
+    "hns_omega_compute": (C.c_float, [C.c_float]),
+    "hns_omega_project": (C.c_float, [C.c_float]),
     "hns_state_advect_scalars": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
     "hns_state_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hns_state_time_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint, C.c_void_p, c_f32p, c_f32p]),

@@ -243,6 +243,34 @@ int hns_state_pressure_solve(hns_state* s, int iterations, float omega, unsigned
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
+int hns_state_pressure_init(hns_state* s, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, (s->n / 2) * sizeof(float), st));
+	HNS_CUDA(cudaMemsetAsync(s->p[1], 0, (s->n / 2) * sizeof(float), st));
+	return HNS_OK;
+}
+int hns_state_pressure_half_sweep(hns_state* s, int color, float omega, int reverse, void* stream) {
+	HNS_REQUIRE(s && (color == 0 || color == 1), "bad argument");
+	launch_rbgs_color(s->grid->view, s->div, s->p, s->grid->voxel_size, color, omega, reverse, static_cast<cudaStream_t>(stream));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+int hns_state_combustion_buoyancy(hns_state* s, float dt, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	if (!s->comb_enabled) return fail(HNS_ERR_RUNTIME, "combustion stage not configured (hns_state_set_combustion)");
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	const int iF = s->comb_idx[0], iW = s->comb_idx[1], iT = s->comb_idx[2], iL = s->comb_idx[3];
+	launch_combustion_oxygen(s->sc[iF], s->sc[iW], s->sc[iT], s->div, s->sc[iL], s->sc_out[iF], s->sc_out[iW], s->sc_out[iT], s->sc_out[iL],
+	                         s->comb.temperatureRelease, s->comb.expansionRate, s->n, st);
+	launch_buoyancy(s->adv, s->sc_out[iT], dt, s->comb.ambientTemp, s->comb.buoyancyStrength, s->n, st);
+	for (int i : {iF, iW, iT, iL}) std::swap(s->sc[i], s->sc_out[i]);
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+float hns_omega_compute(float voxel_size) { return omega_compute(voxel_size); }
+float hns_omega_project(float voxel_size) { return omega_project(voxel_size); }
+
 int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream) {
 	HNS_REQUIRE(s, "null state");
 	cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -256,10 +256,10 @@ int upload_tables() { return HNS_OK; }
 // semi-Lagrangian BFECC advection  (reference Kernel.cu:118-453, samplers src/Utils/Stencils.hpp:25-173)
 // =============================================================================================================
 // Resolves voxel (i,j,k) (global coordinates) to a sidecar index, or -1 when inactive. The 3x3x3 leaf neighbourhood of the
-// CTA's leaf comes from shared memory; anything farther away walks the NanoVDB buffer.
+// current leaf comes from its 27-entry table; anything farther away walks the NanoVDB buffer. Cold path only.
 struct LeafFrame {
 	int ox, oy, oz;
-	const int32_t* s_nbr;  // shared
+	const int32_t* nbr;  // this leaf's row of the neighbour table (global memory)
 };
 __device__ __forceinline__ int64_t voxel_index(const GridView& g, const LeafFrame& f, int i, int j, int k) {
 	const int rx = i - f.ox, ry = j - f.oy, rz = k - f.oz;
@@ -268,7 +268,7 @@ __device__ __forceinline__ int64_t voxel_index(const GridView& g, const LeafFram
 	if (((dx + 1) | (dy + 1) | (dz + 1)) & ~3 || dx == 2 || dy == 2 || dz == 2) {  // outside the 3x3x3 neighbourhood
 		l = probe_leaf(g, i, j, k);
 	} else {
-		l = f.s_nbr[(dx + 1) * 9 + (dy + 1) * 3 + (dz + 1)];
+		l = __ldg(f.nbr + (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1));
 	}
 	return l < 0 ? int64_t(-1) : int64_t(uint64_t(l) * 512u + uint32_t(((rx & 7) << 6) | ((ry & 7) << 3) | (rz & 7)));
 }
@@ -305,28 +305,66 @@ __device__ __noinline__ float trilinear_f(const GridView& g, const LeafFrame& f,
 }
 
 // ---- shared-memory staging of a leaf neighbourhood -------------------------------------------------------------------
-// One CTA of 512 threads per leaf, one thread per voxel. The CTA first copies the field values of the region
+// Persistent CTAs of 512 threads (two per SM), each walking a contiguous range of leaves, one thread per voxel. For every
+// leaf the CTA needs the field values of the region
 //   x, y in [-3, 11), z in [-4, 12)   (leaf-local voxel coordinates; 14 x 14 rows of 16 floats, from up to 27 leaves)
-// into shared memory with 128-bit loads, then every trilinear / nearest fetch whose 2x2x2 footprint lies inside the region
-// is a shared-memory read: no per-sample leaf lookup, no scattered global loads. With the benchmark's CFL <= 2.5 every
-// back-trace lands inside; a sample that leaves the region (the reference has no CFL limit) falls back to the leaf-table /
-// tree-walk path above, so results do not depend on the region size.
-// Row pitch is 24 floats (96 B): keeps float4 alignment and maps the 4 (y) x 8 (z) lanes of a warp to 32 distinct banks.
+// in shared memory; every trilinear / nearest fetch whose 2x2x2 footprint lies inside the region is then a shared-memory read:
+// no per-sample leaf lookup, no scattered global loads. The region of the NEXT leaf (or next group of scalar fields) is copied
+// with 16-byte cp.async into the second half of a double buffer while the current one is being sampled, so HBM/L2 latency is
+// hidden behind the gathers instead of being exposed once per leaf. With the benchmark's CFL <= 2.5 every back-trace lands
+// inside the region; a sample that leaves it (the reference has no CFL limit) falls back to the leaf-table / tree-walk path
+// above, so results do not depend on the region size.
+// Row pitch is 24 floats (96 B): keeps 16-byte alignment and maps the 4 (y) x 8 (z) lanes of a warp to 32 distinct banks.
 constexpr int kRX = 14, kRZ = 16, kPitch = 24, kHaloXY = 3, kHaloZ = 4;
 constexpr int kRegionFloats = kRX * kRX * kPitch;                 // 4704 floats = 18.4 KB per field
-constexpr int kRegionQuads = kRX * kRX * (kRZ / 4);               // float4 loads per field
-constexpr size_t kAdvectSmem = 3 * kRegionFloats * sizeof(float);  // three fields resident at a time
+constexpr int kRegionQuads = kRX * kRX * (kRZ / 4);               // 16-byte quads per field
+constexpr int kStageFloats = 3 * kRegionFloats;                   // one pipeline stage: three fields
+constexpr size_t kAdvectSmem = 2 * kStageFloats * sizeof(float);  // double buffer: 110.25 KB per CTA, two CTAs per SM
 
-// fills region `dst` with field `f`; cells of missing leaves get `fill`
-__device__ __forceinline__ void stage_region(const LeafFrame& fr, const float* __restrict__ f, float* __restrict__ dst, float fill) {
-	for (int it = threadIdx.x; it < kRegionQuads; it += 512) {
-		const int q = it & 3, row = it >> 2, rx = row / kRX, ry = row - rx * kRX;
-		const int lx = rx - kHaloXY, ly = ry - kHaloXY;           // leaf-local x, y in [-3, 11)
-		const int dz = q == 0 ? -1 : (q == 3 ? 1 : 0);
-		const int32_t l = fr.s_nbr[((lx >> 3) + 1) * 9 + ((ly >> 3) + 1) * 3 + dz + 1];
-		float4 v = make_float4(fill, fill, fill, fill);
-		if (l >= 0) v = __ldg(reinterpret_cast<const float4*>(f + uint64_t(l) * 512u + uint32_t(((lx & 7) << 6) | ((ly & 7) << 3))) + (q == 1 || q == 3 ? 0 : 1));
-		*reinterpret_cast<float4*>(dst + row * kPitch + q * 4) = v;
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+	const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+	asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// Staging plan of one thread: which two 16-byte quads of the region it copies (the same for every field, so it is decoded once
+// per CTA and kept in registers). The 784 quads of a field are dealt so that every group of 8 consecutive lanes covers 4 rows x
+// 2 quads: with the 24-float row pitch those eight 16-byte shared-memory stores hit 32 distinct banks.
+struct StagePlan {
+	uint32_t src[2];  // float index of the quad in a brick field, 0xffffffff: leaf missing / nothing to do
+	int dst[2];       // float offset in the region, -1: nothing to do
+};
+__device__ __forceinline__ StagePlan make_stage_plan(const int32_t* __restrict__ nbr) {
+	StagePlan p;
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		const int it = threadIdx.x + 512 * k;
+		p.src[k] = 0xffffffffu, p.dst[k] = -1;
+		if (it < kRegionQuads) {
+			const int sub = it & 15, row = (it >> 4) * 4 + (sub & 3), q = ((sub >> 3) << 1) | ((sub >> 2) & 1);
+			const int rx = row / kRX, ry = row - rx * kRX;
+			const int lx = rx - kHaloXY, ly = ry - kHaloXY;       // leaf-local x, y in [-3, 11)
+			const int dz = q == 0 ? -1 : (q == 3 ? 1 : 0);        // z in [-4,0) | [0,4) | [4,8) | [8,12)
+			const int32_t l = __ldg(nbr + ((lx >> 3) + 1) * 9 + ((ly >> 3) + 1) * 3 + dz + 1);
+			p.dst[k] = row * kPitch + q * 4;
+			if (l >= 0) p.src[k] = uint32_t(l) * 512u + uint32_t(((lx & 7) << 6) | ((ly & 7) << 3)) + ((q == 1 || q == 3) ? 0u : 4u);
+		}
+	}
+	return p;
+}
+// starts the asynchronous fill of region `dst` with field `f`; cells of missing leaves get `fill` (stored directly)
+__device__ __forceinline__ void stage_region(const StagePlan& p, const float* __restrict__ f, float* __restrict__ dst, float fill) {
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		if (p.dst[k] < 0) continue;
+		if (p.src[k] != 0xffffffffu)
+			cp_async16(dst + p.dst[k], f + p.src[k]);
+		else
+			*reinterpret_cast<float4*>(dst + p.dst[k]) = make_float4(fill, fill, fill, fill);
 	}
 }
 // region offset of global voxel (i,j,k), or -1 if the 2x2x2 footprint starting there is not fully inside the region
@@ -342,13 +380,16 @@ __device__ __forceinline__ float tri8(const float* __restrict__ r, int b, float 
 	return lerpf(lerpf(z0, z1, fy), lerpf(z2, z3, fy), fx);
 }
 
-__device__ __forceinline__ void leaf_frame(const GridView& g, int32_t* s_nbr, LeafFrame& f, int& x, int& y, int& z) {
-	const uint32_t leaf = blockIdx.x;
-	if (threadIdx.x < 27) s_nbr[threadIdx.x] = __ldg(g.nbr + uint64_t(leaf) * 27u + threadIdx.x);
+__device__ __forceinline__ LeafFrame leaf_frame(const GridView& g, uint32_t leaf) {
 	const int4 o = __ldg(g.origin + leaf);
-	f.ox = o.x, f.oy = o.y, f.oz = o.z, f.s_nbr = s_nbr;
-	x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
-	__syncthreads();
+	return LeafFrame{o.x, o.y, o.z, g.nbr + uint64_t(leaf) * 27u};
+}
+// leaves [first, last) of this CTA
+__device__ __forceinline__ bool cta_leaf_range(const GridView& g, uint32_t& first, uint32_t& last) {
+	const uint32_t per = (g.num_leaves + gridDim.x - 1) / gridDim.x;
+	first = blockIdx.x * per;
+	last = min(first + per, g.num_leaves);
+	return first < last;
 }
 
 // TrilinearSampler<Vec3f>::sample through the staged region when possible
@@ -366,56 +407,82 @@ __device__ __forceinline__ void sample_vec(const GridView& g, const LeafFrame& f
 }
 
 __global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const float* __restrict__ u, const float* __restrict__ v,
-                                                       const float* __restrict__ w, float* __restrict__ ou, float* __restrict__ ov,
-                                                       float* __restrict__ ow, float sdt) {
+                                                          const float* __restrict__ w, float* __restrict__ ou, float* __restrict__ ov,
+                                                          float* __restrict__ ow, float sdt) {
 	extern __shared__ __align__(16) float region[];
-	__shared__ int32_t s_nbr[27];
-	float *ru = region, *rv = region + kRegionFloats, *rw = region + 2 * kRegionFloats;
-	LeafFrame f;
-	int x, y, z;
-	leaf_frame(g, s_nbr, f, x, y, z);
-	stage_region(f, u, ru, 0.f);
-	stage_region(f, v, rv, 0.f);
-	stage_region(f, w, rw, 0.f);
-	__syncthreads();
-	const uint64_t self = uint64_t(blockIdx.x) * 512u + threadIdx.x;
-	const int ci = f.ox + x, cj = f.oy + y, ck = f.oz + z;
+	uint32_t first, last;
+	if (!cta_leaf_range(g, first, last)) return;
+	const int x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
 	const int c = ((x + kHaloXY) * kRX + (y + kHaloXY)) * kPitch + z + kHaloZ;
-	const float u0 = ru[c], v0 = rv[c], w0 = rw[c];
-	// backtrace: pos - velOrig * scaled_dt  (Kernel.cu:374)
-	const float bx = fmaf(-sdt, u0, float(ci)), by = fmaf(-sdt, v0, float(cj)), bz = fmaf(-sdt, w0, float(ck));
-	float uf, vf, wf, ub, vb, wb;
-	sample_vec(g, f, ru, rv, rw, u, v, w, bx, by, bz, uf, vf, wf);
-	const float fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :387
-	sample_vec(g, f, ru, rv, rw, u, v, w, fx, fy, fz, ub, vb, wb);
-	const float cu = fmaf(0.5f, u0 - ub, uf), cv = fmaf(0.5f, v0 - vb, vf), cw = fmaf(0.5f, w0 - wb, wf);  // :399-400
-	float mnu = u0, mxu = u0, mnv = v0, mxv = v0, mnw = w0, mxw = w0;
-	const int d6[6] = {-kRX * kPitch, kRX * kPitch, -kPitch, kPitch, -1, 1};  // -x, +x, -y, +y, -z, +z  (:410-421)
+	auto issue = [&](uint32_t leaf, int buf) {
+		const StagePlan plan = make_stage_plan(g.nbr + uint64_t(leaf) * 27u);
+		float* r = region + buf * kStageFloats;
+		stage_region(plan, u, r, 0.f);
+		stage_region(plan, v, r + kRegionFloats, 0.f);
+		stage_region(plan, w, r + 2 * kRegionFloats, 0.f);
+		cp_async_commit();
+	};
+	issue(first, 0);
+	for (uint32_t leaf = first; leaf < last; ++leaf) {
+		const int buf = (leaf - first) & 1;
+		if (leaf + 1 < last) {
+			issue(leaf + 1, buf ^ 1);
+			cp_async_wait<1>();
+		} else {
+			cp_async_wait<0>();
+		}
+		__syncthreads();
+		const float *ru = region + buf * kStageFloats, *rv = ru + kRegionFloats, *rw = ru + 2 * kRegionFloats;
+		const LeafFrame f = leaf_frame(g, leaf);
+		const uint64_t self = uint64_t(leaf) * 512u + threadIdx.x;
+		const int ci = f.ox + x, cj = f.oy + y, ck = f.oz + z;
+		const float u0 = ru[c], v0 = rv[c], w0 = rw[c];
+		// backtrace: pos - velOrig * scaled_dt  (Kernel.cu:374)
+		const float bx = fmaf(-sdt, u0, float(ci)), by = fmaf(-sdt, v0, float(cj)), bz = fmaf(-sdt, w0, float(ck));
+		float uf, vf, wf, ub, vb, wb;
+		sample_vec(g, f, ru, rv, rw, u, v, w, bx, by, bz, uf, vf, wf);
+		const float fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :387
+		sample_vec(g, f, ru, rv, rw, u, v, w, fx, fy, fz, ub, vb, wb);
+		const float cu = fmaf(0.5f, u0 - ub, uf), cv = fmaf(0.5f, v0 - vb, vf), cw = fmaf(0.5f, w0 - wb, wf);  // :399-400
+		float mnu = u0, mxu = u0, mnv = v0, mxv = v0, mnw = w0, mxw = w0;
+		const int d6[6] = {-kRX * kPitch, kRX * kPitch, -kPitch, kPitch, -1, 1};  // -x, +x, -y, +y, -z, +z  (:410-421)
 #pragma unroll
-	for (int q = 0; q < 6; ++q) {
-		const float nu = ru[c + d6[q]], nv = rv[c + d6[q]], nw = rw[c + d6[q]];
-		mnu = fminf(mnu, nu), mxu = fmaxf(mxu, nu);
-		mnv = fminf(mnv, nv), mxv = fmaxf(mxv, nv);
-		mnw = fminf(mnw, nw), mxw = fmaxf(mxw, nw);
+		for (int q = 0; q < 6; ++q) {
+			const float nu = ru[c + d6[q]], nv = rv[c + d6[q]], nw = rw[c + d6[q]];
+			mnu = fminf(mnu, nu), mxu = fmaxf(mxu, nu);
+			mnv = fminf(mnv, nv), mxv = fmaxf(mxv, nv);
+			mnw = fminf(mnw, nw), mxw = fmaxf(mxw, nw);
+		}
+		mnu = fminf(mnu, uf), mxu = fmaxf(mxu, uf);
+		mnv = fminf(mnv, vf), mxv = fmaxf(mxv, vf);
+		mnw = fminf(mnw, wf), mxw = fmaxf(mxw, wf);
+		ou[self] = fmaxf(mnu, fminf(cu, mxu));  // :429
+		ov[self] = fmaxf(mnv, fminf(cv, mxv));
+		ow[self] = fmaxf(mnw, fminf(cw, mxw));
+		__syncthreads();  // this buffer is refilled two iterations from now
 	}
-	mnu = fminf(mnu, uf), mxu = fmaxf(mxu, uf);
-	mnv = fminf(mnv, vf), mxv = fmaxf(mxv, vf);
-	mnw = fminf(mnw, wf), mxw = fmaxf(mxw, wf);
-	ou[self] = fmaxf(mnu, fminf(cu, mxu));  // :429
-	ov[self] = fmaxf(mnv, fminf(cv, mxv));
-	ow[self] = fmaxf(mnw, fminf(cw, mxw));
 }
-static int set_advect_smem() {
-	static bool done = false;
-	if (!done) {
-		HNS_CUDA(cudaFuncSetAttribute(k_advect_vector, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAdvectSmem)));
-		done = true;
+// persistent launch: two CTAs per SM
+static int advect_grid(uint32_t num_leaves) {
+	static int sms = 0;
+	if (!sms) {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (sms <= 0) sms = 148;
 	}
-	return HNS_OK;
+	return int(min(uint32_t(2 * sms), num_leaves));
+}
+template <typename K>
+static void advect_attrs(K kernel) {
+	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAdvectSmem));
+	cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st) {
-	if (!g.num_leaves || set_advect_smem() != HNS_OK) return;
-	HNS_LAUNCH(k_advect_vector, g.num_leaves, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], dt * inv_dx);
+	if (!g.num_leaves) return;
+	static bool attr = false;
+	if (!attr) advect_attrs(k_advect_vector), attr = true;
+	HNS_LAUNCH(k_advect_vector, advect_grid(g.num_leaves), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], dt * inv_dx);
 }
 
 // advect_scalars (Kernel.cu:118-266) [kSemantics 0]: explicit corner weights, fma accumulation in corner order
@@ -445,113 +512,138 @@ __device__ __noinline__ float far_weighted(const GridView& g, const LeafFrame& f
 
 template <int kSemantics>
 __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const float* __restrict__ u, const float* __restrict__ v,
-                                                        const float* __restrict__ w, ScalarPtrs sp, int S, float sdt) {
+                                                           const float* __restrict__ w, ScalarPtrs sp, int S, float sdt) {
 	extern __shared__ __align__(16) float region[];
-	__shared__ int32_t s_nbr[27];
-	LeafFrame f;
-	int x, y, z;
-	leaf_frame(g, s_nbr, f, x, y, z);
-	const uint64_t self = uint64_t(blockIdx.x) * 512u + threadIdx.x;
-	const int ci = f.ox + x, cj = f.oy + y, ck = f.oz + z;
+	uint32_t first, last;
+	if (!cta_leaf_range(g, first, last)) return;
+	const int x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
 	const int c = ((x + kHaloXY) * kRX + (y + kHaloXY)) * kPitch + z + kHaloZ;
-	// ---- phase 1: the shared trace through the staged velocity ----
-	float bx, by, bz, fx, fy, fz;
-	{
-		float *ru = region, *rv = region + kRegionFloats, *rw = region + 2 * kRegionFloats;
-		stage_region(f, u, ru, kSemantics == 0 ? __ldg(u) : 0.f);  // advect_scalars samples the velocity with "inactive -> element 0" too (:192,204)
-		stage_region(f, v, rv, kSemantics == 0 ? __ldg(v) : 0.f);
-		stage_region(f, w, rw, kSemantics == 0 ? __ldg(w) : 0.f);
-		__syncthreads();
-		bx = fmaf(-sdt, ru[c], float(ci)), by = fmaf(-sdt, rv[c], float(cj)), bz = fmaf(-sdt, rw[c], float(ck));
-		float uf, vf, wf;
-		if (kSemantics == 0) {
-			const int i0 = __float2int_rd(bx), j0 = __float2int_rd(by), k0 = __float2int_rd(bz);
-			float wt[8];
-			corner_weights(bx - float(i0), by - float(j0), bz - float(k0), wt);
-			const int b = region_base(f, i0, j0, k0);
-			uf = vf = wf = 0.f;
-			if (b >= 0) {
-#pragma unroll
-				for (int q = 0; q < 8; ++q) {  // :201-206
-					uf = fmaf(wt[q], ru[b + corner_off(q)], uf);
-					vf = fmaf(wt[q], rv[b + corner_off(q)], vf);
-					wf = fmaf(wt[q], rw[b + corner_off(q)], wf);
-				}
-			} else {
-				const float tx = bx - float(i0), ty = by - float(j0), tz = bz - float(k0);
-				uf = far_weighted(g, f, u, i0, j0, k0, tx, ty, tz);
-				vf = far_weighted(g, f, v, i0, j0, k0, tx, ty, tz);
-				wf = far_weighted(g, f, w, i0, j0, k0, tx, ty, tz);
-			}
+	// pipeline jobs: per leaf one velocity stage (the shared trace) and ceil(S/3) stages of up to three scalar fields
+	const int jobs_per_leaf = 1 + (S + 2) / 3;
+	const int n_jobs = int(last - first) * jobs_per_leaf;
+	auto issue = [&](int job) {
+		const uint32_t leaf = first + uint32_t(job / jobs_per_leaf);
+		const int jj = job % jobs_per_leaf;
+		const StagePlan plan = make_stage_plan(g.nbr + uint64_t(leaf) * 27u);
+		float* r = region + (job & 1) * kStageFloats;
+		if (jj == 0) {
+			// advect_scalars samples the velocity with "inactive -> element 0" as well (Kernel.cu:192,204)
+			stage_region(plan, u, r, kSemantics == 0 ? __ldg(u) : 0.f);
+			stage_region(plan, v, r + kRegionFloats, kSemantics == 0 ? __ldg(v) : 0.f);
+			stage_region(plan, w, r + 2 * kRegionFloats, kSemantics == 0 ? __ldg(w) : 0.f);
 		} else {
-			sample_vec(g, f, ru, rv, rw, u, v, w, bx, by, bz, uf, vf, wf);
+			const int s0 = 3 * (jj - 1), ns = min(3, S - s0);
+			for (int k = 0; k < ns; ++k) stage_region(plan, sp.in[s0 + k], r + k * kRegionFloats, kSemantics == 0 ? __ldg(sp.in[s0 + k]) : 0.f);
 		}
-		fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :208
-	}
-	const int bi = __float2int_rd(bx), bj = __float2int_rd(by), bk = __float2int_rd(bz);
-	const int fi = __float2int_rd(fx), fj = __float2int_rd(fy), fk = __float2int_rd(fz);
-	const int bB = region_base(f, bi, bj, bk), bF = region_base(f, fi, fj, fk);
-	const float btx = bx - float(bi), bty = by - float(bj), btz = bz - float(bk);
-	const float ftx = fx - float(fi), fty = fy - float(fj), ftz = fz - float(fk);
-	const int d6[6] = {-kRX * kPitch, kRX * kPitch, -kPitch, kPitch, -1, 1};
-	// ---- phase 2: the scalar fields, three staged at a time in the same shared memory ----
-	for (int s0 = 0; s0 < S; s0 += 3) {
-		__syncthreads();  // everyone is done with the previous contents
-		const int ns = min(3, S - s0);
-		for (int k = 0; k < ns; ++k) stage_region(f, sp.in[s0 + k], region + k * kRegionFloats, kSemantics == 0 ? __ldg(sp.in[s0 + k]) : 0.f);
+		cp_async_commit();
+	};
+	// the trace of the current leaf, shared by all its scalar jobs
+	LeafFrame f{};
+	float bx = 0.f, by = 0.f, bz = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
+	int bB = -1, bF = -1;
+	issue(0);
+	for (int job = 0; job < n_jobs; ++job) {
+		if (job + 1 < n_jobs) {
+			issue(job + 1);
+			cp_async_wait<1>();
+		} else {
+			cp_async_wait<0>();
+		}
 		__syncthreads();
-		for (int k = 0; k < ns; ++k) {
-			const float* __restrict__ r = region + k * kRegionFloats;
-			const float* __restrict__ a = sp.in[s0 + k];
-			const float phi0 = r[c];
-			float phiF, phiB;
+		const uint32_t leaf = first + uint32_t(job / jobs_per_leaf);
+		const int jj = job % jobs_per_leaf;
+		const float* __restrict__ base = region + (job & 1) * kStageFloats;
+		if (jj == 0) {
+			// ---- the shared trace through the staged velocity ----
+			const float *ru = base, *rv = base + kRegionFloats, *rw = base + 2 * kRegionFloats;
+			f = leaf_frame(g, leaf);
+			const int ci = f.ox + x, cj = f.oy + y, ck = f.oz + z;
+			bx = fmaf(-sdt, ru[c], float(ci)), by = fmaf(-sdt, rv[c], float(cj)), bz = fmaf(-sdt, rw[c], float(ck));
+			float uf, vf, wf;
 			if (kSemantics == 0) {
-				phiF = phiB = 0.f;
-				if (bB >= 0) {
-					float wB[8];
-					corner_weights(btx, bty, btz, wB);
+				const int i0 = __float2int_rd(bx), j0 = __float2int_rd(by), k0 = __float2int_rd(bz);
+				const int b = region_base(f, i0, j0, k0);
+				const float tx = bx - float(i0), ty = by - float(j0), tz = bz - float(k0);
+				uf = vf = wf = 0.f;
+				if (b >= 0) {
+					float wt[8];
+					corner_weights(tx, ty, tz, wt);
 #pragma unroll
-					for (int q = 0; q < 8; ++q) phiF = fmaf(r[bB + corner_off(q)], wB[q], phiF);  // :239-243
+					for (int q = 0; q < 8; ++q) {  // :201-206
+						uf = fmaf(wt[q], ru[b + corner_off(q)], uf);
+						vf = fmaf(wt[q], rv[b + corner_off(q)], vf);
+						wf = fmaf(wt[q], rw[b + corner_off(q)], wf);
+					}
 				} else {
-					phiF = far_weighted(g, f, a, bi, bj, bk, btx, bty, btz);
-				}
-				if (bF >= 0) {
-					float wF[8];
-					corner_weights(ftx, fty, ftz, wF);
-#pragma unroll
-					for (int q = 0; q < 8; ++q) phiB = fmaf(r[bF + corner_off(q)], wF[q], phiB);
-				} else {
-					phiB = far_weighted(g, f, a, fi, fj, fk, ftx, fty, ftz);
+					uf = far_weighted(g, f, u, i0, j0, k0, tx, ty, tz);
+					vf = far_weighted(g, f, v, i0, j0, k0, tx, ty, tz);
+					wf = far_weighted(g, f, w, i0, j0, k0, tx, ty, tz);
 				}
 			} else {
-				phiF = bB >= 0 ? tri8(r, bB, btx, bty, btz) : trilinear_f(g, f, a, bx, by, bz);
-				phiB = bF >= 0 ? tri8(r, bF, ftx, fty, ftz) : trilinear_f(g, f, a, fx, fy, fz);
+				sample_vec(g, f, ru, rv, rw, u, v, w, bx, by, bz, uf, vf, wf);
 			}
-			const float corr = fmaf(0.5f, phi0 - phiB, phiF);  // :246-247
-			float mn = phi0, mx = phi0;
+			fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :208
+			bB = region_base(f, __float2int_rd(bx), __float2int_rd(by), __float2int_rd(bz));
+			bF = region_base(f, __float2int_rd(fx), __float2int_rd(fy), __float2int_rd(fz));
+		} else {
+			// ---- up to three scalar fields ----
+			const int s0 = 3 * (jj - 1), ns = min(3, S - s0);
+			const uint64_t self = uint64_t(leaf) * 512u + threadIdx.x;
+			const int bi = __float2int_rd(bx), bj = __float2int_rd(by), bk = __float2int_rd(bz);
+			const int fi = __float2int_rd(fx), fj = __float2int_rd(fy), fk = __float2int_rd(fz);
+			const float btx = bx - float(bi), bty = by - float(bj), btz = bz - float(bk);
+			const float ftx = fx - float(fi), fty = fy - float(fj), ftz = fz - float(fk);
+			const int d6[6] = {-kRX * kPitch, kRX * kPitch, -kPitch, kPitch, -1, 1};
+			for (int k = 0; k < ns; ++k) {
+				const float* __restrict__ r = base + k * kRegionFloats;
+				const float* __restrict__ a = sp.in[s0 + k];
+				const float phi0 = r[c];
+				float phiF, phiB;
+				if (kSemantics == 0) {
+					phiF = phiB = 0.f;
+					if (bB >= 0) {
+						float wB[8];
+						corner_weights(btx, bty, btz, wB);
 #pragma unroll
-			for (int q = 0; q < 6; ++q) {  // :253-258
-				const float val = r[c + d6[q]];
-				mn = fminf(mn, val), mx = fmaxf(mx, val);
+						for (int q = 0; q < 8; ++q) phiF = fmaf(r[bB + corner_off(q)], wB[q], phiF);  // :239-243
+					} else {
+						phiF = far_weighted(g, f, a, bi, bj, bk, btx, bty, btz);
+					}
+					if (bF >= 0) {
+						float wF[8];
+						corner_weights(ftx, fty, ftz, wF);
+#pragma unroll
+						for (int q = 0; q < 8; ++q) phiB = fmaf(r[bF + corner_off(q)], wF[q], phiB);
+					} else {
+						phiB = far_weighted(g, f, a, fi, fj, fk, ftx, fty, ftz);
+					}
+				} else {
+					phiF = bB >= 0 ? tri8(r, bB, btx, bty, btz) : trilinear_f(g, f, a, bx, by, bz);
+					phiB = bF >= 0 ? tri8(r, bF, ftx, fty, ftz) : trilinear_f(g, f, a, fx, fy, fz);
+				}
+				const float corr = fmaf(0.5f, phi0 - phiB, phiF);  // :246-247
+				float mn = phi0, mx = phi0;
+#pragma unroll
+				for (int q = 0; q < 6; ++q) {  // :253-258
+					const float val = r[c + d6[q]];
+					mn = fminf(mn, val), mx = fmaxf(mx, val);
+				}
+				mn = fminf(mn, phiF), mx = fmaxf(mx, phiF);
+				sp.out[s0 + k][self] = fmaxf(mn, fminf(corr, mx));  // :264
 			}
-			mn = fminf(mn, phiF), mx = fmaxf(mx, phiF);
-			sp.out[s0 + k][self] = fmaxf(mn, fminf(corr, mx));  // :264
 		}
+		__syncthreads();  // this buffer is refilled two jobs from now
 	}
 }
 void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx,
                            int sampler_semantics, cudaStream_t st) {
 	if (!g.num_leaves || S <= 0) return;
 	static bool attr = false;
-	if (!attr) {
-		cudaFuncSetAttribute(k_advect_scalars<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAdvectSmem));
-		cudaFuncSetAttribute(k_advect_scalars<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAdvectSmem));
-		attr = true;
-	}
+	if (!attr) advect_attrs(k_advect_scalars<0>), advect_attrs(k_advect_scalars<1>), attr = true;
 	if (sampler_semantics == 0)
-		HNS_LAUNCH(k_advect_scalars<0>, g.num_leaves, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx);
+		HNS_LAUNCH(k_advect_scalars<0>, advect_grid(g.num_leaves), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx);
 	else
-		HNS_LAUNCH(k_advect_scalars<1>, g.num_leaves, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx);
+		HNS_LAUNCH(k_advect_scalars<1>, advect_grid(g.num_leaves), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx);
 }
 
 // =============================================================================================================

@@ -1,0 +1,327 @@
+"""Spatially sharded frames: one process per GPU, leaves partitioned into contiguous ranges of the NanoVDB-ordered leaf list,
+ghost leaves (26-neighbourhood) exchanged over NCCL between the steps that need them.
+
+The reference is single-GPU (no NCCL/MPI anywhere); this module is new. What it must preserve is the result:
+the concatenation of the ranks' owned leaves equals the single-GPU frame bit for bit (tests/test_dist_cpu.py checks the
+decomposition logic with world_size 2 over gloo, the GPU scaling run checks it over NCCL).
+
+Exchange points of one frame (ghost depth = one leaf = 8 voxels; valid for back-traces up to 3 voxels + the BFECC forward step):
+    velocity                       -> advect_vector
+    advected velocity              -> divergence
+    red pressure after a red sweep, black pressure after a black sweep     (2 x iterations, half bricks: 1 KB per ghost leaf)
+    projected velocity + scalars   -> advect_scalars
+Divergence needs no exchange (a half-sweep reads it only at the voxels it updates). Ghost leaves are swept like owned leaves;
+what a rank computes on them is overwritten by the owner's values at the next exchange.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import synth
+
+# field ids of hns_state_pack_leaves / hns_state_unpack_leaves (include/hns_b200.h)
+F_VEL, F_ADV, F_P_RED, F_P_BLK, F_DIV_RED, F_DIV_BLK, F_SCALAR0 = (0, 1, 2), (3, 4, 5), 6, 7, 8, 9, 10
+
+
+def floats_per_leaf(field: int) -> int:
+    return 256 if 6 <= field <= 9 else 512
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# partition (pure numpy: runs identically on every rank)
+# ------------------------------------------------------------------------------------------------------------------
+def _coord_keys(origins: np.ndarray) -> np.ndarray:
+    o = (origins.astype(np.int64) >> 3) + (1 << 20)
+    return (o[:, 0] << 42) | (o[:, 1] << 21) | o[:, 2]
+
+
+@dataclass
+class ShardPlan:
+    rank: int
+    world: int
+    ranges: np.ndarray            # [world+1] leaf-range boundaries in the global NanoVDB-ordered list
+    local_ids: np.ndarray         # global leaf ids present on this rank (owned + ghost), ascending == NanoVDB order
+    owned_local: np.ndarray       # bool [n_local]
+    send: dict                    # peer -> local indices of owned leaves the peer holds as ghosts (ascending global id)
+    recv: dict                    # peer -> local indices of ghost leaves owned by the peer   (ascending global id)
+
+    @property
+    def n_owned(self) -> int:
+        return int(self.owned_local.sum())
+
+    @property
+    def n_local(self) -> int:
+        return int(self.local_ids.shape[0])
+
+
+def make_plan(global_origins: np.ndarray, world: int, rank: int) -> ShardPlan:
+    """Contiguous, count-balanced ranges of the sorted leaf list; ghosts = 26-neighbours owned by another rank."""
+    L = global_origins.shape[0]
+    ranges = np.array([(L * r) // world for r in range(world + 1)], np.int64)
+    owner = np.searchsorted(ranges, np.arange(L), side="right") - 1
+    keys = _coord_keys(global_origins)
+    order = np.argsort(keys, kind="stable")
+    skeys = keys[order]
+    lo, hi = int(ranges[rank]), int(ranges[rank + 1])
+    mine = np.arange(lo, hi)
+    send = {}
+    recv = {}
+    ghost = set()
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                if dx == dy == dz == 0:
+                    continue
+                q = keys[mine] + (np.int64(dx) << 42) + (np.int64(dy) << 21) + np.int64(dz)
+                pos = np.searchsorted(skeys, q)
+                pos[pos >= L] = L - 1 if L else 0
+                ok = skeys[pos] == q
+                nbr = order[pos[ok]]
+                src = mine[ok]
+                far = owner[nbr] != rank
+                for peer in np.unique(owner[nbr[far]]):
+                    sel = far & (owner[nbr] == peer)
+                    send.setdefault(int(peer), set()).update(src[sel].tolist())   # my leaves the peer needs
+                    recv.setdefault(int(peer), set()).update(nbr[sel].tolist())   # the peer's leaves I need
+                ghost.update(nbr[far].tolist())
+    local_ids = np.array(sorted(set(mine.tolist()) | ghost), np.int64)
+    owned_local = (local_ids >= lo) & (local_ids < hi)
+    to_local = {int(g): i for i, g in enumerate(local_ids.tolist())}
+    send = {p: np.array([to_local[g] for g in sorted(v)], np.int32) for p, v in sorted(send.items())}
+    recv = {p: np.array([to_local[g] for g in sorted(v)], np.int32) for p, v in sorted(recv.items())}
+    return ShardPlan(rank, world, ranges, local_ids, owned_local, send, recv)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# halo exchange over torch.distributed (NCCL on GPUs, gloo in the CPU tests)
+# ------------------------------------------------------------------------------------------------------------------
+class HaloExchanger:
+    """pack(field, local_ids_tensor, out_tensor) / unpack(field, local_ids_tensor, in_tensor) are supplied by the owner of the
+    fields (CUDA kernels of libhns_b200 on the GPU; numpy indexing in the CPU tests)."""
+
+    def __init__(self, plan: ShardPlan, device, pack, unpack, max_fields: int = 8):
+        import torch
+
+        self.plan, self.pack, self.unpack = plan, pack, unpack
+        self.device = device
+        self.ids_send = {p: torch.as_tensor(v, dtype=torch.int32, device=device) for p, v in plan.send.items()}
+        self.ids_recv = {p: torch.as_tensor(v, dtype=torch.int32, device=device) for p, v in plan.recv.items()}
+        self.buf_send = {p: torch.empty(len(v) * 512 * max_fields, dtype=torch.float32, device=device) for p, v in plan.send.items()}
+        self.buf_recv = {p: torch.empty(len(v) * 512 * max_fields, dtype=torch.float32, device=device) for p, v in plan.recv.items()}
+        self.max_fields = max_fields
+        self.bytes_sent = 0
+        self.exchanges = 0
+
+    def exchange(self, fields) -> None:
+        import torch.distributed as dist
+
+        fields = list(fields)
+        assert len(fields) <= self.max_fields
+        ops, views = [], {}
+        for p in sorted(set(self.ids_send) | set(self.ids_recv)):
+            ns, nr = len(self.plan.send.get(p, ())), len(self.plan.recv.get(p, ()))
+            off_s = off_r = 0
+            vs, vr = [], []
+            for f in fields:
+                fpl = floats_per_leaf(f)
+                if ns:
+                    seg = self.buf_send[p][off_s:off_s + ns * fpl]
+                    self.pack(f, self.ids_send[p], seg)
+                    off_s += ns * fpl
+                if nr:
+                    vr.append((f, self.buf_recv[p][off_r:off_r + nr * fpl]))
+                    off_r += nr * fpl
+            if ns:
+                ops.append(dist.P2POp(dist.isend, self.buf_send[p][:off_s], p))
+                self.bytes_sent += off_s * 4
+            if nr:
+                ops.append(dist.P2POp(dist.irecv, self.buf_recv[p][:off_r], p))
+            views[p] = vr
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for p, vr in views.items():
+            for f, seg in vr:
+                self.unpack(f, self.ids_recv[p], seg)
+        self.exchanges += 1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU driver
+# ------------------------------------------------------------------------------------------------------------------
+class ShardedSimulation:
+    """Device-resident state of this rank's shard (owned + ghost leaves) and the frame with ghost exchanges."""
+
+    def __init__(self, plan: ShardPlan, local_origins: np.ndarray, voxel_size: float, n_scalars: int, device):
+        import torch
+
+        from . import launchers as H
+
+        self.plan, self.device = plan, device
+        self.grid = H.create_index_grid_from_origins(local_origins, voxel_size)
+        self.sim = H.Simulation(self.grid, n_scalars)
+        self.voxel_size = voxel_size
+        self.n_scalars = n_scalars
+        self.omega = H.omega_compute(voxel_size)
+        self.full = False
+        self._torch = torch
+
+        def stream():
+            return torch.cuda.current_stream(device).cuda_stream
+
+        def pack(field, ids, out):
+            self.sim.pack_leaves(field, ids.data_ptr(), ids.numel(), out.data_ptr(), stream())
+
+        def unpack(field, ids, src):
+            self.sim.unpack_leaves(field, ids.data_ptr(), ids.numel(), src.data_ptr(), stream())
+
+        self.ex = HaloExchanger(plan, device, pack, unpack, max_fields=3 + n_scalars)
+        self._stream = stream
+
+    def set_combustion(self, names, params):
+        self.sim.set_combustion(True, names.index("fuel"), names.index("waste"), names.index("temperature"), names.index("flame"), params)
+        self.full = True
+
+    def upload(self, velocity, scalars):
+        self.sim.upload(velocity, scalars)
+
+    def frame(self, iterations: int, dt: float) -> None:
+        s, ex, st = self.sim, self.ex, self._stream()
+        ex.exchange(F_VEL)
+        s.advect_velocity(dt, st)
+        ex.exchange(F_ADV)
+        s.divergence(True, st)
+        if self.full:
+            s.combustion_buoyancy(dt, st)
+        s.pressure_init(st)
+        for _ in range(iterations):
+            s.pressure_half_sweep(0, self.omega, False, st)
+            ex.exchange([F_P_RED])
+            s.pressure_half_sweep(1, self.omega, True, st)
+            ex.exchange([F_P_BLK])
+        s.subtract_gradient(True, st)
+        ex.exchange(list(F_VEL) + [F_SCALAR0 + i for i in range(self.n_scalars)])
+        s.advect_scalars(dt, 0, st)
+
+    def owned(self, arr: np.ndarray) -> np.ndarray:
+        """Rows of a per-voxel local array that belong to owned leaves."""
+        m = np.repeat(self.plan.owned_local, 512)
+        return arr[m]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# weak-scaling workload: the bounding box grows with the number of ranks
+# ------------------------------------------------------------------------------------------------------------------
+WEAK_BOX = {1: (512, 512, 512), 2: (1024, 512, 512), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}
+
+
+def global_sparse_origins(box, fill: float = 0.30, seed: int = 4) -> np.ndarray:
+    """Leaf origins of the blobby sparse smoke (config 4 recipe) inside an arbitrary box, NanoVDB order. For (512,512,512) this is
+    exactly synth.sparse_smoke(512)."""
+    n = tuple(b // 8 for b in box)
+    noise = synth.smooth_lattice_noise(n, tuple(max(2, k // 8) for k in n) if len(set(n)) > 1 else max(2, n[0] // 8), seed)
+    mask = noise > np.quantile(noise, 1.0 - fill)
+    return synth.origins_from_mask(mask)
+
+
+def build_sharded_workload(name: str, rank: int, world: int):
+    """(workload of the LOCAL leaves, field names, fields, frame kind); the plan is attached as workload.meta['plan']."""
+    if name not in ("c4", "c5"):
+        raise SystemExit("multi-GPU bench: use --workload c4 (weak scaling of the 512^3 sparse smoke box per GPU)")
+    box = WEAK_BOX.get(world)
+    if box is None:
+        raise SystemExit(f"no weak-scaling box defined for {world} ranks (1, 2, 4, 8)")
+    gorigins = global_sparse_origins(box)
+    plan = make_plan(gorigins, world, rank)
+    local = np.ascontiguousarray(gorigins[plan.local_ids])
+    vel, density, temperature = synth._swirl_fields(max(box))
+    w = synth._finish(f"sparse{box[0]}x{box[1]}x{box[2]}/rank{rank}", local, vel, [density, temperature], ["density", "temperature"], 40, 4,
+                      with_coords=False, meta=dict(box=box, global_leaves=int(gorigins.shape[0])))
+    w.meta["plan"] = plan
+    fields = dict(density=w.scalars[0], **synth.combustion_fields(w))
+    return w, list(fields), list(fields.values()), "full"
+
+
+def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, world, local_rank):
+    """Timed region per the bench contract: W warm-up frames, K frames bracketed by barrier + synchronize, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+    from . import launchers as H
+
+    plan: ShardPlan = w.meta["plan"]
+    dev = torch.device("cuda", local_rank)
+    sh = ShardedSimulation(plan, w.origins, w.voxel_size, len(fields), dev)
+    if full:
+        sh.set_combustion(names, H.CombustionParams(*params6))
+    vel_pinned = torch.from_numpy(w.velocity).pin_memory()
+    sc_pinned = [torch.from_numpy(a).pin_memory() for a in fields]
+
+    def restore():
+        sh.upload(vel_pinned.numpy(), [t.numpy() for t in sc_pinned])
+
+    restore()
+    for _ in range(args.warmup):
+        sh.frame(iterations, w.dt)
+    torch.cuda.synchronize()
+    restore()
+    # K timed frames on the evolving state (every frame does the same amount of work), device time from CUDA events on the launch stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _lib.lib().hns_launch_count_reset()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        sh.frame(iterations, w.dt)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = torch.tensor([float(_lib.lib().hns_launch_count())], device=dev)
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    owned = torch.tensor([float(plan.n_owned * 512), float(plan.n_local * 512), float(sh.ex.bytes_sent)], device=dev)
+    dist.all_reduce(owned, op=dist.ReduceOp.SUM)
+    ms_step = float(ms.item()) / args.steps
+    n_owned_total, n_local_total = int(owned[0].item()), int(owned[1].item())
+
+    # end to end: pinned host -> device, frame, device -> pinned host, every step
+    out_vel = torch.empty_like(vel_pinned).pin_memory()
+    out_sc = [torch.empty_like(t).pin_memory() for t in sc_pinned]
+
+    def cook():
+        sh.upload(vel_pinned.numpy(), [t.numpy() for t in sc_pinned])
+        sh.frame(iterations, w.dt)
+        torch.cuda.synchronize()
+        out_vel.numpy()[:] = sh.sim.velocity()
+        for i, t in enumerate(out_sc):
+            t.numpy()[:] = sh.sim.scalar(i)
+
+    cook()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        cook()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.e2e_steps], device=dev)
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    S = len(fields)
+    box = w.meta["box"]
+    return {"metric": "active voxel-updates/s per advect+project frame", "value": n_owned_total / (ms_step * 1e-3), "unit": "voxel-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"c4 weak scaling: sparse smoke ~30% of a {box[0]}x{box[1]}x{box[2]} box, {n_owned_total} active voxels over "
+                                   f"{world} GPUs (+{n_local_total - n_owned_total} ghost voxels), frame=full, I={iterations}, S={S}",
+                       "parallelism": f"spatial leaf-range sharding x{world}, NCCL ghost-leaf exchange ({sh.ex.exchanges // (args.steps + args.warmup + args.e2e_steps + 1)} exchanges/frame)",
+                       "l2": "per-rank fields larger than L2; no flush"},
+            "e2e": {"value": n_owned_total / (float(e2e.item()) * 1e-3), "unit": "voxel-updates/s", "ms_per_step": float(e2e.item()),
+                    "h2d_bytes_per_step": int(n_local_total * (12 + 4 * S)), "d2h_bytes_per_step": int(n_local_total * (12 + 4 * S)),
+                    "call": "ShardedSimulation.upload + frame + download per rank on pinned host buffers"},
+            "gpu_launches": int(launches.item()),
+            "halo_bytes_per_frame": int(owned[2].item() / (args.steps + args.warmup + args.e2e_steps + 1))}

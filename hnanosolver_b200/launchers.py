@@ -38,6 +38,11 @@ def _ip(a: np.ndarray):
     return a.ctypes.data_as(c_i32p)
 
 
+def omega_compute(voxel_size: float) -> float:
+    """omega of the all-in-one frame: 2/(1+sinf(float(3.14159)*h)) in float (reference src/Cuda/HNanoSolver.cu:257)"""
+    return float(_lib.lib().hns_omega_compute(voxel_size))
+
+
 def _stream(stream) -> C.c_void_p:
     if stream is None:
         return C.c_void_p(0)
@@ -253,6 +258,15 @@ class Simulation:
 
     def pressure_solve(self, iterations, omega, flags=0, stream=None):
         check(_lib.lib().hns_state_pressure_solve(self._h, iterations, omega, flags, _stream(stream)))
+
+    def pressure_init(self, stream=None):
+        check(_lib.lib().hns_state_pressure_init(self._h, _stream(stream)))
+
+    def pressure_half_sweep(self, color: int, omega: float, reverse: bool = False, stream=None):
+        check(_lib.lib().hns_state_pressure_half_sweep(self._h, color, omega, int(reverse), _stream(stream)))
+
+    def combustion_buoyancy(self, dt: float, stream=None):
+        check(_lib.lib().hns_state_combustion_buoyancy(self._h, dt, _stream(stream)))
 
     def subtract_gradient(self, from_advected=True, stream=None):
         check(_lib.lib().hns_state_subtract_gradient(self._h, int(from_advected), _stream(stream)))

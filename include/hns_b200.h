@@ -140,6 +140,13 @@ int hns_state_advect_velocity(hns_state* s, float dt, void* stream);            
 int hns_state_divergence(hns_state* s, int of_advected, void* stream);               /* adv|vel -> div          */
 int hns_state_pressure_solve(hns_state* s, int iterations, float omega, unsigned flags, void* stream); /* p = 0; RBGS   */
 int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream);      /* adv|vel, p -> vel       */
+/* Pieces of the pressure solve and of the combustion stage, for drivers that interleave ghost exchanges (sharded runs). */
+int hns_state_pressure_init(hns_state* s, void* stream);                              /* p = 0                   */
+int hns_state_pressure_half_sweep(hns_state* s, int color, float omega, int reverse, void* stream); /* one red (0) / black (1) sweep */
+int hns_state_combustion_buoyancy(hns_state* s, float dt, void* stream);              /* combustion_oxygen + temperature_buoyancy */
+/* omega exactly as Compute() (src/Cuda/HNanoSolver.cu:257, float sinf) and pressure_projection_idx (PressureProjection.cu:53, double sin) evaluate it */
+float hns_omega_compute(float voxel_size);
+float hns_omega_project(float voxel_size);
 int hns_state_advect_scalars(hns_state* s, float dt, int sampler_semantics, void* stream); /* 0: advect_scalars, 1: advect_scalar */
 int hns_state_sync(hns_state* s, void* stream);
 /* Timed run of `frames` identical frames (state is restored between frames) with CUDA events on `stream`;

@@ -193,6 +193,13 @@ class OracleIndex:
                                omega)
         return p
 
+    def rbgs_color(self, div, p, voxel_size, color, omega):
+        """one half-sweep in place on p (a float32 array)"""
+        div, dp = _f32(div)
+        assert p.dtype == np.float32 and p.flags.c_contiguous
+        lib().ora_rbgs(self._h, self.coords.ctypes.data_as(c_i32p), dp, p.ctypes.data_as(c_f32p), voxel_size, self.n, color, omega)
+        return p
+
     def subtract_gradient(self, vel, p, voxel_size):
         vel, vp = _f32(vel)
         p, pp = _f32(p)
