@@ -222,7 +222,7 @@ def global_sparse_origins(box, fill: float = 0.30, seed: int = 4) -> np.ndarray:
     """Leaf origins of the blobby sparse smoke (config 4 recipe) inside an arbitrary box, NanoVDB order. For (512,512,512) this is
     exactly synth.sparse_smoke(512)."""
     n = tuple(b // 8 for b in box)
-    noise = synth.smooth_lattice_noise(n, tuple(max(2, k // 8) for k in n) if len(set(n)) > 1 else max(2, n[0] // 8), seed)
+    noise = synth.smooth_lattice_noise(n, tuple(max(2, k // 8) for k in n), seed)
     mask = noise > np.quantile(noise, 1.0 - fill)
     return synth.origins_from_mask(mask)
 

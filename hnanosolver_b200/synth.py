@@ -98,11 +98,12 @@ def hash_noise(seed: int, ijk: np.ndarray, channel: int) -> np.ndarray:
     return ((h >> np.uint64(40)).astype(np.float64) / float(1 << 24)).astype(np.float32)
 
 
-def smooth_lattice_noise(shape, cells: int, seed: int) -> np.ndarray:
-    """Trilinear value noise on a lattice of `shape`, `cells` random cells per axis."""
+def smooth_lattice_noise(shape, cells, seed: int) -> np.ndarray:
+    """Trilinear value noise on a lattice of `shape`, `cells` random cells per axis (an int, or one count per axis)."""
     rng = np.random.default_rng(seed)
-    g = rng.random((cells + 1,) * 3)
-    ax = [np.linspace(0, cells, s, endpoint=False) for s in shape]
+    cells = (cells,) * 3 if np.isscalar(cells) else tuple(cells)
+    g = rng.random(tuple(c + 1 for c in cells))
+    ax = [np.linspace(0, c, s, endpoint=False) for c, s in zip(cells, shape)]
     i = [np.floor(a).astype(int) for a in ax]
     f = [a - ii for a, ii in zip(ax, i)]
     f = [t * t * (3 - 2 * t) for t in f]
