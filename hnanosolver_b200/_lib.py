@@ -69,6 +69,8 @@ SIGNATURES = {
     "hns_state_advect_scalars": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
     "hns_state_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hns_state_time_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint, C.c_void_p, c_f32p, c_f32p]),
+    "hns_state_gather_element0": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hns_state_set_element0": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hns_state_pack_leaves": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "hns_state_unpack_leaves": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "hns_state_field_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),

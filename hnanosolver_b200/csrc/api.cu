@@ -79,7 +79,7 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 			sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i];
 			++S;
 		}
-		launch_advect_scalars(g, s->vel, sp, S, dt, inv, 0, st);
+		launch_advect_scalars(g, s->vel, sp, S, dt, inv, 0, s->elem0, st);
 		for (int i = 0; i < s->n_scalars; ++i)
 			if (i != s->skip_scalar) std::swap(s->sc[i], s->sc_out[i]);
 	}
@@ -286,10 +286,21 @@ int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream) {
 int hns_state_advect_scalars(hns_state* s, float dt, int sampler_semantics, void* stream) {
 	HNS_REQUIRE(s, "null state");
 	if (!s->n_scalars || !s->n) return HNS_OK;
-	launch_advect_scalars(s->grid->view, s->vel, scalar_ptrs(s), s->n_scalars, dt, 1.0f / s->grid->voxel_size, sampler_semantics,
+	launch_advect_scalars(s->grid->view, s->vel, scalar_ptrs(s), s->n_scalars, dt, 1.0f / s->grid->voxel_size, sampler_semantics, s->elem0,
 	                      static_cast<cudaStream_t>(stream));
 	for (int i = 0; i < s->n_scalars; ++i) std::swap(s->sc[i], s->sc_out[i]);
 	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+int hns_state_gather_element0(hns_state* s, float* dst_dev, void* stream) {
+	HNS_REQUIRE(s && dst_dev, "null argument");
+	launch_gather_element0(s->vel, scalar_ptrs(s), s->n_scalars, dst_dev, static_cast<cudaStream_t>(stream));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+int hns_state_set_element0(hns_state* s, const float* values_dev) {
+	HNS_REQUIRE(s, "null state");
+	s->elem0 = values_dev;
 	return HNS_OK;
 }
 int hns_state_sync(hns_state* s, void* stream) {
@@ -473,7 +484,7 @@ int hns_advect_index_grid(const int32_t* coords, uint64_t n, const float* veloci
 		if (!fields[i]) return fail(HNS_ERR_RUNTIME, "Block not found or type mismatch");
 		HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, st));
 	}
-	launch_advect_scalars(sc.grid->view, s->vel, scalar_ptrs(s), n_float, dt, 1.0f / voxel_size, 1, st);  // advect_scalar semantics (Advection.cu:89)
+	launch_advect_scalars(sc.grid->view, s->vel, scalar_ptrs(s), n_float, dt, 1.0f / voxel_size, 1, nullptr, st);  // advect_scalar semantics (Advection.cu:89)
 	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc_out[i], n * 4, cudaMemcpyDeviceToHost, st));
 	HNS_CUDA(cudaStreamSynchronize(st));
 	HNS_CUDA(cudaGetLastError());

@@ -107,4 +107,5 @@ struct hns_state {
 	int comb_idx[4] = {-1, -1, -1, -1};  // fuel, waste, temperature, flame
 	hns_combustion_params comb{};
 	int skip_scalar = -1;  // scalar that is carried but not advected ("collision_sdf")
+	const float* elem0 = nullptr;  // device float[3 + n_scalars]: element 0 of the global arrays (sharded runs), else null
 };

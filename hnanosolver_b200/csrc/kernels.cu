@@ -315,11 +315,15 @@ __device__ __noinline__ float trilinear_f(const GridView& g, const LeafFrame& f,
 // inside the region; a sample that leaves it (the reference has no CFL limit) falls back to the leaf-table / tree-walk path
 // above, so results do not depend on the region size.
 // Row pitch is 24 floats (96 B): keeps 16-byte alignment and maps the 4 (y) x 8 (z) lanes of a warp to 32 distinct banks.
+// (Padding the x-plane pitch to a multiple of 32 floats would also keep lanes whose samples straddle an integer x on disjoint
+// banks, but 2 buffers x 3 fields x 19.25 KB no longer fits two CTAs per SM; measured trade-off in DESIGN.md.)
 constexpr int kRX = 14, kRZ = 16, kPitch = 24, kHaloXY = 3, kHaloZ = 4;
-constexpr int kRegionFloats = kRX * kRX * kPitch;                 // 4704 floats = 18.4 KB per field
+constexpr int kPlane = kRX * kPitch;                              // 336 floats per x-plane
+constexpr int kRegionFloats = kRX * kPlane;                       // 4704 floats = 18.4 KB per field
 constexpr int kRegionQuads = kRX * kRX * (kRZ / 4);               // 16-byte quads per field
 constexpr int kStageFloats = 3 * kRegionFloats;                   // one pipeline stage: three fields
 constexpr size_t kAdvectSmem = 2 * kStageFloats * sizeof(float);  // double buffer: 110.25 KB per CTA, two CTAs per SM
+static_assert(2 * (kAdvectSmem + 1024) <= 233472, "two CTAs of the advection pipeline must fit one SM's shared memory");
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 	const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
@@ -350,7 +354,7 @@ __device__ __forceinline__ StagePlan make_stage_plan(const int32_t* __restrict__
 			const int lx = rx - kHaloXY, ly = ry - kHaloXY;       // leaf-local x, y in [-3, 11)
 			const int dz = q == 0 ? -1 : (q == 3 ? 1 : 0);        // z in [-4,0) | [0,4) | [4,8) | [8,12)
 			const int32_t l = __ldg(nbr + ((lx >> 3) + 1) * 9 + ((ly >> 3) + 1) * 3 + dz + 1);
-			p.dst[k] = row * kPitch + q * 4;
+			p.dst[k] = rx * kPlane + ry * kPitch + q * 4;
 			if (l >= 0) p.src[k] = uint32_t(l) * 512u + uint32_t(((lx & 7) << 6) | ((ly & 7) << 3)) + ((q == 1 || q == 3) ? 0u : 4u);
 		}
 	}
@@ -371,12 +375,12 @@ __device__ __forceinline__ void stage_region(const StagePlan& p, const float* __
 __device__ __forceinline__ int region_base(const LeafFrame& fr, int i, int j, int k) {
 	const int rx = i - fr.ox + kHaloXY, ry = j - fr.oy + kHaloXY, rz = k - fr.oz + kHaloZ;
 	if (unsigned(rx) >= unsigned(kRX - 1) || unsigned(ry) >= unsigned(kRX - 1) || unsigned(rz) >= unsigned(kRZ - 1)) return -1;
-	return (rx * kRX + ry) * kPitch + rz;
+	return rx * kPlane + ry * kPitch + rz;
 }
 __device__ __forceinline__ float tri8(const float* __restrict__ r, int b, float fx, float fy, float fz) {
-	// v[a][b][c] = r[b + a*14*24 + b*24 + c]; lerp z, then y, then x (Stencils.hpp:144-152)
+	// v[a][b][c] = r[base + a*kPlane + b*kPitch + c]; lerp z, then y, then x (Stencils.hpp:144-152)
 	const float z0 = lerpf(r[b], r[b + 1], fz), z1 = lerpf(r[b + kPitch], r[b + kPitch + 1], fz);
-	const float z2 = lerpf(r[b + kRX * kPitch], r[b + kRX * kPitch + 1], fz), z3 = lerpf(r[b + kRX * kPitch + kPitch], r[b + kRX * kPitch + kPitch + 1], fz);
+	const float z2 = lerpf(r[b + kPlane], r[b + kPlane + 1], fz), z3 = lerpf(r[b + kPlane + kPitch], r[b + kPlane + kPitch + 1], fz);
 	return lerpf(lerpf(z0, z1, fy), lerpf(z2, z3, fy), fx);
 }
 
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const floa
 	uint32_t first, last;
 	if (!cta_leaf_range(g, first, last)) return;
 	const int x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
-	const int c = ((x + kHaloXY) * kRX + (y + kHaloXY)) * kPitch + z + kHaloZ;
+	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
 	auto issue = [&](uint32_t leaf, int buf) {
 		const StagePlan plan = make_stage_plan(g.nbr + uint64_t(leaf) * 27u);
 		float* r = region + buf * kStageFloats;
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const floa
 		sample_vec(g, f, ru, rv, rw, u, v, w, fx, fy, fz, ub, vb, wb);
 		const float cu = fmaf(0.5f, u0 - ub, uf), cv = fmaf(0.5f, v0 - vb, vf), cw = fmaf(0.5f, w0 - wb, wf);  // :399-400
 		float mnu = u0, mxu = u0, mnv = v0, mxv = v0, mnw = w0, mxw = w0;
-		const int d6[6] = {-kRX * kPitch, kRX * kPitch, -kPitch, kPitch, -1, 1};  // -x, +x, -y, +y, -z, +z  (:410-421)
+		const int d6[6] = {-kPlane, kPlane, -kPitch, kPitch, -1, 1};  // -x, +x, -y, +y, -z, +z  (:410-421)
 #pragma unroll
 		for (int q = 0; q < 6; ++q) {
 			const float nu = ru[c + d6[q]], nv = rv[c + d6[q]], nw = rw[c + d6[q]];
@@ -495,29 +499,30 @@ __device__ __forceinline__ void corner_weights(float tx, float ty, float tz, flo
 	w[4] = w00 * tz, w[5] = w10 * tz, w[6] = w01 * tz, w[7] = w11 * tz;
 }
 // region offsets of the eight corners in the reference's accumulation order: bit0 -> i, bit1 -> j, bit2 -> k
-__device__ __forceinline__ int corner_off(int q) { return (q & 1) * kRX * kPitch + ((q >> 1) & 1) * kPitch + (q >> 2); }
+__device__ __forceinline__ int corner_off(int q) { return (q & 1) * kPlane + ((q >> 1) & 1) * kPitch + (q >> 2); }
 // cold path: weighted 8-corner sums through the leaf table / tree walk, for samples outside the staged region
-__device__ __noinline__ float far_weighted(const GridView& g, const LeafFrame& f, const float* __restrict__ a, int i0, int j0, int k0, float tx,
-                                           float ty, float tz) {
+__device__ __noinline__ float far_weighted(const GridView& g, const LeafFrame& f, const float* __restrict__ a, const float* __restrict__ e0, int i0,
+                                           int j0, int k0, float tx, float ty, float tz) {
 	float wt[8];
 	corner_weights(tx, ty, tz, wt);
 	float acc = 0.f;
 #pragma unroll 1
 	for (int q = 0; q < 8; ++q) {
 		const int64_t t = voxel_index(g, f, i0 + (q & 1), j0 + ((q >> 1) & 1), k0 + (q >> 2));
-		acc = fmaf(__ldg(a + (t < 0 ? 0 : t)), wt[q], acc);
+		acc = fmaf(t < 0 ? __ldg(e0) : __ldg(a + t), wt[q], acc);
 	}
 	return acc;
 }
 
 template <int kSemantics>
 __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const float* __restrict__ u, const float* __restrict__ v,
-                                                           const float* __restrict__ w, ScalarPtrs sp, int S, float sdt) {
+                                                           const float* __restrict__ w, ScalarPtrs sp, int S, float sdt,
+                                                           const float* __restrict__ elem0) {
 	extern __shared__ __align__(16) float region[];
 	uint32_t first, last;
 	if (!cta_leaf_range(g, first, last)) return;
 	const int x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
-	const int c = ((x + kHaloXY) * kRX + (y + kHaloXY)) * kPitch + z + kHaloZ;
+	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
 	// pipeline jobs: per leaf one velocity stage (the shared trace) and ceil(S/3) stages of up to three scalar fields
 	const int jobs_per_leaf = 1 + (S + 2) / 3;
 	const int n_jobs = int(last - first) * jobs_per_leaf;
@@ -527,13 +532,15 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 		const StagePlan plan = make_stage_plan(g.nbr + uint64_t(leaf) * 27u);
 		float* r = region + (job & 1) * kStageFloats;
 		if (jj == 0) {
-			// advect_scalars samples the velocity with "inactive -> element 0" as well (Kernel.cu:192,204)
-			stage_region(plan, u, r, kSemantics == 0 ? __ldg(u) : 0.f);
-			stage_region(plan, v, r + kRegionFloats, kSemantics == 0 ? __ldg(v) : 0.f);
-			stage_region(plan, w, r + 2 * kRegionFloats, kSemantics == 0 ? __ldg(w) : 0.f);
+			// advect_scalars samples the velocity with "inactive -> element 0" as well (Kernel.cu:192,204). elem0, when given,
+			// holds element 0 of the GLOBAL arrays (velocity x,y,z then the S scalars): on a shard the local element 0 is another voxel.
+			stage_region(plan, u, r, kSemantics == 0 ? __ldg(elem0 ? elem0 : u) : 0.f);
+			stage_region(plan, v, r + kRegionFloats, kSemantics == 0 ? __ldg(elem0 ? elem0 + 1 : v) : 0.f);
+			stage_region(plan, w, r + 2 * kRegionFloats, kSemantics == 0 ? __ldg(elem0 ? elem0 + 2 : w) : 0.f);
 		} else {
 			const int s0 = 3 * (jj - 1), ns = min(3, S - s0);
-			for (int k = 0; k < ns; ++k) stage_region(plan, sp.in[s0 + k], r + k * kRegionFloats, kSemantics == 0 ? __ldg(sp.in[s0 + k]) : 0.f);
+			for (int k = 0; k < ns; ++k)
+				stage_region(plan, sp.in[s0 + k], r + k * kRegionFloats, kSemantics == 0 ? __ldg(elem0 ? elem0 + 3 + s0 + k : sp.in[s0 + k]) : 0.f);
 		}
 		cp_async_commit();
 	};
@@ -575,9 +582,9 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 						wf = fmaf(wt[q], rw[b + corner_off(q)], wf);
 					}
 				} else {
-					uf = far_weighted(g, f, u, i0, j0, k0, tx, ty, tz);
-					vf = far_weighted(g, f, v, i0, j0, k0, tx, ty, tz);
-					wf = far_weighted(g, f, w, i0, j0, k0, tx, ty, tz);
+					uf = far_weighted(g, f, u, elem0 ? elem0 : u, i0, j0, k0, tx, ty, tz);
+					vf = far_weighted(g, f, v, elem0 ? elem0 + 1 : v, i0, j0, k0, tx, ty, tz);
+					wf = far_weighted(g, f, w, elem0 ? elem0 + 2 : w, i0, j0, k0, tx, ty, tz);
 				}
 			} else {
 				sample_vec(g, f, ru, rv, rw, u, v, w, bx, by, bz, uf, vf, wf);
@@ -593,7 +600,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 			const int fi = __float2int_rd(fx), fj = __float2int_rd(fy), fk = __float2int_rd(fz);
 			const float btx = bx - float(bi), bty = by - float(bj), btz = bz - float(bk);
 			const float ftx = fx - float(fi), fty = fy - float(fj), ftz = fz - float(fk);
-			const int d6[6] = {-kRX * kPitch, kRX * kPitch, -kPitch, kPitch, -1, 1};
+			const int d6[6] = {-kPlane, kPlane, -kPitch, kPitch, -1, 1};
 			for (int k = 0; k < ns; ++k) {
 				const float* __restrict__ r = base + k * kRegionFloats;
 				const float* __restrict__ a = sp.in[s0 + k];
@@ -607,7 +614,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 #pragma unroll
 						for (int q = 0; q < 8; ++q) phiF = fmaf(r[bB + corner_off(q)], wB[q], phiF);  // :239-243
 					} else {
-						phiF = far_weighted(g, f, a, bi, bj, bk, btx, bty, btz);
+						phiF = far_weighted(g, f, a, elem0 ? elem0 + 3 + s0 + k : a, bi, bj, bk, btx, bty, btz);
 					}
 					if (bF >= 0) {
 						float wF[8];
@@ -615,7 +622,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 #pragma unroll
 						for (int q = 0; q < 8; ++q) phiB = fmaf(r[bF + corner_off(q)], wF[q], phiB);
 					} else {
-						phiB = far_weighted(g, f, a, fi, fj, fk, ftx, fty, ftz);
+						phiB = far_weighted(g, f, a, elem0 ? elem0 + 3 + s0 + k : a, fi, fj, fk, ftx, fty, ftz);
 					}
 				} else {
 					phiF = bB >= 0 ? tri8(r, bB, btx, bty, btz) : trilinear_f(g, f, a, bx, by, bz);
@@ -636,14 +643,26 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 	}
 }
 void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx,
-                           int sampler_semantics, cudaStream_t st) {
+                           int sampler_semantics, const float* elem0, cudaStream_t st) {
 	if (!g.num_leaves || S <= 0) return;
 	static bool attr = false;
 	if (!attr) advect_attrs(k_advect_scalars<0>), advect_attrs(k_advect_scalars<1>), attr = true;
 	if (sampler_semantics == 0)
-		HNS_LAUNCH(k_advect_scalars<0>, advect_grid(g.num_leaves), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx);
+		HNS_LAUNCH(k_advect_scalars<0>, advect_grid(g.num_leaves), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0);
 	else
-		HNS_LAUNCH(k_advect_scalars<1>, advect_grid(g.num_leaves), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx);
+		HNS_LAUNCH(k_advect_scalars<1>, advect_grid(g.num_leaves), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0);
+}
+
+// element 0 of velocity (x,y,z) and of each scalar field -> dst[3 + S]
+__global__ void k_gather_element0(const float* u, const float* v, const float* w, ScalarPtrs sp, int S, float* __restrict__ dst) {
+	const int t = threadIdx.x;
+	if (t == 0) dst[0] = u[0];
+	if (t == 1) dst[1] = v[0];
+	if (t == 2) dst[2] = w[0];
+	if (t >= 3 && t < 3 + S) dst[t] = sp.in[t - 3][0];
+}
+void launch_gather_element0(const float* const vel[3], const ScalarPtrs& sp, int S, float* dst, cudaStream_t st) {
+	HNS_LAUNCH(k_gather_element0, 1, 32, 0, st, vel[0], vel[1], vel[2], sp, S, dst);
 }
 
 // =============================================================================================================

@@ -18,8 +18,11 @@ void launch_soa_to_aos(const float* u, const float* v, const float* w, float* ao
 // advect_vector (reference src/Cuda/Kernel.cu:354-453), hasCollision == false
 void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st);
 // advect_scalars (Kernel.cu:118-266) when sampler_semantics == 0; advect_scalar (Kernel.cu:269-352) per field when == 1
+// elem0 (device, float[3 + S], may be null): element 0 of the GLOBAL velocity / scalar arrays, the value advect_scalars reads for
+// inactive voxels; null = element 0 of the arrays passed in (single-GPU runs).
 void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx,
-                           int sampler_semantics, cudaStream_t st);
+                           int sampler_semantics, const float* elem0, cudaStream_t st);
+void launch_gather_element0(const float* const vel[3], const ScalarPtrs& sp, int S, float* dst, cudaStream_t st);
 // divergence (Kernel.cu:499-519)
 void launch_divergence(const GridView& g, const float* const vel[3], float* const div[2], float inv_dx, cudaStream_t st);
 // redBlackGaussSeidelUpdate (Kernel.cu:591-623): one colour per launch, in place, on the colour-split layout (p[0] red, p[1] black)

@@ -26,6 +26,11 @@ from . import synth
 F_VEL, F_ADV, F_P_RED, F_P_BLK, F_DIV_RED, F_DIV_BLK, F_SCALAR0 = (0, 1, 2), (3, 4, 5), 6, 7, 8, 9, 10
 
 
+import os as _os
+
+_DEBUG_SYNC = bool(int(_os.environ.get("HNS_DEBUG_SYNC", "0")))
+
+
 def floats_per_leaf(field: int) -> int:
     return 256 if 6 <= field <= 9 else 512
 
@@ -143,6 +148,10 @@ class HaloExchanger:
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
+        if _DEBUG_SYNC:
+            import torch
+
+            torch.cuda.synchronize()
         for p, vr in views.items():
             for f, seg in vr:
                 self.unpack(f, self.ids_recv[p], seg)
@@ -180,6 +189,9 @@ class ShardedSimulation:
 
         self.ex = HaloExchanger(plan, device, pack, unpack, max_fields=3 + n_scalars)
         self._stream = stream
+        # element 0 of the global arrays (the "inactive" value of advect_scalars, reference Kernel.cu:192,225): owned by rank 0
+        self.elem0 = torch.zeros(3 + n_scalars, dtype=torch.float32, device=device)
+        self.sim.set_element0(self.elem0.data_ptr())
 
     def set_combustion(self, names, params):
         self.sim.set_combustion(True, names.index("fuel"), names.index("waste"), names.index("temperature"), names.index("flame"), params)
@@ -204,6 +216,12 @@ class ShardedSimulation:
             ex.exchange([F_P_BLK])
         s.subtract_gradient(True, st)
         ex.exchange(list(F_VEL) + [F_SCALAR0 + i for i in range(self.n_scalars)])
+        if self.plan.rank == 0:
+            s.gather_element0(self.elem0.data_ptr(), st)
+        if self.plan.world > 1:
+            import torch.distributed as dist
+
+            dist.broadcast(self.elem0, src=0)
         s.advect_scalars(dt, 0, st)
 
     def owned(self, arr: np.ndarray) -> np.ndarray:

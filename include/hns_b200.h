@@ -160,6 +160,12 @@ int hns_state_time_frames(hns_state* s, int frames, int iterations, float dt, un
  * 10+i scalar i. Pressure and divergence are stored colour-split (red = (x+y+z) even): 256 floats per leaf and half; every other
  * field has 512 floats per leaf (hns_state_field_floats_per_leaf). */
 int hns_state_field_floats_per_leaf(int field);
+/* advect_scalars reads "array element 0" for inactive voxels (reference src/Cuda/Kernel.cu:192,225). On a shard the local element 0
+ * is a different voxel than on the whole grid, so the owner of global voxel 0 gathers the 3 + n_scalars values (velocity x,y,z,
+ * scalars) with hns_state_gather_element0, they are broadcast, and every rank installs them with hns_state_set_element0 (device
+ * pointer, must stay valid; NULL restores the single-GPU behaviour). */
+int hns_state_gather_element0(hns_state* s, float* dst_dev, void* stream);
+int hns_state_set_element0(hns_state* s, const float* values_dev);
 int hns_state_pack_leaves(hns_state* s, int field, const int32_t* leaf_ids_dev, uint64_t n_ids, float* dst_dev, void* stream);
 int hns_state_unpack_leaves(hns_state* s, int field, const int32_t* leaf_ids_dev, uint64_t n_ids, const float* src_dev, void* stream);
 void* hns_state_field_device_ptr(hns_state* s, int field);
