@@ -344,12 +344,45 @@ class RefHostGrid:
 # oracle/_ref/libhns_ref.so: the unmodified reference launchers + kernels (needs a GPU)
 # --------------------------------------------------------------------------------------------------
 _ref = None
+_ref_libs: dict = {}
+_COMPAT_DRIVER_SO = os.path.join(_HERE, "_ref", "libcompat_driver.so")
+
+
+def compat_driver_available() -> bool:
+    return os.path.exists(_COMPAT_DRIVER_SO)
+
+
+class reference_library:
+    """Context manager selecting which implementation of the seven launcher symbols the Ref* helpers drive:
+    "reference" = oracle/_ref/libhns_ref.so (the unmodified reference), "compat" = oracle/_ref/libcompat_driver.so
+    (the same plain-C driver, oracle/ref_shim.cu, linked against compat/libhns_compat.so, i.e. the product)."""
+
+    def __init__(self, which: str):
+        self.path = {"reference": _REF_SO, "compat": _COMPAT_DRIVER_SO}[which]
+
+    def __enter__(self):
+        global _ref
+        self._saved = _ref
+        _ref = _load_ref(self.path)
+        return self
+
+    def __exit__(self, *a):
+        global _ref
+        _ref = self._saved
 
 
 def ref() -> C.CDLL:
     global _ref
     if _ref is None:
-        L = C.CDLL(_REF_SO)
+        _ref = _load_ref(_REF_SO)
+    return _ref
+
+
+def _load_ref(path: str) -> C.CDLL:
+    if path in _ref_libs:
+        return _ref_libs[path]
+    if True:
+        L = C.CDLL(path)
         L.ref_last_error.restype = C.c_char_p
         L.ref_data_create.restype = C.c_void_p
         L.ref_data_create.argtypes = [C.c_uint64, C.c_int]
@@ -372,13 +405,14 @@ def ref() -> C.CDLL:
         L.ref_advect_index_grid_velocity.argtypes = [C.c_void_p, C.c_float, C.c_float]
         L.ref_project_non_divergent.argtypes = [C.c_void_p, C.c_uint64, C.c_float]
         L.ref_divergence.argtypes = [C.c_void_p, C.c_float]
-        L.ref_frame_create.restype = C.c_void_p
-        L.ref_frame_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
-        L.ref_frame_destroy.argtypes = [C.c_void_p]
-        L.ref_frame_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, c_f32p]
-        L.ref_frame_download.argtypes = [C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, C.POINTER(c_f32p)]
-        _ref = L
-    return _ref
+        if hasattr(L, "ref_frame_create"):
+            L.ref_frame_create.restype = C.c_void_p
+            L.ref_frame_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
+            L.ref_frame_destroy.argtypes = [C.c_void_p]
+            L.ref_frame_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, c_f32p]
+            L.ref_frame_download.argtypes = [C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, C.POINTER(c_f32p)]
+        _ref_libs[path] = L
+    return L
 
 
 class _Quiet:
@@ -408,6 +442,7 @@ class RefData:
     def __init__(self, coords, alloc_type: int = 0):
         coords = np.ascontiguousarray(np.asarray(coords, np.int32).reshape(-1, 3))
         self.n = coords.shape[0]
+        self._lib = ref()
         self._h = ref().ref_data_create(self.n, alloc_type)
         if not self._h:
             raise RuntimeError("ref_data_create failed")
@@ -418,7 +453,7 @@ class RefData:
     def __del__(self):
         if getattr(self, "_h", None):
             self.blocks = {}
-            ref().ref_data_destroy(self._h)
+            self._lib.ref_data_destroy(self._h)
             self._h = None
 
     def add_float(self, name: str, values) -> np.ndarray:
@@ -439,6 +474,7 @@ class RefData:
 class RefGrid:
     def __init__(self, data: RefData, voxel_size: float):
         h = C.c_void_p()
+        self._lib = ref()
         with _Quiet():
             rc = ref().ref_create_index_grid(data._h, voxel_size, C.byref(h))
         _rcheck(rc)
@@ -446,18 +482,18 @@ class RefGrid:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            ref().ref_grid_destroy(self._h)
+            self._lib.ref_grid_destroy(self._h)
             self._h = None
 
     def buffer(self) -> np.ndarray:
-        buf = np.empty(ref().ref_grid_bytes(self._h), np.uint8)
-        _rcheck(ref().ref_grid_download(self._h, buf.ctypes.data_as(C.c_void_p)))
+        buf = np.empty(self._lib.ref_grid_bytes(self._h), np.uint8)
+        _rcheck(self._lib.ref_grid_download(self._h, buf.ctypes.data_as(C.c_void_p)))
         return buf
 
     def get_values(self, ijk) -> np.ndarray:
         ijk, p = _i32(np.asarray(ijk).reshape(-1, 3))
         out = np.empty(ijk.shape[0], np.uint64)
-        _rcheck(ref().ref_grid_get_values(self._h, p, ijk.shape[0], out.ctypes.data_as(c_u64p)))
+        _rcheck(self._lib.ref_grid_get_values(self._h, p, ijk.shape[0], out.ctypes.data_as(c_u64p)))
         return out
 
 

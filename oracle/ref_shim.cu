@@ -21,7 +21,13 @@
 #include <string>
 
 #include "../Utils/GridData.hpp"
+#ifndef HNS_SHIM_LAUNCHERS_ONLY
 #include "Kernels.cuh"
+#else
+struct CombustionParams {
+	float expansionRate, temperatureRelease, buoyancyStrength, ambientTemp, vorticityScale, factorScale;
+};
+#endif
 #include "nanovdb/GridHandle.h"
 #include "nanovdb/NanoVDB.h"
 #include "nanovdb/cuda/DeviceBuffer.h"
@@ -193,6 +199,7 @@ int ref_divergence(void* data, float voxelSize) {
 	REF_CATCH
 }
 
+#ifndef HNS_SHIM_LAUNCHERS_ONLY
 // ---- device-resident "north-star frame" with the reference's own kernels ----
 // Same step list as the product's resident frame (advect_vector -> divergence -> I x (red, black) ->
 // subtractPressureGradient -> advect_scalars; combustion/buoyancy/vorticity off), launched exactly as
@@ -282,5 +289,7 @@ int ref_frame_download(void* f_, float* velProj, float* pressure, float* div, fl
 			if (scalars[s]) cudaMemcpy(scalars[s], f->out[s], f->n * 4, cudaMemcpyDeviceToHost);
 	return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
+
+#endif  // HNS_SHIM_LAUNCHERS_ONLY
 
 }  // extern "C"

@@ -420,3 +420,74 @@ def test_every_launch_is_counted():
     sim.step(10, w.dt)
     sim.sync()
     assert _lib.lib().hns_launch_count() == 1 + 1 + 2 * 10 + 1 + 1  # advect_vector, divergence, 10 x (red, black), gradient, advect_scalars
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the drop-in: the reference's own seven symbols (compat/libhns_compat.so) driven by the same C++ caller code as the reference
+# ------------------------------------------------------------------------------------------------------------------
+needs_compat = pytest.mark.skipif(not (O.compat_driver_available() and O.ref_gpu_available()), reason="compat driver / reference build not present")
+
+
+def _drive(which, w, fields, iterations):
+    """CreateIndexGrid + Compute_Sim + the four stand-alone launchers through the reference's C++ signatures."""
+    out = {}
+    with O.reference_library(which):
+        d = O.RefData(w.coords)
+        d.add_vec3("vel", w.velocity)
+        for k, v in fields.items():
+            d.add_float(k, v)
+        g = O.RefGrid(d, w.voxel_size)
+        out["nanovdb"] = g.buffer()
+        O.ref_compute_sim(d, g, iterations, w.dt, w.voxel_size, PARAMS6, False)
+        out["sim_vel"] = d.blocks["vel"].copy()
+        for k in fields:
+            out["sim_" + k] = d.blocks[k].copy()
+        d = O.RefData(w.coords)
+        d.add_vec3("vel", w.velocity)
+        for n, s in zip(w.scalar_names, w.scalars):
+            d.add_float(n, s)
+        O.ref_advect_index_grid(d, w.dt, w.voxel_size)
+        for n in w.scalar_names:
+            out["adv_" + n] = d.blocks[n].copy()
+        d = O.RefData(w.coords)
+        d.add_vec3("vel", w.velocity)
+        O.ref_advect_index_grid_velocity(d, w.dt, w.voxel_size)
+        out["advvel"] = d.blocks["vel"].copy()
+        d = O.RefData(w.coords)
+        d.add_vec3("vel", w.velocity)
+        O.ref_project_non_divergent(d, iterations, w.voxel_size)
+        out["proj"] = d.blocks["vel"].copy()
+        d = O.RefData(w.coords)
+        d.add_vec3("vel", w.velocity)
+        d.add_float("divergence", np.zeros(w.num_voxels, np.float32))
+        O.ref_divergence(d, w.voxel_size)
+        out["div"] = d.blocks["divergence"].copy()
+    return out
+
+
+@needs_compat
+def test_compat_library_is_a_drop_in_for_the_reference_launchers(case):
+    w = case
+    fields = dict(density=w.scalars[0], **_combustion_fields(w.num_voxels))
+    ref = _drive("reference", w, fields, 7)
+    mine = _drive("compat", w, fields, 7)
+    T = int(np.frombuffer(ref["nanovdb"][672 + 40:672 + 44].tobytes(), np.uint32)[0])
+    assert ref["nanovdb"].size == mine["nanovdb"].size
+    assert not ((ref["nanovdb"] != mine["nanovdb"]) & nanovdb_compare_mask(ref["nanovdb"].size, T)).any()
+    for k in ref:
+        if k != "nanovdb":
+            assert_close(mine[k], ref[k], k)
+
+
+@needs_compat
+def test_compat_library_throws_the_reference_exception_types():
+    w = synth.random_leaves(4, 2, 1, S=1)
+    with O.reference_library("compat"):
+        d = O.RefData(w.coords)
+        d.add_vec3("vel", w.velocity)
+        d.add_float("density", w.scalars[0])
+        g = O.RefGrid(d, w.voxel_size)
+        with pytest.raises(RuntimeError, match="Missing required input field for combustion"):
+            O.ref_compute_sim(d, g, 4, w.dt, w.voxel_size, PARAMS6, False)
+        with pytest.raises(RuntimeError, match="voxelSize must be positive"):
+            O.ref_compute_sim(d, g, 4, w.dt, 0.0, PARAMS6, False)
