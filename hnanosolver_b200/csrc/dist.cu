@@ -1,0 +1,221 @@
+// Spatially sharded frame, one process per GPU: the whole frame with its ghost-leaf exchanges as ONE library call, NCCL issued
+// from C++ on the same stream as the kernels (no Python between the launches: a pressure half-sweep takes ~60 us, a round trip
+// through the interpreter per exchange more than that).
+//
+// The reference is single-GPU (no NCCL/MPI anywhere); this is new code. The decomposition itself -- contiguous
+// ranges of the NanoVDB-ordered leaf list, 26-neighbour ghost leaves, per-peer send/recv leaf lists -- is computed on the host
+// (hnanosolver_b200/dist.py::make_plan) and handed in through hns_dist_set_plan.
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2") so that libhns_b200.so has no link-time dependency on it and shares the
+// NCCL instance torch has already loaded in the same process.
+#include <dlfcn.h>
+
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace hns {
+
+// ---- minimal NCCL binding ------------------------------------------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+struct ncclUniqueId {
+	char internal[128];
+};
+enum { ncclSuccess = 0 };
+enum { ncclFloat = 7 };  // ncclFloat32
+struct Nccl {
+	void* lib = nullptr;
+	int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	int (*CommDestroy)(ncclComm_t) = nullptr;
+	int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+};
+static Nccl g_nccl;
+static int load_nccl() {
+	if (g_nccl.lib) return HNS_OK;
+	void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) return fail(HNS_ERR_RUNTIME, std::string("cannot load NCCL: ") + dlerror());
+#define HNS_SYM(field, name)                                                                 \
+	*reinterpret_cast<void**>(&g_nccl.field) = dlsym(h, name);                               \
+	if (!g_nccl.field) return fail(HNS_ERR_RUNTIME, std::string("NCCL symbol missing: ") + name);
+	HNS_SYM(GetUniqueId, "ncclGetUniqueId")
+	HNS_SYM(CommInitRank, "ncclCommInitRank")
+	HNS_SYM(CommDestroy, "ncclCommDestroy")
+	HNS_SYM(Send, "ncclSend")
+	HNS_SYM(Recv, "ncclRecv")
+	HNS_SYM(Broadcast, "ncclBroadcast")
+	HNS_SYM(GroupStart, "ncclGroupStart")
+	HNS_SYM(GroupEnd, "ncclGroupEnd")
+	HNS_SYM(GetErrorString, "ncclGetErrorString")
+#undef HNS_SYM
+	g_nccl.lib = h;
+	return HNS_OK;
+}
+#define HNS_NCCL(call)                                                                                              \
+	do {                                                                                                            \
+		const int r_ = (call);                                                                                      \
+		if (r_ != ncclSuccess) return ::hns::fail(HNS_ERR_RUNTIME, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+	} while (0)
+
+}  // namespace hns
+
+using namespace hns;
+
+struct hns_dist {
+	ncclComm_t comm = nullptr;
+	int rank = 0, world = 1;
+	struct Peer {
+		int rank;
+		uint64_t n_send, n_recv;
+		int32_t *d_send = nullptr, *d_recv = nullptr;  // local leaf ids
+		float *buf_send = nullptr, *buf_recv = nullptr;
+	};
+	std::vector<Peer> peers;
+	int max_fields = 0;
+	float* d_elem0 = nullptr;
+	uint64_t bytes_sent = 0, exchanges = 0;
+};
+
+static int floats_per_leaf(int field) { return (field >= 6 && field <= 9) ? 256 : 512; }
+
+extern "C" {
+
+int hns_dist_unique_id(uint8_t* out128) {
+	if (!out128) return fail(HNS_ERR_INVALID_ARGUMENT, "null argument");
+	int rc = load_nccl();
+	if (rc) return rc;
+	ncclUniqueId id;
+	HNS_NCCL(g_nccl.GetUniqueId(&id));
+	std::memcpy(out128, id.internal, 128);
+	return HNS_OK;
+}
+
+int hns_dist_create(const uint8_t* id128, int rank, int world, hns_dist** out) {
+	if (!id128 || !out || world < 1 || rank < 0 || rank >= world) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	int rc = load_nccl();
+	if (rc) return rc;
+	auto* d = new hns_dist();
+	d->rank = rank, d->world = world;
+	ncclUniqueId id;
+	std::memcpy(id.internal, id128, 128);
+	const int r = g_nccl.CommInitRank(&d->comm, world, id, rank);
+	if (r != ncclSuccess) {
+		delete d;
+		return fail(HNS_ERR_RUNTIME, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+	}
+	*out = d;
+	return HNS_OK;
+}
+
+void hns_dist_destroy(hns_dist* d) {
+	if (!d) return;
+	for (auto& p : d->peers) cudaFree(p.d_send), cudaFree(p.d_recv), cudaFree(p.buf_send), cudaFree(p.buf_recv);
+	cudaFree(d->d_elem0);
+	if (d->comm) g_nccl.CommDestroy(d->comm);
+	delete d;
+}
+
+int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ranks, const uint64_t* n_send, const int32_t* const* send_ids,
+                      const uint64_t* n_recv, const int32_t* const* recv_ids) {
+	if (!d || !s || n_peers < 0) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	for (auto& p : d->peers) cudaFree(p.d_send), cudaFree(p.d_recv), cudaFree(p.buf_send), cudaFree(p.buf_recv);
+	d->peers.clear();
+	d->max_fields = 3 + s->n_scalars;
+	for (int i = 0; i < n_peers; ++i) {
+		hns_dist::Peer p{};
+		p.rank = peer_ranks[i], p.n_send = n_send[i], p.n_recv = n_recv[i];
+		if (p.n_send) {
+			HNS_CUDA(cudaMalloc(&p.d_send, p.n_send * sizeof(int32_t)));
+			HNS_CUDA(cudaMemcpy(p.d_send, send_ids[i], p.n_send * sizeof(int32_t), cudaMemcpyHostToDevice));
+			HNS_CUDA(cudaMalloc(&p.buf_send, p.n_send * 512 * sizeof(float) * d->max_fields));
+		}
+		if (p.n_recv) {
+			HNS_CUDA(cudaMalloc(&p.d_recv, p.n_recv * sizeof(int32_t)));
+			HNS_CUDA(cudaMemcpy(p.d_recv, recv_ids[i], p.n_recv * sizeof(int32_t), cudaMemcpyHostToDevice));
+			HNS_CUDA(cudaMalloc(&p.buf_recv, p.n_recv * 512 * sizeof(float) * d->max_fields));
+		}
+		d->peers.push_back(p);
+	}
+	if (!d->d_elem0) HNS_CUDA(cudaMalloc(&d->d_elem0, 32 * sizeof(float)));
+	s->elem0 = d->d_elem0;
+	return HNS_OK;
+}
+
+// pack -> grouped send/recv -> unpack of the given fields' ghost bricks, all on `stream`
+int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields, void* stream) {
+	if (!d || !s || n_fields <= 0 || n_fields > d->max_fields) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	for (auto& p : d->peers) {
+		uint64_t off = 0;
+		for (int k = 0; k < n_fields && p.n_send; ++k) {
+			const int fpl = floats_per_leaf(fields[k]);
+			float* f = static_cast<float*>(hns_state_field_device_ptr(s, fields[k]));
+			if (!f) return fail(HNS_ERR_INVALID_ARGUMENT, "bad field id");
+			launch_pack_leaves(f, p.d_send, p.n_send, p.buf_send + off, fpl, st);
+			off += p.n_send * fpl;
+		}
+	}
+	HNS_NCCL(g_nccl.GroupStart());
+	for (auto& p : d->peers) {
+		uint64_t cs = 0, cr = 0;
+		for (int k = 0; k < n_fields; ++k) cs += p.n_send * floats_per_leaf(fields[k]), cr += p.n_recv * floats_per_leaf(fields[k]);
+		if (cs) HNS_NCCL(g_nccl.Send(p.buf_send, cs, ncclFloat, p.rank, d->comm, st));
+		if (cr) HNS_NCCL(g_nccl.Recv(p.buf_recv, cr, ncclFloat, p.rank, d->comm, st));
+		d->bytes_sent += cs * 4;
+	}
+	HNS_NCCL(g_nccl.GroupEnd());
+	for (auto& p : d->peers) {
+		uint64_t off = 0;
+		for (int k = 0; k < n_fields && p.n_recv; ++k) {
+			const int fpl = floats_per_leaf(fields[k]);
+			float* f = static_cast<float*>(hns_state_field_device_ptr(s, fields[k]));
+			launch_unpack_leaves(f, p.d_recv, p.n_recv, p.buf_recv + off, fpl, st);
+			off += p.n_recv * fpl;
+		}
+	}
+	++d->exchanges;
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+
+// The sharded frame: Compute()'s step order (reference src/Cuda/HNanoSolver.cu:159-356) with a ghost exchange in front of every step
+// that reads a neighbour leaf. Asynchronous on `stream`.
+int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream) {
+	if (!d || !s || iterations <= 0 || dt < 0.f) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	int rc;
+	const int fvel[3] = {0, 1, 2}, fadv[3] = {3, 4, 5}, fred[1] = {6}, fblk[1] = {7};
+	if ((rc = hns_dist_exchange(d, s, 3, fvel, stream))) return rc;
+	if ((rc = hns_state_advect_velocity(s, dt, stream))) return rc;
+	if ((rc = hns_dist_exchange(d, s, 3, fadv, stream))) return rc;
+	if ((rc = hns_state_divergence(s, 1, stream))) return rc;
+	if (s->comb_enabled && (rc = hns_state_combustion_buoyancy(s, dt, stream))) return rc;
+	if ((rc = hns_state_pressure_init(s, stream))) return rc;
+	const float omega = hns_omega_compute(s->grid->voxel_size);
+	for (int it = 0; it < iterations; ++it) {
+		if ((rc = hns_state_pressure_half_sweep(s, 0, omega, 0, stream))) return rc;
+		if ((rc = hns_dist_exchange(d, s, 1, fred, stream))) return rc;
+		if ((rc = hns_state_pressure_half_sweep(s, 1, omega, 1, stream))) return rc;
+		if ((rc = hns_dist_exchange(d, s, 1, fblk, stream))) return rc;
+	}
+	if ((rc = hns_state_subtract_gradient(s, 1, stream))) return rc;
+	std::vector<int> last = {0, 1, 2};
+	for (int i = 0; i < s->n_scalars; ++i) last.push_back(10 + i);
+	if ((rc = hns_dist_exchange(d, s, int(last.size()), last.data(), stream))) return rc;
+	// advect_scalars' "inactive -> element 0" value is global voxel 0's (reference Kernel.cu:192,225): rank 0 owns it
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (d->rank == 0 && (rc = hns_state_gather_element0(s, d->d_elem0, stream))) return rc;
+	if (d->world > 1) HNS_NCCL(g_nccl.Broadcast(d->d_elem0, d->d_elem0, size_t(3 + s->n_scalars), ncclFloat, 0, d->comm, st));
+	return hns_state_advect_scalars(s, dt, 0, stream);
+}
+
+uint64_t hns_dist_bytes_sent(const hns_dist* d) { return d ? d->bytes_sent : 0; }
+uint64_t hns_dist_exchanges(const hns_dist* d) { return d ? d->exchanges : 0; }
+
+}  // extern "C"

@@ -162,11 +162,19 @@ class HaloExchanger:
 # GPU driver
 # ------------------------------------------------------------------------------------------------------------------
 class ShardedSimulation:
-    """Device-resident state of this rank's shard (owned + ghost leaves) and the frame with ghost exchanges."""
+    """Device-resident state of this rank's shard (owned + ghost leaves) and the frame with ghost exchanges.
 
-    def __init__(self, plan: ShardPlan, local_origins: np.ndarray, voxel_size: float, n_scalars: int, device):
+    native=True (default): the frame is ONE call into libhns_b200 (hns_dist_frame): kernels and NCCL send/recv are issued from
+    C++ on one stream. native=False drives the same steps from Python through HaloExchanger / torch.distributed (slower: a
+    trip through the interpreter per exchange); kept as an independent cross-check."""
+
+    def __init__(self, plan: ShardPlan, local_origins: np.ndarray, voxel_size: float, n_scalars: int, device, native: bool = True):
+        import ctypes as C
+
         import torch
+        import torch.distributed as tdist
 
+        from . import _lib
         from . import launchers as H
 
         self.plan, self.device = plan, device
@@ -176,22 +184,68 @@ class ShardedSimulation:
         self.n_scalars = n_scalars
         self.omega = H.omega_compute(voxel_size)
         self.full = False
+        self.native = native
         self._torch = torch
 
         def stream():
             return torch.cuda.current_stream(device).cuda_stream
 
-        def pack(field, ids, out):
-            self.sim.pack_leaves(field, ids.data_ptr(), ids.numel(), out.data_ptr(), stream())
-
-        def unpack(field, ids, src):
-            self.sim.unpack_leaves(field, ids.data_ptr(), ids.numel(), src.data_ptr(), stream())
-
-        self.ex = HaloExchanger(plan, device, pack, unpack, max_fields=3 + n_scalars)
         self._stream = stream
-        # element 0 of the global arrays (the "inactive" value of advect_scalars, reference Kernel.cu:192,225): owned by rank 0
-        self.elem0 = torch.zeros(3 + n_scalars, dtype=torch.float32, device=device)
-        self.sim.set_element0(self.elem0.data_ptr())
+        self._dist = None
+        if native:
+            L = _lib.lib()
+            uid = (C.c_uint8 * 128)()
+            if plan.rank == 0:
+                _lib.check(L.hns_dist_unique_id(uid))
+            box = [bytes(uid)]
+            if plan.world > 1:
+                tdist.broadcast_object_list(box, src=0)
+            uid = (C.c_uint8 * 128).from_buffer_copy(box[0])
+            h = C.c_void_p()
+            _lib.check(L.hns_dist_create(uid, plan.rank, plan.world, C.byref(h)))
+            self._dist = h
+            peers = sorted(set(plan.send) | set(plan.recv))
+            n = len(peers)
+            empty = np.zeros(0, np.int32)
+            snd = [np.ascontiguousarray(plan.send.get(p, empty), np.int32) for p in peers]
+            rcv = [np.ascontiguousarray(plan.recv.get(p, empty), np.int32) for p in peers]
+            self._keep = (snd, rcv)
+            _lib.check(L.hns_dist_set_plan(
+                h, self.sim._h, n, (C.c_int * max(n, 1))(*peers), (C.c_uint64 * max(n, 1))(*[len(a) for a in snd]),
+                (_lib.c_i32p * max(n, 1))(*[a.ctypes.data_as(_lib.c_i32p) for a in snd]), (C.c_uint64 * max(n, 1))(*[len(a) for a in rcv]),
+                (_lib.c_i32p * max(n, 1))(*[a.ctypes.data_as(_lib.c_i32p) for a in rcv])))
+            self.ex = None
+        else:
+            def pack(field, ids, out):
+                self.sim.pack_leaves(field, ids.data_ptr(), ids.numel(), out.data_ptr(), stream())
+
+            def unpack(field, ids, src):
+                self.sim.unpack_leaves(field, ids.data_ptr(), ids.numel(), src.data_ptr(), stream())
+
+            self.ex = HaloExchanger(plan, device, pack, unpack, max_fields=3 + n_scalars)
+            # element 0 of the global arrays (the "inactive" value of advect_scalars, reference Kernel.cu:192,225): owned by rank 0
+            self.elem0 = torch.zeros(3 + n_scalars, dtype=torch.float32, device=device)
+            self.sim.set_element0(self.elem0.data_ptr())
+
+    def close(self):
+        if self._dist is not None:
+            from . import _lib
+
+            self._torch.cuda.synchronize()
+            _lib.lib().hns_dist_destroy(self._dist)
+            self._dist = None
+
+    @property
+    def exchanges(self) -> int:
+        from . import _lib
+
+        return int(_lib.lib().hns_dist_exchanges(self._dist)) if self.native else self.ex.exchanges
+
+    @property
+    def bytes_sent(self) -> int:
+        from . import _lib
+
+        return int(_lib.lib().hns_dist_bytes_sent(self._dist)) if self.native else self.ex.bytes_sent
 
     def set_combustion(self, names, params):
         self.sim.set_combustion(True, names.index("fuel"), names.index("waste"), names.index("temperature"), names.index("flame"), params)
@@ -201,6 +255,13 @@ class ShardedSimulation:
         self.sim.upload(velocity, scalars)
 
     def frame(self, iterations: int, dt: float) -> None:
+        if self.native:
+            import ctypes as C
+
+            from . import _lib
+
+            _lib.check(_lib.lib().hns_dist_frame(self._dist, self.sim._h, iterations, dt, C.c_void_p(self._stream())))
+            return
         s, ex, st = self.sim, self.ex, self._stream()
         ex.exchange(F_VEL)
         s.advect_velocity(dt, st)
@@ -302,7 +363,7 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = torch.tensor([float(_lib.lib().hns_launch_count())], device=dev)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-    owned = torch.tensor([float(plan.n_owned * 512), float(plan.n_local * 512), float(sh.ex.bytes_sent)], device=dev)
+    owned = torch.tensor([float(plan.n_owned * 512), float(plan.n_local * 512), float(sh.bytes_sent)], device=dev)
     dist.all_reduce(owned, op=dist.ReduceOp.SUM)
     ms_step = float(ms.item()) / args.steps
     n_owned_total, n_local_total = int(owned[0].item()), int(owned[1].item())
@@ -336,7 +397,7 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"c4 weak scaling: sparse smoke ~30% of a {box[0]}x{box[1]}x{box[2]} box, {n_owned_total} active voxels over "
                                    f"{world} GPUs (+{n_local_total - n_owned_total} ghost voxels), frame=full, I={iterations}, S={S}",
-                       "parallelism": f"spatial leaf-range sharding x{world}, NCCL ghost-leaf exchange ({sh.ex.exchanges // (args.steps + args.warmup + args.e2e_steps + 1)} exchanges/frame)",
+                       "parallelism": f"spatial leaf-range sharding x{world}, NCCL ghost-leaf exchange issued from C++ on the compute stream ({sh.exchanges // (args.steps + args.warmup + args.e2e_steps + 1)} exchanges/frame)",
                        "l2": "per-rank fields larger than L2; no flush"},
             "e2e": {"value": n_owned_total / (float(e2e.item()) * 1e-3), "unit": "voxel-updates/s", "ms_per_step": float(e2e.item()),
                     "h2d_bytes_per_step": int(n_local_total * (12 + 4 * S)), "d2h_bytes_per_step": int(n_local_total * (12 + 4 * S)),

@@ -170,6 +170,26 @@ int hns_state_pack_leaves(hns_state* s, int field, const int32_t* leaf_ids_dev, 
 int hns_state_unpack_leaves(hns_state* s, int field, const int32_t* leaf_ids_dev, uint64_t n_ids, const float* src_dev, void* stream);
 void* hns_state_field_device_ptr(hns_state* s, int field);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Spatially sharded runs (one process per GPU). New: the reference is single-GPU. The partition (contiguous leaf ranges of the
+ * NanoVDB-ordered leaf list + 26-neighbour ghost leaves) is computed by the caller; a rank's hns_grid / hns_state cover its owned
+ * + ghost leaves. NCCL (bound at run time) carries the ghost bricks on the same stream as the kernels.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct hns_dist hns_dist;
+int hns_dist_unique_id(uint8_t* out128);                                  /* rank 0: ncclGetUniqueId; ship the 128 bytes to all ranks */
+int hns_dist_create(const uint8_t* id128, int rank, int world, hns_dist** out); /* ncclCommInitRank on the current device */
+void hns_dist_destroy(hns_dist* d);
+/* per peer: LOCAL leaf ids (HOST arrays) of the owned leaves it holds as ghosts (send) and of the ghost leaves it owns (recv),
+ * both in ascending global leaf order so that the two sides agree. Installs the element-0 override on `s`. */
+int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ranks, const uint64_t* n_send, const int32_t* const* send_ids,
+                      const uint64_t* n_recv, const int32_t* const* recv_ids);
+/* ghost exchange of the given fields (ids as for hns_state_pack_leaves): pack, grouped ncclSend/ncclRecv, unpack; asynchronous */
+int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields, void* stream);
+/* the whole sharded frame (same steps as hns_state_step) with its 3 + 2*iterations ghost exchanges; asynchronous */
+int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream);
+uint64_t hns_dist_bytes_sent(const hns_dist* d);
+uint64_t hns_dist_exchanges(const hns_dist* d);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,8 @@ lo = (np.repeat(plan.local_ids, 512) * 512 + np.tile(np.arange(512), plan.n_loca
 comb = synth.combustion_fields(wg)
 names = ["density", "fuel", "waste", "temperature", "flame"]
 gfields = [wg.scalars[0]] + [comb[k] for k in names[1:]]
-sh = hdist.ShardedSimulation(plan, np.ascontiguousarray(go[plan.local_ids]), wg.voxel_size, 5, torch.device("cuda", lr))
+sh = hdist.ShardedSimulation(plan, np.ascontiguousarray(go[plan.local_ids]), wg.voxel_size, 5, torch.device("cuda", lr),
+                             native=not int(os.environ.get("PY_EXCHANGE", "0")))
 P = H.CombustionParams(0.5, 2.0, 1.5, 0.1, 0.0, 1.0)
 if not int(os.environ.get("NO_COMB", "0")): sh.set_combustion(names, P)
 sh.upload(wg.velocity[lo], [f[lo] for f in gfields])
@@ -48,6 +49,7 @@ if rank == 0:
         bad = np.nonzero((got != ref[k]).reshape(got.shape[0], -1).any(1))[0]
         print(f"  {nm:12s} sharded({world}) == single GPU bitwise: {same}  mismatching voxels {bad.size}/{got.shape[0]} "
               f"max|diff| {np.abs(got.astype(np.float64) - ref[k]).max():.3e} first leaves {np.unique(bad // 512)[:8]}")
-    print("SHARDED PARITY", "OK" if ok else "FAILED", f"leaves={go.shape[0]} exchanges/frame={sh.ex.exchanges // NF}", flush=True)
+    print("SHARDED PARITY", "OK" if ok else "FAILED", f"leaves={go.shape[0]} exchanges/frame={sh.exchanges // NF} native={sh.native}", flush=True)
 dist.barrier()
+sh.close()
 dist.destroy_process_group()
