@@ -79,7 +79,7 @@ SIGNATURES = {
     "hns_dist_create": (C.c_int, [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "hns_dist_destroy": (None, [C.c_void_p]),
     "hns_dist_set_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(c_i32p),
-                                    C.POINTER(C.c_uint64), C.POINTER(c_i32p)]),
+                                    C.POINTER(C.c_uint64), C.POINTER(c_i32p), C.c_uint64, c_i32p]),
     "hns_dist_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "hns_dist_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "hns_dist_bytes_sent": (C.c_uint64, [C.c_void_p]),

@@ -32,7 +32,7 @@ static inline float omega_compute(float voxelSize) { return 2.0f / (1.0f + sinf(
 static inline float omega_project(float voxelSize) { return float(2.0f / (1.0f + sin(3.14159 * voxelSize))); }
 
 static int pressure_solve(hns_state* s, int iterations, float dx, float omega, unsigned flags, cudaStream_t st) {
-	const GridView& g = s->grid->view;
+	const GridView g = s->view();
 	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, (s->n / 2) * sizeof(float), st));  // initial guess 0 (HNanoSolver.cu:113)
 	HNS_CUDA(cudaMemsetAsync(s->p[1], 0, (s->n / 2) * sizeof(float), st));
 	const bool alternate = !(flags & 2u);  // red sweeps walk the leaves front to back, black sweeps back to front (L2 reuse)
@@ -55,7 +55,7 @@ static ScalarPtrs scalar_ptrs(const hns_state* s) {
 // `voxel_size` is the launcher argument (the reference's kernels use it, not the grid's map).
 static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsigned flags, cudaStream_t st, cudaEvent_t ev_p0 = nullptr,
                  cudaEvent_t ev_p1 = nullptr) {
-	const GridView& g = s->grid->view;
+	const GridView g = s->view();
 	const float h = voxel_size, inv = 1.0f / h;
 	launch_advect_vector(g, s->vel, s->adv, dt, inv, st);
 	launch_divergence(g, s->adv, s->div, inv, st);
@@ -225,13 +225,13 @@ int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void*
 }
 int hns_state_advect_velocity(hns_state* s, float dt, void* stream) {
 	HNS_REQUIRE(s, "null state");
-	launch_advect_vector(s->grid->view, s->vel, s->adv, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream));
+	launch_advect_vector(s->view(), s->vel, s->adv, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
 int hns_state_divergence(hns_state* s, int of_advected, void* stream) {
 	HNS_REQUIRE(s, "null state");
-	launch_divergence(s->grid->view, of_advected ? s->adv : s->vel, s->div, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream));
+	launch_divergence(s->view(), of_advected ? s->adv : s->vel, s->div, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
@@ -252,7 +252,7 @@ int hns_state_pressure_init(hns_state* s, void* stream) {
 }
 int hns_state_pressure_half_sweep(hns_state* s, int color, float omega, int reverse, void* stream) {
 	HNS_REQUIRE(s && (color == 0 || color == 1), "bad argument");
-	launch_rbgs_color(s->grid->view, s->div, s->p, s->grid->voxel_size, color, omega, reverse, static_cast<cudaStream_t>(stream));
+	launch_rbgs_color(s->view(), s->div, s->p, s->grid->voxel_size, color, omega, reverse, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
@@ -275,10 +275,10 @@ int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream) {
 	HNS_REQUIRE(s, "null state");
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if (from_advected) {
-		launch_subtract_gradient(s->grid->view, s->adv, s->p, s->vel, 1.0f / s->grid->voxel_size, st);
+		launch_subtract_gradient(s->view(), s->adv, s->p, s->vel, 1.0f / s->grid->voxel_size, st);
 	} else {
 		// in place is safe: every thread reads only its own velocity row (the reference does the same, PressureProjection.cu:64)
-		launch_subtract_gradient(s->grid->view, s->vel, s->p, s->vel, 1.0f / s->grid->voxel_size, st);
+		launch_subtract_gradient(s->view(), s->vel, s->p, s->vel, 1.0f / s->grid->voxel_size, st);
 	}
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
@@ -286,7 +286,7 @@ int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream) {
 int hns_state_advect_scalars(hns_state* s, float dt, int sampler_semantics, void* stream) {
 	HNS_REQUIRE(s, "null state");
 	if (!s->n_scalars || !s->n) return HNS_OK;
-	launch_advect_scalars(s->grid->view, s->vel, scalar_ptrs(s), s->n_scalars, dt, 1.0f / s->grid->voxel_size, sampler_semantics, s->elem0,
+	launch_advect_scalars(s->view(), s->vel, scalar_ptrs(s), s->n_scalars, dt, 1.0f / s->grid->voxel_size, sampler_semantics, s->elem0,
 	                      static_cast<cudaStream_t>(stream));
 	for (int i = 0; i < s->n_scalars; ++i) std::swap(s->sc[i], s->sc_out[i]);
 	HNS_CUDA(cudaGetLastError());

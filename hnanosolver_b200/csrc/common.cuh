@@ -48,6 +48,14 @@ struct GridView {
 	uint32_t num_leaves;
 	uint32_t num_tiles;
 	uint64_t off_root, off_leaf;  // byte offsets of RootData and of the first leaf inside nvdb
+	// optional work list: when set, a launch processes leaves list[0..num_list) instead of 0..num_leaves (sharded runs: owned leaves
+	// only, or the boundary / interior split that lets a ghost exchange overlap the interior sweep)
+	const int32_t* list;
+	uint32_t num_list;
+	__host__ __device__ uint32_t count() const { return list ? num_list : num_leaves; }
+#ifdef __CUDACC__
+	__device__ __forceinline__ uint32_t leaf_at(uint32_t i) const { return list ? uint32_t(__ldg(list + i)) : i; }
+#endif
 };
 
 // slot ids of the six face neighbours
@@ -108,4 +116,11 @@ struct hns_state {
 	hns_combustion_params comb{};
 	int skip_scalar = -1;  // scalar that is carried but not advected ("collision_sdf")
 	const float* elem0 = nullptr;  // device float[3 + n_scalars]: element 0 of the global arrays (sharded runs), else null
+	const int32_t* active = nullptr;  // device list of the leaves the kernels process (sharded runs: the owned leaves), null = all
+	uint32_t n_active = 0;
+	hns::GridView view() const {
+		hns::GridView v = grid->view;
+		v.list = active, v.num_list = n_active;
+		return v;
+	}
 };

@@ -81,6 +81,11 @@ struct hns_dist {
 	int max_fields = 0;
 	float* d_elem0 = nullptr;
 	uint64_t bytes_sent = 0, exchanges = 0;
+	// work lists (local leaf ids, device): owned = boundary (sent to some peer) + interior
+	int32_t *d_owned = nullptr, *d_boundary = nullptr, *d_interior = nullptr;
+	uint32_t n_owned = 0, n_boundary = 0, n_interior = 0;
+	cudaStream_t comm_stream = nullptr;  // the exchange of a swept colour runs here, next to the interior sweep
+	cudaEvent_t ev_boundary = nullptr, ev_exchanged = nullptr;
 };
 
 static int floats_per_leaf(int field) { return (field >= 6 && field <= 9) ? 256 : 512; }
@@ -117,14 +122,42 @@ int hns_dist_create(const uint8_t* id128, int rank, int world, hns_dist** out) {
 void hns_dist_destroy(hns_dist* d) {
 	if (!d) return;
 	for (auto& p : d->peers) cudaFree(p.d_send), cudaFree(p.d_recv), cudaFree(p.buf_send), cudaFree(p.buf_recv);
-	cudaFree(d->d_elem0);
+	cudaFree(d->d_elem0), cudaFree(d->d_owned), cudaFree(d->d_boundary), cudaFree(d->d_interior);
+	if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
+	if (d->ev_boundary) cudaEventDestroy(d->ev_boundary);
+	if (d->ev_exchanged) cudaEventDestroy(d->ev_exchanged);
 	if (d->comm) g_nccl.CommDestroy(d->comm);
 	delete d;
 }
 
 int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ranks, const uint64_t* n_send, const int32_t* const* send_ids,
-                      const uint64_t* n_recv, const int32_t* const* recv_ids) {
-	if (!d || !s || n_peers < 0) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+                      const uint64_t* n_recv, const int32_t* const* recv_ids, uint64_t n_owned, const int32_t* owned_ids) {
+	if (!d || !s || n_peers < 0 || (n_owned && !owned_ids)) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	{
+		// owned = boundary (in some send list) + interior; kernels then skip the ghost leaves altogether
+		std::vector<char> is_boundary(s->grid->num_leaves, 0);
+		for (int i = 0; i < n_peers; ++i)
+			for (uint64_t k = 0; k < n_send[i]; ++k) is_boundary[send_ids[i][k]] = 1;
+		std::vector<int32_t> bnd, inter;
+		for (uint64_t k = 0; k < n_owned; ++k) (is_boundary[owned_ids[k]] ? bnd : inter).push_back(owned_ids[k]);
+		cudaFree(d->d_owned), cudaFree(d->d_boundary), cudaFree(d->d_interior);
+		d->d_owned = d->d_boundary = d->d_interior = nullptr;
+		d->n_owned = uint32_t(n_owned), d->n_boundary = uint32_t(bnd.size()), d->n_interior = uint32_t(inter.size());
+		auto up = [](const std::vector<int32_t>& v, int32_t** dst) {
+			if (v.empty()) return cudaSuccess;
+			cudaError_t e = cudaMalloc(dst, v.size() * sizeof(int32_t));
+			return e != cudaSuccess ? e : cudaMemcpy(*dst, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+		};
+		HNS_CUDA(up(std::vector<int32_t>(owned_ids, owned_ids + n_owned), &d->d_owned));
+		HNS_CUDA(up(bnd, &d->d_boundary));
+		HNS_CUDA(up(inter, &d->d_interior));
+		s->active = d->d_owned, s->n_active = d->n_owned;
+		if (!d->comm_stream) {
+			HNS_CUDA(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
+			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_boundary, cudaEventDisableTiming));
+			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_exchanged, cudaEventDisableTiming));
+		}
+	}
 	for (auto& p : d->peers) cudaFree(p.d_send), cudaFree(p.d_recv), cudaFree(p.buf_send), cudaFree(p.buf_recv);
 	d->peers.clear();
 	d->max_fields = 3 + s->n_scalars;
@@ -198,11 +231,28 @@ int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* st
 	if (s->comb_enabled && (rc = hns_state_combustion_buoyancy(s, dt, stream))) return rc;
 	if ((rc = hns_state_pressure_init(s, stream))) return rc;
 	const float omega = hns_omega_compute(s->grid->voxel_size);
-	for (int it = 0; it < iterations; ++it) {
-		if ((rc = hns_state_pressure_half_sweep(s, 0, omega, 0, stream))) return rc;
-		if ((rc = hns_dist_exchange(d, s, 1, fred, stream))) return rc;
-		if ((rc = hns_state_pressure_half_sweep(s, 1, omega, 1, stream))) return rc;
-		if ((rc = hns_dist_exchange(d, s, 1, fblk, stream))) return rc;
+	{
+		// Per half-sweep: boundary leaves first, then their freshly swept colour travels to the peers on comm_stream while the
+		// interior leaves are swept on the main stream. The interior sweep reads only the OTHER colour, the exchange moves only
+		// THIS colour, so they do not touch the same data; the next half-sweep (which reads this colour's ghosts) waits for it.
+		cudaStream_t st = static_cast<cudaStream_t>(stream);
+		GridView vb = s->grid->view, vi = s->grid->view;
+		vb.list = d->d_boundary, vb.num_list = d->n_boundary;
+		vi.list = d->d_interior, vi.num_list = d->n_interior;
+		const float dx = s->grid->voxel_size;
+		bool pending = false;
+		for (int it = 0; it < iterations; ++it)
+			for (int color = 0; color < 2; ++color) {
+				if (pending) HNS_CUDA(cudaStreamWaitEvent(st, d->ev_exchanged, 0));
+				if (d->n_boundary) launch_rbgs_color(vb, s->div, s->p, dx, color, omega, color, st);
+				HNS_CUDA(cudaEventRecord(d->ev_boundary, st));
+				if (d->n_interior) launch_rbgs_color(vi, s->div, s->p, dx, color, omega, color, st);
+				HNS_CUDA(cudaStreamWaitEvent(d->comm_stream, d->ev_boundary, 0));
+				if ((rc = hns_dist_exchange(d, s, 1, color ? fblk : fred, d->comm_stream))) return rc;
+				HNS_CUDA(cudaEventRecord(d->ev_exchanged, d->comm_stream));
+				pending = true;
+			}
+		if (pending) HNS_CUDA(cudaStreamWaitEvent(st, d->ev_exchanged, 0));
 	}
 	if ((rc = hns_state_subtract_gradient(s, 1, stream))) return rc;
 	std::vector<int> last = {0, 1, 2};

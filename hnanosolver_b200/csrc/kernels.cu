@@ -63,8 +63,9 @@ struct RowCtx {
 	}
 };
 __device__ __forceinline__ bool make_row_ctx(const GridView& g, RowCtx& c) {
-	const uint32_t leaf = blockIdx.x * (blockDim.x >> 6) + (threadIdx.x >> 6);
-	if (leaf >= g.num_leaves) return false;
+	const uint32_t i = blockIdx.x * (blockDim.x >> 6) + (threadIdx.x >> 6);
+	if (i >= g.count()) return false;
+	const uint32_t leaf = g.leaf_at(i);
 	const int r = threadIdx.x & 63;
 	c.leaf = leaf, c.x = r >> 3, c.y = r & 7, c.nbr = g.nbr + uint64_t(leaf) * 27u;
 	return true;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) k_divergence(GridView g, const float* __r
 	st_split(div_red, div_blk, c, o);
 }
 void launch_divergence(const GridView& g, const float* const vel[3], float* const div[2], float inv_dx, cudaStream_t st) {
-	if (g.num_leaves) HNS_LAUNCH(k_divergence, (g.num_leaves + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], div[0], div[1], inv_dx);
+	if (g.count()) HNS_LAUNCH(k_divergence, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], div[0], div[1], inv_dx);
 }
 
 // =============================================================================================================
@@ -184,8 +185,8 @@ __global__ void __launch_bounds__(256) k_subtract_gradient(GridView g, const flo
 }
 void launch_subtract_gradient(const GridView& g, const float* const vel[3], const float* const p[2], float* const out[3], float inv_dx,
                               cudaStream_t st) {
-	if (g.num_leaves)
-		HNS_LAUNCH(k_subtract_gradient, (g.num_leaves + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], p[0], p[1], out[0], out[1], out[2], inv_dx);
+	if (g.count())
+		HNS_LAUNCH(k_subtract_gradient, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], p[0], p[1], out[0], out[1], out[2], inv_dx);
 }
 
 // =============================================================================================================
@@ -210,9 +211,10 @@ __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __r
                                                     const float* __restrict__ p_o, float dx2, int color, float omega, int reverse) {
 	RowCtx c;
 	{
-		uint32_t leaf = blockIdx.x * 4u + (threadIdx.x >> 6);
-		if (leaf >= g.num_leaves) return;
-		if (reverse) leaf = g.num_leaves - 1u - leaf;
+		uint32_t i = blockIdx.x * 4u + (threadIdx.x >> 6);
+		if (i >= g.count()) return;
+		if (reverse) i = g.count() - 1u - i;
+		const uint32_t leaf = g.leaf_at(i);
 		const int r = threadIdx.x & 63;
 		c.leaf = leaf, c.x = r >> 3, c.y = r & 7, c.nbr = g.nbr + uint64_t(leaf) * 27u;
 	}
@@ -246,8 +248,8 @@ __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __r
 }
 void launch_rbgs_color(const GridView& g, const float* const div[2], float* const p[2], float dx, int color, float omega, int reverse,
                        cudaStream_t st) {
-	if (g.num_leaves)
-		HNS_LAUNCH(k_rbgs_split, (g.num_leaves + 3) / 4, 256, 0, st, g, div[color], p[color], p[color ^ 1], dx * dx, color, omega, reverse);
+	if (g.count())
+		HNS_LAUNCH(k_rbgs_split, (g.count() + 3) / 4, 256, 0, st, g, div[color], p[color], p[color ^ 1], dx * dx, color, omega, reverse);
 }
 
 int upload_tables() { return HNS_OK; }
@@ -388,11 +390,11 @@ __device__ __forceinline__ LeafFrame leaf_frame(const GridView& g, uint32_t leaf
 	const int4 o = __ldg(g.origin + leaf);
 	return LeafFrame{o.x, o.y, o.z, g.nbr + uint64_t(leaf) * 27u};
 }
-// leaves [first, last) of this CTA
+// work items [first, last) of this CTA (indices into the launch's leaf list, see GridView::leaf_at)
 __device__ __forceinline__ bool cta_leaf_range(const GridView& g, uint32_t& first, uint32_t& last) {
-	const uint32_t per = (g.num_leaves + gridDim.x - 1) / gridDim.x;
+	const uint32_t per = (g.count() + gridDim.x - 1) / gridDim.x;
 	first = blockIdx.x * per;
-	last = min(first + per, g.num_leaves);
+	last = min(first + per, g.count());
 	return first < last;
 }
 
@@ -418,8 +420,8 @@ __global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const floa
 	if (!cta_leaf_range(g, first, last)) return;
 	const int x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
 	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
-	auto issue = [&](uint32_t leaf, int buf) {
-		const StagePlan plan = make_stage_plan(g.nbr + uint64_t(leaf) * 27u);
+	auto issue = [&](uint32_t item, int buf) {
+		const StagePlan plan = make_stage_plan(g.nbr + uint64_t(g.leaf_at(item)) * 27u);
 		float* r = region + buf * kStageFloats;
 		stage_region(plan, u, r, 0.f);
 		stage_region(plan, v, r + kRegionFloats, 0.f);
@@ -427,16 +429,17 @@ __global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const floa
 		cp_async_commit();
 	};
 	issue(first, 0);
-	for (uint32_t leaf = first; leaf < last; ++leaf) {
-		const int buf = (leaf - first) & 1;
-		if (leaf + 1 < last) {
-			issue(leaf + 1, buf ^ 1);
+	for (uint32_t item = first; item < last; ++item) {
+		const int buf = (item - first) & 1;
+		if (item + 1 < last) {
+			issue(item + 1, buf ^ 1);
 			cp_async_wait<1>();
 		} else {
 			cp_async_wait<0>();
 		}
 		__syncthreads();
 		const float *ru = region + buf * kStageFloats, *rv = ru + kRegionFloats, *rw = ru + 2 * kRegionFloats;
+		const uint32_t leaf = g.leaf_at(item);
 		const LeafFrame f = leaf_frame(g, leaf);
 		const uint64_t self = uint64_t(leaf) * 512u + threadIdx.x;
 		const int ci = f.ox + x, cj = f.oy + y, ck = f.oz + z;
@@ -475,7 +478,7 @@ static int advect_grid(uint32_t num_leaves) {
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 		if (sms <= 0) sms = 148;
 	}
-	return int(min(uint32_t(2 * sms), num_leaves));
+	return int(min(uint32_t(2 * sms), num_leaves));  // num_leaves = work items of the launch
 }
 template <typename K>
 static void advect_attrs(K kernel) {
@@ -483,10 +486,10 @@ static void advect_attrs(K kernel) {
 	cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st) {
-	if (!g.num_leaves) return;
+	if (!g.count()) return;
 	static bool attr = false;
 	if (!attr) advect_attrs(k_advect_vector), attr = true;
-	HNS_LAUNCH(k_advect_vector, advect_grid(g.num_leaves), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], dt * inv_dx);
+	HNS_LAUNCH(k_advect_vector, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], dt * inv_dx);
 }
 
 // advect_scalars (Kernel.cu:118-266) [kSemantics 0]: explicit corner weights, fma accumulation in corner order
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 	const int jobs_per_leaf = 1 + (S + 2) / 3;
 	const int n_jobs = int(last - first) * jobs_per_leaf;
 	auto issue = [&](int job) {
-		const uint32_t leaf = first + uint32_t(job / jobs_per_leaf);
+		const uint32_t leaf = g.leaf_at(first + uint32_t(job / jobs_per_leaf));
 		const int jj = job % jobs_per_leaf;
 		const StagePlan plan = make_stage_plan(g.nbr + uint64_t(leaf) * 27u);
 		float* r = region + (job & 1) * kStageFloats;
@@ -557,7 +560,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 			cp_async_wait<0>();
 		}
 		__syncthreads();
-		const uint32_t leaf = first + uint32_t(job / jobs_per_leaf);
+		const uint32_t leaf = g.leaf_at(first + uint32_t(job / jobs_per_leaf));
 		const int jj = job % jobs_per_leaf;
 		const float* __restrict__ base = region + (job & 1) * kStageFloats;
 		if (jj == 0) {
@@ -644,13 +647,13 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 }
 void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx,
                            int sampler_semantics, const float* elem0, cudaStream_t st) {
-	if (!g.num_leaves || S <= 0) return;
+	if (!g.count() || S <= 0) return;
 	static bool attr = false;
 	if (!attr) advect_attrs(k_advect_scalars<0>), advect_attrs(k_advect_scalars<1>), attr = true;
 	if (sampler_semantics == 0)
-		HNS_LAUNCH(k_advect_scalars<0>, advect_grid(g.num_leaves), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0);
+		HNS_LAUNCH(k_advect_scalars<0>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0);
 	else
-		HNS_LAUNCH(k_advect_scalars<1>, advect_grid(g.num_leaves), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0);
+		HNS_LAUNCH(k_advect_scalars<1>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0);
 }
 
 // element 0 of velocity (x,y,z) and of each scalar field -> dst[3 + S]

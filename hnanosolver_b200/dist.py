@@ -209,11 +209,12 @@ class ShardedSimulation:
             empty = np.zeros(0, np.int32)
             snd = [np.ascontiguousarray(plan.send.get(p, empty), np.int32) for p in peers]
             rcv = [np.ascontiguousarray(plan.recv.get(p, empty), np.int32) for p in peers]
-            self._keep = (snd, rcv)
+            owned = np.ascontiguousarray(np.nonzero(plan.owned_local)[0], np.int32)
+            self._keep = (snd, rcv, owned)
             _lib.check(L.hns_dist_set_plan(
                 h, self.sim._h, n, (C.c_int * max(n, 1))(*peers), (C.c_uint64 * max(n, 1))(*[len(a) for a in snd]),
                 (_lib.c_i32p * max(n, 1))(*[a.ctypes.data_as(_lib.c_i32p) for a in snd]), (C.c_uint64 * max(n, 1))(*[len(a) for a in rcv]),
-                (_lib.c_i32p * max(n, 1))(*[a.ctypes.data_as(_lib.c_i32p) for a in rcv])))
+                (_lib.c_i32p * max(n, 1))(*[a.ctypes.data_as(_lib.c_i32p) for a in rcv]), len(owned), owned.ctypes.data_as(_lib.c_i32p)))
             self.ex = None
         else:
             def pack(field, ids, out):

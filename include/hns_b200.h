@@ -180,12 +180,14 @@ int hns_dist_unique_id(uint8_t* out128);                                  /* ran
 int hns_dist_create(const uint8_t* id128, int rank, int world, hns_dist** out); /* ncclCommInitRank on the current device */
 void hns_dist_destroy(hns_dist* d);
 /* per peer: LOCAL leaf ids (HOST arrays) of the owned leaves it holds as ghosts (send) and of the ghost leaves it owns (recv),
- * both in ascending global leaf order so that the two sides agree. Installs the element-0 override on `s`. */
+ * both in ascending global leaf order so that the two sides agree; owned_ids: LOCAL ids of all owned leaves (kernels skip the
+ * ghost leaves). Installs the element-0 override and the owned-leaf work list on `s`. */
 int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ranks, const uint64_t* n_send, const int32_t* const* send_ids,
-                      const uint64_t* n_recv, const int32_t* const* recv_ids);
+                      const uint64_t* n_recv, const int32_t* const* recv_ids, uint64_t n_owned, const int32_t* owned_ids);
 /* ghost exchange of the given fields (ids as for hns_state_pack_leaves): pack, grouped ncclSend/ncclRecv, unpack; asynchronous */
 int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields, void* stream);
-/* the whole sharded frame (same steps as hns_state_step) with its 3 + 2*iterations ghost exchanges; asynchronous */
+/* the whole sharded frame (same steps as hns_state_step) with its 3 + 2*iterations ghost exchanges; the exchange of a swept
+ * pressure colour overlaps the sweep of the interior leaves; asynchronous */
 int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream);
 uint64_t hns_dist_bytes_sent(const hns_dist* d);
 uint64_t hns_dist_exchanges(const hns_dist* d);
