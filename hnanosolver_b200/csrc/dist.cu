@@ -153,7 +153,9 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 		HNS_CUDA(up(inter, &d->d_interior));
 		s->active = d->d_owned, s->n_active = d->n_owned;
 		if (!d->comm_stream) {
-			HNS_CUDA(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
+			int prio_lo = 0, prio_hi = 0;  // the exchange kernels are tiny and latency-critical: let their CTAs overtake the queued interior sweep
+			cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+			HNS_CUDA(cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, prio_hi));
 			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_boundary, cudaEventDisableTiming));
 			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_exchanged, cudaEventDisableTiming));
 		}
