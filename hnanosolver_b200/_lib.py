@@ -41,6 +41,7 @@ SIGNATURES = {
     "hns_grid_nanovdb_download": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hns_grid_get_values": (C.c_int, [C.c_void_p, c_i32p, C.c_uint64, c_u64p]),
     "hns_grid_neighbors_download": (C.c_int, [C.c_void_p, c_i32p]),
+    "hns_release_scratch": (None, []),
     "hns_compute_sim": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_f32p), C.c_int, C.c_float, C.c_float,
                                   C.POINTER(CombustionParams), C.c_int, C.c_void_p]),
     "hns_advect_index_grid": (C.c_int, [c_i32p, C.c_uint64, c_f32p, C.c_int, C.POINTER(c_f32p), C.c_float, C.c_float, C.c_void_p]),
@@ -82,6 +83,7 @@ SIGNATURES = {
                                     C.POINTER(C.c_uint64), C.POINTER(c_i32p), C.c_uint64, c_i32p]),
     "hns_dist_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "hns_dist_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "hns_dist_frame_timed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, c_f32p]),
     "hns_dist_bytes_sent": (C.c_uint64, [C.c_void_p]),
     "hns_dist_exchanges": (C.c_uint64, [C.c_void_p]),
 }

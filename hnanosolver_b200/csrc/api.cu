@@ -1,6 +1,7 @@
 // C ABI of libhns_b200 (include/hns_b200.h): resident simulation state, the frame, and the one-shot host-sidecar launchers.
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -53,12 +54,19 @@ static ScalarPtrs scalar_ptrs(const hns_state* s) {
 //   advect_vector -> [vorticity: scale 0 == identity] -> divergence -> [combustion_oxygen -> temperature_buoyancy] ->
 //   iterations x (red, black) -> subtractPressureGradient -> advect_scalars over all scalar fields.
 // `voxel_size` is the launcher argument (the reference's kernels use it, not the grid's map).
+// Optional stream dependencies of a frame whose inputs arrive / outputs leave on a copy stream while it runs (hns_compute_sim):
+// the frame waits for `combustion_inputs` before the combustion stage and for `scalar_inputs` before advect_scalars, and records
+// `velocity_done` once the projected velocity is final.
+struct FrameDeps {
+	cudaEvent_t combustion_inputs = nullptr, scalar_inputs = nullptr, velocity_done = nullptr;
+};
 static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsigned flags, cudaStream_t st, cudaEvent_t ev_p0 = nullptr,
-                 cudaEvent_t ev_p1 = nullptr) {
+                 cudaEvent_t ev_p1 = nullptr, const FrameDeps* deps = nullptr) {
 	const GridView g = s->view();
 	const float h = voxel_size, inv = 1.0f / h;
 	launch_advect_vector(g, s->vel, s->adv, dt, inv, st);
 	launch_divergence(g, s->adv, s->div, inv, st);
+	if (deps && deps->combustion_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->combustion_inputs, 0));
 	if (s->comb_enabled) {
 		const int iF = s->comb_idx[0], iW = s->comb_idx[1], iT = s->comb_idx[2], iL = s->comb_idx[3];
 		launch_combustion_oxygen(s->sc[iF], s->sc[iW], s->sc[iT], s->div, s->sc[iL], s->sc_out[iF], s->sc_out[iW], s->sc_out[iT], s->sc_out[iL],
@@ -71,6 +79,11 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 	if (rc) return rc;
 	if (ev_p1) cudaEventRecord(ev_p1, st);
 	launch_subtract_gradient(g, s->adv, s->p, s->vel, inv, st);
+	if (deps && deps->velocity_done) {
+		launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, s->n, st);
+		HNS_CUDA(cudaEventRecord(deps->velocity_done, st));
+	}
+	if (deps && deps->scalar_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->scalar_inputs, 0));
 	if (s->n_scalars) {
 		ScalarPtrs sp{};
 		int S = 0;
@@ -394,13 +407,67 @@ int hns_state_unpack_leaves(hns_state* s, int field, const int32_t* ids, uint64_
 }
 
 // ---- one-shot launchers on host sidecar arrays --------------------------------------------------------------------
-// Shared helper: RAII for a temporary grid + state.
+// The reference allocates and frees every device buffer on every call (HNanoSolver.cu:87-106; cudaMalloc/cudaFree of a few GB cost
+// milliseconds). The one-shot launchers here keep ONE scratch state per process and reuse it while the voxel count and the
+// number of float blocks stay the same (the usual case: a simulation is cooked frame after frame); hns_release_scratch() frees it.
+namespace {
+std::mutex g_scratch_mu;
+hns_state* g_scratch = nullptr;
+int g_scratch_device = -1;
+struct Streams {
+	cudaStream_t copy = nullptr;
+	cudaEvent_t ev[6] = {};
+	int device = -1;
+} g_streams;
+
+int acquire_scratch(const hns_grid* g, int n_scalars, hns_state** out) {
+	int dev = 0;
+	HNS_CUDA(cudaGetDevice(&dev));
+	if (g_scratch && (g_scratch_device != dev || g_scratch->n != g->num_leaves * 512 || g_scratch->n_scalars != n_scalars)) {
+		hns_state_destroy(g_scratch);
+		g_scratch = nullptr;
+	}
+	if (!g_scratch) {
+		int rc = hns_state_create(g, n_scalars, &g_scratch);
+		if (rc) return rc;
+		g_scratch_device = dev;
+	}
+	g_scratch->grid = g;
+	g_scratch->comb_enabled = false, g_scratch->skip_scalar = -1, g_scratch->elem0 = nullptr, g_scratch->active = nullptr, g_scratch->n_active = 0;
+	*out = g_scratch;
+	return HNS_OK;
+}
+int acquire_streams(Streams** out) {
+	int dev = 0;
+	HNS_CUDA(cudaGetDevice(&dev));
+	if (g_streams.device != dev) {
+		if (g_streams.copy) {
+			cudaStreamDestroy(g_streams.copy);
+			for (auto& e : g_streams.ev) cudaEventDestroy(e);
+		}
+		HNS_CUDA(cudaStreamCreateWithFlags(&g_streams.copy, cudaStreamNonBlocking));
+		for (auto& e : g_streams.ev) HNS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		g_streams.device = dev;
+	}
+	*out = &g_streams;
+	return HNS_OK;
+}
+}  // namespace
+
+void hns_release_scratch(void) {
+	std::lock_guard<std::mutex> lk(g_scratch_mu);
+	hns_state_destroy(g_scratch);
+	g_scratch = nullptr;
+}
+
+// Shared helper: a temporary grid for the stand-alone launchers + the process-wide scratch state.
 struct Scoped {
 	hns_grid* grid = nullptr;
-	hns_state* state = nullptr;
+	hns_state* state = nullptr;  // borrowed from the scratch cache
 	bool own_grid = false;
+	std::unique_lock<std::mutex> lock{g_scratch_mu};
 	~Scoped() {
-		hns_state_destroy(state);
+		if (state) state->grid = nullptr;
 		if (own_grid) hns_grid_destroy(grid);
 	}
 };
@@ -434,26 +501,44 @@ int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char*
 		if (!found) return fail(HNS_ERR_RUNTIME, std::string("Missing required input field for combustion: ") + req);
 	}
 	Scoped sc;
-	int rc = hns_state_create(g, n_float, &sc.state);
+	int rc = acquire_scratch(g, n_float, &sc.state);
 	if (rc) return rc;
 	hns_state* s = sc.state;
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if ((rc = hns_state_set_combustion(s, 1, iF, iW, iT, iL, params))) return rc;
 	s->skip_scalar = iSdf;
 	if ((rc = ensure_aos(s))) return rc;
-	// H2D of the whole state (HNanoSolver.cu:120-133) -- the coords are not needed on the device here
-	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
+	Streams* ss = nullptr;
+	if ((rc = acquire_streams(&ss))) return rc;
+	cudaStream_t cs = ss->copy;
+	cudaEvent_t e_start = ss->ev[0], e_vel_in = ss->ev[1], e_comb_in = ss->ev[2], e_all_in = ss->ev[3], e_vel_out = ss->ev[4], e_done = ss->ev[5];
+	// The whole state crosses PCIe in both directions (HNanoSolver.cu:120-133, 361-369; the coords are not needed on the device
+	// here). Transfers run on a copy stream and overlap the kernels: velocity first (advect_vector + divergence start as soon as
+	// it has landed), then the four combustion fields, then the remaining scalars while the pressure solve runs; the projected
+	// velocity goes back while advect_scalars runs.
+	HNS_CUDA(cudaEventRecord(e_start, st));
+	HNS_CUDA(cudaStreamWaitEvent(cs, e_start, 0));  // everything the caller queued on `stream` before this call stays ordered
+	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, cs));
+	HNS_CUDA(cudaEventRecord(e_vel_in, cs));
+	for (int i : {iF, iW, iT, iL}) HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, cs));
+	HNS_CUDA(cudaEventRecord(e_comb_in, cs));
+	for (int i = 0; i < n_float; ++i)
+		if (i != iF && i != iW && i != iT && i != iL) HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, cs));
+	HNS_CUDA(cudaEventRecord(e_all_in, cs));
+	HNS_CUDA(cudaStreamWaitEvent(st, e_vel_in, 0));
 	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
-	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, st));
-	if ((rc = frame(s, iterations, dt, voxel_size, 0u, st))) return rc;
+	FrameDeps deps;
+	deps.combustion_inputs = e_comb_in, deps.scalar_inputs = e_all_in, deps.velocity_done = e_vel_out;
+	if ((rc = frame(s, iterations, dt, voxel_size, 0u, st, nullptr, nullptr, &deps))) return rc;
 	// results back into the same host arrays (HNanoSolver.cu:361-369); a collision_sdf block comes back zeroed like the
 	// reference's never-written output buffer
-	launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, n, st);
-	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, st));
-	for (int i = 0; i < n_float; ++i) {
-		if (i == iSdf) HNS_CUDA(cudaMemsetAsync(s->sc[i], 0, n * 4, st));
-		HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc[i], n * 4, cudaMemcpyDeviceToHost, st));
-	}
+	HNS_CUDA(cudaStreamWaitEvent(cs, e_vel_out, 0));
+	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, cs));
+	if (iSdf >= 0) HNS_CUDA(cudaMemsetAsync(s->sc[iSdf], 0, n * 4, st));
+	HNS_CUDA(cudaEventRecord(e_done, st));
+	HNS_CUDA(cudaStreamWaitEvent(cs, e_done, 0));
+	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc[i], n * 4, cudaMemcpyDeviceToHost, cs));
+	HNS_CUDA(cudaStreamSynchronize(cs));
 	HNS_CUDA(cudaStreamSynchronize(st));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
@@ -463,7 +548,7 @@ static int temp_grid(const int32_t* coords, uint64_t n, float voxel_size, Scoped
 	int rc = hns_grid_create_from_coords(coords, n, voxel_size, 0, &sc.grid);
 	if (rc) return rc;
 	sc.own_grid = true;
-	return hns_state_create(sc.grid, n_scalars, &sc.state);
+	return acquire_scratch(sc.grid, n_scalars, &sc.state);
 }
 
 int hns_advect_index_grid(const int32_t* coords, uint64_t n, const float* velocity, int n_float, float* const* fields, float dt, float voxel_size,

@@ -222,15 +222,42 @@ int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields
 
 // The sharded frame: Compute()'s step order (reference src/Cuda/HNanoSolver.cu:159-356) with a ghost exchange in front of every step
 // that reads a neighbour leaf. Asynchronous on `stream`.
-int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream) {
+static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, cudaEvent_t* marks);
+
+int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream) { return dist_frame(d, s, iterations, dt, stream, nullptr); }
+
+// Same frame with CUDA events between the phases; ms_out[8] = exchange velocity, advect_vector, exchange advected, divergence(+combustion),
+// pressure solve incl. its exchanges, gradient, final exchange (+element-0 broadcast), advect_scalars. Synchronises the stream.
+int hns_dist_frame_timed(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, float* ms_out) {
+	if (!ms_out) return fail(HNS_ERR_INVALID_ARGUMENT, "null argument");
+	cudaEvent_t ev[9];
+	for (auto& e : ev) cudaEventCreate(&e);
+	int rc = dist_frame(d, s, iterations, dt, stream, ev);
+	cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+	if (rc == HNS_OK)
+		for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+	for (auto& e : ev) cudaEventDestroy(e);
+	return rc;
+}
+
+static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, cudaEvent_t* marks) {
 	if (!d || !s || iterations <= 0 || dt < 0.f) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
 	int rc;
+	int mark_i = 0;
+	auto mark = [&]() {
+		if (marks) cudaEventRecord(marks[mark_i++], static_cast<cudaStream_t>(stream));
+	};
+	mark();
 	const int fvel[3] = {0, 1, 2}, fadv[3] = {3, 4, 5}, fred[1] = {6}, fblk[1] = {7};
 	if ((rc = hns_dist_exchange(d, s, 3, fvel, stream))) return rc;
+	mark();
 	if ((rc = hns_state_advect_velocity(s, dt, stream))) return rc;
+	mark();
 	if ((rc = hns_dist_exchange(d, s, 3, fadv, stream))) return rc;
+	mark();
 	if ((rc = hns_state_divergence(s, 1, stream))) return rc;
 	if (s->comb_enabled && (rc = hns_state_combustion_buoyancy(s, dt, stream))) return rc;
+	mark();
 	if ((rc = hns_state_pressure_init(s, stream))) return rc;
 	const float omega = hns_omega_compute(s->grid->voxel_size);
 	{
@@ -256,7 +283,9 @@ int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* st
 			}
 		if (pending) HNS_CUDA(cudaStreamWaitEvent(st, d->ev_exchanged, 0));
 	}
+	mark();
 	if ((rc = hns_state_subtract_gradient(s, 1, stream))) return rc;
+	mark();
 	std::vector<int> last = {0, 1, 2};
 	for (int i = 0; i < s->n_scalars; ++i) last.push_back(10 + i);
 	if ((rc = hns_dist_exchange(d, s, int(last.size()), last.data(), stream))) return rc;
@@ -264,7 +293,10 @@ int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* st
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if (d->rank == 0 && (rc = hns_state_gather_element0(s, d->d_elem0, stream))) return rc;
 	if (d->world > 1) HNS_NCCL(g_nccl.Broadcast(d->d_elem0, d->d_elem0, size_t(3 + s->n_scalars), ncclFloat, 0, d->comm, st));
-	return hns_state_advect_scalars(s, dt, 0, stream);
+	mark();
+	rc = hns_state_advect_scalars(s, dt, 0, stream);
+	mark();
+	return rc;
 }
 
 uint64_t hns_dist_bytes_sent(const hns_dist* d) { return d ? d->bytes_sent : 0; }

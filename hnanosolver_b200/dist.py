@@ -286,6 +286,17 @@ class ShardedSimulation:
             dist.broadcast(self.elem0, src=0)
         s.advect_scalars(dt, 0, st)
 
+    PHASES = ("exch_vel", "advect_vector", "exch_adv", "div+comb", "pressure", "gradient", "exch_final", "advect_scalars")
+
+    def frame_timed(self, iterations: int, dt: float) -> dict:
+        import ctypes as C
+
+        from . import _lib
+
+        ms = (C.c_float * 8)()
+        _lib.check(_lib.lib().hns_dist_frame_timed(self._dist, self.sim._h, iterations, dt, C.c_void_p(self._stream()), ms))
+        return dict(zip(self.PHASES, [float(x) for x in ms]))
+
     def owned(self, arr: np.ndarray) -> np.ndarray:
         """Rows of a per-voxel local array that belong to owned leaves."""
         m = np.repeat(self.plan.owned_local, 512)
@@ -360,6 +371,10 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
+    phases = sh.frame_timed(iterations, w.dt) if sh.native else {}
+    log = __import__("sys").stderr
+    print(f"[rank {rank}] owned {plan.n_owned} ghost {plan.n_local - plan.n_owned} peers { {p: len(v) for p, v in plan.send.items()} } "
+          f"phases(ms) { {k: round(v, 3) for k, v in phases.items()} }", file=log, flush=True)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = torch.tensor([float(_lib.lib().hns_launch_count())], device=dev)

@@ -90,6 +90,9 @@ int hns_grid_neighbors_download(const hns_grid* g, int32_t* dst_host);
  * One-shot launchers on HOST sidecar arrays, in place, synchronous -- the drop-in equivalents of the reference's
  * extern "C" launchers. `stream` is a cudaStream_t passed as void* (may be NULL).
  * ------------------------------------------------------------------------------------------------------- */
+/* The one-shot launchers keep one scratch set of device buffers per process and reuse it while the problem size stays the same
+ * (the reference allocates and frees everything on every call); this frees it. */
+void hns_release_scratch(void);
 /* Compute_Sim (src/Cuda/HNanoSolver.cu:9-372,393-396): advect velocity -> [vorticity] -> divergence -> combustion ->
  * buoyancy -> iterations x (red, black) -> gradient subtract -> advect all float fields. float_names/float_fields are
  * the float blocks in insertion order (GridData.hpp:136-145); fuel, waste, temperature, flame must be among them. */
@@ -189,6 +192,9 @@ int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields
 /* the whole sharded frame (same steps as hns_state_step) with its 3 + 2*iterations ghost exchanges; the exchange of a swept
  * pressure colour overlaps the sweep of the interior leaves; asynchronous */
 int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream);
+/* the same frame with CUDA events between its phases (ms_out[8]: exchange velocity, advect_vector, exchange advected velocity,
+ * divergence + combustion, pressure solve incl. exchanges, gradient, final exchange, advect_scalars); synchronises the stream */
+int hns_dist_frame_timed(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, float* ms_out);
 uint64_t hns_dist_bytes_sent(const hns_dist* d);
 uint64_t hns_dist_exchanges(const hns_dist* d);
 
