@@ -76,6 +76,10 @@ struct hns_dist {
 		uint64_t n_send, n_recv;
 		int32_t *d_send = nullptr, *d_recv = nullptr;  // local leaf ids
 		float *buf_send = nullptr, *buf_recv = nullptr;
+		// direct peer-memory path: where this peer's bricks land in MY block, and where mine land in ITS block
+		uint64_t region_off = 0;
+		uint8_t* remote_region = nullptr;
+		void* ipc_base = nullptr;
 	};
 	std::vector<Peer> peers;
 	int max_fields = 0;
@@ -84,9 +88,64 @@ struct hns_dist {
 	// work lists (local leaf ids, device): owned = boundary (sent to some peer) + interior
 	int32_t *d_owned = nullptr, *d_boundary = nullptr, *d_interior = nullptr;
 	uint32_t n_owned = 0, n_boundary = 0, n_interior = 0;
-	cudaStream_t comm_stream = nullptr;  // the exchange of a swept colour runs here, next to the interior sweep
+	cudaStream_t comm_stream = nullptr;  // boundary sweeps + ghost exchange run here, next to the interior sweep on the caller's stream
 	cudaEvent_t ev_boundary = nullptr, ev_exchanged = nullptr;
+	cudaEvent_t ev_I[2] = {}, ev_B[2] = {};
+	// direct peer-memory ghost exchange (CUDA IPC over NVLink): one block of device memory per rank holding, per peer, five
+	// channels of landing space + their arrival flags. Peers store bricks straight into it and then raise the channel's flag.
+	bool p2p = false;
+	uint8_t* block = nullptr;
+	uint64_t block_bytes = 0;
+	uint32_t** d_remote_flags = nullptr;  // [n_peers] flag words in the peers' blocks
+	uint32_t** d_local_flags = nullptr;   // [n_peers] flag words in my block
+	uint32_t seq[5] = {};
+	uint32_t* d_err = nullptr;
+	int n_scalars = 0;
 };
+
+// ---- layout of one peer region: [flags 128 B][ch0 velocity 3 x 512n][ch1 advected velocity 3 x 512n][ch2 red p 256n][ch3 black p 256n]
+//      [ch4 velocity + scalars (3+S) x 512n] floats, n = number of ghost leaves exchanged with that peer
+static uint64_t channel_floats(int ch, uint64_t n, int S) {
+	switch (ch) {
+		case 0:
+		case 1: return 3 * 512 * n;
+		case 2:
+		case 3: return 256 * n;
+		default: return uint64_t(3 + S) * 512 * n;
+	}
+}
+static uint64_t channel_offset(int ch, uint64_t n, int S) {  // bytes from the region start
+	uint64_t off = 128;
+	for (int c = 0; c < ch; ++c) off += channel_floats(c, n, S) * sizeof(float);
+	return off;
+}
+static uint64_t region_bytes(uint64_t n, int S) { return (channel_offset(5, n, S) + 255) & ~uint64_t(255); }
+
+namespace hns {
+// raise channel `ch` of every peer to `seq`: everything this stream wrote into the peers' blocks before is visible first
+__global__ void k_signal(uint32_t* const* __restrict__ flags, int n, int ch, uint32_t seq) {
+	__threadfence_system();
+	const int t = threadIdx.x;
+	if (t < n && flags[t]) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags[t] + ch), "r"(seq) : "memory");
+}
+// wait until every peer has raised channel `ch` of my block to `seq` (bounded: ~4 s, then the error word is set instead of hanging)
+__global__ void k_wait(uint32_t* const* __restrict__ flags, int n, int ch, uint32_t seq, uint32_t* __restrict__ err) {
+	const int t = threadIdx.x;
+	if (t < n && flags[t]) {
+		uint32_t v = 0;
+		const long long t0 = clock64();
+		for (;;) {
+			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags[t] + ch) : "memory");
+			if (int32_t(v - seq) >= 0) break;
+			if (clock64() - t0 > 8000000000ll) {
+				atomicExch(err, 1u + uint32_t(ch));
+				break;
+			}
+			__nanosleep(64);
+		}
+	}
+}
+}  // namespace hns
 
 static int floats_per_leaf(int field) { return (field >= 6 && field <= 9) ? 256 : 512; }
 
@@ -123,6 +182,13 @@ void hns_dist_destroy(hns_dist* d) {
 	if (!d) return;
 	for (auto& p : d->peers) cudaFree(p.d_send), cudaFree(p.d_recv), cudaFree(p.buf_send), cudaFree(p.buf_recv);
 	cudaFree(d->d_elem0), cudaFree(d->d_owned), cudaFree(d->d_boundary), cudaFree(d->d_interior);
+	for (auto& p : d->peers)
+		if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base);
+	cudaFree(d->block), cudaFree(d->d_remote_flags), cudaFree(d->d_local_flags), cudaFree(d->d_err);
+	for (auto& e : d->ev_I)
+		if (e) cudaEventDestroy(e);
+	for (auto& e : d->ev_B)
+		if (e) cudaEventDestroy(e);
 	if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
 	if (d->ev_boundary) cudaEventDestroy(d->ev_boundary);
 	if (d->ev_exchanged) cudaEventDestroy(d->ev_exchanged);
@@ -158,6 +224,8 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 			HNS_CUDA(cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, prio_hi));
 			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_boundary, cudaEventDisableTiming));
 			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_exchanged, cudaEventDisableTiming));
+			for (auto& e : d->ev_I) HNS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+			for (auto& e : d->ev_B) HNS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		}
 	}
 	for (auto& p : d->peers) cudaFree(p.d_send), cudaFree(p.d_recv), cudaFree(p.buf_send), cudaFree(p.buf_recv);
@@ -180,7 +248,112 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 	}
 	if (!d->d_elem0) HNS_CUDA(cudaMalloc(&d->d_elem0, 32 * sizeof(float)));
 	s->elem0 = d->d_elem0;
+	d->n_scalars = s->n_scalars;
 	return HNS_OK;
+}
+
+int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields, void* stream);
+
+// ---- direct peer-memory exchange: setup -------------------------------------------------------------------------------
+// 1. every rank: hns_dist_ipc_prepare -> its block's IPC handle + the offset of each peer's region inside it
+// 2. the caller all-gathers (handle, offsets);  3. per peer: hns_dist_ipc_connect(handle of that peer, offset of MY region in ITS block)
+// 4. hns_dist_ipc_finish switches the exchanges from NCCL send/recv to peer stores + flags
+int hns_dist_ipc_prepare(hns_dist* d, uint8_t* handle_out64, uint64_t* region_offsets_out) {
+	if (!d || !handle_out64 || (!region_offsets_out && !d->peers.empty())) return fail(HNS_ERR_INVALID_ARGUMENT, "null argument");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	uint64_t total = 256;
+	for (size_t i = 0; i < d->peers.size(); ++i) {
+		d->peers[i].region_off = total;
+		region_offsets_out[i] = total;
+		total += region_bytes(d->peers[i].n_recv, d->n_scalars);
+	}
+	cudaFree(d->block);
+	d->block = nullptr;
+	HNS_CUDA(cudaMalloc(&d->block, total));
+	HNS_CUDA(cudaMemset(d->block, 0, total));
+	d->block_bytes = total;
+	cudaIpcMemHandle_t h;
+	HNS_CUDA(cudaIpcGetMemHandle(&h, d->block));
+	std::memcpy(handle_out64, &h, 64);
+	return HNS_OK;
+}
+int hns_dist_ipc_connect(hns_dist* d, int peer_index, const uint8_t* peer_handle64, uint64_t my_region_offset_in_peer_block) {
+	if (!d || peer_index < 0 || peer_index >= int(d->peers.size()) || !peer_handle64) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	auto& p = d->peers[peer_index];
+	cudaIpcMemHandle_t h;
+	std::memcpy(&h, peer_handle64, 64);
+	if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base), p.ipc_base = nullptr;
+	HNS_CUDA(cudaIpcOpenMemHandle(&p.ipc_base, h, cudaIpcMemLazyEnablePeerAccess));
+	p.remote_region = static_cast<uint8_t*>(p.ipc_base) + my_region_offset_in_peer_block;
+	return HNS_OK;
+}
+int hns_dist_ipc_finish(hns_dist* d) {
+	if (!d || !d->block) return fail(HNS_ERR_INVALID_ARGUMENT, "hns_dist_ipc_prepare has not been called");
+	const size_t n = d->peers.size();
+	std::vector<uint32_t*> rem(std::max<size_t>(n, 1), nullptr), loc(std::max<size_t>(n, 1), nullptr);
+	for (size_t i = 0; i < n; ++i) {
+		if (!d->peers[i].remote_region) return fail(HNS_ERR_RUNTIME, "peer " + std::to_string(d->peers[i].rank) + " is not connected");
+		rem[i] = d->peers[i].n_send ? reinterpret_cast<uint32_t*>(d->peers[i].remote_region) : nullptr;
+		loc[i] = d->peers[i].n_recv ? reinterpret_cast<uint32_t*>(d->block + d->peers[i].region_off) : nullptr;
+	}
+	if (n > 32) return fail(HNS_ERR_UNSUPPORTED, "more than 32 peers");
+	cudaFree(d->d_remote_flags), cudaFree(d->d_local_flags);
+	HNS_CUDA(cudaMalloc(&d->d_remote_flags, rem.size() * sizeof(uint32_t*)));
+	HNS_CUDA(cudaMalloc(&d->d_local_flags, loc.size() * sizeof(uint32_t*)));
+	HNS_CUDA(cudaMemcpy(d->d_remote_flags, rem.data(), rem.size() * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+	HNS_CUDA(cudaMemcpy(d->d_local_flags, loc.data(), loc.size() * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+	if (!d->d_err) {
+		HNS_CUDA(cudaMalloc(&d->d_err, sizeof(uint32_t)));
+		HNS_CUDA(cudaMemset(d->d_err, 0, sizeof(uint32_t)));
+	}
+	d->p2p = true;
+	return HNS_OK;
+}
+// 0 = no flag wait has timed out so far; otherwise 1 + the channel that did
+int hns_dist_error(hns_dist* d, uint32_t* out) {
+	if (!d || !out) return fail(HNS_ERR_INVALID_ARGUMENT, "null argument");
+	*out = 0;
+	if (d->d_err) HNS_CUDA(cudaMemcpy(out, d->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return HNS_OK;
+}
+
+// Ghost exchange through peer memory: every owned boundary brick is stored straight into the peer's landing region over NVLink
+// (the pack kernel with a remote destination), the channel flag is raised, the peers' flags are awaited, the landed bricks are
+// scattered into the ghost leaves. Four small launches, no library call, NVLink bandwidth instead of NCCL's p2p channel bandwidth.
+static int exchange_p2p(hns_dist* d, hns_state* s, int channel, int n_fields, const int* fields, cudaStream_t st) {
+	const int S = d->n_scalars;
+	for (auto& p : d->peers) {
+		if (!p.n_send) continue;
+		float* dst = reinterpret_cast<float*>(p.remote_region + channel_offset(channel, p.n_send, S));
+		for (int k = 0; k < n_fields; ++k) {
+			const int fpl = floats_per_leaf(fields[k]);
+			float* f = static_cast<float*>(hns_state_field_device_ptr(s, fields[k]));
+			if (!f) return fail(HNS_ERR_INVALID_ARGUMENT, "bad field id");
+			launch_pack_leaves(f, p.d_send, p.n_send, dst, fpl, st);
+			dst += p.n_send * fpl;
+			d->bytes_sent += p.n_send * fpl * 4;
+		}
+	}
+	const uint32_t seq = ++d->seq[channel];
+	const int np = int(d->peers.size());
+	HNS_LAUNCH(k_signal, 1, 32, 0, st, d->d_remote_flags, np, channel, seq);
+	HNS_LAUNCH(k_wait, 1, 32, 0, st, d->d_local_flags, np, channel, seq, d->d_err);
+	for (auto& p : d->peers) {
+		if (!p.n_recv) continue;
+		const float* src = reinterpret_cast<const float*>(d->block + p.region_off + channel_offset(channel, p.n_recv, S));
+		for (int k = 0; k < n_fields; ++k) {
+			const int fpl = floats_per_leaf(fields[k]);
+			float* f = static_cast<float*>(hns_state_field_device_ptr(s, fields[k]));
+			launch_unpack_leaves(f, p.d_recv, p.n_recv, src, fpl, st);
+			src += p.n_recv * fpl;
+		}
+	}
+	++d->exchanges;
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+static int exchange_channel(hns_dist* d, hns_state* s, int channel, int n_fields, const int* fields, cudaStream_t st) {
+	return d->p2p ? exchange_p2p(d, s, channel, n_fields, fields, st) : hns_dist_exchange(d, s, n_fields, fields, st);
 }
 
 // pack -> grouped send/recv -> unpack of the given fields' ghost bricks, all on `stream`
@@ -249,11 +422,12 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	};
 	mark();
 	const int fvel[3] = {0, 1, 2}, fadv[3] = {3, 4, 5}, fred[1] = {6}, fblk[1] = {7};
-	if ((rc = hns_dist_exchange(d, s, 3, fvel, stream))) return rc;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if ((rc = exchange_channel(d, s, 0, 3, fvel, st))) return rc;
 	mark();
 	if ((rc = hns_state_advect_velocity(s, dt, stream))) return rc;
 	mark();
-	if ((rc = hns_dist_exchange(d, s, 3, fadv, stream))) return rc;
+	if ((rc = exchange_channel(d, s, 1, 3, fadv, st))) return rc;
 	mark();
 	if ((rc = hns_state_divergence(s, 1, stream))) return rc;
 	if (s->comb_enabled && (rc = hns_state_combustion_buoyancy(s, dt, stream))) return rc;
@@ -261,36 +435,41 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	if ((rc = hns_state_pressure_init(s, stream))) return rc;
 	const float omega = hns_omega_compute(s->grid->voxel_size);
 	{
-		// Per half-sweep: boundary leaves first, then their freshly swept colour travels to the peers on comm_stream while the
-		// interior leaves are swept on the main stream. The interior sweep reads only the OTHER colour, the exchange moves only
-		// THIS colour, so they do not touch the same data; the next half-sweep (which reads this colour's ghosts) waits for it.
-		cudaStream_t st = static_cast<cudaStream_t>(stream);
+		// Two software-pipelined streams. Interior leaves (no ghost neighbour) are swept on the caller's stream, boundary leaves
+		// and the exchange of their freshly swept colour on comm_stream:
+		//   caller's stream:  I_1        I_2        I_3   ...      I_k needs I_{k-1} (in order) and B_{k-1} (event)
+		//   comm_stream:      B_1 x_1    B_2 x_2    B_3 x_3 ...    B_k needs B_{k-1}, x_{k-1} (in order) and I_{k-1} (event)
+		// Half-sweep k reads colour c_{k-1} and writes colour c_k, so I_k and B_k/x_k never touch the same colour of the same leaf
+		// at the same time, and the exchange latency disappears behind the interior sweep as long as B + x is the shorter chain.
 		GridView vb = s->grid->view, vi = s->grid->view;
 		vb.list = d->d_boundary, vb.num_list = d->n_boundary;
 		vi.list = d->d_interior, vi.num_list = d->n_interior;
 		const float dx = s->grid->voxel_size;
-		bool pending = false;
+		cudaStream_t bs = d->comm_stream;
+		HNS_CUDA(cudaEventRecord(d->ev_I[1], st));  // "I_0": everything before the solve
+		HNS_CUDA(cudaEventRecord(d->ev_B[1], bs));  // "B_0": nothing
+		int k = 0;
 		for (int it = 0; it < iterations; ++it)
-			for (int color = 0; color < 2; ++color) {
-				if (pending) HNS_CUDA(cudaStreamWaitEvent(st, d->ev_exchanged, 0));
-				if (d->n_boundary) launch_rbgs_color(vb, s->div, s->p, dx, color, omega, color, st);
-				HNS_CUDA(cudaEventRecord(d->ev_boundary, st));
+			for (int color = 0; color < 2; ++color, ++k) {
+				const int cur = k & 1, prev = cur ^ 1;
+				HNS_CUDA(cudaStreamWaitEvent(bs, d->ev_I[prev], 0));
+				if (d->n_boundary) launch_rbgs_color(vb, s->div, s->p, dx, color, omega, color, bs);
+				HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
+				HNS_CUDA(cudaStreamWaitEvent(st, d->ev_B[prev], 0));
 				if (d->n_interior) launch_rbgs_color(vi, s->div, s->p, dx, color, omega, color, st);
-				HNS_CUDA(cudaStreamWaitEvent(d->comm_stream, d->ev_boundary, 0));
-				if ((rc = hns_dist_exchange(d, s, 1, color ? fblk : fred, d->comm_stream))) return rc;
-				HNS_CUDA(cudaEventRecord(d->ev_exchanged, d->comm_stream));
-				pending = true;
+				HNS_CUDA(cudaEventRecord(d->ev_I[cur], st));
+				if ((rc = exchange_channel(d, s, 2 + color, 1, color ? fblk : fred, bs))) return rc;
 			}
-		if (pending) HNS_CUDA(cudaStreamWaitEvent(st, d->ev_exchanged, 0));
+		HNS_CUDA(cudaEventRecord(d->ev_exchanged, bs));
+		HNS_CUDA(cudaStreamWaitEvent(st, d->ev_exchanged, 0));
 	}
 	mark();
 	if ((rc = hns_state_subtract_gradient(s, 1, stream))) return rc;
 	mark();
 	std::vector<int> last = {0, 1, 2};
 	for (int i = 0; i < s->n_scalars; ++i) last.push_back(10 + i);
-	if ((rc = hns_dist_exchange(d, s, int(last.size()), last.data(), stream))) return rc;
+	if ((rc = exchange_channel(d, s, 4, int(last.size()), last.data(), st))) return rc;
 	// advect_scalars' "inactive -> element 0" value is global voxel 0's (reference Kernel.cu:192,225): rank 0 owns it
-	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if (d->rank == 0 && (rc = hns_state_gather_element0(s, d->d_elem0, stream))) return rc;
 	if (d->world > 1) HNS_NCCL(g_nccl.Broadcast(d->d_elem0, d->d_elem0, size_t(3 + s->n_scalars), ncclFloat, 0, d->comm, st));
 	mark();

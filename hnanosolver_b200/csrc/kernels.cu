@@ -741,6 +741,7 @@ __global__ void __launch_bounds__(128) k_pack_leaves(const float* __restrict__ f
 	if (int(threadIdx.x) >= quads) return;
 	const int32_t l = __ldg(ids + blockIdx.x);
 	reinterpret_cast<float4*>(dst)[uint64_t(blockIdx.x) * quads + threadIdx.x] = __ldg(reinterpret_cast<const float4*>(field) + uint64_t(l) * quads + threadIdx.x);
+	__threadfence_system();  // dst may be a peer GPU's memory (direct ghost exchange): order the store before the flag that follows
 }
 __global__ void __launch_bounds__(128) k_unpack_leaves(float* __restrict__ field, const int32_t* __restrict__ ids, const float* __restrict__ src, int quads) {
 	if (int(threadIdx.x) >= quads) return;

@@ -216,6 +216,21 @@ class ShardedSimulation:
                 (_lib.c_i32p * max(n, 1))(*[a.ctypes.data_as(_lib.c_i32p) for a in snd]), (C.c_uint64 * max(n, 1))(*[len(a) for a in rcv]),
                 (_lib.c_i32p * max(n, 1))(*[a.ctypes.data_as(_lib.c_i32p) for a in rcv]), len(owned), owned.ctypes.data_as(_lib.c_i32p)))
             self.ex = None
+            self.p2p = False
+            if plan.world > 1 and bool(int(_os.environ.get("HNS_P2P", "1"))):
+                # direct peer-memory exchange: all-gather every rank's IPC handle and region offsets, connect to the peers
+                handle = (C.c_uint8 * 64)()
+                offs = (C.c_uint64 * max(n, 1))()
+                _lib.check(L.hns_dist_ipc_prepare(h, handle, offs))
+                mine = (bytes(handle), {p: int(offs[i]) for i, p in enumerate(peers)})
+                allinfo = [None] * plan.world
+                tdist.all_gather_object(allinfo, mine)
+                for i, p in enumerate(peers):
+                    ph, poffs = allinfo[p]
+                    _lib.check(L.hns_dist_ipc_connect(h, i, (C.c_uint8 * 64).from_buffer_copy(ph), poffs[plan.rank]))
+                _lib.check(L.hns_dist_ipc_finish(h))
+                tdist.barrier()
+                self.p2p = True
         else:
             def pack(field, ids, out):
                 self.sim.pack_leaves(field, ids.data_ptr(), ids.numel(), out.data_ptr(), stream())
@@ -228,11 +243,27 @@ class ShardedSimulation:
             self.elem0 = torch.zeros(3 + n_scalars, dtype=torch.float32, device=device)
             self.sim.set_element0(self.elem0.data_ptr())
 
+    def check_errors(self) -> None:
+        """raises if a peer-flag wait timed out on the device (the frame then ran on stale ghosts)"""
+        if self._dist is not None:
+            import ctypes as C
+
+            from . import _lib
+
+            e = C.c_uint32()
+            _lib.check(_lib.lib().hns_dist_error(self._dist, C.byref(e)))
+            if e.value:
+                raise RuntimeError(f"ghost exchange timed out waiting for a peer on channel {e.value - 1}")
+
     def close(self):
         if self._dist is not None:
             from . import _lib
 
             self._torch.cuda.synchronize()
+            if self.plan.world > 1:
+                import torch.distributed as tdist
+
+                tdist.barrier()  # nobody unmaps a block a peer may still be writing to
             _lib.lib().hns_dist_destroy(self._dist)
             self._dist = None
 
@@ -381,6 +412,7 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     owned = torch.tensor([float(plan.n_owned * 512), float(plan.n_local * 512), float(sh.bytes_sent)], device=dev)
     dist.all_reduce(owned, op=dist.ReduceOp.SUM)
+    sh.check_errors()
     ms_step = float(ms.item()) / args.steps
     n_owned_total, n_local_total = int(owned[0].item()), int(owned[1].item())
 
@@ -413,7 +445,7 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"c4 weak scaling: sparse smoke ~30% of a {box[0]}x{box[1]}x{box[2]} box, {n_owned_total} active voxels over "
                                    f"{world} GPUs (+{n_local_total - n_owned_total} ghost voxels), frame=full, I={iterations}, S={S}",
-                       "parallelism": f"spatial leaf-range sharding x{world}, NCCL ghost-leaf exchange issued from C++ on the compute stream ({sh.exchanges // (args.steps + args.warmup + args.e2e_steps + 1)} exchanges/frame)",
+                       "parallelism": f"spatial leaf-range sharding x{world}, ghost-leaf exchange by " + ("direct peer-memory stores + flags over NVLink (CUDA IPC)" if getattr(sh, "p2p", False) else "ncclSend/ncclRecv") + f", issued from C++, boundary sweeps + exchange pipelined against interior sweeps ({sh.exchanges // (args.steps + args.warmup + args.e2e_steps + 1)} exchanges/frame)",
                        "l2": "per-rank fields larger than L2; no flush"},
             "e2e": {"value": n_owned_total / (float(e2e.item()) * 1e-3), "unit": "voxel-updates/s", "ms_per_step": float(e2e.item()),
                     "h2d_bytes_per_step": int(n_local_total * (12 + 4 * S)), "d2h_bytes_per_step": int(n_local_total * (12 + 4 * S)),

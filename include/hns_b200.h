@@ -187,6 +187,15 @@ void hns_dist_destroy(hns_dist* d);
  * ghost leaves). Installs the element-0 override and the owned-leaf work list on `s`. */
 int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ranks, const uint64_t* n_send, const int32_t* const* send_ids,
                       const uint64_t* n_recv, const int32_t* const* recv_ids, uint64_t n_owned, const int32_t* owned_ids);
+/* Direct peer-memory ghost exchange (CUDA IPC over NVLink/NVSwitch) instead of ncclSend/ncclRecv: bricks are stored straight into
+ * the peer's landing block and a flag is raised. Setup: every rank calls _prepare (its block's 64-byte IPC handle + the byte offset
+ * of each peer's region inside it, in the order of hns_dist_set_plan's peers), the caller all-gathers them, calls _connect once per
+ * peer with that peer's handle and the offset of ITS OWN region inside the peer's block, then _finish. hns_dist_error reports a
+ * flag wait that timed out (0 = none). */
+int hns_dist_ipc_prepare(hns_dist* d, uint8_t* handle_out64, uint64_t* region_offsets_out);
+int hns_dist_ipc_connect(hns_dist* d, int peer_index, const uint8_t* peer_handle64, uint64_t my_region_offset_in_peer_block);
+int hns_dist_ipc_finish(hns_dist* d);
+int hns_dist_error(hns_dist* d, uint32_t* out);
 /* ghost exchange of the given fields (ids as for hns_state_pack_leaves): pack, grouped ncclSend/ncclRecv, unpack; asynchronous */
 int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields, void* stream);
 /* the whole sharded frame (same steps as hns_state_step) with its 3 + 2*iterations ghost exchanges; the exchange of a swept

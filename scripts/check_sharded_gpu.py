@@ -49,7 +49,8 @@ if rank == 0:
         bad = np.nonzero((got != ref[k]).reshape(got.shape[0], -1).any(1))[0]
         print(f"  {nm:12s} sharded({world}) == single GPU bitwise: {same}  mismatching voxels {bad.size}/{got.shape[0]} "
               f"max|diff| {np.abs(got.astype(np.float64) - ref[k]).max():.3e} first leaves {np.unique(bad // 512)[:8]}")
-    print("SHARDED PARITY", "OK" if ok else "FAILED", f"leaves={go.shape[0]} exchanges/frame={sh.exchanges // NF} native={sh.native}", flush=True)
+    print("SHARDED PARITY", "OK" if ok else "FAILED", f"leaves={go.shape[0]} exchanges/frame={sh.exchanges // NF} native={sh.native} p2p={getattr(sh, 'p2p', False)}", flush=True)
+sh.check_errors()
 dist.barrier()
 sh.close()
 dist.destroy_process_group()
