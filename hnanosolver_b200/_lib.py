@@ -82,12 +82,13 @@ SIGNATURES = {
     "hns_dist_set_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(c_i32p),
                                     C.POINTER(C.c_uint64), C.POINTER(c_i32p), C.c_uint64, c_i32p]),
     "hns_dist_ipc_prepare": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]),
-    "hns_dist_ipc_connect": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.c_uint64]),
+    "hns_dist_ipc_connect": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.c_uint64, c_i32p]),
     "hns_dist_ipc_finish": (C.c_int, [C.c_void_p]),
     "hns_dist_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "hns_dist_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "hns_dist_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "hns_dist_frame_timed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, c_f32p]),
+    "hns_dist_debug_step": (C.c_int, [C.c_void_p, c_f32p]),
     "hns_dist_bytes_sent": (C.c_uint64, [C.c_void_p]),
     "hns_dist_exchanges": (C.c_uint64, [C.c_void_p]),
 }

@@ -80,6 +80,8 @@ struct hns_dist {
 		uint64_t region_off = 0;
 		uint8_t* remote_region = nullptr;
 		void* ipc_base = nullptr;
+		void* ipc_p[2] = {nullptr, nullptr};      // the peer's p[red], p[black] arrays mapped into this process
+		std::vector<int32_t> peer_leaf;            // for each entry of my send list: that leaf's id in the PEER's local numbering
 	};
 	std::vector<Peer> peers;
 	int max_fields = 0;
@@ -101,6 +103,17 @@ struct hns_dist {
 	uint32_t seq[5] = {};
 	uint32_t* d_err = nullptr;
 	int n_scalars = 0;
+	// timed mode: events inside one pressure half-sweep (k = 20): bs: before B, after B, after push, after signal+wait, after unpack; st: before I, after I
+	cudaEvent_t dbg[7] = {};
+	bool dbg_valid = false;
+	// fused boundary sweep + push: CSR over the boundary work list -> (peer index, leaf id on that peer)
+	uint32_t* d_push_off = nullptr;
+	int32_t *d_push_peer = nullptr, *d_push_leaf = nullptr;
+	float** d_remote_p[2] = {nullptr, nullptr};  // [n_peers] per colour
+	uint32_t* d_counter = nullptr;
+	uint32_t seq_p[2] = {0, 0}, frame_id = 0;
+	std::vector<int32_t> h_boundary;             // host copy of the boundary work list
+	const hns_state* bound_state = nullptr;
 };
 
 // ---- layout of one peer region: [flags 128 B][ch0 velocity 3 x 512n][ch1 advected velocity 3 x 512n][ch2 red p 256n][ch3 black p 256n]
@@ -182,8 +195,13 @@ void hns_dist_destroy(hns_dist* d) {
 	if (!d) return;
 	for (auto& p : d->peers) cudaFree(p.d_send), cudaFree(p.d_recv), cudaFree(p.buf_send), cudaFree(p.buf_recv);
 	cudaFree(d->d_elem0), cudaFree(d->d_owned), cudaFree(d->d_boundary), cudaFree(d->d_interior);
-	for (auto& p : d->peers)
+	for (auto& p : d->peers) {
 		if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base);
+		for (void* q : p.ipc_p)
+			if (q) cudaIpcCloseMemHandle(q);
+	}
+	cudaFree(d->d_push_off), cudaFree(d->d_push_peer), cudaFree(d->d_push_leaf), cudaFree(d->d_remote_p[0]), cudaFree(d->d_remote_p[1]),
+	    cudaFree(d->d_counter);
 	cudaFree(d->block), cudaFree(d->d_remote_flags), cudaFree(d->d_local_flags), cudaFree(d->d_err);
 	for (auto& e : d->ev_I)
 		if (e) cudaEventDestroy(e);
@@ -216,6 +234,7 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 		};
 		HNS_CUDA(up(std::vector<int32_t>(owned_ids, owned_ids + n_owned), &d->d_owned));
 		HNS_CUDA(up(bnd, &d->d_boundary));
+		d->h_boundary = bnd;
 		HNS_CUDA(up(inter, &d->d_interior));
 		s->active = d->d_owned, s->n_active = d->n_owned;
 		if (!d->comm_stream) {
@@ -249,6 +268,7 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 	if (!d->d_elem0) HNS_CUDA(cudaMalloc(&d->d_elem0, 32 * sizeof(float)));
 	s->elem0 = d->d_elem0;
 	d->n_scalars = s->n_scalars;
+	d->bound_state = s;
 	return HNS_OK;
 }
 
@@ -259,7 +279,7 @@ int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields
 // 2. the caller all-gathers (handle, offsets);  3. per peer: hns_dist_ipc_connect(handle of that peer, offset of MY region in ITS block)
 // 4. hns_dist_ipc_finish switches the exchanges from NCCL send/recv to peer stores + flags
 int hns_dist_ipc_prepare(hns_dist* d, uint8_t* handle_out64, uint64_t* region_offsets_out) {
-	if (!d || !handle_out64 || (!region_offsets_out && !d->peers.empty())) return fail(HNS_ERR_INVALID_ARGUMENT, "null argument");
+	if (!d || !handle_out64 || (!region_offsets_out && !d->peers.empty()) || !d->bound_state) return fail(HNS_ERR_INVALID_ARGUMENT, "null argument");
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
 	uint64_t total = 256;
 	for (size_t i = 0; i < d->peers.size(); ++i) {
@@ -275,16 +295,28 @@ int hns_dist_ipc_prepare(hns_dist* d, uint8_t* handle_out64, uint64_t* region_of
 	cudaIpcMemHandle_t h;
 	HNS_CUDA(cudaIpcGetMemHandle(&h, d->block));
 	std::memcpy(handle_out64, &h, 64);
+	for (int c = 0; c < 2; ++c) {  // handles 1, 2: the red / black pressure arrays (peers store swept ghost values straight into them)
+		HNS_CUDA(cudaIpcGetMemHandle(&h, d->bound_state->p[c]));
+		std::memcpy(handle_out64 + 64 * (1 + c), &h, 64);
+	}
 	return HNS_OK;
 }
-int hns_dist_ipc_connect(hns_dist* d, int peer_index, const uint8_t* peer_handle64, uint64_t my_region_offset_in_peer_block) {
-	if (!d || peer_index < 0 || peer_index >= int(d->peers.size()) || !peer_handle64) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+int hns_dist_ipc_connect(hns_dist* d, int peer_index, const uint8_t* peer_handles192, uint64_t my_region_offset_in_peer_block,
+                         const int32_t* peer_leaf_ids) {
+	if (!d || peer_index < 0 || peer_index >= int(d->peers.size()) || !peer_handles192) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
 	auto& p = d->peers[peer_index];
+	if (p.n_send && !peer_leaf_ids) return fail(HNS_ERR_INVALID_ARGUMENT, "peer_leaf_ids is null");
 	cudaIpcMemHandle_t h;
-	std::memcpy(&h, peer_handle64, 64);
+	std::memcpy(&h, peer_handles192, 64);
 	if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base), p.ipc_base = nullptr;
 	HNS_CUDA(cudaIpcOpenMemHandle(&p.ipc_base, h, cudaIpcMemLazyEnablePeerAccess));
 	p.remote_region = static_cast<uint8_t*>(p.ipc_base) + my_region_offset_in_peer_block;
+	for (int c = 0; c < 2; ++c) {
+		std::memcpy(&h, peer_handles192 + 64 * (1 + c), 64);
+		if (p.ipc_p[c]) cudaIpcCloseMemHandle(p.ipc_p[c]), p.ipc_p[c] = nullptr;
+		HNS_CUDA(cudaIpcOpenMemHandle(&p.ipc_p[c], h, cudaIpcMemLazyEnablePeerAccess));
+	}
+	p.peer_leaf.assign(peer_leaf_ids, peer_leaf_ids + p.n_send);
 	return HNS_OK;
 }
 int hns_dist_ipc_finish(hns_dist* d) {
@@ -306,6 +338,43 @@ int hns_dist_ipc_finish(hns_dist* d) {
 		HNS_CUDA(cudaMalloc(&d->d_err, sizeof(uint32_t)));
 		HNS_CUDA(cudaMemset(d->d_err, 0, sizeof(uint32_t)));
 	}
+	{
+		// CSR over the boundary work list: which peers hold a ghost copy of boundary leaf i, and under which leaf id
+		std::vector<std::vector<std::pair<int32_t, int32_t>>> per_leaf(d->bound_state->grid->num_leaves);
+		std::vector<int32_t> host_send;
+		for (size_t i = 0; i < n; ++i) {
+			const auto& p = d->peers[i];
+			host_send.resize(p.n_send);
+			if (p.n_send) HNS_CUDA(cudaMemcpy(host_send.data(), p.d_send, p.n_send * sizeof(int32_t), cudaMemcpyDeviceToHost));
+			for (uint64_t k = 0; k < p.n_send; ++k) per_leaf[host_send[k]].push_back({int32_t(i), p.peer_leaf[k]});
+		}
+		std::vector<uint32_t> off(d->h_boundary.size() + 1, 0);
+		std::vector<int32_t> peer, leaf;
+		for (size_t b = 0; b < d->h_boundary.size(); ++b) {
+			for (const auto& e : per_leaf[d->h_boundary[b]]) peer.push_back(e.first), leaf.push_back(e.second);
+			off[b + 1] = uint32_t(peer.size());
+		}
+		cudaFree(d->d_push_off), cudaFree(d->d_push_peer), cudaFree(d->d_push_leaf);
+		HNS_CUDA(cudaMalloc(&d->d_push_off, off.size() * sizeof(uint32_t)));
+		HNS_CUDA(cudaMemcpy(d->d_push_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		HNS_CUDA(cudaMalloc(&d->d_push_peer, std::max<size_t>(peer.size(), 1) * sizeof(int32_t)));
+		HNS_CUDA(cudaMalloc(&d->d_push_leaf, std::max<size_t>(leaf.size(), 1) * sizeof(int32_t)));
+		if (!peer.empty()) {
+			HNS_CUDA(cudaMemcpy(d->d_push_peer, peer.data(), peer.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+			HNS_CUDA(cudaMemcpy(d->d_push_leaf, leaf.data(), leaf.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+		}
+		for (int c = 0; c < 2; ++c) {
+			std::vector<float*> rp(std::max<size_t>(n, 1), nullptr);
+			for (size_t i = 0; i < n; ++i) rp[i] = static_cast<float*>(d->peers[i].ipc_p[c]);
+			cudaFree(d->d_remote_p[c]);
+			HNS_CUDA(cudaMalloc(&d->d_remote_p[c], rp.size() * sizeof(float*)));
+			HNS_CUDA(cudaMemcpy(d->d_remote_p[c], rp.data(), rp.size() * sizeof(float*), cudaMemcpyHostToDevice));
+		}
+		if (!d->d_counter) {
+			HNS_CUDA(cudaMalloc(&d->d_counter, sizeof(uint32_t)));
+			HNS_CUDA(cudaMemset(d->d_counter, 0, sizeof(uint32_t)));
+		}
+	}
 	d->p2p = true;
 	return HNS_OK;
 }
@@ -320,7 +389,7 @@ int hns_dist_error(hns_dist* d, uint32_t* out) {
 // Ghost exchange through peer memory: every owned boundary brick is stored straight into the peer's landing region over NVLink
 // (the pack kernel with a remote destination), the channel flag is raised, the peers' flags are awaited, the landed bricks are
 // scattered into the ghost leaves. Four small launches, no library call, NVLink bandwidth instead of NCCL's p2p channel bandwidth.
-static int exchange_p2p(hns_dist* d, hns_state* s, int channel, int n_fields, const int* fields, cudaStream_t st) {
+static int exchange_p2p(hns_dist* d, hns_state* s, int channel, int n_fields, const int* fields, cudaStream_t st, cudaEvent_t* dbg = nullptr) {
 	const int S = d->n_scalars;
 	for (auto& p : d->peers) {
 		if (!p.n_send) continue;
@@ -336,8 +405,10 @@ static int exchange_p2p(hns_dist* d, hns_state* s, int channel, int n_fields, co
 	}
 	const uint32_t seq = ++d->seq[channel];
 	const int np = int(d->peers.size());
+	if (dbg) cudaEventRecord(dbg[2], st);
 	HNS_LAUNCH(k_signal, 1, 32, 0, st, d->d_remote_flags, np, channel, seq);
 	HNS_LAUNCH(k_wait, 1, 32, 0, st, d->d_local_flags, np, channel, seq, d->d_err);
+	if (dbg) cudaEventRecord(dbg[3], st);
 	for (auto& p : d->peers) {
 		if (!p.n_recv) continue;
 		const float* src = reinterpret_cast<const float*>(d->block + p.region_off + channel_offset(channel, p.n_recv, S));
@@ -348,12 +419,13 @@ static int exchange_p2p(hns_dist* d, hns_state* s, int channel, int n_fields, co
 			src += p.n_recv * fpl;
 		}
 	}
+	if (dbg) cudaEventRecord(dbg[4], st);
 	++d->exchanges;
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
-static int exchange_channel(hns_dist* d, hns_state* s, int channel, int n_fields, const int* fields, cudaStream_t st) {
-	return d->p2p ? exchange_p2p(d, s, channel, n_fields, fields, st) : hns_dist_exchange(d, s, n_fields, fields, st);
+static int exchange_channel(hns_dist* d, hns_state* s, int channel, int n_fields, const int* fields, cudaStream_t st, cudaEvent_t* dbg = nullptr) {
+	return d->p2p ? exchange_p2p(d, s, channel, n_fields, fields, st, dbg) : hns_dist_exchange(d, s, n_fields, fields, st);
 }
 
 // pack -> grouped send/recv -> unpack of the given fields' ghost bricks, all on `stream`
@@ -446,20 +518,56 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 		vi.list = d->d_interior, vi.num_list = d->n_interior;
 		const float dx = s->grid->voxel_size;
 		cudaStream_t bs = d->comm_stream;
+		const int np = int(d->peers.size());
+		const bool fused = d->p2p && d->n_boundary > 0;
+		if (fused) {
+			// "my pressure arrays are zeroed and nobody reads last frame's ghosts any more": peers may start pushing into them
+			++d->frame_id;
+			HNS_LAUNCH(k_signal, 1, 32, 0, st, d->d_remote_flags, np, 5, d->frame_id);
+		}
 		HNS_CUDA(cudaEventRecord(d->ev_I[1], st));  // "I_0": everything before the solve
 		HNS_CUDA(cudaEventRecord(d->ev_B[1], bs));  // "B_0": nothing
 		int k = 0;
 		for (int it = 0; it < iterations; ++it)
 			for (int color = 0; color < 2; ++color, ++k) {
 				const int cur = k & 1, prev = cur ^ 1;
+				cudaEvent_t* dbg = nullptr;
+				if (marks && k == 20 && d->p2p) {
+					if (!d->dbg[0])
+						for (auto& e : d->dbg) cudaEventCreate(&e);
+					dbg = d->dbg, d->dbg_valid = true;
+				}
 				HNS_CUDA(cudaStreamWaitEvent(bs, d->ev_I[prev], 0));
-				if (d->n_boundary) launch_rbgs_color(vb, s->div, s->p, dx, color, omega, color, bs);
-				HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
+				if (dbg) cudaEventRecord(dbg[0], bs);
+				if (fused) {
+					// ghosts of the colour this sweep reads: pushed by the peers' previous boundary sweep (first sweep: their init signal)
+					if (k == 0)
+						HNS_LAUNCH(k_wait, 1, 32, 0, bs, d->d_local_flags, np, 5, d->frame_id, d->d_err);
+					else
+						HNS_LAUNCH(k_wait, 1, 32, 0, bs, d->d_local_flags, np, 2 + (color ^ 1), d->seq_p[color ^ 1], d->d_err);
+					if (dbg) cudaEventRecord(dbg[2], bs);
+					RbgsPush push;
+					push.dst_off = d->d_push_off, push.dst_peer = d->d_push_peer, push.dst_leaf = d->d_push_leaf;
+					push.remote_pc = d->d_remote_p[color], push.signal_flags = d->d_remote_flags, push.n_peers = np;
+					push.signal_ch = 2 + color, push.signal_seq = ++d->seq_p[color], push.counter = d->d_counter;
+					launch_rbgs_color_push(vb, s->div, s->p, dx, color, omega, color, push, bs);
+					d->bytes_sent += uint64_t(d->n_boundary) * 1024u;
+					++d->exchanges;
+					HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
+					if (dbg) cudaEventRecord(dbg[1], bs), cudaEventRecord(dbg[3], bs), cudaEventRecord(dbg[4], bs);
+				} else {
+					if (d->n_boundary) launch_rbgs_color(vb, s->div, s->p, dx, color, omega, color, bs);
+					HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
+					if (dbg) cudaEventRecord(dbg[1], bs);
+				}
 				HNS_CUDA(cudaStreamWaitEvent(st, d->ev_B[prev], 0));
+				if (dbg) cudaEventRecord(dbg[5], st);
 				if (d->n_interior) launch_rbgs_color(vi, s->div, s->p, dx, color, omega, color, st);
 				HNS_CUDA(cudaEventRecord(d->ev_I[cur], st));
-				if ((rc = exchange_channel(d, s, 2 + color, 1, color ? fblk : fred, bs))) return rc;
+				if (dbg) cudaEventRecord(dbg[6], st);
+				if (!fused && (rc = exchange_channel(d, s, 2 + color, 1, color ? fblk : fred, bs, dbg))) return rc;
 			}
+		if (fused) HNS_LAUNCH(k_wait, 1, 32, 0, bs, d->d_local_flags, np, 3, d->seq_p[1], d->d_err);  // the peers' last black push
 		HNS_CUDA(cudaEventRecord(d->ev_exchanged, bs));
 		HNS_CUDA(cudaStreamWaitEvent(st, d->ev_exchanged, 0));
 	}
@@ -478,6 +586,18 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	return rc;
 }
 
+// after hns_dist_frame_timed: microseconds inside pressure half-sweep 20, all relative to the start of its boundary sweep:
+// out[0..4] = end of boundary sweep, end of push, end of signal+wait, end of unpack, (unused); out[5], out[6] = start / end of the interior sweep
+int hns_dist_debug_step(hns_dist* d, float* out7) {
+	if (!d || !out7 || !d->dbg_valid) return fail(HNS_ERR_RUNTIME, "no timed frame recorded");
+	for (int i = 1; i < 7; ++i) {
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, d->dbg[0], d->dbg[i]);
+		out7[i - 1] = ms * 1e3f;
+	}
+	out7[6] = 0.f;
+	return HNS_OK;
+}
 uint64_t hns_dist_bytes_sent(const hns_dist* d) { return d ? d->bytes_sent : 0; }
 uint64_t hns_dist_exchanges(const hns_dist* d) { return d ? d->exchanges : 0; }
 

@@ -6,6 +6,8 @@
 // of eight z-consecutive voxels move as two 128-bit accesses, and the pressure sweep stages brick + halo in shared memory
 // so that a red and a black half-sweep cost one pass over HBM. Arithmetic follows the reference kernels operation by
 // operation, with the multiply-adds ptxas fuses in the reference build written as explicit fmaf (see oracle/hns_oracle.c).
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace hns {
@@ -207,49 +209,80 @@ __device__ __forceinline__ float sor_update(float pxp, float pxm, float pyp, flo
 // traffic is: other-colour p (read), this-colour p (read + write), this-colour div (read) = 8 B per voxel of the grid.
 // `reverse` walks the leaves back to front: consecutive launches alternate direction so that each one starts on the bricks the
 // previous launch touched last, which are still resident in the 126 MB L2.
-__global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __restrict__ div_c, float* __restrict__ p_c,
-                                                    const float* __restrict__ p_o, float dx2, int color, float omega, int reverse) {
+// kPush: the sharded run's boundary sweep -- every freshly swept quad is also stored straight into the ghost copy of the leaf on
+// each peer GPU that holds one (NVLink peer memory, CUDA IPC), and the last block to finish raises the peers' arrival flags:
+// compute and ghost exchange are one kernel, nothing is packed, sent or unpacked afterwards.
+template <bool kPush>
+__global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __restrict__ div_c, float* __restrict__ p_c, const float* p_o,
+                                                    float dx2, int color, float omega, int reverse, RbgsPush push) {
 	RowCtx c;
-	{
-		uint32_t i = blockIdx.x * 4u + (threadIdx.x >> 6);
-		if (i >= g.count()) return;
+	uint32_t i = blockIdx.x * 4u + (threadIdx.x >> 6);
+	const bool active = i < g.count();
+	if (!kPush && !active) return;
+	if (active) {
 		if (reverse) i = g.count() - 1u - i;
 		const uint32_t leaf = g.leaf_at(i);
 		const int r = threadIdx.x & 63;
 		c.leaf = leaf, c.x = r >> 3, c.y = r & 7, c.nbr = g.nbr + uint64_t(leaf) * 27u;
+		const uint64_t q = split_idx(c.self());
+		const int sc = (c.x + c.y + color) & 1;  // swept voxels of this row are z = 2j + sc
+		const float4 C = ld4(p_c, q);            // old values of the swept colour (only this thread writes them)
+		// other colour: plain (coherent) loads when peers write ghost values into this array, read-only path otherwise
+		auto ldo = [&](uint64_t idx) { return kPush ? ld4(p_o, idx) : ldg4(p_o, idx); };
+		const float4 O = ldo(q);                 // own row: the z neighbours
+		int64_t t;
+		const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+		const float4 Oxp = (t = c.row(1, 0)) >= 0 ? ldo(split_idx(uint64_t(t))) : zero4;
+		const float4 Oxm = (t = c.row(-1, 0)) >= 0 ? ldo(split_idx(uint64_t(t))) : zero4;
+		const float4 Oyp = (t = c.row(0, 1)) >= 0 ? ldo(split_idx(uint64_t(t))) : zero4;
+		const float4 Oym = (t = c.row(0, -1)) >= 0 ? ldo(split_idx(uint64_t(t))) : zero4;
+		const float4 D = ldg4(div_c, q);
+		// z neighbours: sc == 0: voxel j (z = 2j) has below = O[j-1] (j = 0: last other-colour voxel of the -z leaf), above = O[j]
+		//               sc == 1: voxel j (z = 2j+1) has below = O[j], above = O[j+1] (j = 3: first other-colour voxel of the +z leaf)
+		float halo = 0.f;
+		if (sc == 0) {
+			if ((t = c.zminus()) >= 0) halo = p_o[split_idx(uint64_t(t) & ~uint64_t(7)) + 3];
+		} else {
+			if ((t = c.zplus()) >= 0) halo = p_o[split_idx(uint64_t(t))];
+		}
+		const float b0 = sc ? O.x : halo, b1 = sc ? O.y : O.x, b2 = sc ? O.z : O.y, b3 = sc ? O.w : O.z;  // below (z-1)
+		const float a0 = sc ? O.y : O.x, a1 = sc ? O.z : O.y, a2 = sc ? O.w : O.z, a3 = sc ? halo : O.w;  // above (z+1)
+		float4 n;
+		n.x = sor_update(Oxp.x, Oxm.x, Oyp.x, Oym.x, a0, b0, D.x, C.x, dx2, omega);
+		n.y = sor_update(Oxp.y, Oxm.y, Oyp.y, Oym.y, a1, b1, D.y, C.y, dx2, omega);
+		n.z = sor_update(Oxp.z, Oxm.z, Oyp.z, Oym.z, a2, b2, D.z, C.z, dx2, omega);
+		n.w = sor_update(Oxp.w, Oxm.w, Oyp.w, Oym.w, a3, b3, D.w, C.w, dx2, omega);
+		*reinterpret_cast<float4*>(p_c + q) = n;
+		if (kPush) {
+			const uint32_t row4 = uint32_t(q) & 255u;  // quad offset inside the half-brick
+			for (uint32_t e = __ldg(push.dst_off + i), e1 = __ldg(push.dst_off + i + 1); e < e1; ++e)
+				*reinterpret_cast<float4*>(push.remote_pc[__ldg(push.dst_peer + e)] + (uint64_t(__ldg(push.dst_leaf + e)) * 256u + row4)) = n;
+		}
 	}
-	const uint64_t q = split_idx(c.self());
-	const int sc = (c.x + c.y + color) & 1;  // swept voxels of this row are z = 2j + sc
-	const float4 C = ld4(p_c, q);            // old values of the swept colour (only this thread writes them)
-	const float4 O = ldg4(p_o, q);           // other colour, own row: the z neighbours
-	int64_t i;
-	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-	const float4 Oxp = (i = c.row(1, 0)) >= 0 ? ldg4(p_o, split_idx(uint64_t(i))) : zero4;
-	const float4 Oxm = (i = c.row(-1, 0)) >= 0 ? ldg4(p_o, split_idx(uint64_t(i))) : zero4;
-	const float4 Oyp = (i = c.row(0, 1)) >= 0 ? ldg4(p_o, split_idx(uint64_t(i))) : zero4;
-	const float4 Oym = (i = c.row(0, -1)) >= 0 ? ldg4(p_o, split_idx(uint64_t(i))) : zero4;
-	const float4 D = ldg4(div_c, q);
-	// z neighbours: sc == 0: voxel j (z = 2j) has below = O[j-1] (j = 0: last other-colour voxel of the -z leaf), above = O[j]
-	//               sc == 1: voxel j (z = 2j+1) has below = O[j], above = O[j+1] (j = 3: first other-colour voxel of the +z leaf)
-	float halo = 0.f;
-	if (sc == 0) {
-		if ((i = c.zminus()) >= 0) halo = __ldg(p_o + (split_idx(uint64_t(i) & ~uint64_t(7)) + 3));
-	} else {
-		if ((i = c.zplus()) >= 0) halo = __ldg(p_o + split_idx(uint64_t(i)));
+	if (kPush) {
+		__threadfence_system();  // this block's peer stores are performed before it counts itself done
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			const uint32_t done = atomicAdd(push.counter, 1u);
+			if (done == gridDim.x - 1u) {
+				*push.counter = 0u;
+				__threadfence_system();
+				for (int pp = 0; pp < push.n_peers; ++pp)
+					if (push.signal_flags[pp]) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(push.signal_flags[pp] + push.signal_ch), "r"(push.signal_seq) : "memory");
+			}
+		}
 	}
-	const float b0 = sc ? O.x : halo, b1 = sc ? O.y : O.x, b2 = sc ? O.z : O.y, b3 = sc ? O.w : O.z;  // below (z-1)
-	const float a0 = sc ? O.y : O.x, a1 = sc ? O.z : O.y, a2 = sc ? O.w : O.z, a3 = sc ? halo : O.w;  // above (z+1)
-	float4 n;
-	n.x = sor_update(Oxp.x, Oxm.x, Oyp.x, Oym.x, a0, b0, D.x, C.x, dx2, omega);
-	n.y = sor_update(Oxp.y, Oxm.y, Oyp.y, Oym.y, a1, b1, D.y, C.y, dx2, omega);
-	n.z = sor_update(Oxp.z, Oxm.z, Oyp.z, Oym.z, a2, b2, D.z, C.z, dx2, omega);
-	n.w = sor_update(Oxp.w, Oxm.w, Oyp.w, Oym.w, a3, b3, D.w, C.w, dx2, omega);
-	*reinterpret_cast<float4*>(p_c + q) = n;
 }
 void launch_rbgs_color(const GridView& g, const float* const div[2], float* const p[2], float dx, int color, float omega, int reverse,
                        cudaStream_t st) {
 	if (g.count())
-		HNS_LAUNCH(k_rbgs_split, (g.count() + 3) / 4, 256, 0, st, g, div[color], p[color], p[color ^ 1], dx * dx, color, omega, reverse);
+		HNS_LAUNCH(k_rbgs_split<false>, (g.count() + 3) / 4, 256, 0, st, g, div[color], p[color], p[color ^ 1], dx * dx, color, omega, reverse,
+		           RbgsPush{});
+}
+void launch_rbgs_color_push(const GridView& g, const float* const div[2], float* const p[2], float dx, int color, float omega, int reverse,
+                            const RbgsPush& push, cudaStream_t st) {
+	if (g.count())
+		HNS_LAUNCH(k_rbgs_split<true>, (g.count() + 3) / 4, 256, 0, st, g, div[color], p[color], p[color ^ 1], dx * dx, color, omega, reverse, push);
 }
 
 int upload_tables() { return HNS_OK; }
@@ -736,23 +769,35 @@ void launch_split_to_brick(const float* const f[2], float* out, uint64_t n, cuda
 // =============================================================================================================
 // brick gather / scatter for ghost-leaf exchange
 // =============================================================================================================
-// quads = float4 per leaf: 128 for a brick field (512 floats), 64 for one half of a colour-split field (256 floats)
-__global__ void __launch_bounds__(128) k_pack_leaves(const float* __restrict__ field, const int32_t* __restrict__ ids, float* __restrict__ dst, int quads) {
-	if (int(threadIdx.x) >= quads) return;
-	const int32_t l = __ldg(ids + blockIdx.x);
-	reinterpret_cast<float4*>(dst)[uint64_t(blockIdx.x) * quads + threadIdx.x] = __ldg(reinterpret_cast<const float4*>(field) + uint64_t(l) * quads + threadIdx.x);
-	__threadfence_system();  // dst may be a peer GPU's memory (direct ghost exchange): order the store before the flag that follows
+// qshift = log2(float4 per leaf): 7 for a brick field (512 floats), 6 for one half of a colour-split field (256 floats).
+// Grid-stride over all quads of all listed leaves; `dst` of the pack kernel may be a peer GPU's memory (direct ghost exchange):
+// plain 16-byte stores, no fence here -- the flag that publishes them is raised by a later kernel in the same stream.
+__global__ void __launch_bounds__(256) k_pack_leaves(const float* __restrict__ field, const int32_t* __restrict__ ids, float* __restrict__ dst,
+                                                     uint32_t total_quads, int qshift) {
+	for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total_quads; i += gridDim.x * 256u) {
+		const int32_t l = __ldg(ids + (i >> qshift));
+		reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(field) + ((uint64_t(l) << qshift) | (i & ((1u << qshift) - 1u))));
+	}
 }
-__global__ void __launch_bounds__(128) k_unpack_leaves(float* __restrict__ field, const int32_t* __restrict__ ids, const float* __restrict__ src, int quads) {
-	if (int(threadIdx.x) >= quads) return;
-	const int32_t l = __ldg(ids + blockIdx.x);
-	reinterpret_cast<float4*>(field)[uint64_t(l) * quads + threadIdx.x] = __ldg(reinterpret_cast<const float4*>(src) + uint64_t(blockIdx.x) * quads + threadIdx.x);
+__global__ void __launch_bounds__(256) k_unpack_leaves(float* __restrict__ field, const int32_t* __restrict__ ids, const float* __restrict__ src,
+                                                       uint32_t total_quads, int qshift) {
+	for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total_quads; i += gridDim.x * 256u) {
+		const int32_t l = __ldg(ids + (i >> qshift));
+		reinterpret_cast<float4*>(field)[(uint64_t(l) << qshift) | (i & ((1u << qshift) - 1u))] = reinterpret_cast<const float4*>(src)[i];
+	}
 }
+static unsigned copy_grid(uint32_t total_quads) { return std::min<unsigned>((total_quads + 255u) / 256u, 4u * 148u); }
 void launch_pack_leaves(const float* field, const int32_t* ids, uint64_t n_ids, float* dst, int floats_per_leaf, cudaStream_t st) {
-	if (n_ids) HNS_LAUNCH(k_pack_leaves, unsigned(n_ids), 128, 0, st, field, ids, dst, floats_per_leaf / 4);
+	if (!n_ids) return;
+	const int qshift = floats_per_leaf == 512 ? 7 : 6;
+	const uint32_t total = uint32_t(n_ids) << qshift;
+	HNS_LAUNCH(k_pack_leaves, copy_grid(total), 256, 0, st, field, ids, dst, total, qshift);
 }
 void launch_unpack_leaves(float* field, const int32_t* ids, uint64_t n_ids, const float* src, int floats_per_leaf, cudaStream_t st) {
-	if (n_ids) HNS_LAUNCH(k_unpack_leaves, unsigned(n_ids), 128, 0, st, field, ids, src, floats_per_leaf / 4);
+	if (!n_ids) return;
+	const int qshift = floats_per_leaf == 512 ? 7 : 6;
+	const uint32_t total = uint32_t(n_ids) << qshift;
+	HNS_LAUNCH(k_unpack_leaves, copy_grid(total), 256, 0, st, field, ids, src, total, qshift);
 }
 
 }  // namespace hns

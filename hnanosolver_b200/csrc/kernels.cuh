@@ -28,6 +28,21 @@ void launch_divergence(const GridView& g, const float* const vel[3], float* cons
 // redBlackGaussSeidelUpdate (Kernel.cu:591-623): one colour per launch, in place, on the colour-split layout (p[0] red, p[1] black)
 void launch_rbgs_color(const GridView& g, const float* const div[2], float* const p[2], float dx, int color, float omega, int reverse,
                        cudaStream_t st);
+// Boundary sweep of a sharded run with the ghost exchange fused in: besides writing p[color] locally, every swept quad of work item i
+// is stored into the ghost copies listed in dst_peer/dst_leaf[dst_off[i] .. dst_off[i+1]) (peer index, leaf id in that peer's local
+// numbering) through remote_pc[peer] = that peer's p[color] array mapped over NVLink; the last block raises signal_flags[*][signal_ch].
+struct RbgsPush {
+	const uint32_t* dst_off = nullptr;
+	const int32_t* dst_peer = nullptr;
+	const int32_t* dst_leaf = nullptr;
+	float* const* remote_pc = nullptr;
+	uint32_t* const* signal_flags = nullptr;
+	int n_peers = 0, signal_ch = 0;
+	uint32_t signal_seq = 0;
+	uint32_t* counter = nullptr;
+};
+void launch_rbgs_color_push(const GridView& g, const float* const div[2], float* const p[2], float dx, int color, float omega, int reverse,
+                            const RbgsPush& push, cudaStream_t st);
 // subtractPressureGradient (Kernel.cu:765-829)
 void launch_subtract_gradient(const GridView& g, const float* const vel[3], const float* const p[2], float* const out[3], float inv_dx,
                               cudaStream_t st);

@@ -219,15 +219,19 @@ class ShardedSimulation:
             self.p2p = False
             if plan.world > 1 and bool(int(_os.environ.get("HNS_P2P", "1"))):
                 # direct peer-memory exchange: all-gather every rank's IPC handle and region offsets, connect to the peers
-                handle = (C.c_uint8 * 64)()
+                handle = (C.c_uint8 * 192)()
                 offs = (C.c_uint64 * max(n, 1))()
                 _lib.check(L.hns_dist_ipc_prepare(h, handle, offs))
-                mine = (bytes(handle), {p: int(offs[i]) for i, p in enumerate(peers)})
+                mine = (bytes(handle), {p: int(offs[i]) for i, p in enumerate(peers)}, {p: np.asarray(v, np.int32) for p, v in plan.recv.items()})
                 allinfo = [None] * plan.world
                 tdist.all_gather_object(allinfo, mine)
                 for i, p in enumerate(peers):
-                    ph, poffs = allinfo[p]
-                    _lib.check(L.hns_dist_ipc_connect(h, i, (C.c_uint8 * 64).from_buffer_copy(ph), poffs[plan.rank]))
+                    ph, poffs, precv = allinfo[p]
+                    # the peer's recv list for me lists, in the same (global id) order as my send list, its local ids of my leaves
+                    theirs = np.ascontiguousarray(precv.get(plan.rank, empty), np.int32)
+                    assert len(theirs) == len(snd[i])
+                    _lib.check(L.hns_dist_ipc_connect(h, i, (C.c_uint8 * 192).from_buffer_copy(ph), poffs.get(plan.rank, 0),
+                                                      theirs.ctypes.data_as(_lib.c_i32p)))
                 _lib.check(L.hns_dist_ipc_finish(h))
                 tdist.barrier()
                 self.p2p = True
@@ -326,7 +330,11 @@ class ShardedSimulation:
 
         ms = (C.c_float * 8)()
         _lib.check(_lib.lib().hns_dist_frame_timed(self._dist, self.sim._h, iterations, dt, C.c_void_p(self._stream()), ms))
-        return dict(zip(self.PHASES, [float(x) for x in ms]))
+        out = dict(zip(self.PHASES, [float(x) for x in ms]))
+        step = (C.c_float * 7)()
+        if _lib.lib().hns_dist_debug_step(self._dist, step) == 0:
+            out["step20_us(B_end,push_end,wait_end,unpack_end,I_start,I_end)"] = [round(float(x), 1) for x in step[:6]]
+        return out
 
     def owned(self, arr: np.ndarray) -> np.ndarray:
         """Rows of a per-voxel local array that belong to owned leaves."""
@@ -405,7 +413,7 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
     phases = sh.frame_timed(iterations, w.dt) if sh.native else {}
     log = __import__("sys").stderr
     print(f"[rank {rank}] owned {plan.n_owned} ghost {plan.n_local - plan.n_owned} peers { {p: len(v) for p, v in plan.send.items()} } "
-          f"phases(ms) { {k: round(v, 3) for k, v in phases.items()} }", file=log, flush=True)
+          f"phases(ms) { {k: (round(v, 3) if isinstance(v, float) else v) for k, v in phases.items()} }", file=log, flush=True)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = torch.tensor([float(_lib.lib().hns_launch_count())], device=dev)

@@ -188,12 +188,16 @@ void hns_dist_destroy(hns_dist* d);
 int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ranks, const uint64_t* n_send, const int32_t* const* send_ids,
                       const uint64_t* n_recv, const int32_t* const* recv_ids, uint64_t n_owned, const int32_t* owned_ids);
 /* Direct peer-memory ghost exchange (CUDA IPC over NVLink/NVSwitch) instead of ncclSend/ncclRecv: bricks are stored straight into
- * the peer's landing block and a flag is raised. Setup: every rank calls _prepare (its block's 64-byte IPC handle + the byte offset
- * of each peer's region inside it, in the order of hns_dist_set_plan's peers), the caller all-gathers them, calls _connect once per
- * peer with that peer's handle and the offset of ITS OWN region inside the peer's block, then _finish. hns_dist_error reports a
- * flag wait that timed out (0 = none). */
+ * the peer's landing block and a flag is raised; in the pressure solve the boundary sweep kernel itself stores every swept quad into
+ * the peers' ghost copies (their pressure arrays mapped over NVLink) and raises the flag -- no pack / send / unpack at all.
+ * Setup: every rank calls _prepare (three 64-byte IPC handles: landing block, red and black pressure arrays; plus the byte offset of
+ * each peer's region inside the block, in the order of hns_dist_set_plan's peers), the caller all-gathers them together with its recv
+ * leaf lists, calls _connect once per peer with that peer's 192 handle bytes, the offset of ITS OWN region inside the peer's block and,
+ * for every leaf of its send list to that peer, the leaf's id in the peer's local numbering (= the peer's recv list for this rank),
+ * then _finish. hns_dist_error reports a flag wait that timed out (0 = none). */
 int hns_dist_ipc_prepare(hns_dist* d, uint8_t* handle_out64, uint64_t* region_offsets_out);
-int hns_dist_ipc_connect(hns_dist* d, int peer_index, const uint8_t* peer_handle64, uint64_t my_region_offset_in_peer_block);
+int hns_dist_ipc_connect(hns_dist* d, int peer_index, const uint8_t* peer_handles192, uint64_t my_region_offset_in_peer_block,
+                         const int32_t* peer_leaf_ids);
 int hns_dist_ipc_finish(hns_dist* d);
 int hns_dist_error(hns_dist* d, uint32_t* out);
 /* ghost exchange of the given fields (ids as for hns_state_pack_leaves): pack, grouped ncclSend/ncclRecv, unpack; asynchronous */
@@ -204,6 +208,7 @@ int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* st
 /* the same frame with CUDA events between its phases (ms_out[8]: exchange velocity, advect_vector, exchange advected velocity,
  * divergence + combustion, pressure solve incl. exchanges, gradient, final exchange, advect_scalars); synchronises the stream */
 int hns_dist_frame_timed(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, float* ms_out);
+int hns_dist_debug_step(hns_dist* d, float* out7); /* sub-step timing of one pressure half-sweep of the last timed frame (us) */
 uint64_t hns_dist_bytes_sent(const hns_dist* d);
 uint64_t hns_dist_exchanges(const hns_dist* d);
 
