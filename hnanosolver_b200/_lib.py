@@ -89,6 +89,7 @@ SIGNATURES = {
     "hns_dist_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "hns_dist_frame_timed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, c_f32p]),
     "hns_dist_debug_step": (C.c_int, [C.c_void_p, c_f32p]),
+    "hns_dist_time_sweeps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, c_f32p]),
     "hns_dist_bytes_sent": (C.c_uint64, [C.c_void_p]),
     "hns_dist_exchanges": (C.c_uint64, [C.c_void_p]),
 }

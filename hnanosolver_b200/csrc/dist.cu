@@ -598,6 +598,50 @@ int hns_dist_debug_step(hns_dist* d, float* out7) {
 	out7[6] = 0.f;
 	return HNS_OK;
 }
+// Diagnostic: n pressure half-sweeps WITHOUT any exchange, timed with events (ms for all n). mode 0: every local leaf, no work list;
+// 1: owned list; 2: interior list only; 3: boundary list only; 4: interior on `stream` + boundary on the comm stream, pipelined like
+// the real solve. Ghost values go stale, so only the timing is meaningful.
+int hns_dist_time_sweeps(hns_dist* d, hns_state* s, int mode, int n, void* stream, float* ms_out) {
+	if (!d || !s || !ms_out || n <= 0 || mode < 0 || mode > 4) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	cudaStream_t st = static_cast<cudaStream_t>(stream), bs = d->comm_stream;
+	GridView vb = s->grid->view, vi = s->grid->view, vo = s->grid->view, va = s->grid->view;
+	vb.list = d->d_boundary, vb.num_list = d->n_boundary;
+	vi.list = d->d_interior, vi.num_list = d->n_interior;
+	vo.list = d->d_owned, vo.num_list = d->n_owned;
+	const float dx = s->grid->voxel_size, omega = hns_omega_compute(dx);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0), cudaEventCreate(&e1);
+	cudaStreamSynchronize(st), cudaStreamSynchronize(bs);
+	cudaEventRecord(e0, st);
+	HNS_CUDA(cudaEventRecord(d->ev_I[1], st));
+	HNS_CUDA(cudaEventRecord(d->ev_B[1], bs));
+	for (int k = 0; k < n; ++k) {
+		const int color = k & 1, cur = k & 1, prev = cur ^ 1;
+		switch (mode) {
+			case 0: launch_rbgs_color(va, s->div, s->p, dx, color, omega, color, st); break;
+			case 1: launch_rbgs_color(vo, s->div, s->p, dx, color, omega, color, st); break;
+			case 2: launch_rbgs_color(vi, s->div, s->p, dx, color, omega, color, st); break;
+			case 3: launch_rbgs_color(vb, s->div, s->p, dx, color, omega, color, st); break;
+			default:
+				HNS_CUDA(cudaStreamWaitEvent(bs, d->ev_I[prev], 0));
+				launch_rbgs_color(vb, s->div, s->p, dx, color, omega, color, bs);
+				HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
+				HNS_CUDA(cudaStreamWaitEvent(st, d->ev_B[prev], 0));
+				launch_rbgs_color(vi, s->div, s->p, dx, color, omega, color, st);
+				HNS_CUDA(cudaEventRecord(d->ev_I[cur], st));
+		}
+	}
+	if (mode == 4) {
+		HNS_CUDA(cudaEventRecord(d->ev_exchanged, bs));
+		HNS_CUDA(cudaStreamWaitEvent(st, d->ev_exchanged, 0));
+	}
+	cudaEventRecord(e1, st);
+	cudaStreamSynchronize(st);
+	cudaEventElapsedTime(ms_out, e0, e1);
+	cudaEventDestroy(e0), cudaEventDestroy(e1);
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
 uint64_t hns_dist_bytes_sent(const hns_dist* d) { return d ? d->bytes_sent : 0; }
 uint64_t hns_dist_exchanges(const hns_dist* d) { return d ? d->exchanges : 0; }
 

@@ -209,6 +209,9 @@ int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* st
  * divergence + combustion, pressure solve incl. exchanges, gradient, final exchange, advect_scalars); synchronises the stream */
 int hns_dist_frame_timed(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, float* ms_out);
 int hns_dist_debug_step(hns_dist* d, float* out7); /* sub-step timing of one pressure half-sweep of the last timed frame (us) */
+/* diagnostic: n exchange-free pressure half-sweeps over (mode) 0 all local leaves, 1 owned, 2 interior, 3 boundary, 4 interior and
+ * boundary pipelined on two streams; *ms_out = elapsed milliseconds */
+int hns_dist_time_sweeps(hns_dist* d, hns_state* s, int mode, int n, void* stream, float* ms_out);
 uint64_t hns_dist_bytes_sent(const hns_dist* d);
 uint64_t hns_dist_exchanges(const hns_dist* d);
 
