@@ -52,6 +52,9 @@ struct GridView {
 	// only, or the boundary / interior split that lets a ghost exchange overlap the interior sweep)
 	const int32_t* list;
 	uint32_t num_list;
+	// optional companion of `list`: the neighbour rows gathered in list order, [num_list][27] with slot 13 = the leaf id itself. One
+	// dependent load then yields the leaf id AND its neighbours (list -> nbr -> data would be three hops; this is two, like no list).
+	const int32_t* list_nbr;
 	__host__ __device__ uint32_t count() const { return list ? num_list : num_leaves; }
 #ifdef __CUDACC__
 	__device__ __forceinline__ uint32_t leaf_at(uint32_t i) const { return list ? uint32_t(__ldg(list + i)) : i; }

@@ -10,6 +10,7 @@
 // NCCL instance torch has already loaded in the same process.
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -89,6 +90,7 @@ struct hns_dist {
 	uint64_t bytes_sent = 0, exchanges = 0;
 	// work lists (local leaf ids, device): owned = boundary (sent to some peer) + interior
 	int32_t *d_owned = nullptr, *d_boundary = nullptr, *d_interior = nullptr;
+	int32_t *d_boundary_nbr = nullptr, *d_interior_nbr = nullptr;  // GridView::list_nbr of the two pressure work lists
 	uint32_t n_owned = 0, n_boundary = 0, n_interior = 0;
 	cudaStream_t comm_stream = nullptr;  // boundary sweeps + ghost exchange run here, next to the interior sweep on the caller's stream
 	cudaEvent_t ev_boundary = nullptr, ev_exchanged = nullptr;
@@ -114,6 +116,8 @@ struct hns_dist {
 	uint32_t seq_p[2] = {0, 0}, frame_id = 0;
 	std::vector<int32_t> h_boundary;             // host copy of the boundary work list
 	const hns_state* bound_state = nullptr;
+	bool fused_push = true;         // HNS_FUSED_PUSH=0: pack / push / signal / wait / unpack kernels instead (A/B switch)
+	bool signal_in_kernel = false;  // HNS_SIGNAL_IN_KERNEL=1: the boundary sweep raises the arrival flags itself (A/B switch)
 };
 
 // ---- layout of one peer region: [flags 128 B][ch0 velocity 3 x 512n][ch1 advected velocity 3 x 512n][ch2 red p 256n][ch3 black p 256n]
@@ -195,6 +199,7 @@ void hns_dist_destroy(hns_dist* d) {
 	if (!d) return;
 	for (auto& p : d->peers) cudaFree(p.d_send), cudaFree(p.d_recv), cudaFree(p.buf_send), cudaFree(p.buf_recv);
 	cudaFree(d->d_elem0), cudaFree(d->d_owned), cudaFree(d->d_boundary), cudaFree(d->d_interior);
+	cudaFree(d->d_boundary_nbr), cudaFree(d->d_interior_nbr);
 	for (auto& p : d->peers) {
 		if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base);
 		for (void* q : p.ipc_p)
@@ -236,6 +241,16 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 		HNS_CUDA(up(bnd, &d->d_boundary));
 		d->h_boundary = bnd;
 		HNS_CUDA(up(inter, &d->d_interior));
+		cudaFree(d->d_boundary_nbr), cudaFree(d->d_interior_nbr);
+		d->d_boundary_nbr = d->d_interior_nbr = nullptr;
+		const char* e = std::getenv("HNS_LIST_NBR");  // A/B switch, default on
+		if (!e || std::atoi(e) != 0) {
+			HNS_CUDA(cudaMalloc(&d->d_boundary_nbr, std::max<size_t>(bnd.size(), 1) * 27 * sizeof(int32_t)));
+			HNS_CUDA(cudaMalloc(&d->d_interior_nbr, std::max<size_t>(inter.size(), 1) * 27 * sizeof(int32_t)));
+			launch_gather_nbr_rows(s->grid->view.nbr, d->d_boundary, d->n_boundary, d->d_boundary_nbr, nullptr);
+			launch_gather_nbr_rows(s->grid->view.nbr, d->d_interior, d->n_interior, d->d_interior_nbr, nullptr);
+			HNS_CUDA(cudaDeviceSynchronize());
+		}
 		s->active = d->d_owned, s->n_active = d->n_owned;
 		if (!d->comm_stream) {
 			int prio_lo = 0, prio_hi = 0;  // the exchange kernels are tiny and latency-critical: let their CTAs overtake the queued interior sweep
@@ -269,6 +284,8 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 	s->elem0 = d->d_elem0;
 	d->n_scalars = s->n_scalars;
 	d->bound_state = s;
+	if (const char* e = std::getenv("HNS_SIGNAL_IN_KERNEL")) d->signal_in_kernel = std::atoi(e) != 0;
+	if (const char* e = std::getenv("HNS_FUSED_PUSH")) d->fused_push = std::atoi(e) != 0;
 	return HNS_OK;
 }
 
@@ -514,12 +531,12 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 		// Half-sweep k reads colour c_{k-1} and writes colour c_k, so I_k and B_k/x_k never touch the same colour of the same leaf
 		// at the same time, and the exchange latency disappears behind the interior sweep as long as B + x is the shorter chain.
 		GridView vb = s->grid->view, vi = s->grid->view;
-		vb.list = d->d_boundary, vb.num_list = d->n_boundary;
-		vi.list = d->d_interior, vi.num_list = d->n_interior;
+		vb.list = d->d_boundary, vb.num_list = d->n_boundary, vb.list_nbr = d->d_boundary_nbr;
+		vi.list = d->d_interior, vi.num_list = d->n_interior, vi.list_nbr = d->d_interior_nbr;
 		const float dx = s->grid->voxel_size;
 		cudaStream_t bs = d->comm_stream;
 		const int np = int(d->peers.size());
-		const bool fused = d->p2p && d->n_boundary > 0;
+		const bool fused = d->p2p && d->fused_push && d->n_boundary > 0;
 		if (fused) {
 			// "my pressure arrays are zeroed and nobody reads last frame's ghosts any more": peers may start pushing into them
 			++d->frame_id;
@@ -549,8 +566,9 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 					RbgsPush push;
 					push.dst_off = d->d_push_off, push.dst_peer = d->d_push_peer, push.dst_leaf = d->d_push_leaf;
 					push.remote_pc = d->d_remote_p[color], push.signal_flags = d->d_remote_flags, push.n_peers = np;
-					push.signal_ch = 2 + color, push.signal_seq = ++d->seq_p[color], push.counter = d->d_counter;
+					push.signal_ch = 2 + color, push.signal_seq = ++d->seq_p[color], push.counter = d->signal_in_kernel ? d->d_counter : nullptr;
 					launch_rbgs_color_push(vb, s->div, s->p, dx, color, omega, color, push, bs);
+					if (!d->signal_in_kernel) HNS_LAUNCH(k_signal, 1, 32, 0, bs, d->d_remote_flags, np, 2 + color, d->seq_p[color]);
 					d->bytes_sent += uint64_t(d->n_boundary) * 1024u;
 					++d->exchanges;
 					HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
@@ -605,8 +623,8 @@ int hns_dist_time_sweeps(hns_dist* d, hns_state* s, int mode, int n, void* strea
 	if (!d || !s || !ms_out || n <= 0 || mode < 0 || mode > 4) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
 	cudaStream_t st = static_cast<cudaStream_t>(stream), bs = d->comm_stream;
 	GridView vb = s->grid->view, vi = s->grid->view, vo = s->grid->view, va = s->grid->view;
-	vb.list = d->d_boundary, vb.num_list = d->n_boundary;
-	vi.list = d->d_interior, vi.num_list = d->n_interior;
+	vb.list = d->d_boundary, vb.num_list = d->n_boundary, vb.list_nbr = d->d_boundary_nbr;
+	vi.list = d->d_interior, vi.num_list = d->n_interior, vi.list_nbr = d->d_interior_nbr;
 	vo.list = d->d_owned, vo.num_list = d->n_owned;
 	const float dx = s->grid->voxel_size, omega = hns_omega_compute(dx);
 	cudaEvent_t e0, e1;

@@ -218,12 +218,18 @@ __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __r
 	RowCtx c;
 	uint32_t i = blockIdx.x * 4u + (threadIdx.x >> 6);
 	const bool active = i < g.count();
-	if (!kPush && !active) return;
+	if (!active && !(kPush && push.counter)) return;
 	if (active) {
 		if (reverse) i = g.count() - 1u - i;
-		const uint32_t leaf = g.leaf_at(i);
 		const int r = threadIdx.x & 63;
-		c.leaf = leaf, c.x = r >> 3, c.y = r & 7, c.nbr = g.nbr + uint64_t(leaf) * 27u;
+		c.x = r >> 3, c.y = r & 7;
+		if (g.list_nbr) {
+			c.nbr = g.list_nbr + uint64_t(i) * 27u;
+			c.leaf = uint32_t(__ldg(c.nbr + kSlotSelf));
+		} else {
+			c.leaf = g.leaf_at(i);
+			c.nbr = g.nbr + uint64_t(c.leaf) * 27u;
+		}
 		const uint64_t q = split_idx(c.self());
 		const int sc = (c.x + c.y + color) & 1;  // swept voxels of this row are z = 2j + sc
 		const float4 C = ld4(p_c, q);            // old values of the swept colour (only this thread writes them)
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __r
 				*reinterpret_cast<float4*>(push.remote_pc[__ldg(push.dst_peer + e)] + (uint64_t(__ldg(push.dst_leaf + e)) * 256u + row4)) = n;
 		}
 	}
-	if (kPush) {
+	if (kPush && push.counter) {  // in-kernel arrival signal (otherwise the caller launches a signal kernel behind this one)
 		__threadfence_system();  // this block's peer stores are performed before it counts itself done
 		__syncthreads();
 		if (threadIdx.x == 0) {
@@ -283,6 +289,18 @@ void launch_rbgs_color_push(const GridView& g, const float* const div[2], float*
                             const RbgsPush& push, cudaStream_t st) {
 	if (g.count())
 		HNS_LAUNCH(k_rbgs_split<true>, (g.count() + 3) / 4, 256, 0, st, g, div[color], p[color], p[color ^ 1], dx * dx, color, omega, reverse, push);
+}
+
+// rows of the neighbour table in work-list order, slot 13 = the leaf id (GridView::list_nbr)
+__global__ void k_gather_nbr_rows(const int32_t* __restrict__ nbr, const int32_t* __restrict__ list, uint32_t n, int32_t* __restrict__ out) {
+	const uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+	if (t >= uint64_t(n) * 27u) return;
+	const uint32_t i = uint32_t(t / 27u), k = uint32_t(t % 27u);
+	const int32_t leaf = list[i];
+	out[t] = k == uint32_t(kSlotSelf) ? leaf : nbr[uint64_t(leaf) * 27u + k];
+}
+void launch_gather_nbr_rows(const int32_t* nbr, const int32_t* list, uint32_t n, int32_t* out, cudaStream_t st) {
+	if (n) HNS_LAUNCH(k_gather_nbr_rows, uint32_t((uint64_t(n) * 27u + 255u) / 256u), 256, 0, st, nbr, list, n, out);
 }
 
 int upload_tables() { return HNS_OK; }

@@ -30,7 +30,8 @@ void launch_rbgs_color(const GridView& g, const float* const div[2], float* cons
                        cudaStream_t st);
 // Boundary sweep of a sharded run with the ghost exchange fused in: besides writing p[color] locally, every swept quad of work item i
 // is stored into the ghost copies listed in dst_peer/dst_leaf[dst_off[i] .. dst_off[i+1]) (peer index, leaf id in that peer's local
-// numbering) through remote_pc[peer] = that peer's p[color] array mapped over NVLink; the last block raises signal_flags[*][signal_ch].
+// numbering) through remote_pc[peer] = that peer's p[color] array mapped over NVLink. With a counter the last block to finish also
+// raises signal_flags[*][signal_ch] (every block then pays a system fence); without one the caller signals from a follow-up kernel.
 struct RbgsPush {
 	const uint32_t* dst_off = nullptr;
 	const int32_t* dst_peer = nullptr;
@@ -50,6 +51,8 @@ void launch_subtract_gradient(const GridView& g, const float* const vel[3], cons
 void launch_combustion_oxygen(const float* fuel, const float* waste, const float* temp, float* const div[2], const float* flame, float* oFuel,
                               float* oWaste, float* oTemp, float* oFlame, float temp_gain, float expansion, uint64_t n, cudaStream_t st);
 void launch_buoyancy(float* const vel[3], const float* temp, float dt, float ambient, float strength, uint64_t n, cudaStream_t st);
+// GridView::list_nbr for a work list: out[n][27]
+void launch_gather_nbr_rows(const int32_t* nbr, const int32_t* list, uint32_t n, int32_t* out, cudaStream_t st);
 // whole-brick gather / scatter by leaf id (ghost exchange)
 void launch_pack_leaves(const float* field, const int32_t* ids, uint64_t n_ids, float* dst, int floats_per_leaf, cudaStream_t st);
 void launch_unpack_leaves(float* field, const int32_t* ids, uint64_t n_ids, const float* src, int floats_per_leaf, cudaStream_t st);

@@ -229,6 +229,7 @@ static int build_grid(const int32_t* origins, uint64_t L, float voxel_size, hns_
 	g->view.off_leaf = g->nvdb_bytes - nvdb::kLeaf * L;
 	g->view.list = nullptr;
 	g->view.num_list = 0;
+	g->view.list_nbr = nullptr;
 	if (L) {
 		const uint32_t n = uint32_t(L) * 27u;
 		HNS_LAUNCH(k_neighbor_table, (n + 255) / 256, 256, 0, 0, g->view, g->d_nbr);
