@@ -170,6 +170,7 @@ int hns_state_upload_velocity(hns_state* s, const float* host) {
 	HNS_CUDA(cudaMemcpy(s->aos, host, s->n * 12, cudaMemcpyHostToDevice));
 	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], s->n, 0);
 	HNS_CUDA(cudaDeviceSynchronize());
+	++s->vel_version;
 	return HNS_OK;
 }
 int hns_state_download_velocity(hns_state* s, float* host) {
@@ -234,6 +235,7 @@ int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void*
 	HNS_REQUIRE(iterations > 0, "Number of pressure iterations must be positive.");
 	HNS_REQUIRE(dt >= 0.0f, "dt (time step) cannot be negative.");
 	if (!s->n) return HNS_OK;
+	++s->vel_version;
 	return frame(s, iterations, dt, s->grid->voxel_size, flags, static_cast<cudaStream_t>(stream));
 }
 int hns_state_advect_velocity(hns_state* s, float dt, void* stream) {
@@ -286,6 +288,7 @@ float hns_omega_project(float voxel_size) { return omega_project(voxel_size); }
 
 int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream) {
 	HNS_REQUIRE(s, "null state");
+	++s->vel_version;
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if (from_advected) {
 		launch_subtract_gradient(s->view(), s->adv, s->p, s->vel, 1.0f / s->grid->voxel_size, st);
@@ -325,6 +328,7 @@ int hns_state_sync(hns_state* s, void* stream) {
 int hns_state_time_frames(hns_state* s, int frames, int iterations, float dt, unsigned flags, void* stream, float* ms_total, float* ms_pressure) {
 	HNS_REQUIRE(s && frames > 0 && iterations > 0, "bad argument");
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	++s->vel_version;
 	// Every frame must do identical work on identical data: keep a pristine copy of the inputs and restore it (outside
 	// the per-frame events would need a sync per frame; instead the restore copies are timed separately and subtracted).
 	const size_t fb = s->n * sizeof(float);
@@ -384,6 +388,7 @@ static float* field_ptr(hns_state* s, int field, int* floats_per_leaf) {
 }
 void* hns_state_field_device_ptr(hns_state* s, int field) {
 	int fpl;
+	if (s && field >= 0 && field < 3) ++s->vel_version;  // the caller may write through the pointer
 	return s ? field_ptr(s, field, &fpl) : nullptr;
 }
 int hns_state_field_floats_per_leaf(int field) { return (field >= 6 && field <= 9) ? 256 : 512; }
@@ -401,6 +406,7 @@ int hns_state_unpack_leaves(hns_state* s, int field, const int32_t* ids, uint64_
 	int fpl;
 	float* f = field_ptr(s, field, &fpl);
 	HNS_REQUIRE(f, "bad field id");
+	if (field < 3) ++s->vel_version;
 	launch_unpack_leaves(f, ids, n_ids, src, fpl, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;

@@ -119,6 +119,7 @@ struct hns_state {
 	hns_combustion_params comb{};
 	int skip_scalar = -1;  // scalar that is carried but not advected ("collision_sdf")
 	const float* elem0 = nullptr;  // device float[3 + n_scalars]: element 0 of the global arrays (sharded runs), else null
+	uint64_t vel_version = 0;  // bumped by every entry point that (may) overwrite the velocity planes; lets a sharded run skip a ghost exchange of unchanged data
 	const int32_t* active = nullptr;  // device list of the leaves the kernels process (sharded runs: the owned leaves), null = all
 	uint32_t n_active = 0;
 	hns::GridView view() const {

@@ -94,6 +94,9 @@ struct hns_dist {
 	uint32_t n_owned = 0, n_boundary = 0, n_interior = 0;
 	cudaStream_t comm_stream = nullptr;  // boundary sweeps + ghost exchange run here, next to the interior sweep on the caller's stream
 	cudaEvent_t ev_boundary = nullptr, ev_exchanged = nullptr;
+	cudaStream_t aux_stream = nullptr;  // the scalars' ghost exchange, hidden behind the pressure solve
+	cudaEvent_t ev_scalars_final = nullptr, ev_scalars_exchanged = nullptr;
+	uint64_t vel_exchanged_version = ~uint64_t(0);  // hns_state::vel_version whose velocity ghosts are current on every rank
 	cudaEvent_t ev_I[2] = {}, ev_B[2] = {};
 	// direct peer-memory ghost exchange (CUDA IPC over NVLink): one block of device memory per rank holding, per peer, five
 	// channels of landing space + their arrival flags. Peers store bricks straight into it and then raise the channel's flag.
@@ -102,7 +105,7 @@ struct hns_dist {
 	uint64_t block_bytes = 0;
 	uint32_t** d_remote_flags = nullptr;  // [n_peers] flag words in the peers' blocks
 	uint32_t** d_local_flags = nullptr;   // [n_peers] flag words in my block
-	uint32_t seq[5] = {};
+	uint32_t seq[8] = {};
 	uint32_t* d_err = nullptr;
 	int n_scalars = 0;
 	// timed mode: events inside one pressure half-sweep (k = 20): bs: before B, after B, after push, after signal+wait, after unpack; st: before I, after I
@@ -213,6 +216,9 @@ void hns_dist_destroy(hns_dist* d) {
 	for (auto& e : d->ev_B)
 		if (e) cudaEventDestroy(e);
 	if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
+	if (d->aux_stream) cudaStreamDestroy(d->aux_stream);
+	if (d->ev_scalars_final) cudaEventDestroy(d->ev_scalars_final);
+	if (d->ev_scalars_exchanged) cudaEventDestroy(d->ev_scalars_exchanged);
 	if (d->ev_boundary) cudaEventDestroy(d->ev_boundary);
 	if (d->ev_exchanged) cudaEventDestroy(d->ev_exchanged);
 	if (d->comm) g_nccl.CommDestroy(d->comm);
@@ -256,6 +262,9 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 			int prio_lo = 0, prio_hi = 0;  // the exchange kernels are tiny and latency-critical: let their CTAs overtake the queued interior sweep
 			cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
 			HNS_CUDA(cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, prio_hi));
+			HNS_CUDA(cudaStreamCreateWithFlags(&d->aux_stream, cudaStreamNonBlocking));
+			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_scalars_final, cudaEventDisableTiming));
+			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_scalars_exchanged, cudaEventDisableTiming));
 			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_boundary, cudaEventDisableTiming));
 			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_exchanged, cudaEventDisableTiming));
 			for (auto& e : d->ev_I) HNS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -284,6 +293,7 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 	s->elem0 = d->d_elem0;
 	d->n_scalars = s->n_scalars;
 	d->bound_state = s;
+	d->vel_exchanged_version = ~uint64_t(0);
 	if (const char* e = std::getenv("HNS_SIGNAL_IN_KERNEL")) d->signal_in_kernel = std::atoi(e) != 0;
 	if (const char* e = std::getenv("HNS_FUSED_PUSH")) d->fused_push = std::atoi(e) != 0;
 	return HNS_OK;
@@ -406,11 +416,15 @@ int hns_dist_error(hns_dist* d, uint32_t* out) {
 // Ghost exchange through peer memory: every owned boundary brick is stored straight into the peer's landing region over NVLink
 // (the pack kernel with a remote destination), the channel flag is raised, the peers' flags are awaited, the landed bricks are
 // scattered into the ghost leaves. Four small launches, no library call, NVLink bandwidth instead of NCCL's p2p channel bandwidth.
-static int exchange_p2p(hns_dist* d, hns_state* s, int channel, int n_fields, const int* fields, cudaStream_t st, cudaEvent_t* dbg = nullptr) {
+// `channel` selects the arrival flag; the bricks land in region `region_ch` starting `skip_fields` whole fields in, so two exchanges
+// with different flags can share one region (velocity and scalars of channel 4).
+static int exchange_p2p(hns_dist* d, hns_state* s, int channel, int n_fields, const int* fields, cudaStream_t st, cudaEvent_t* dbg = nullptr,
+                        int region_ch = -1, int skip_fields = 0) {
 	const int S = d->n_scalars;
+	if (region_ch < 0) region_ch = channel;
 	for (auto& p : d->peers) {
 		if (!p.n_send) continue;
-		float* dst = reinterpret_cast<float*>(p.remote_region + channel_offset(channel, p.n_send, S));
+		float* dst = reinterpret_cast<float*>(p.remote_region + channel_offset(region_ch, p.n_send, S)) + uint64_t(skip_fields) * 512u * p.n_send;
 		for (int k = 0; k < n_fields; ++k) {
 			const int fpl = floats_per_leaf(fields[k]);
 			float* f = static_cast<float*>(hns_state_field_device_ptr(s, fields[k]));
@@ -428,7 +442,7 @@ static int exchange_p2p(hns_dist* d, hns_state* s, int channel, int n_fields, co
 	if (dbg) cudaEventRecord(dbg[3], st);
 	for (auto& p : d->peers) {
 		if (!p.n_recv) continue;
-		const float* src = reinterpret_cast<const float*>(d->block + p.region_off + channel_offset(channel, p.n_recv, S));
+		const float* src = reinterpret_cast<const float*>(d->block + p.region_off + channel_offset(region_ch, p.n_recv, S)) + uint64_t(skip_fields) * 512u * p.n_recv;
 		for (int k = 0; k < n_fields; ++k) {
 			const int fpl = floats_per_leaf(fields[k]);
 			float* f = static_cast<float*>(hns_state_field_device_ptr(s, fields[k]));
@@ -512,7 +526,9 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	mark();
 	const int fvel[3] = {0, 1, 2}, fadv[3] = {3, 4, 5}, fred[1] = {6}, fblk[1] = {7};
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
-	if ((rc = exchange_channel(d, s, 0, 3, fvel, st))) return rc;
+	// the velocity ghosts are still current when the last thing that wrote the velocity was the previous sharded frame (its final
+	// exchange refreshed them and advect_scalars does not touch the velocity)
+	if (d->vel_exchanged_version != s->vel_version && (rc = exchange_channel(d, s, 0, 3, fvel, st))) return rc;
 	mark();
 	if ((rc = hns_state_advect_velocity(s, dt, stream))) return rc;
 	mark();
@@ -520,6 +536,16 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	mark();
 	if ((rc = hns_state_divergence(s, 1, stream))) return rc;
 	if (s->comb_enabled && (rc = hns_state_combustion_buoyancy(s, dt, stream))) return rc;
+	// The scalars are final until advect_scalars: exchange their ghosts now, on a third stream, behind the pressure solve.
+	const bool scalars_early = d->p2p && s->n_scalars > 0;
+	if (scalars_early) {
+		std::vector<int> fsc;
+		for (int i = 0; i < s->n_scalars; ++i) fsc.push_back(10 + i);
+		HNS_CUDA(cudaEventRecord(d->ev_scalars_final, st));
+		HNS_CUDA(cudaStreamWaitEvent(d->aux_stream, d->ev_scalars_final, 0));
+		if ((rc = exchange_p2p(d, s, 6, int(fsc.size()), fsc.data(), d->aux_stream, nullptr, 4, 3))) return rc;
+		HNS_CUDA(cudaEventRecord(d->ev_scalars_exchanged, d->aux_stream));
+	}
 	mark();
 	if ((rc = hns_state_pressure_init(s, stream))) return rc;
 	const float omega = hns_omega_compute(s->grid->voxel_size);
@@ -593,13 +619,16 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	if ((rc = hns_state_subtract_gradient(s, 1, stream))) return rc;
 	mark();
 	std::vector<int> last = {0, 1, 2};
-	for (int i = 0; i < s->n_scalars; ++i) last.push_back(10 + i);
+	if (!scalars_early)
+		for (int i = 0; i < s->n_scalars; ++i) last.push_back(10 + i);
 	if ((rc = exchange_channel(d, s, 4, int(last.size()), last.data(), st))) return rc;
+	if (scalars_early) HNS_CUDA(cudaStreamWaitEvent(st, d->ev_scalars_exchanged, 0));
 	// advect_scalars' "inactive -> element 0" value is global voxel 0's (reference Kernel.cu:192,225): rank 0 owns it
 	if (d->rank == 0 && (rc = hns_state_gather_element0(s, d->d_elem0, stream))) return rc;
 	if (d->world > 1) HNS_NCCL(g_nccl.Broadcast(d->d_elem0, d->d_elem0, size_t(3 + s->n_scalars), ncclFloat, 0, d->comm, st));
 	mark();
 	rc = hns_state_advect_scalars(s, dt, 0, stream);
+	d->vel_exchanged_version = s->vel_version;
 	mark();
 	return rc;
 }

@@ -203,7 +203,11 @@ int hns_dist_error(hns_dist* d, uint32_t* out);
 /* ghost exchange of the given fields (ids as for hns_state_pack_leaves): pack, grouped ncclSend/ncclRecv, unpack; asynchronous */
 int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields, void* stream);
 /* the whole sharded frame (same steps as hns_state_step) with its 3 + 2*iterations ghost exchanges; the exchange of a swept
- * pressure colour overlaps the sweep of the interior leaves; asynchronous */
+ * pressure colour overlaps the sweep of the interior leaves, the scalars' exchange hides behind the pressure solve (peer-memory
+ * mode); asynchronous. COLLECTIVE: every rank calls it, and every call that overwrites the state's velocity between two frames
+ * (hns_state_upload_velocity, hns_state_step, ...) must be made on all ranks alike -- a frame whose velocity is untouched since the
+ * previous sharded frame skips the leading velocity-ghost exchange (those ghosts are still current), and the ranks must agree on
+ * that; a disagreement surfaces as a flag time-out in hns_dist_error, not as wrong values. */
 int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream);
 /* the same frame with CUDA events between its phases (ms_out[8]: exchange velocity, advect_vector, exchange advected velocity,
  * divergence + combustion, pressure solve incl. exchanges, gradient, final exchange, advect_scalars); synchronises the stream */
