@@ -119,6 +119,7 @@ struct hns_dist {
 	uint32_t seq_p[2] = {0, 0}, frame_id = 0;
 	std::vector<int32_t> h_boundary;             // host copy of the boundary work list
 	const hns_state* bound_state = nullptr;
+	int aux_blocks = 148;           // HNS_AUX_BLOCKS: CTA cap of the background scalar exchange (it must not starve the sweeps)
 	bool fused_push = true;         // HNS_FUSED_PUSH=0: pack / push / signal / wait / unpack kernels instead (A/B switch)
 	bool signal_in_kernel = false;  // HNS_SIGNAL_IN_KERNEL=1: the boundary sweep raises the arrival flags itself (A/B switch)
 };
@@ -296,6 +297,7 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 	d->vel_exchanged_version = ~uint64_t(0);
 	if (const char* e = std::getenv("HNS_SIGNAL_IN_KERNEL")) d->signal_in_kernel = std::atoi(e) != 0;
 	if (const char* e = std::getenv("HNS_FUSED_PUSH")) d->fused_push = std::atoi(e) != 0;
+	if (const char* e = std::getenv("HNS_AUX_BLOCKS")) d->aux_blocks = std::atoi(e);
 	return HNS_OK;
 }
 
@@ -419,7 +421,7 @@ int hns_dist_error(hns_dist* d, uint32_t* out) {
 // `channel` selects the arrival flag; the bricks land in region `region_ch` starting `skip_fields` whole fields in, so two exchanges
 // with different flags can share one region (velocity and scalars of channel 4).
 static int exchange_p2p(hns_dist* d, hns_state* s, int channel, int n_fields, const int* fields, cudaStream_t st, cudaEvent_t* dbg = nullptr,
-                        int region_ch = -1, int skip_fields = 0) {
+                        int region_ch = -1, int skip_fields = 0, int max_blocks = 0) {
 	const int S = d->n_scalars;
 	if (region_ch < 0) region_ch = channel;
 	for (auto& p : d->peers) {
@@ -429,7 +431,7 @@ static int exchange_p2p(hns_dist* d, hns_state* s, int channel, int n_fields, co
 			const int fpl = floats_per_leaf(fields[k]);
 			float* f = static_cast<float*>(hns_state_field_device_ptr(s, fields[k]));
 			if (!f) return fail(HNS_ERR_INVALID_ARGUMENT, "bad field id");
-			launch_pack_leaves(f, p.d_send, p.n_send, dst, fpl, st);
+			launch_pack_leaves(f, p.d_send, p.n_send, dst, fpl, st, max_blocks);
 			dst += p.n_send * fpl;
 			d->bytes_sent += p.n_send * fpl * 4;
 		}
@@ -446,7 +448,7 @@ static int exchange_p2p(hns_dist* d, hns_state* s, int channel, int n_fields, co
 		for (int k = 0; k < n_fields; ++k) {
 			const int fpl = floats_per_leaf(fields[k]);
 			float* f = static_cast<float*>(hns_state_field_device_ptr(s, fields[k]));
-			launch_unpack_leaves(f, p.d_recv, p.n_recv, src, fpl, st);
+			launch_unpack_leaves(f, p.d_recv, p.n_recv, src, fpl, st, max_blocks);
 			src += p.n_recv * fpl;
 		}
 	}
@@ -543,7 +545,7 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 		for (int i = 0; i < s->n_scalars; ++i) fsc.push_back(10 + i);
 		HNS_CUDA(cudaEventRecord(d->ev_scalars_final, st));
 		HNS_CUDA(cudaStreamWaitEvent(d->aux_stream, d->ev_scalars_final, 0));
-		if ((rc = exchange_p2p(d, s, 6, int(fsc.size()), fsc.data(), d->aux_stream, nullptr, 4, 3))) return rc;
+		if ((rc = exchange_p2p(d, s, 6, int(fsc.size()), fsc.data(), d->aux_stream, nullptr, 4, 3, d->aux_blocks))) return rc;
 		HNS_CUDA(cudaEventRecord(d->ev_scalars_exchanged, d->aux_stream));
 	}
 	mark();

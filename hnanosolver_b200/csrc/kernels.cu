@@ -804,18 +804,20 @@ __global__ void __launch_bounds__(256) k_unpack_leaves(float* __restrict__ field
 		reinterpret_cast<float4*>(field)[(uint64_t(l) << qshift) | (i & ((1u << qshift) - 1u))] = reinterpret_cast<const float4*>(src)[i];
 	}
 }
-static unsigned copy_grid(uint32_t total_quads) { return std::min<unsigned>((total_quads + 255u) / 256u, 4u * 148u); }
-void launch_pack_leaves(const float* field, const int32_t* ids, uint64_t n_ids, float* dst, int floats_per_leaf, cudaStream_t st) {
-	if (!n_ids) return;
-	const int qshift = floats_per_leaf == 512 ? 7 : 6;
-	const uint32_t total = uint32_t(n_ids) << qshift;
-	HNS_LAUNCH(k_pack_leaves, copy_grid(total), 256, 0, st, field, ids, dst, total, qshift);
+static unsigned copy_grid(uint32_t total_quads, int max_blocks) {
+	return std::min<unsigned>((total_quads + 255u) / 256u, max_blocks > 0 ? unsigned(max_blocks) : 4u * 148u);
 }
-void launch_unpack_leaves(float* field, const int32_t* ids, uint64_t n_ids, const float* src, int floats_per_leaf, cudaStream_t st) {
+void launch_pack_leaves(const float* field, const int32_t* ids, uint64_t n_ids, float* dst, int floats_per_leaf, cudaStream_t st, int max_blocks) {
 	if (!n_ids) return;
 	const int qshift = floats_per_leaf == 512 ? 7 : 6;
 	const uint32_t total = uint32_t(n_ids) << qshift;
-	HNS_LAUNCH(k_unpack_leaves, copy_grid(total), 256, 0, st, field, ids, src, total, qshift);
+	HNS_LAUNCH(k_pack_leaves, copy_grid(total, max_blocks), 256, 0, st, field, ids, dst, total, qshift);
+}
+void launch_unpack_leaves(float* field, const int32_t* ids, uint64_t n_ids, const float* src, int floats_per_leaf, cudaStream_t st, int max_blocks) {
+	if (!n_ids) return;
+	const int qshift = floats_per_leaf == 512 ? 7 : 6;
+	const uint32_t total = uint32_t(n_ids) << qshift;
+	HNS_LAUNCH(k_unpack_leaves, copy_grid(total, max_blocks), 256, 0, st, field, ids, src, total, qshift);
 }
 
 }  // namespace hns

@@ -54,8 +54,9 @@ void launch_buoyancy(float* const vel[3], const float* temp, float dt, float amb
 // GridView::list_nbr for a work list: out[n][27]
 void launch_gather_nbr_rows(const int32_t* nbr, const int32_t* list, uint32_t n, int32_t* out, cudaStream_t st);
 // whole-brick gather / scatter by leaf id (ghost exchange)
-void launch_pack_leaves(const float* field, const int32_t* ids, uint64_t n_ids, float* dst, int floats_per_leaf, cudaStream_t st);
-void launch_unpack_leaves(float* field, const int32_t* ids, uint64_t n_ids, const float* src, int floats_per_leaf, cudaStream_t st);
+// max_blocks > 0 caps the grid: a background exchange then never takes more than that many CTA slots from a concurrent sweep
+void launch_pack_leaves(const float* field, const int32_t* ids, uint64_t n_ids, float* dst, int floats_per_leaf, cudaStream_t st, int max_blocks = 0);
+void launch_unpack_leaves(float* field, const int32_t* ids, uint64_t n_ids, const float* src, int floats_per_leaf, cudaStream_t st, int max_blocks = 0);
 // colour-split (red, black) -> brick order
 void launch_split_to_brick(const float* const f[2], float* out, uint64_t n, cudaStream_t st);
 
