@@ -51,12 +51,29 @@ static ScalarPtrs scalar_ptrs(const hns_state* s) {
 }
 
 // One frame on resident state = Compute() (reference src/Cuda/HNanoSolver.cu:159-356) without the host copies:
-//   advect_vector -> [vorticity: scale 0 == identity] -> divergence -> [combustion_oxygen -> temperature_buoyancy] ->
+//   advect_vector -> [vorticityConfinement, out of place] -> divergence -> [combustion_oxygen -> temperature_buoyancy] ->
 //   iterations x (red, black) -> subtractPressureGradient -> advect_scalars over all scalar fields.
 // `voxel_size` is the launcher argument (the reference's kernels use it, not the grid's map).
 // Optional stream dependencies of a frame whose inputs arrive / outputs leave on a copy stream while it runs (hns_compute_sim):
 // the frame waits for `combustion_inputs` before the combustion stage and for `scalar_inputs` before advect_scalars, and records
 // `velocity_done` once the projected velocity is final.
+// vorticityConfinement on the advected velocity (reference HNanoSolver.cu:172-176), out of place into scratch planes that then trade
+// places with s->adv. A zero scale, or a factorScale that truncates to a zero offset (the SOP's default 0.5), makes the force
+// (+-0) * dt: the pass is skipped (identical values; only the sign of an exact zero could differ).
+static bool vorticity_active(float scale, float factor_scale) { return scale != 0.0f && int(factor_scale) != 0; }
+static int vorticity_pass(hns_state* s, float dt, float inv_dx, float scale, float factor_scale, cudaStream_t st) {
+	if (!vorticity_active(scale, factor_scale) || !s->n) return HNS_OK;
+	for (float*& v : s->vort)
+		if (!v) {
+			HNS_CUDA(cudaMalloc(&v, s->n * sizeof(float)));
+			HNS_CUDA(cudaMemsetAsync(v, 0, s->n * sizeof(float), st));
+		}
+	launch_vorticity_confinement(s->view(), s->adv, s->vort[3], s->vort, dt, inv_dx, scale, factor_scale, st);
+	for (int c = 0; c < 3; ++c) std::swap(s->adv[c], s->vort[c]);
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+
 struct FrameDeps {
 	cudaEvent_t combustion_inputs = nullptr, scalar_inputs = nullptr, velocity_done = nullptr;
 };
@@ -65,6 +82,10 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 	const GridView g = s->view();
 	const float h = voxel_size, inv = 1.0f / h;
 	launch_advect_vector(g, s->vel, s->adv, dt, inv, st);
+	if (s->comb_enabled) {
+		const int rc = vorticity_pass(s, dt, inv, s->comb.vorticityScale, s->comb.factorScale, st);
+		if (rc) return rc;
+	}
 	launch_divergence(g, s->adv, s->div, inv, st);
 	if (deps && deps->combustion_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->combustion_inputs, 0));
 	if (s->comb_enabled) {
@@ -155,6 +176,7 @@ void hns_state_destroy(hns_state* s) {
 	cudaFree(s->div[0]), cudaFree(s->div[1]), cudaFree(s->p[0]), cudaFree(s->p[1]);
 	for (int i = 0; i < 16; ++i) cudaFree(s->sc[i]), cudaFree(s->sc_out[i]);
 	cudaFree(s->aos);
+	for (float* v : s->vort) cudaFree(v);
 	delete s;
 }
 
@@ -221,9 +243,6 @@ int hns_state_set_combustion(hns_state* s, int enabled, int i_fuel, int i_waste,
 		HNS_REQUIRE(idx[a] >= 0 && idx[a] < s->n_scalars, "combustion field index out of range");
 		for (int b = 0; b < a; ++b) HNS_REQUIRE(idx[a] != idx[b], "combustion field indices must be distinct");
 	}
-	if (params->vorticityScale != 0.0f)
-		return fail(HNS_ERR_UNSUPPORTED, "vorticityScale != 0: the reference applies vorticity confinement in place with a data race "
-		                                 "(HNanoSolver.cu:174), so no reference result exists to reproduce; not implemented in this build");
 	std::memcpy(s->comb_idx, idx, sizeof(idx));
 	s->comb = *params;
 	s->comb_enabled = true;
@@ -243,6 +262,10 @@ int hns_state_advect_velocity(hns_state* s, float dt, void* stream) {
 	launch_advect_vector(s->view(), s->vel, s->adv, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
+}
+int hns_state_vorticity_confinement(hns_state* s, float dt, float scale, float factor_scale, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	return vorticity_pass(s, dt, 1.0f / s->grid->voxel_size, scale, factor_scale, static_cast<cudaStream_t>(stream));
 }
 int hns_state_divergence(hns_state* s, int of_advected, void* stream) {
 	HNS_REQUIRE(s, "null state");

@@ -785,6 +785,160 @@ void launch_split_to_brick(const float* const f[2], float* out, uint64_t n, cuda
 }
 
 // =============================================================================================================
+// vorticity confinement  (reference Kernel.cu:969-1025, computeVorticityMag Utils.cuh:226-243), out of place
+//   w = curl(u) by central differences * (0.5*inv_dx);  m(c) = |w(c)|;  g = ((m(c+fs) - m(c-fs)) * 0.5) * inv_dx per axis, fs = (int)factorScale;
+//   N = g / (|g| + 1e-5);  u += scale * (N x w) * dt.   Inactive velocity samples are 0, and m is ALSO evaluated at inactive
+//   positions (from whatever active voxels surround them).
+// The reference evaluates 42 index-grid lookups per voxel, in place (a race, HNanoSolver.cu:174). Here: pass 1 writes m for every
+// active voxel (one row per thread, like the divergence), pass 2 recomputes the voxel's own w from the same rows, reads m at the six
+// offset positions from the m plane and only falls back to evaluating the curl at a position when that position is inactive (or
+// |fs| > 8, beyond the neighbour table). Arithmetic and FMA contraction as in the reference SASS (see oracle/hns_oracle.c).
+// =============================================================================================================
+struct CurlRows {
+	Row8 wx, wy, wz;
+};
+// curl * factor of the eight voxels of row c; cu, cv = the row's own u and v (also needed by the caller)
+__device__ __forceinline__ CurlRows curl_rows(const RowCtx& c, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ w,
+                                              const Row8& cu, const Row8& cv, float factor) {
+	int64_t i;
+	Row8 w_xp = zero_row(), v_xp = zero_row(), w_xm = zero_row(), v_xm = zero_row();
+	Row8 w_yp = zero_row(), u_yp = zero_row(), w_ym = zero_row(), u_ym = zero_row();
+	if ((i = c.row(1, 0)) >= 0) w_xp = ld_row(w, i), v_xp = ld_row(v, i);
+	if ((i = c.row(-1, 0)) >= 0) w_xm = ld_row(w, i), v_xm = ld_row(v, i);
+	if ((i = c.row(0, 1)) >= 0) w_yp = ld_row(w, i), u_yp = ld_row(u, i);
+	if ((i = c.row(0, -1)) >= 0) w_ym = ld_row(w, i), u_ym = ld_row(u, i);
+	float u_zm = 0.f, v_zm = 0.f, u_zp = 0.f, v_zp = 0.f;
+	if ((i = c.zminus()) >= 0) u_zm = __ldg(u + i), v_zm = __ldg(v + i);
+	if ((i = c.zplus()) >= 0) u_zp = __ldg(u + i), v_zp = __ldg(v + i);
+	CurlRows r;
+#pragma unroll
+	for (int z = 0; z < 8; ++z) {
+		const float up = z < 7 ? cu.v[z < 7 ? z + 1 : 7] : u_zp, um = z > 0 ? cu.v[z > 0 ? z - 1 : 0] : u_zm;
+		const float vp = z < 7 ? cv.v[z < 7 ? z + 1 : 7] : v_zp, vm = z > 0 ? cv.v[z > 0 ? z - 1 : 0] : v_zm;
+		r.wx.v[z] = ((w_yp.v[z] - w_ym.v[z]) - (vp - vm)) * factor;
+		r.wy.v[z] = ((up - um) - (w_xp.v[z] - w_xm.v[z])) * factor;
+		r.wz.v[z] = ((v_xp.v[z] - v_xm.v[z]) - (u_yp.v[z] - u_ym.v[z])) * factor;
+	}
+	return r;
+}
+__device__ __forceinline__ float vort_norm(float wx, float wy, float wz) { return sqrtf(fmaf(wz, wz, fmaf(wy, wy, __fmul_rn(wx, wx)))); }
+
+__global__ void __launch_bounds__(256) k_vorticity_mag(GridView g, const float* __restrict__ u, const float* __restrict__ v,
+                                                       const float* __restrict__ w, float* __restrict__ mag, float factor) {
+	RowCtx c;
+	if (!make_row_ctx(g, c)) return;
+	const uint64_t self = c.self();
+	const Row8 cu = ld_row(u, self), cv = ld_row(v, self);
+	const CurlRows r = curl_rows(c, u, v, w, cu, cv, factor);
+	Row8 m;
+#pragma unroll
+	for (int z = 0; z < 8; ++z) m.v[z] = vort_norm(r.wx.v[z], r.wy.v[z], r.wz.v[z]);
+	st_row(mag, self, m);
+}
+
+// |curl| at an arbitrary position (i,j,k), evaluated from the velocity planes: the cold path of pass 2 (inactive positions, far offsets)
+__device__ __noinline__ float vorticity_mag_at(const GridView& g, const LeafFrame& f, const float* __restrict__ u, const float* __restrict__ v,
+                                               const float* __restrict__ w, int i, int j, int k, float factor) {
+	float s[6][3];
+#pragma unroll
+	for (int q = 0; q < 6; ++q) {  // +x, -x, +y, -y, +z, -z
+		const int d = (q & 1) ? -1 : 1;
+		const int64_t idx = voxel_index(g, f, i + (q < 2 ? d : 0), j + ((q >> 1) == 1 ? d : 0), k + (q >= 4 ? d : 0));
+		s[q][0] = idx < 0 ? 0.f : __ldg(u + idx);
+		s[q][1] = idx < 0 ? 0.f : __ldg(v + idx);
+		s[q][2] = idx < 0 ? 0.f : __ldg(w + idx);
+	}
+	const float wx = ((s[2][2] - s[3][2]) - (s[4][1] - s[5][1])) * factor;
+	const float wy = ((s[4][0] - s[5][0]) - (s[0][2] - s[1][2])) * factor;
+	const float wz = ((s[0][1] - s[1][1]) - (s[2][0] - s[3][0])) * factor;
+	return vort_norm(wx, wy, wz);
+}
+
+// row of m at (x + dx, y + dy) of the leaf neighbourhood, |dx|, |dy| <= 8 (one of them 0); -1 when that leaf is missing
+__device__ __forceinline__ int64_t row_far(const RowCtx& c, int dx, int dy) {
+	int xx = c.x + dx, yy = c.y + dy;
+	int slot = kSlotSelf;
+	if (xx < 0) slot = kSlotXm, xx += 8;
+	else if (xx > 7) slot = kSlotXp, xx -= 8;
+	if (yy < 0) slot = kSlotYm, yy += 8;
+	else if (yy > 7) slot = kSlotYp, yy -= 8;
+	const int32_t l = slot == kSlotSelf ? int32_t(c.leaf) : __ldg(c.nbr + slot);
+	return l < 0 ? int64_t(-1) : int64_t(uint64_t(l) * 512u + uint32_t(xx * 64 + yy * 8));
+}
+
+__global__ void __launch_bounds__(256) k_vorticity_force(GridView g, const float* __restrict__ u, const float* __restrict__ v,
+                                                         const float* __restrict__ w, const float* __restrict__ mag, float* __restrict__ ou,
+                                                         float* __restrict__ ov, float* __restrict__ ow, float factor, float inv_dx, float scale,
+                                                         float dt, int fs) {
+	RowCtx c;
+	if (!make_row_ctx(g, c)) return;
+	const uint64_t self = c.self();
+	const int4 o = __ldg(g.origin + c.leaf);
+	const LeafFrame f{o.x, o.y, o.z, c.nbr};
+	const int gx = o.x + c.x, gy = o.y + c.y;
+	const bool far = fs > 8 || fs < -8;
+	// m at the six offset positions, then the gradient ((m+ - m-) * 0.5) * inv_dx per axis
+	Row8 G[3];
+#pragma unroll
+	for (int axis = 0; axis < 2; ++axis) {
+		Row8 mp, mm;
+		const int64_t ip = far ? -1 : row_far(c, axis == 0 ? fs : 0, axis == 1 ? fs : 0);
+		const int64_t im = far ? -1 : row_far(c, axis == 0 ? -fs : 0, axis == 1 ? -fs : 0);
+		if (ip >= 0) {
+			mp = ld_row(mag, ip);
+		} else {
+			for (int z = 0; z < 8; ++z) mp.v[z] = vorticity_mag_at(g, f, u, v, w, gx + (axis == 0 ? fs : 0), gy + (axis == 1 ? fs : 0), o.z + z, factor);
+		}
+		if (im >= 0) {
+			mm = ld_row(mag, im);
+		} else {
+			for (int z = 0; z < 8; ++z) mm.v[z] = vorticity_mag_at(g, f, u, v, w, gx - (axis == 0 ? fs : 0), gy - (axis == 1 ? fs : 0), o.z + z, factor);
+		}
+#pragma unroll
+		for (int z = 0; z < 8; ++z) G[axis].v[z] = ((mp.v[z] - mm.v[z]) * 0.5f) * inv_dx;
+	}
+	{
+		// z axis: the own row of m shifted by fs, continued into the rows (x, y) of the -z / +z leaves (scalar loads, L1-resident rows)
+		const int32_t lzm = __ldg(c.nbr + kSlotZm), lzp = __ldg(c.nbr + kSlotZp);
+		const uint32_t rxy = uint32_t(c.x * 64 + c.y * 8);
+		auto m_at = [&](int zz) -> float {  // m at (x, y, zz) relative to this leaf, zz in [-8, 16)
+			if (!far && zz >= 0 && zz < 8) return __ldg(mag + self + zz);
+			if (!far && zz < 0 && lzm >= 0) return __ldg(mag + uint64_t(lzm) * 512u + rxy + uint32_t(zz + 8));
+			if (!far && zz >= 8 && lzp >= 0) return __ldg(mag + uint64_t(lzp) * 512u + rxy + uint32_t(zz - 8));
+			return vorticity_mag_at(g, f, u, v, w, gx, gy, o.z + zz, factor);
+		};
+#pragma unroll
+		for (int z = 0; z < 8; ++z) G[2].v[z] = ((m_at(z + fs) - m_at(z - fs)) * 0.5f) * inv_dx;
+	}
+	const Row8 cu = ld_row(u, self), cv = ld_row(v, self), cw = ld_row(w, self);
+	const CurlRows r = curl_rows(c, u, v, w, cu, cv, factor);
+	Row8 a, b, d;
+#pragma unroll
+	for (int z = 0; z < 8; ++z) {
+		const float g0 = G[0].v[z], g1 = G[1].v[z], g2 = G[2].v[z];
+		const float len = sqrtf(fmaf(g2, g2, fmaf(g1, g1, __fmul_rn(g0, g0)))) + 1e-5f;
+		const float Nx = __fdiv_rn(g0, len), Ny = __fdiv_rn(g1, len), Nz = __fdiv_rn(g2, len);
+		const float fx = fmaf(-Nz, r.wy.v[z], __fmul_rn(Ny, r.wz.v[z]));
+		const float fy = fmaf(-Nx, r.wz.v[z], __fmul_rn(Nz, r.wx.v[z]));
+		const float fz = fmaf(-Ny, r.wx.v[z], __fmul_rn(Nx, r.wy.v[z]));
+		a.v[z] = fmaf(__fmul_rn(scale, fx), dt, cu.v[z]);
+		b.v[z] = fmaf(__fmul_rn(scale, fy), dt, cv.v[z]);
+		d.v[z] = fmaf(__fmul_rn(scale, fz), dt, cw.v[z]);
+	}
+	st_row(ou, self, a);
+	st_row(ov, self, b);
+	st_row(ow, self, d);
+}
+void launch_vorticity_confinement(const GridView& g, const float* const vel[3], float* mag, float* const out[3], float dt, float inv_dx, float scale,
+                                  float factor_scale, cudaStream_t st) {
+	if (!g.count()) return;
+	const float factor = 0.5f * inv_dx;
+	const int fs = int(factor_scale);  // Coord's int constructor truncates (F2I.TRUNC in the reference SASS)
+	HNS_LAUNCH(k_vorticity_mag, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], mag, factor);
+	HNS_LAUNCH(k_vorticity_force, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], mag, out[0], out[1], out[2], factor, inv_dx, scale, dt, fs);
+}
+
+// =============================================================================================================
 // brick gather / scatter for ghost-leaf exchange
 // =============================================================================================================
 // qshift = log2(float4 per leaf): 7 for a brick field (512 floats), 6 for one half of a colour-split field (256 floats).

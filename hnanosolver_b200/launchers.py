@@ -253,6 +253,10 @@ class Simulation:
     def advect_velocity(self, dt, stream=None):
         check(_lib.lib().hns_state_advect_velocity(self._h, dt, _stream(stream)))
 
+    def vorticity_confinement(self, dt, scale, factor_scale, stream=None):
+        """vorticityConfinement (reference Kernel.cu:969-1025) on the advected velocity, out of place"""
+        check(_lib.lib().hns_state_vorticity_confinement(self._h, dt, scale, factor_scale, _stream(stream)))
+
     def divergence(self, of_advected=True, stream=None):
         check(_lib.lib().hns_state_divergence(self._h, int(of_advected), _stream(stream)))
 

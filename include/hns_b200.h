@@ -127,7 +127,9 @@ int hns_state_download_scalar(hns_state* s, int index, float* host);
 int hns_state_download_aux(hns_state* s, int which, float* host);
 
 /* Enables the combustion_oxygen + temperature_buoyancy stage of the all-in-one frame (src/Cuda/HNanoSolver.cu:190-250) on the
- * scalar fields with the given indices; params->vorticityScale must be 0 (the reference's in-place vorticity pass races). */
+ * scalar fields with the given indices, and the vorticityConfinement pass (Kernel.cu:969-1025) between advect_vector and the
+ * divergence when params->vorticityScale != 0 and (int)params->factorScale != 0. The reference runs that kernel in place
+ * (HNanoSolver.cu:174), which races; here it is evaluated out of place (what the kernel computes when given two buffers). */
 int hns_state_set_combustion(hns_state* s, int enabled, int i_fuel, int i_waste, int i_temperature, int i_flame,
                              const hns_combustion_params* params);
 
@@ -140,6 +142,7 @@ int hns_state_set_combustion(hns_state* s, int enabled, int i_fuel, int i_waste,
 int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void* stream);
 /* Individual steps on resident state (asynchronous). */
 int hns_state_advect_velocity(hns_state* s, float dt, void* stream);                 /* vel -> adv              */
+int hns_state_vorticity_confinement(hns_state* s, float dt, float scale, float factor_scale, void* stream); /* adv -> adv, out of place */
 int hns_state_divergence(hns_state* s, int of_advected, void* stream);               /* adv|vel -> div          */
 int hns_state_pressure_solve(hns_state* s, int iterations, float omega, unsigned flags, void* stream); /* p = 0; RBGS   */
 int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream);      /* adv|vel, p -> vel       */

@@ -572,6 +572,50 @@ void ora_divergence(const ora_index* ix, const int32_t* coords, const float* vel
 	}
 }
 
+/* vorticityConfinement (Kernel.cu:969-1025) with computeVorticityMag (Utils.cuh:226-243), restated OUT OF PLACE: every sample reads
+ * `vel`, the result goes to `out`. The reference launches it in place (HNanoSolver.cu:174: input == output buffer), so for
+ * (int)factorScale != 0 its own result depends on thread timing; the out-of-place evaluation is the kernel's meaning and is what the
+ * reference kernel itself computes when given two buffers (that is how tests/ pin this function, through oracle/ref_shim.cu).
+ * Arithmetic as compiled in the reference SASS: |w|^2 = fma(wz,wz, fma(wy,wy, wx*wx)) under an IEEE sqrt; grad = ((p - m) * 0.5) * inv_dx;
+ * N = grad / (sqrt(fma(gz,gz, fma(gy,gy, gx*gx))) + 1e-5) with IEEE division; cross product a*b - c*d = fma(-c, d, rnd(a*b));
+ * out = fma(scale * cross, dt, vel). The neighbour offset is (int)factorScale, truncated (Coord's int constructor, F2I.TRUNC). */
+static void ora_curl(const ora_index* ix, const float* vel, int32_t i, int32_t j, int32_t k, float factor, float* w) {
+	float pX[3], mX[3], pY[3], mY[3], pZ[3], mZ[3];
+	ora_nearest_v(ix, vel, i + 1, j, k, pX), ora_nearest_v(ix, vel, i - 1, j, k, mX);
+	ora_nearest_v(ix, vel, i, j + 1, k, pY), ora_nearest_v(ix, vel, i, j - 1, k, mY);
+	ora_nearest_v(ix, vel, i, j, k + 1, pZ), ora_nearest_v(ix, vel, i, j, k - 1, mZ);
+	w[0] = ((pY[2] - mY[2]) - (pZ[1] - mZ[1])) * factor;
+	w[1] = ((pZ[0] - mZ[0]) - (pX[2] - mX[2])) * factor;
+	w[2] = ((pX[1] - mX[1]) - (pY[0] - mY[0])) * factor;
+}
+static float ora_vort_mag(const ora_index* ix, const float* vel, int32_t i, int32_t j, int32_t k, float factor) {
+	float w[3];
+	ora_curl(ix, vel, i, j, k, factor, w);
+	return sqrtf(fmaf(w[2], w[2], fmaf(w[1], w[1], w[0] * w[0])));
+}
+void ora_vorticity_confinement(const ora_index* ix, const int32_t* coords, const float* vel, float* out, uint64_t n, float dt, float inv_dx,
+                               float confinementScale, float factorScale) {
+	const float factor = (float)(0.5 * inv_dx); /* :982, a double product; exact either way */
+	const int32_t fs = (int32_t)factorScale;
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const int32_t i = coords[3 * t], j = coords[3 * t + 1], k = coords[3 * t + 2];
+		float w[3];
+		ora_curl(ix, vel, i, j, k, factor, w);
+		const float gx = ((ora_vort_mag(ix, vel, i + fs, j, k, factor) - ora_vort_mag(ix, vel, i - fs, j, k, factor)) * 0.5f) * inv_dx;
+		const float gy = ((ora_vort_mag(ix, vel, i, j + fs, k, factor) - ora_vort_mag(ix, vel, i, j - fs, k, factor)) * 0.5f) * inv_dx;
+		const float gz = ((ora_vort_mag(ix, vel, i, j, k + fs, factor) - ora_vort_mag(ix, vel, i, j, k - fs, factor)) * 0.5f) * inv_dx;
+		const float len = sqrtf(fmaf(gz, gz, fmaf(gy, gy, gx * gx))) + 1e-5f;
+		const float Nx = gx / len, Ny = gy / len, Nz = gz / len;
+		const float fx = fmaf(-Nz, w[1], Ny * w[2]);
+		const float fy = fmaf(-Nx, w[2], Nz * w[0]);
+		const float fz = fmaf(-Ny, w[0], Nx * w[1]);
+		out[3 * t] = fmaf(confinementScale * fx, dt, vel[3 * t]);
+		out[3 * t + 1] = fmaf(confinementScale * fy, dt, vel[3 * t + 1]);
+		out[3 * t + 2] = fmaf(confinementScale * fz, dt, vel[3 * t + 2]);
+	}
+}
+
 /* redBlackGaussSeidelUpdate (Kernel.cu:591-623); the _opt variant (:521-588) computes the same update.
  * SASS of the reference: s = fma(-div, dx*dx, sum6); d = fma(s, 1/6, -pOld); p = fma(d, omega, pOld). */
 void ora_rbgs(const ora_index* ix, const int32_t* coords, const float* div, float* p, float dx, uint64_t n, int color, float omega) {
@@ -686,8 +730,8 @@ void ora_frame(const ora_index* ix, const int32_t* coords, uint64_t n, float* ve
 	free(adv), free(div), free(p);
 }
 
-/* Compute() in full for hasCollision == false (HNanoSolver.cu:9-372): advect_vector -> vorticityConfinement (only
- * vorticityScale == 0 is restated: the reference runs it in place, racing, :174) -> divergence -> combustion_oxygen ->
+/* Compute() in full for hasCollision == false (HNanoSolver.cu:9-372): advect_vector -> vorticityConfinement (restated
+ * out of place: the reference runs it in place, racing, :174) -> divergence -> combustion_oxygen ->
  * temperature_buoyancy -> RBGS -> subtractPressureGradient -> advect_scalars over ALL float blocks in insertion order.
  * names[s] identify fuel / waste / temperature / flame (:193); returns 1 if one is missing (the reference throws). */
 int ora_compute_sim(const ora_index* ix, const int32_t* coords, uint64_t n, float* vel, float* const* scalars, const char* const* names, int S,
@@ -706,7 +750,14 @@ int ora_compute_sim(const ora_index* ix, const int32_t* coords, uint64_t n, floa
 	float* div = (float*)malloc(n * 4);
 	float* p = (float*)calloc(n, 4);
 	ora_advect_vector(ix, coords, vel, adv, n, dt, inv);
-	/* vorticityConfinement with scale 0 adds (0 * x) * dt == +0 to every component: identity for finite inputs */
+	/* vorticityConfinement (:172-176) on the advected velocity; params6[4] = vorticityScale, [5] = factorScale. A zero scale, or a
+	 * factorScale that truncates to a zero offset (the SOP default 0.5), adds (+-0) * dt to every component: identity for finite inputs */
+	if (params6[4] != 0.0f && (int32_t)params6[5] != 0) {
+		float* conf = (float*)malloc(n * 12);
+		ora_vorticity_confinement(ix, coords, adv, conf, n, dt, inv, params6[4], params6[5]);
+		memcpy(adv, conf, n * 12);
+		free(conf);
+	}
 	ora_divergence(ix, coords, adv, div, inv, n);
 	float *oF = (float*)malloc(n * 4), *oW = (float*)malloc(n * 4), *oT = (float*)malloc(n * 4), *oL = (float*)malloc(n * 4);
 	ora_combustion_oxygen(scalars[iF], scalars[iW], scalars[iT], div, scalars[iL], oF, oW, oT, oL, temperatureRelease, expansionRate, n);

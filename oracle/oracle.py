@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
         L.ora_advect_scalars.argtypes = [C.c_void_p, c_i32p, c_f32p, C.POINTER(c_f32p), C.POINTER(c_f32p), C.c_int, C.c_uint64,
                                          C.c_float, C.c_float]
         L.ora_divergence.argtypes = [C.c_void_p, c_i32p, c_f32p, c_f32p, C.c_float, C.c_uint64]
+        L.ora_vorticity_confinement.argtypes = [C.c_void_p, c_i32p, c_f32p, c_f32p, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float]
         L.ora_rbgs.argtypes = [C.c_void_p, c_i32p, c_f32p, c_f32p, C.c_float, C.c_uint64, C.c_int, C.c_float]
         L.ora_subtract_gradient.argtypes = [C.c_void_p, c_i32p, C.c_uint64, c_f32p, c_f32p, c_f32p, C.c_float]
         L.ora_omega_compute.restype = C.c_float
@@ -181,6 +182,14 @@ class OracleIndex:
         out = np.empty(self.n, np.float32)
         lib().ora_divergence(self._h, self.coords.ctypes.data_as(c_i32p), vp, out.ctypes.data_as(c_f32p),
                              np.float32(1.0) / np.float32(voxel_size), self.n)
+        return out
+
+    def vorticity_confinement(self, vel, dt, voxel_size, scale, factor_scale):
+        """out-of-place vorticityConfinement (Kernel.cu:969-1025) of an (N, 3) velocity"""
+        vel, vp = _f32(vel)
+        out = np.empty((self.n, 3), np.float32)
+        lib().ora_vorticity_confinement(self._h, self.coords.ctypes.data_as(c_i32p), vp, out.ctypes.data_as(c_f32p), self.n, dt,
+                                        np.float32(1.0) / np.float32(voxel_size), scale, factor_scale)
         return out
 
     def rbgs(self, div, p, voxel_size, iterations, omega):
@@ -411,6 +420,8 @@ def _load_ref(path: str) -> C.CDLL:
             L.ref_frame_destroy.argtypes = [C.c_void_p]
             L.ref_frame_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, c_f32p]
             L.ref_frame_download.argtypes = [C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, C.POINTER(c_f32p)]
+            if hasattr(L, "ref_frame_vorticity"):
+                L.ref_frame_vorticity.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, c_f32p]
         _ref_libs[path] = L
     return L
 
@@ -558,6 +569,14 @@ class RefFrame:
             rc = ref().ref_frame_run(self._h, self.grid._h, iterations, dt, voxel_size, frames, C.byref(ms))
         _rcheck(rc)
         return ms.value
+
+    def vorticity(self, dt, voxel_size, scale, factor_scale):
+        """the reference's vorticityConfinement kernel, out of place, on the frame's input velocity -> (N, 3)"""
+        out = np.empty((self.data.n, 3), np.float32)
+        with _Quiet():
+            rc = ref().ref_frame_vorticity(self._h, self.grid._h, dt, voxel_size, scale, factor_scale, out.ctypes.data_as(c_f32p))
+        _rcheck(rc)
+        return out
 
     def download(self):
         n = self.data.n

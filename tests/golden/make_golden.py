@@ -67,6 +67,11 @@ def make(name, iterations):
     out.update(frame_adv=r["adv"], frame_div=r["div"], frame_p=r["p"], frame_vel=r["vel"])
     for i, s in enumerate(r["scalars"]):
         out[f"frame_scalar{i}"] = s
+    # vorticityConfinement, the reference kernel launched out of place on the input velocity
+    vc = [(1.0, 1.0), (0.7, 2.9), (1.3, -1.0)]
+    out["vorticity_cases"] = np.array(vc, np.float32)
+    for i, (sc, fs) in enumerate(vc):
+        out[f"vorticity_{i}"] = f.vorticity(w.dt, w.voxel_size, sc, fs)
     # stand-alone launchers
     d = data(floats=list(zip(w.scalar_names, w.scalars)))
     O.ref_advect_index_grid(d, w.dt, w.voxel_size)
@@ -89,6 +94,14 @@ def make(name, iterations):
     out["compute_sim_vel"] = d.blocks["vel"].copy()
     for nm, _ in fl:
         out[f"compute_sim_{nm}"] = d.blocks[nm].copy()
+    # the same with the SOP's default vorticity parameters (scale 1, factor_scale 0.5: the offset truncates to 0, the in-place pass
+    # then adds exactly zero)
+    pv = PARAMS.copy()
+    pv[4], pv[5] = 1.0, 0.5
+    d = data(floats=fl)
+    g3 = O.RefGrid(d, w.voxel_size)
+    O.ref_compute_sim(d, g3, iterations, w.dt, w.voxel_size, pv, False)
+    out["compute_sim_sopdefault_vel"] = d.blocks["vel"].copy()
     np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), **out)
     print(name, "leaves", w.num_leaves, "voxels", w.num_voxels, "->", f"ref_{name}.npz")
 

@@ -259,6 +259,99 @@ def test_compute_sim_matches_reference_compute_sim(case):
         assert_close(d.pValues(FLOAT, k), rd.blocks[k], f"Compute_Sim {k}")
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# vorticity confinement: out-of-place evaluation of the reference kernel
+# ------------------------------------------------------------------------------------------------------------------
+VORTICITY_CASES = [(1.0, 1.0), (0.7, 2.9), (1.3, -1.0), (1.0, 7.0), (0.5, 8.0), (1.0, 9.5)]  # (scale, factorScale); 9.5 -> offset 9: far path
+
+
+def _product_vorticity(w, scale, factor_scale):
+    g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    sim = H.Simulation(g, len(w.scalars))
+    sim.upload(w.velocity, w.scalars)
+    sim.advect_velocity(0.0)          # dt = 0: the advected velocity is the input velocity (BFECC of a zero displacement is exact)
+    before = sim.aux(H.Simulation.AUX_ADVECTED)
+    sim.vorticity_confinement(w.dt, scale, factor_scale)
+    sim.sync()
+    return before, sim.aux(H.Simulation.AUX_ADVECTED)
+
+
+@pytest.mark.parametrize("scale,factor_scale", VORTICITY_CASES)
+def test_vorticity_confinement_matches_oracle(case, scale, factor_scale):
+    w = case
+    before, got = _product_vorticity(w, scale, factor_scale)
+    assert np.array_equal(before, w.velocity)
+    want = O.OracleIndex(w.coords).vorticity_confinement(w.velocity, w.dt, w.voxel_size, scale, factor_scale)
+    assert np.array_equal(got, want), f"max |diff| {np.abs(got - want).max()}"
+    assert not np.array_equal(got, w.velocity) or w.num_leaves == 1
+
+
+@needs_ref
+@pytest.mark.parametrize("scale,factor_scale", VORTICITY_CASES[:4])
+def test_vorticity_confinement_matches_reference_kernel_out_of_place(case, scale, factor_scale):
+    """The reference kernel itself, given separate input and output buffers (Compute() passes the same buffer twice and races)."""
+    w = case
+    rd = O.RefData(w.coords)
+    rd.add_vec3("vel", w.velocity)
+    for n, a in zip(w.scalar_names, w.scalars):
+        rd.add_float(n, a)
+    rg = O.RefGrid(rd, w.voxel_size)
+    want = O.RefFrame(rd, rg, w.scalar_names).vorticity(w.dt, w.voxel_size, scale, factor_scale)
+    _, got = _product_vorticity(w, scale, factor_scale)
+    assert_close(got, want, "vorticityConfinement")
+    assert np.array_equal(got, want), "expected bit-exact agreement with the reference kernel"
+
+
+def test_vorticity_identity_cases(case):
+    """scale 0, or a factorScale below 1 (the SOP default 0.5 truncates to a zero offset): the force is exactly zero"""
+    w = case
+    for scale, fs in ((0.0, 3.0), (1.0, 0.5), (2.0, -0.9)):
+        _, got = _product_vorticity(w, scale, fs)
+        assert np.array_equal(got, w.velocity)
+        want = O.OracleIndex(w.coords).vorticity_confinement(w.velocity, w.dt, w.voxel_size, scale, fs)
+        assert np.array_equal(want, w.velocity)
+
+
+def test_compute_sim_with_vorticity_matches_oracle(case):
+    w = case
+    params = PARAMS6.copy()
+    params[4], params[5] = 0.8, 1.0
+    ix = O.OracleIndex(w.coords)
+    fields = dict(density=w.scalars[0], **_combustion_fields(w.num_voxels))
+    want_vel, want = ix.compute_sim(w.velocity, fields, 5, w.dt, w.voxel_size, params)
+    off_vel, _ = ix.compute_sim(w.velocity, fields, 5, w.dt, w.voxel_size, PARAMS6)
+    d = _sidecar(w, fields)
+    g = H.CreateIndexGrid(d, w.voxel_size)
+    H.Compute_Sim(d, g, 5, w.dt, w.voxel_size, H.CombustionParams(*params.tolist()), False)
+    assert_close(d.pValues(VEC3F, "vel"), want_vel, "Compute_Sim velocity (vorticity on)")
+    for k, v in want.items():
+        assert_close(d.pValues(FLOAT, k), v, f"Compute_Sim {k} (vorticity on)")
+    if w.num_leaves > 1:
+        assert not np.array_equal(want_vel, off_vel)
+
+
+@needs_ref
+def test_compute_sim_default_sop_vorticity_parameters_match_reference(case):
+    """SOP defaults: vorticity 1, factor_scale 0.5 (SOP_HNanoSolver.cpp:73-86). The offset truncates to 0, the in-place race of the
+    reference is then harmless, and both sides must agree."""
+    w = case
+    params = PARAMS6.copy()
+    params[4], params[5] = 1.0, 0.5
+    fields = dict(density=w.scalars[0], **_combustion_fields(w.num_voxels))
+    rd = O.RefData(w.coords)
+    rd.add_vec3("vel", w.velocity)
+    for k, v in fields.items():
+        rd.add_float(k, v)
+    rg = O.RefGrid(rd, w.voxel_size)
+    O.ref_compute_sim(rd, rg, 6, w.dt, w.voxel_size, params, False)
+    d = _sidecar(w, fields)
+    g = H.CreateIndexGrid(d, w.voxel_size)
+    H.Compute_Sim(d, g, 6, w.dt, w.voxel_size, H.CombustionParams(*params.tolist()), False)
+    assert_close(d.pValues(VEC3F, "vel"), rd.blocks["vel"], "Compute_Sim velocity")
+    for k in fields:
+        assert_close(d.pValues(FLOAT, k), rd.blocks[k], f"Compute_Sim {k}")
+
+
 @needs_ref
 def test_standalone_launchers_match_reference_launchers(case):
     w = case

@@ -67,3 +67,30 @@ def test_compute_sim(gold):
     assert_close(vel, gold["compute_sim_vel"], "Compute_Sim velocity")
     for k, v in out.items():
         assert_close(v, gold[f"compute_sim_{k}"], f"Compute_Sim {k}")
+
+
+def test_vorticity_confinement(gold):
+    """oracle vs the reference's vorticityConfinement kernel launched out of place (tests/golden/make_golden.py)"""
+    if "vorticity_cases" not in gold:
+        pytest.skip("fixture predates the vorticity vectors")
+    ix = O.OracleIndex(gold["coords"])
+    h, dt = float(gold["voxel_size"]), float(gold["dt"])
+    for i, (scale, fs) in enumerate(gold["vorticity_cases"]):
+        got = ix.vorticity_confinement(gold["velocity"], dt, h, float(scale), float(fs))
+        assert_close(got, gold[f"vorticity_{i}"], f"vorticityConfinement scale={scale} factorScale={fs}")
+        assert np.array_equal(got, gold[f"vorticity_{i}"])
+        assert not np.array_equal(got, gold["velocity"])
+
+
+def test_compute_sim_sop_default_vorticity_is_identity(gold):
+    if "compute_sim_sopdefault_vel" not in gold:
+        pytest.skip("fixture predates the vorticity vectors")
+    assert np.array_equal(gold["compute_sim_sopdefault_vel"], gold["compute_sim_vel"])
+    ix = O.OracleIndex(gold["coords"])
+    h, dt, I = float(gold["voxel_size"]), float(gold["dt"]), int(gold["iterations"])
+    fields = dict(density=gold["scalar0"], fuel=gold["comb_fuel"], waste=gold["comb_waste"], temperature=gold["comb_temperature"],
+                  flame=gold["comb_flame"])
+    p = gold["params"].copy()
+    p[4], p[5] = 1.0, 0.5
+    vel, _ = ix.compute_sim(gold["velocity"], fields, I, dt, h, p)
+    assert_close(vel, gold["compute_sim_sopdefault_vel"], "Compute_Sim velocity, SOP default vorticity parameters")

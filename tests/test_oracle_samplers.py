@@ -60,3 +60,60 @@ def test_samplers_match_reference_host_code():
     tol = 4 * np.finfo(np.float32).eps * 4.0
     assert np.abs(ix.trilinear_f(f, xyz) - rh.trilinear_f(f, xyz)).max() <= tol
     assert np.abs(ix.trilinear_v(v, xyz) - rh.trilinear_v(v, xyz)).max() <= tol
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# vorticity confinement (Kernel.cu:969-1025), out-of-place restatement: properties that hold by construction
+# ------------------------------------------------------------------------------------------------------------------
+class _Block:
+    """all leaves of an m x m x m block, sidecar (leaf-major, x<<6|y<<3|z) order, with a smooth + noisy velocity"""
+
+    def __init__(self, m=3, seed=3):
+        a = np.arange(m, dtype=np.int32) * 8
+        origins = np.stack(np.meshgrid(a, a, a, indexing="ij"), -1).reshape(-1, 3)  # x-major == NanoVDB order inside one lower node
+        o = np.arange(8, dtype=np.int32)
+        off = np.stack(np.meshgrid(o, o, o, indexing="ij"), -1).reshape(-1, 3)
+        self.coords = (origins[:, None, :] + off[None, :, :]).reshape(-1, 3).astype(np.int32)
+        rng = np.random.default_rng(seed)
+        c = self.coords.astype(np.float32)
+        self.velocity = (np.stack([np.sin(0.3 * c[:, 1]), np.cos(0.2 * c[:, 2]), np.sin(0.25 * c[:, 0] + 0.1 * c[:, 1])], 1)
+                         + 0.2 * rng.standard_normal((len(c), 3))).astype(np.float32)
+        self.dt, self.voxel_size = 1.0 / 24.0, 0.1
+
+
+def _dense_block(m=3):
+    return _Block(m)
+
+
+def test_vorticity_identity_when_scale_or_offset_is_zero():
+    w = _dense_block()
+    ix = O.OracleIndex(w.coords)
+    for scale, fs in ((0.0, 2.0), (1.0, 0.5), (3.0, -0.99), (1.0, 0.0)):
+        assert np.array_equal(ix.vorticity_confinement(w.velocity, w.dt, w.voxel_size, scale, fs), w.velocity)
+
+
+def test_vorticity_of_a_rigid_rotation_is_uniform_so_the_force_vanishes_inside():
+    # u = k * (-y, x, 0): curl = (0, 0, 2k) everywhere away from the domain boundary -> |curl| constant -> grad 0 -> no force
+    w = _dense_block(3)
+    c = w.coords.astype(np.float32)
+    vel = np.stack([-(c[:, 1] - 12.0), c[:, 0] - 12.0, np.zeros(len(c), np.float32)], 1).astype(np.float32) * np.float32(0.25)
+    ix = O.OracleIndex(w.coords)
+    out = ix.vorticity_confinement(vel, w.dt, w.voxel_size, 1.0, 1.0)
+    lo, hi = w.coords.min(0), w.coords.max(0)
+    inside = np.all((w.coords >= lo + 2) & (w.coords <= hi - 2), axis=1)  # stencil radius 1 + offset 1
+    assert inside.sum() > 1000
+    assert np.array_equal(out[inside], vel[inside])
+    assert not np.array_equal(out[~inside], vel[~inside])  # at the boundary inactive samples (0) create a gradient
+
+
+def test_vorticity_offset_is_truncated_toward_zero_and_odd_in_sign():
+    w = _dense_block(2)
+    ix = O.OracleIndex(w.coords)
+    a = ix.vorticity_confinement(w.velocity, w.dt, w.voxel_size, 1.0, 2.0)
+    b = ix.vorticity_confinement(w.velocity, w.dt, w.voxel_size, 1.0, 2.9)
+    assert np.array_equal(a, b)                      # (int)2.9 == 2
+    m = ix.vorticity_confinement(w.velocity, w.dt, w.voxel_size, 1.0, -2.0)
+    # a negative offset swaps the +/- samples: the gradient, hence the force, changes sign exactly
+    assert np.array_equal((a - w.velocity != 0), (m - w.velocity != 0))
+    f_pos, f_neg = a.astype(np.float64) - w.velocity, m.astype(np.float64) - w.velocity
+    assert np.allclose(f_pos, -f_neg, rtol=1e-4, atol=1e-7)
