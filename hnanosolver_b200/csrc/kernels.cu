@@ -821,7 +821,9 @@ __device__ __forceinline__ CurlRows curl_rows(const RowCtx& c, const float* __re
 	}
 	return r;
 }
+// |w| and |g| as the reference compiles them (checked bit for bit against its kernel): the sums of squares contract differently
 __device__ __forceinline__ float vort_norm(float wx, float wy, float wz) { return sqrtf(fmaf(wz, wz, fmaf(wy, wy, __fmul_rn(wx, wx)))); }
+__device__ __forceinline__ float grad_norm(float gx, float gy, float gz) { return sqrtf(fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy)))); }
 
 __global__ void __launch_bounds__(256) k_vorticity_mag(GridView g, const float* __restrict__ u, const float* __restrict__ v,
                                                        const float* __restrict__ w, float* __restrict__ mag, float factor) {
@@ -916,11 +918,11 @@ __global__ void __launch_bounds__(256) k_vorticity_force(GridView g, const float
 #pragma unroll
 	for (int z = 0; z < 8; ++z) {
 		const float g0 = G[0].v[z], g1 = G[1].v[z], g2 = G[2].v[z];
-		const float len = sqrtf(fmaf(g2, g2, fmaf(g1, g1, __fmul_rn(g0, g0)))) + 1e-5f;
+		const float len = grad_norm(g0, g1, g2) + 1e-5f;
 		const float Nx = __fdiv_rn(g0, len), Ny = __fdiv_rn(g1, len), Nz = __fdiv_rn(g2, len);
-		const float fx = fmaf(-Nz, r.wy.v[z], __fmul_rn(Ny, r.wz.v[z]));
-		const float fy = fmaf(-Nx, r.wz.v[z], __fmul_rn(Nz, r.wx.v[z]));
-		const float fz = fmaf(-Ny, r.wx.v[z], __fmul_rn(Nx, r.wy.v[z]));
+		const float fx = fmaf(Ny, r.wz.v[z], -__fmul_rn(Nz, r.wy.v[z]));  // a*b - c*d = fma(a, b, -rnd(c*d))
+		const float fy = fmaf(Nz, r.wx.v[z], -__fmul_rn(Nx, r.wz.v[z]));
+		const float fz = fmaf(Nx, r.wy.v[z], -__fmul_rn(Ny, r.wx.v[z]));
 		a.v[z] = fmaf(__fmul_rn(scale, fx), dt, cu.v[z]);
 		b.v[z] = fmaf(__fmul_rn(scale, fy), dt, cv.v[z]);
 		d.v[z] = fmaf(__fmul_rn(scale, fz), dt, cw.v[z]);

@@ -576,8 +576,10 @@ void ora_divergence(const ora_index* ix, const int32_t* coords, const float* vel
  * `vel`, the result goes to `out`. The reference launches it in place (HNanoSolver.cu:174: input == output buffer), so for
  * (int)factorScale != 0 its own result depends on thread timing; the out-of-place evaluation is the kernel's meaning and is what the
  * reference kernel itself computes when given two buffers (that is how tests/ pin this function, through oracle/ref_shim.cu).
- * Arithmetic as compiled in the reference SASS: |w|^2 = fma(wz,wz, fma(wy,wy, wx*wx)) under an IEEE sqrt; grad = ((p - m) * 0.5) * inv_dx;
- * N = grad / (sqrt(fma(gz,gz, fma(gy,gy, gx*gx))) + 1e-5) with IEEE division; cross product a*b - c*d = fma(-c, d, rnd(a*b));
+ * Arithmetic as compiled in the reference SASS (which product of a sum of products nvcc rounds and which it fuses was settled
+ * against the reference kernel's output, tests/golden): |w|^2 = fma(wz,wz, fma(wy,wy, rnd(wx*wx))) under an IEEE sqrt;
+ * grad = ((p - m) * 0.5) * inv_dx; N = grad / (sqrt(fma(gz,gz, fma(gx,gx, rnd(gy*gy)))) + 1e-5) with IEEE division;
+ * cross product a*b - c*d = fma(a, b, -rnd(c*d));
  * out = fma(scale * cross, dt, vel). The neighbour offset is (int)factorScale, truncated (Coord's int constructor, F2I.TRUNC). */
 static void ora_curl(const ora_index* ix, const float* vel, int32_t i, int32_t j, int32_t k, float factor, float* w) {
 	float pX[3], mX[3], pY[3], mY[3], pZ[3], mZ[3];
@@ -605,11 +607,11 @@ void ora_vorticity_confinement(const ora_index* ix, const int32_t* coords, const
 		const float gx = ((ora_vort_mag(ix, vel, i + fs, j, k, factor) - ora_vort_mag(ix, vel, i - fs, j, k, factor)) * 0.5f) * inv_dx;
 		const float gy = ((ora_vort_mag(ix, vel, i, j + fs, k, factor) - ora_vort_mag(ix, vel, i, j - fs, k, factor)) * 0.5f) * inv_dx;
 		const float gz = ((ora_vort_mag(ix, vel, i, j, k + fs, factor) - ora_vort_mag(ix, vel, i, j, k - fs, factor)) * 0.5f) * inv_dx;
-		const float len = sqrtf(fmaf(gz, gz, fmaf(gy, gy, gx * gx))) + 1e-5f;
+		const float len = sqrtf(fmaf(gz, gz, fmaf(gx, gx, gy * gy))) + 1e-5f;
 		const float Nx = gx / len, Ny = gy / len, Nz = gz / len;
-		const float fx = fmaf(-Nz, w[1], Ny * w[2]);
-		const float fy = fmaf(-Nx, w[2], Nz * w[0]);
-		const float fz = fmaf(-Ny, w[0], Nx * w[1]);
+		const float fx = fmaf(Ny, w[2], -(Nz * w[1]));
+		const float fy = fmaf(Nz, w[0], -(Nx * w[2]));
+		const float fz = fmaf(Nx, w[1], -(Ny * w[0]));
 		out[3 * t] = fmaf(confinementScale * fx, dt, vel[3 * t]);
 		out[3 * t + 1] = fmaf(confinementScale * fy, dt, vel[3 * t + 1]);
 		out[3 * t + 2] = fmaf(confinementScale * fz, dt, vel[3 * t + 2]);
