@@ -60,6 +60,9 @@ SIGNATURES = {
     "hns_state_step": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_void_p]),
     "hns_state_advect_velocity": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
     "hns_state_vorticity_confinement": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "hns_state_vorticity_active": (C.c_int, [C.c_void_p]),
+    "hns_state_vorticity_mag": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hns_state_vorticity_force": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "hns_state_divergence": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "hns_state_pressure_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_void_p]),
     "hns_state_subtract_gradient": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

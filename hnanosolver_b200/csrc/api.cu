@@ -61,17 +61,33 @@ static ScalarPtrs scalar_ptrs(const hns_state* s) {
 // places with s->adv. A zero scale, or a factorScale that truncates to a zero offset (the SOP's default 0.5), makes the force
 // (+-0) * dt: the pass is skipped (identical values; only the sign of an exact zero could differ).
 static bool vorticity_active(float scale, float factor_scale) { return scale != 0.0f && int(factor_scale) != 0; }
-static int vorticity_pass(hns_state* s, float dt, float inv_dx, float scale, float factor_scale, cudaStream_t st) {
-	if (!vorticity_active(scale, factor_scale) || !s->n) return HNS_OK;
+static int vorticity_scratch(hns_state* s, cudaStream_t st) {
 	for (float*& v : s->vort)
 		if (!v) {
-			HNS_CUDA(cudaMalloc(&v, s->n * sizeof(float)));
-			HNS_CUDA(cudaMemsetAsync(v, 0, s->n * sizeof(float), st));
+			HNS_CUDA(cudaMalloc(&v, std::max<size_t>(s->n, 1) * sizeof(float)));
+			HNS_CUDA(cudaMemsetAsync(v, 0, std::max<size_t>(s->n, 1) * sizeof(float), st));
 		}
-	launch_vorticity_confinement(s->view(), s->adv, s->vort[3], s->vort, dt, inv_dx, scale, factor_scale, st);
+	return HNS_OK;
+}
+static int vorticity_mag(hns_state* s, float inv_dx, cudaStream_t st) {
+	int rc = vorticity_scratch(s, st);
+	if (rc) return rc;
+	launch_vorticity_mag(s->view(), s->adv, s->vort[3], inv_dx, st);
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+static int vorticity_force(hns_state* s, float dt, float inv_dx, float scale, float factor_scale, cudaStream_t st) {
+	int rc = vorticity_scratch(s, st);
+	if (rc) return rc;
+	launch_vorticity_force(s->view(), s->adv, s->vort[3], s->vort, dt, inv_dx, scale, factor_scale, st);
 	for (int c = 0; c < 3; ++c) std::swap(s->adv[c], s->vort[c]);
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
+}
+static int vorticity_pass(hns_state* s, float dt, float inv_dx, float scale, float factor_scale, cudaStream_t st) {
+	if (!vorticity_active(scale, factor_scale) || !s->n) return HNS_OK;
+	int rc = vorticity_mag(s, inv_dx, st);
+	return rc ? rc : vorticity_force(s, dt, inv_dx, scale, factor_scale, st);
 }
 
 struct FrameDeps {
@@ -267,6 +283,17 @@ int hns_state_vorticity_confinement(hns_state* s, float dt, float scale, float f
 	HNS_REQUIRE(s, "null state");
 	return vorticity_pass(s, dt, 1.0f / s->grid->voxel_size, scale, factor_scale, static_cast<cudaStream_t>(stream));
 }
+int hns_state_vorticity_active(const hns_state* s) {
+	return s && s->comb_enabled && vorticity_active(s->comb.vorticityScale, s->comb.factorScale) ? 1 : 0;
+}
+int hns_state_vorticity_mag(hns_state* s, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	return vorticity_mag(s, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream));
+}
+int hns_state_vorticity_force(hns_state* s, float dt, float scale, float factor_scale, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	return vorticity_force(s, dt, 1.0f / s->grid->voxel_size, scale, factor_scale, static_cast<cudaStream_t>(stream));
+}
 int hns_state_divergence(hns_state* s, int of_advected, void* stream) {
 	HNS_REQUIRE(s, "null state");
 	launch_divergence(s->view(), of_advected ? s->adv : s->vel, s->div, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream));
@@ -407,6 +434,7 @@ static float* field_ptr(hns_state* s, int field, int* floats_per_leaf) {
 	if (field == 6 || field == 7) return s->p[field - 6];
 	if (field == 8 || field == 9) return s->div[field - 8];
 	if (field >= 10 && field < 10 + s->n_scalars) return s->sc[field - 10];
+	if (field == 26) return s->vort[3];  // |curl| plane of the vorticity confinement (null until first used)
 	return nullptr;
 }
 void* hns_state_field_device_ptr(hns_state* s, int field) {

@@ -125,13 +125,15 @@ struct hns_dist {
 };
 
 // ---- layout of one peer region: [flags 128 B][ch0 velocity 3 x 512n][ch1 advected velocity 3 x 512n][ch2 red p 256n][ch3 black p 256n]
-//      [ch4 velocity + scalars (3+S) x 512n] floats, n = number of ghost leaves exchanged with that peer
+//      [ch4 velocity + scalars (3+S) x 512n][ch5 |curl| 512n] floats, n = number of ghost leaves exchanged with that peer.
+//      A region is only reused after a later handshake with the same peer, so a push can never overtake the unpack of the previous use.
 static uint64_t channel_floats(int ch, uint64_t n, int S) {
 	switch (ch) {
 		case 0:
 		case 1: return 3 * 512 * n;
 		case 2:
 		case 3: return 256 * n;
+		case 5: return 512 * n;
 		default: return uint64_t(3 + S) * 512 * n;
 	}
 }
@@ -140,7 +142,7 @@ static uint64_t channel_offset(int ch, uint64_t n, int S) {  // bytes from the r
 	for (int c = 0; c < ch; ++c) off += channel_floats(c, n, S) * sizeof(float);
 	return off;
 }
-static uint64_t region_bytes(uint64_t n, int S) { return (channel_offset(5, n, S) + 255) & ~uint64_t(255); }
+static uint64_t region_bytes(uint64_t n, int S) { return (channel_offset(6, n, S) + 255) & ~uint64_t(255); }
 
 namespace hns {
 // raise channel `ch` of every peer to `seq`: everything this stream wrote into the peers' blocks before is visible first
@@ -535,6 +537,22 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	if ((rc = hns_state_advect_velocity(s, dt, stream))) return rc;
 	mark();
 	if ((rc = exchange_channel(d, s, 1, 3, fadv, st))) return rc;
+	if (hns_state_vorticity_active(s)) {
+		// vorticity confinement reads the advected velocity 1 + |offset| voxels away: |curl| of the owned leaves, its ghost leaves from
+		// the peers, the force on the owned leaves, and the advected velocity's ghosts once more because it has changed
+		const int off = int(s->comb.factorScale);
+		if (off > 7 || off < -7)
+			return fail(HNS_ERR_UNSUPPORTED, "sharded vorticity confinement needs |(int)factorScale| <= 7 (one ghost leaf layer)");
+		const int fmag[1] = {26};
+		if ((rc = hns_state_vorticity_mag(s, stream))) return rc;
+		if (d->p2p) {
+			if ((rc = exchange_p2p(d, s, 7, 1, fmag, st, nullptr, 5, 0))) return rc;
+		} else if ((rc = hns_dist_exchange(d, s, 1, fmag, st))) {
+			return rc;
+		}
+		if ((rc = hns_state_vorticity_force(s, dt, s->comb.vorticityScale, s->comb.factorScale, stream))) return rc;
+		if ((rc = exchange_channel(d, s, 1, 3, fadv, st))) return rc;
+	}
 	mark();
 	if ((rc = hns_state_divergence(s, 1, stream))) return rc;
 	if (s->comb_enabled && (rc = hns_state_combustion_buoyancy(s, dt, stream))) return rc;

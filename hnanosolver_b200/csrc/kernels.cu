@@ -931,13 +931,15 @@ __global__ void __launch_bounds__(256) k_vorticity_force(GridView g, const float
 	st_row(ov, self, b);
 	st_row(ow, self, d);
 }
-void launch_vorticity_confinement(const GridView& g, const float* const vel[3], float* mag, float* const out[3], float dt, float inv_dx, float scale,
-                                  float factor_scale, cudaStream_t st) {
-	if (!g.count()) return;
-	const float factor = 0.5f * inv_dx;
+void launch_vorticity_mag(const GridView& g, const float* const vel[3], float* mag, float inv_dx, cudaStream_t st) {
+	if (g.count()) HNS_LAUNCH(k_vorticity_mag, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], mag, 0.5f * inv_dx);
+}
+void launch_vorticity_force(const GridView& g, const float* const vel[3], const float* mag, float* const out[3], float dt, float inv_dx, float scale,
+                            float factor_scale, cudaStream_t st) {
 	const int fs = int(factor_scale);  // Coord's int constructor truncates (F2I.TRUNC in the reference SASS)
-	HNS_LAUNCH(k_vorticity_mag, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], mag, factor);
-	HNS_LAUNCH(k_vorticity_force, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], mag, out[0], out[1], out[2], factor, inv_dx, scale, dt, fs);
+	if (g.count())
+		HNS_LAUNCH(k_vorticity_force, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], mag, out[0], out[1], out[2], 0.5f * inv_dx, inv_dx, scale,
+		           dt, fs);
 }
 
 // =============================================================================================================

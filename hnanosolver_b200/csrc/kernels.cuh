@@ -47,9 +47,11 @@ void launch_rbgs_color_push(const GridView& g, const float* const div[2], float*
 // subtractPressureGradient (Kernel.cu:765-829)
 void launch_subtract_gradient(const GridView& g, const float* const vel[3], const float* const p[2], float* const out[3], float inv_dx,
                               cudaStream_t st);
-// vorticityConfinement (Kernel.cu:969-1025), out of place: vel -> out, `mag` = scratch plane of n floats (|curl| per voxel)
-void launch_vorticity_confinement(const GridView& g, const float* const vel[3], float* mag, float* const out[3], float dt, float inv_dx, float scale,
-                                  float factor_scale, cudaStream_t st);
+// vorticityConfinement (Kernel.cu:969-1025), out of place, in two launches: |curl| of every listed leaf into the plane `mag`, then
+// vel -> out using mag at the six offset positions (a sharded run exchanges the ghost leaves of `mag` in between)
+void launch_vorticity_mag(const GridView& g, const float* const vel[3], float* mag, float inv_dx, cudaStream_t st);
+void launch_vorticity_force(const GridView& g, const float* const vel[3], const float* mag, float* const out[3], float dt, float inv_dx, float scale,
+                            float factor_scale, cudaStream_t st);
 // combustion_oxygen (Kernel.cu:923-966) and temperature_buoyancy (Kernel.cu:831-847, in place on the y component)
 void launch_combustion_oxygen(const float* fuel, const float* waste, const float* temp, float* const div[2], const float* flame, float* oFuel,
                               float* oWaste, float* oTemp, float* oFlame, float temp_gain, float expansion, uint64_t n, cudaStream_t st);

@@ -143,6 +143,11 @@ int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void*
 /* Individual steps on resident state (asynchronous). */
 int hns_state_advect_velocity(hns_state* s, float dt, void* stream);                 /* vel -> adv              */
 int hns_state_vorticity_confinement(hns_state* s, float dt, float scale, float factor_scale, void* stream); /* adv -> adv, out of place */
+/* the same in its two launches (a sharded run exchanges the ghost leaves of field 26 = |curl| in between); _active: does the
+ * configured frame (hns_state_set_combustion) contain the pass at all? */
+int hns_state_vorticity_active(const hns_state* s);
+int hns_state_vorticity_mag(hns_state* s, void* stream);                                        /* adv -> |curl| (field 26) */
+int hns_state_vorticity_force(hns_state* s, float dt, float scale, float factor_scale, void* stream); /* adv, |curl| -> adv */
 int hns_state_divergence(hns_state* s, int of_advected, void* stream);               /* adv|vel -> div          */
 int hns_state_pressure_solve(hns_state* s, int iterations, float omega, unsigned flags, void* stream); /* p = 0; RBGS   */
 int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream);      /* adv|vel, p -> vel       */

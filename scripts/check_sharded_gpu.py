@@ -20,7 +20,8 @@ names = ["density", "fuel", "waste", "temperature", "flame"]
 gfields = [wg.scalars[0]] + [comb[k] for k in names[1:]]
 sh = hdist.ShardedSimulation(plan, np.ascontiguousarray(go[plan.local_ids]), wg.voxel_size, 5, torch.device("cuda", lr),
                              native=not int(os.environ.get("PY_EXCHANGE", "0")))
-P = H.CombustionParams(0.5, 2.0, 1.5, 0.1, 0.0, 1.0)
+VS, VF = (float(x) for x in os.environ.get("VORT", "0,1").split(","))  # vorticityScale, factorScale (VORT="0.8,2" turns the pass on)
+P = H.CombustionParams(0.5, 2.0, 1.5, 0.1, VS, VF)
 if not int(os.environ.get("NO_COMB", "0")): sh.set_combustion(names, P)
 sh.upload(wg.velocity[lo], [f[lo] for f in gfields])
 I = 12
@@ -49,7 +50,7 @@ if rank == 0:
         bad = np.nonzero((got != ref[k]).reshape(got.shape[0], -1).any(1))[0]
         print(f"  {nm:12s} sharded({world}) == single GPU bitwise: {same}  mismatching voxels {bad.size}/{got.shape[0]} "
               f"max|diff| {np.abs(got.astype(np.float64) - ref[k]).max():.3e} first leaves {np.unique(bad // 512)[:8]}")
-    print("SHARDED PARITY", "OK" if ok else "FAILED", f"leaves={go.shape[0]} exchanges/frame={sh.exchanges // NF} native={sh.native} p2p={getattr(sh, 'p2p', False)}", flush=True)
+    print("SHARDED PARITY", "OK" if ok else "FAILED", f"leaves={go.shape[0]} exchanges/frame={sh.exchanges // NF} native={sh.native} p2p={getattr(sh, 'p2p', False)} vorticity=({VS},{VF})", flush=True)
 sh.check_errors()
 dist.barrier()
 sh.close()
