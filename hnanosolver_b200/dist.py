@@ -299,6 +299,10 @@ class ShardedSimulation:
             _lib.check(_lib.lib().hns_dist_frame(self._dist, self.sim._h, iterations, dt, C.c_void_p(self._stream())))
             return
         s, ex, st = self.sim, self.ex, self._stream()
+        from . import _lib
+
+        if _lib.lib().hns_state_vorticity_active(s._h):
+            raise NotImplementedError("vorticity confinement is only wired into the native sharded frame (native=True)")
         ex.exchange(F_VEL)
         s.advect_velocity(dt, st)
         ex.exchange(F_ADV)
