@@ -120,6 +120,8 @@ struct hns_dist {
 	std::vector<int32_t> h_boundary;             // host copy of the boundary work list
 	const hns_state* bound_state = nullptr;
 	int aux_blocks = 148;           // HNS_AUX_BLOCKS: CTA cap of the background scalar exchange (it must not starve the sweeps)
+	bool push_whole_leaves = false; // HNS_PUSH_WHOLE_LEAVES=1: push every row of every ghost copy (A/B switch)
+	uint64_t push_bytes_per_sweep = 0;
 	bool fused_push = true;         // HNS_FUSED_PUSH=0: pack / push / signal / wait / unpack kernels instead (A/B switch)
 	bool signal_in_kernel = false;  // HNS_SIGNAL_IN_KERNEL=1: the boundary sweep raises the arrival flags itself (A/B switch)
 };
@@ -300,6 +302,7 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 	if (const char* e = std::getenv("HNS_SIGNAL_IN_KERNEL")) d->signal_in_kernel = std::atoi(e) != 0;
 	if (const char* e = std::getenv("HNS_FUSED_PUSH")) d->fused_push = std::atoi(e) != 0;
 	if (const char* e = std::getenv("HNS_AUX_BLOCKS")) d->aux_blocks = std::atoi(e);
+	if (const char* e = std::getenv("HNS_PUSH_WHOLE_LEAVES")) d->push_whole_leaves = std::atoi(e) != 0;
 	return HNS_OK;
 }
 
@@ -370,15 +373,49 @@ int hns_dist_ipc_finish(hns_dist* d) {
 		HNS_CUDA(cudaMemset(d->d_err, 0, sizeof(uint32_t)));
 	}
 	{
-		// CSR over the boundary work list: which peers hold a ghost copy of boundary leaf i, and under which leaf id
-		std::vector<std::vector<std::pair<int32_t, int32_t>>> per_leaf(d->bound_state->grid->num_leaves);
-		std::vector<int32_t> host_send;
+		// CSR over the boundary work list: which peers hold a ghost copy of boundary leaf i, under which leaf id, and which of its
+		// faces touch leaves that peer owns. The 7-point stencil (sweeps, gradient) only ever reads the face layer of a ghost leaf, so
+		// only those rows are pushed: the 8 rows of an x or y face (128 B per colour), every row for a z face (one float of each
+		// quad); a leaf that touches the peer's leaves only across an edge or a corner is not pushed at all.
+		const hns_grid* grid = d->bound_state->grid;
+		const uint64_t L = grid->num_leaves;
+		std::vector<int32_t> nbr(L * 27);
+		if (L) HNS_CUDA(cudaMemcpy(nbr.data(), grid->d_nbr, nbr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+		std::vector<int32_t> owner(L, -1);  // peer index owning a ghost leaf, -1 = this rank
+		std::vector<int32_t> host_ids;
 		for (size_t i = 0; i < n; ++i) {
 			const auto& p = d->peers[i];
-			host_send.resize(p.n_send);
-			if (p.n_send) HNS_CUDA(cudaMemcpy(host_send.data(), p.d_send, p.n_send * sizeof(int32_t), cudaMemcpyDeviceToHost));
-			for (uint64_t k = 0; k < p.n_send; ++k) per_leaf[host_send[k]].push_back({int32_t(i), p.peer_leaf[k]});
+			host_ids.resize(p.n_recv);
+			if (p.n_recv) HNS_CUDA(cudaMemcpy(host_ids.data(), p.d_recv, p.n_recv * sizeof(int32_t), cudaMemcpyDeviceToHost));
+			for (int32_t id : host_ids) owner[id] = int32_t(i);
 		}
+		static const int face_slot[6] = {kSlotXm, kSlotXp, kSlotYm, kSlotYp, kSlotZm, kSlotZp};
+		std::vector<std::vector<std::pair<int32_t, int32_t>>> per_leaf(L);
+		uint64_t quads = 0;
+		for (size_t i = 0; i < n; ++i) {
+			const auto& p = d->peers[i];
+			host_ids.resize(p.n_send);
+			if (p.n_send) HNS_CUDA(cudaMemcpy(host_ids.data(), p.d_send, p.n_send * sizeof(int32_t), cudaMemcpyDeviceToHost));
+			for (uint64_t k = 0; k < p.n_send; ++k) {
+				const int32_t leaf = host_ids[k];
+				int mask = 0;
+				for (int f = 0; f < 6; ++f) {
+					const int32_t nb = nbr[uint64_t(leaf) * 27 + face_slot[f]];
+					if (nb >= 0 && owner[nb] == int32_t(i)) mask |= 1 << f;
+				}
+				if (d->push_whole_leaves) mask = 0x30;
+				if (!mask) continue;
+				per_leaf[leaf].push_back({int32_t(i) | (mask << 8), p.peer_leaf[k]});
+				int rows = 64;
+				if (!(mask & 0x30)) {
+					rows = 0;
+					for (int x = 0; x < 8; ++x)
+						for (int y = 0; y < 8; ++y) rows += ((mask & 1) && x == 0) || ((mask & 2) && x == 7) || ((mask & 4) && y == 0) || ((mask & 8) && y == 7);
+				}
+				quads += rows;
+			}
+		}
+		d->push_bytes_per_sweep = quads * 16;
 		std::vector<uint32_t> off(d->h_boundary.size() + 1, 0);
 		std::vector<int32_t> peer, leaf;
 		for (size_t b = 0; b < d->h_boundary.size(); ++b) {
@@ -615,7 +652,7 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 					push.signal_ch = 2 + color, push.signal_seq = ++d->seq_p[color], push.counter = d->signal_in_kernel ? d->d_counter : nullptr;
 					launch_rbgs_color_push(vb, s->div, s->p, dx, color, omega, color, push, bs);
 					if (!d->signal_in_kernel) HNS_LAUNCH(k_signal, 1, 32, 0, bs, d->d_remote_flags, np, 2 + color, d->seq_p[color]);
-					d->bytes_sent += uint64_t(d->n_boundary) * 1024u;
+					d->bytes_sent += d->push_bytes_per_sweep;
 					++d->exchanges;
 					HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
 					if (dbg) cudaEventRecord(dbg[1], bs), cudaEventRecord(dbg[3], bs), cudaEventRecord(dbg[4], bs);

@@ -261,8 +261,13 @@ __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __r
 		*reinterpret_cast<float4*>(p_c + q) = n;
 		if (kPush) {
 			const uint32_t row4 = uint32_t(q) & 255u;  // quad offset inside the half-brick
-			for (uint32_t e = __ldg(push.dst_off + i), e1 = __ldg(push.dst_off + i + 1); e < e1; ++e)
-				*reinterpret_cast<float4*>(push.remote_pc[__ldg(push.dst_peer + e)] + (uint64_t(__ldg(push.dst_leaf + e)) * 256u + row4)) = n;
+			// bit f of this row's face membership: 0 x==0, 1 x==7, 2 y==0, 3 y==7; a z face (bits 4, 5) involves every row
+			const int mine = (c.x == 0 ? 1 : 0) | (c.x == 7 ? 2 : 0) | (c.y == 0 ? 4 : 0) | (c.y == 7 ? 8 : 0) | 0x30;
+			for (uint32_t e = __ldg(push.dst_off + i), e1 = __ldg(push.dst_off + i + 1); e < e1; ++e) {
+				const int pm = __ldg(push.dst_peer + e);  // peer index | face mask << 8
+				if ((pm >> 8) & mine)
+					*reinterpret_cast<float4*>(push.remote_pc[pm & 255] + (uint64_t(__ldg(push.dst_leaf + e)) * 256u + row4)) = n;
+			}
 		}
 	}
 	if (kPush && push.counter) {  // in-kernel arrival signal (otherwise the caller launches a signal kernel behind this one)

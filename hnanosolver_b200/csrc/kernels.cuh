@@ -29,7 +29,8 @@ void launch_divergence(const GridView& g, const float* const vel[3], float* cons
 void launch_rbgs_color(const GridView& g, const float* const div[2], float* const p[2], float dx, int color, float omega, int reverse,
                        cudaStream_t st);
 // Boundary sweep of a sharded run with the ghost exchange fused in: besides writing p[color] locally, every swept quad of work item i
-// is stored into the ghost copies listed in dst_peer/dst_leaf[dst_off[i] .. dst_off[i+1]) (peer index, leaf id in that peer's local
+// is stored into the ghost copies listed in dst_peer/dst_leaf[dst_off[i] .. dst_off[i+1]) (peer index | face mask << 8 -- only rows on
+// a face the peer's stencil reads are stored: bits 0..3 = x==0, x==7, y==0, y==7, bits 4..5 = a z face = every row --, leaf id in that peer's local
 // numbering) through remote_pc[peer] = that peer's p[color] array mapped over NVLink. With a counter the last block to finish also
 // raises signal_flags[*][signal_ch] (every block then pays a system fence); without one the caller signals from a follow-up kernel.
 struct RbgsPush {
