@@ -487,13 +487,9 @@ __global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const floa
 	issue(first, 0);
 	for (uint32_t item = first; item < last; ++item) {
 		const int buf = (item - first) & 1;
-		if (item + 1 < last) {
-			issue(item + 1, buf ^ 1);
-			cp_async_wait<1>();
-		} else {
-			cp_async_wait<0>();
-		}
-		__syncthreads();
+		cp_async_wait<0>();
+		__syncthreads();  // this item's region has landed for every thread, and every thread is done reading the other buffer
+		if (item + 1 < last) issue(item + 1, buf ^ 1);
 		const float *ru = region + buf * kStageFloats, *rv = ru + kRegionFloats, *rw = ru + 2 * kRegionFloats;
 		const uint32_t leaf = g.leaf_at(item);
 		const LeafFrame f = leaf_frame(g, leaf);
@@ -522,7 +518,6 @@ __global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const floa
 		ou[self] = fmaxf(mnu, fminf(cu, mxu));  // :429
 		ov[self] = fmaxf(mnv, fminf(cv, mxv));
 		ow[self] = fmaxf(mnw, fminf(cw, mxw));
-		__syncthreads();  // this buffer is refilled two iterations from now
 	}
 }
 // persistent launch: two CTAs per SM
@@ -585,10 +580,10 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 	// pipeline jobs: per leaf one velocity stage (the shared trace) and ceil(S/3) stages of up to three scalar fields
 	const int jobs_per_leaf = 1 + (S + 2) / 3;
 	const int n_jobs = int(last - first) * jobs_per_leaf;
+	StagePlan plan{};  // of the leaf whose jobs are being issued; decoded once per leaf
 	auto issue = [&](int job) {
-		const uint32_t leaf = g.leaf_at(first + uint32_t(job / jobs_per_leaf));
 		const int jj = job % jobs_per_leaf;
-		const StagePlan plan = make_stage_plan(g.nbr + uint64_t(leaf) * 27u);
+		if (jj == 0) plan = make_stage_plan(g.nbr + uint64_t(g.leaf_at(first + uint32_t(job / jobs_per_leaf))) * 27u);
 		float* r = region + (job & 1) * kStageFloats;
 		if (jj == 0) {
 			// advect_scalars samples the velocity with "inactive -> element 0" as well (Kernel.cu:192,204). elem0, when given,
@@ -609,13 +604,9 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 	int bB = -1, bF = -1;
 	issue(0);
 	for (int job = 0; job < n_jobs; ++job) {
-		if (job + 1 < n_jobs) {
-			issue(job + 1);
-			cp_async_wait<1>();
-		} else {
-			cp_async_wait<0>();
-		}
-		__syncthreads();
+		cp_async_wait<0>();
+		__syncthreads();  // this job's region has landed for every thread, and every thread is done reading the other buffer
+		if (job + 1 < n_jobs) issue(job + 1);
 		const uint32_t leaf = g.leaf_at(first + uint32_t(job / jobs_per_leaf));
 		const int jj = job % jobs_per_leaf;
 		const float* __restrict__ base = region + (job & 1) * kStageFloats;
@@ -698,7 +689,6 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 				sp.out[s0 + k][self] = fmaxf(mn, fminf(corr, mx));  // :264
 			}
 		}
-		__syncthreads();  // this buffer is refilled two jobs from now
 	}
 }
 void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx,
