@@ -17,7 +17,8 @@ sim = H.Simulation(g, len(fields))
 sim.upload(w.velocity, list(fields.values()))
 sim.set_combustion(True, names.index("fuel"), names.index("waste"), names.index("temperature"), names.index("flame"),
                    H.CombustionParams(0.5, 2.0, 1.5, 0.1, vs, vf))
-omega = H.omega_compute(w.voxel_size)
+from hnanosolver_b200 import launchers as HL
+omega = HL.omega_compute(w.voxel_size)
 st = torch.cuda.current_stream().cuda_stream
 stages = [("advect_vector", lambda: sim.advect_velocity(w.dt, st)),
           ("vorticity", lambda: sim.vorticity_confinement(w.dt, vs, vf, st)),
