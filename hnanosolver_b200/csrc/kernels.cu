@@ -393,6 +393,30 @@ __device__ __forceinline__ void cp_async_wait() {
 	asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+__device__ __forceinline__ void cp_async4(int* smem_dst, const int* gsrc) {
+	const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+// Per-leaf metadata of the pipeline (27 neighbour ids, origin, leaf id) travels through shared memory one leaf ahead of its
+// use, so that neither the staging plan nor the back-trace starts with a dependent global load (list -> neighbour row -> address).
+constexpr int kMetaInts = 32, kMetaOrigin = 27, kMetaLeaf = 30;
+__device__ __forceinline__ void meta_prefetch(const GridView& g, int* __restrict__ slot, uint32_t work_index) {
+	const int t = threadIdx.x;
+	if (t < 31) {
+		const uint32_t leaf = g.leaf_at(work_index);
+		if (t < 27) cp_async4(slot + t, g.nbr + uint64_t(leaf) * 27u + t);
+		else if (t < 30) cp_async4(slot + t, reinterpret_cast<const int*>(g.origin + leaf) + (t - 27));
+		else slot[kMetaLeaf] = int(leaf);
+	}
+}
+__device__ __forceinline__ void meta_load_now(const GridView& g, int* __restrict__ slot, uint32_t work_index) {
+	const int t = threadIdx.x;
+	if (t < 31) {
+		const uint32_t leaf = g.leaf_at(work_index);
+		slot[t] = t < 27 ? __ldg(g.nbr + uint64_t(leaf) * 27u + t) : (t < 30 ? __ldg(reinterpret_cast<const int*>(g.origin + leaf) + (t - 27)) : int(leaf));
+	}
+}
+
 // Staging plan of one thread: which two 16-byte quads of the region it copies (the same for every field, so it is decoded once
 // per CTA and kept in registers). The 784 quads of a field are dealt so that every group of 8 consecutive lanes covers 4 rows x
 // 2 quads: with the 24-float row pitch those eight 16-byte shared-memory stores hit 32 distinct banks.
@@ -400,7 +424,7 @@ struct StagePlan {
 	uint32_t src[2];  // float index of the quad in a brick field, 0xffffffff: leaf missing / nothing to do
 	int dst[2];       // float offset in the region, -1: nothing to do
 };
-__device__ __forceinline__ StagePlan make_stage_plan(const int32_t* __restrict__ nbr) {
+__device__ __forceinline__ StagePlan make_stage_plan(const int32_t* nbr) {  // nbr: a leaf's 27 neighbour ids (shared or global memory)
 	StagePlan p;
 #pragma unroll
 	for (int k = 0; k < 2; ++k) {
@@ -411,7 +435,7 @@ __device__ __forceinline__ StagePlan make_stage_plan(const int32_t* __restrict__
 			const int rx = row / kRX, ry = row - rx * kRX;
 			const int lx = rx - kHaloXY, ly = ry - kHaloXY;       // leaf-local x, y in [-3, 11)
 			const int dz = q == 0 ? -1 : (q == 3 ? 1 : 0);        // z in [-4,0) | [0,4) | [4,8) | [8,12)
-			const int32_t l = __ldg(nbr + ((lx >> 3) + 1) * 9 + ((ly >> 3) + 1) * 3 + dz + 1);
+			const int32_t l = nbr[((lx >> 3) + 1) * 9 + ((ly >> 3) + 1) * 3 + dz + 1];
 			p.dst[k] = rx * kPlane + ry * kPitch + q * 4;
 			if (l >= 0) p.src[k] = uint32_t(l) * 512u + uint32_t(((lx & 7) << 6) | ((ly & 7) << 3)) + ((q == 1 || q == 3) ? 0u : 4u);
 		}
@@ -476,23 +500,28 @@ __global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const floa
 	if (!cta_leaf_range(g, first, last)) return;
 	const int x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
 	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
+	__shared__ int meta[3][kMetaInts];  // ring over the CTA's leaves: in use / being staged / being prefetched
 	auto issue = [&](uint32_t item, int buf) {
-		const StagePlan plan = make_stage_plan(g.nbr + uint64_t(g.leaf_at(item)) * 27u);
+		const StagePlan plan = make_stage_plan(meta[(item - first) % 3]);
 		float* r = region + buf * kStageFloats;
 		stage_region(plan, u, r, 0.f);
 		stage_region(plan, v, r + kRegionFloats, 0.f);
 		stage_region(plan, w, r + 2 * kRegionFloats, 0.f);
+		if (item + 1 < last) meta_prefetch(g, meta[(item + 1 - first) % 3], item + 1);
 		cp_async_commit();
 	};
+	meta_load_now(g, meta[0], first);
+	__syncthreads();
 	issue(first, 0);
 	for (uint32_t item = first; item < last; ++item) {
 		const int buf = (item - first) & 1;
 		cp_async_wait<0>();
-		__syncthreads();  // this item's region has landed for every thread, and every thread is done reading the other buffer
+		__syncthreads();  // this item's region (and the next leaf's metadata) has landed for every thread, and every thread is done reading the other buffer
 		if (item + 1 < last) issue(item + 1, buf ^ 1);
 		const float *ru = region + buf * kStageFloats, *rv = ru + kRegionFloats, *rw = ru + 2 * kRegionFloats;
-		const uint32_t leaf = g.leaf_at(item);
-		const LeafFrame f = leaf_frame(g, leaf);
+		const int* m = meta[(item - first) % 3];
+		const uint32_t leaf = uint32_t(m[kMetaLeaf]);
+		const LeafFrame f{m[kMetaOrigin], m[kMetaOrigin + 1], m[kMetaOrigin + 2], g.nbr + uint64_t(leaf) * 27u};
 		const uint64_t self = uint64_t(leaf) * 512u + threadIdx.x;
 		const int ci = f.ox + x, cj = f.oy + y, ck = f.oz + z;
 		const float u0 = ru[c], v0 = rv[c], w0 = rw[c];
@@ -580,6 +609,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 	// pipeline jobs: per leaf one velocity stage (the shared trace) and ceil(S/3) stages of up to three scalar fields
 	const int jobs_per_leaf = 1 + (S + 2) / 3;
 	const int n_jobs = int(last - first) * jobs_per_leaf;
+	// (the shared-memory metadata ring of k_advect_vector does not pay here: one decode per 1 + ceil(S/3) jobs, measured +2 %)
 	StagePlan plan{};  // of the leaf whose jobs are being issued; decoded once per leaf
 	auto issue = [&](int job) {
 		const int jj = job % jobs_per_leaf;
