@@ -30,6 +30,7 @@ SIGNATURES = {
     "hns_launch_count": (C.c_uint64, []),
     "hns_launch_count_reset": (None, []),
     "hns_set_device": (C.c_int, [C.c_int]),
+    "hns_set_l2_persist_mb": (C.c_int, [C.c_int]),
     "hns_grid_create_from_coords": (C.c_int, [c_i32p, C.c_uint64, C.c_float, C.c_int, C.POINTER(C.c_void_p)]),
     "hns_grid_create_from_origins": (C.c_int, [c_i32p, C.c_uint64, C.c_float, C.POINTER(C.c_void_p)]),
     "hns_grid_destroy": (None, [C.c_void_p]),

@@ -36,10 +36,12 @@ static int pressure_solve(hns_state* s, int iterations, float dx, float omega, u
 	const GridView g = s->view();
 	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, (s->n / 2) * sizeof(float), st));  // initial guess 0 (HNanoSolver.cu:113)
 	HNS_CUDA(cudaMemsetAsync(s->p[1], 0, (s->n / 2) * sizeof(float), st));
+	const L2PressureWindow window(st, s->p[0], s->n * sizeof(float));
 	const bool alternate = !(flags & 2u);  // red sweeps walk the leaves front to back, black sweeps back to front (L2 reuse)
+	const int plain_div = (flags & 4u) ? 2 : 0;  // A/B switch: read-only instead of streaming loads of the divergence
 	for (int it = 0; it < iterations; ++it) {
-		launch_rbgs_color(g, s->div, s->p, dx, 0, omega, 0, st);
-		launch_rbgs_color(g, s->div, s->p, dx, 1, omega, alternate ? 1 : 0, st);
+		launch_rbgs_color(g, s->div, s->p, dx, 0, omega, plain_div, st);
+		launch_rbgs_color(g, s->div, s->p, dx, 1, omega, (alternate ? 1 : 0) | plain_div, st);
 	}
 	return HNS_OK;
 }
@@ -150,6 +152,14 @@ int hns_abi_version(void) { return HNS_B200_ABI_VERSION; }
 const char* hns_last_error(void) { return t_error.c_str(); }
 uint64_t hns_launch_count(void) { return g_launches.load(); }
 void hns_launch_count_reset(void) { g_launches.store(0); }
+int hns_set_l2_persist_mb(int megabytes) {
+	if (megabytes < 0) return fail(HNS_ERR_INVALID_ARGUMENT, "megabytes must be >= 0");
+	L2PressureWindow::requested_mb() = megabytes;
+	L2PressureWindow::applied() = -1;  // re-applied (and clamped) at the next pressure solve
+	cudaCtxResetPersistingL2Cache();
+	cudaGetLastError();
+	return HNS_OK;
+}
 int hns_set_device(int device) {
 	HNS_CUDA(cudaSetDevice(device));
 	return HNS_OK;
@@ -169,7 +179,7 @@ int hns_state_create(const hns_grid* g, int n_scalars, hns_state** out) {
 	const size_t fb = std::max<size_t>(s->n, 1) * sizeof(float);
 	std::vector<float**> all;
 	for (int c = 0; c < 3; ++c) all.push_back(&s->vel[c]), all.push_back(&s->adv[c]);
-	std::vector<float**> halves = {&s->div[0], &s->div[1], &s->p[0], &s->p[1]};
+	std::vector<float**> halves = {&s->div[0], &s->div[1]};
 	for (int i = 0; i < n_scalars; ++i) all.push_back(&s->sc[i]), all.push_back(&s->sc_out[i]);
 	for (int pass = 0; pass < 2; ++pass)
 		for (float** p : pass ? halves : all) {
@@ -182,6 +192,17 @@ int hns_state_create(const hns_grid* g, int n_scalars, hns_state** out) {
 			}
 			cudaMemset(*p, 0, bytes);
 		}
+	{
+		// red and black pressure halves in ONE allocation: a single L2 access-policy window (and a single IPC handle) covers both
+		const cudaError_t e = cudaMalloc(&s->p[0], fb);
+		if (e != cudaSuccess) {
+			const std::string msg = std::string("cudaMalloc(pressure): ") + cudaGetErrorString(e);
+			hns_state_destroy(s);
+			return fail(HNS_ERR_CUDA, msg);
+		}
+		cudaMemset(s->p[0], 0, fb);
+		s->p[1] = s->p[0] + s->n / 2;
+	}
 	*out = s;
 	return HNS_OK;
 }
@@ -189,7 +210,7 @@ int hns_state_create(const hns_grid* g, int n_scalars, hns_state** out) {
 void hns_state_destroy(hns_state* s) {
 	if (!s) return;
 	for (int c = 0; c < 3; ++c) cudaFree(s->vel[c]), cudaFree(s->adv[c]);
-	cudaFree(s->div[0]), cudaFree(s->div[1]), cudaFree(s->p[0]), cudaFree(s->p[1]);
+	cudaFree(s->div[0]), cudaFree(s->div[1]), cudaFree(s->p[0]);  // p[1] lives in p[0]'s allocation
 	for (int i = 0; i < 16; ++i) cudaFree(s->sc[i]), cudaFree(s->sc_out[i]);
 	cudaFree(s->aos);
 	for (float* v : s->vort) cudaFree(v);

@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <string>
 
@@ -59,6 +61,65 @@ struct GridView {
 #ifdef __CUDACC__
 	__device__ __forceinline__ uint32_t leaf_at(uint32_t i) const { return list ? uint32_t(__ldg(list + i)) : i; }
 #endif
+};
+
+// ---- L2 residency of the pressure field during the solve ----------------------------------------------------------------------
+// The two pressure halves (one allocation) are read by every one of the 2 x iterations half-sweeps; everything else a sweep touches
+// streams. An access-policy window marks a fraction of the pressure lines "persisting" in the L2 set-aside for the launches
+// enqueued while it is set, so those lines are served from L2 in every sweep instead of from HBM. Scoped: the previous window of
+// the caller's stream is put back when the object dies (attributes are captured per launch at enqueue time).
+struct L2PressureWindow {
+	cudaStream_t st = nullptr;
+	bool active = false;
+	cudaStreamAttrValue saved{};
+	static long long& requested_mb() {  // HNS_L2_PERSIST_MB (default 64; 0 disables); hns_set_l2_persist_mb() overrides it
+		static long long mb = [] {
+			const char* e = std::getenv("HNS_L2_PERSIST_MB");
+			return e ? std::atoll(e) : 64ll;
+		}();
+		return mb;
+	}
+	static long long& applied() {
+		static long long bytes = -1;  // -1: device limit not set yet
+		return bytes;
+	}
+	static size_t persist_bytes() {  // set-aside size, clamped to the device limit
+		long long& cached = applied();
+		if (cached < 0) {
+			int dev = 0, max_persist = 0;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+			cached = std::max(0ll, std::min<long long>(requested_mb() << 20, max_persist));
+			if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(cached)) != cudaSuccess) cached = 0;
+			cudaGetLastError();
+		}
+		return size_t(cached);
+	}
+	L2PressureWindow(cudaStream_t stream, const void* base, size_t bytes) : st(stream) {
+		const size_t persist = persist_bytes();
+		if (!persist || !bytes || bytes <= persist / 2) return;  // small fields live in the L2 anyway
+		int dev = 0, max_window = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+		if (max_window <= 0) return;
+		if (cudaStreamGetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &saved) != cudaSuccess) {
+			cudaGetLastError();
+			return;
+		}
+		cudaStreamAttrValue v{};
+		v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+		v.accessPolicyWindow.num_bytes = std::min(bytes, size_t(max_window));
+		v.accessPolicyWindow.hitRatio = float(std::min(1.0, double(persist) / double(v.accessPolicyWindow.num_bytes)));
+		v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+		if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess) active = true;
+		else cudaGetLastError();
+	}
+	~L2PressureWindow() {
+		if (active) cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &saved);
+	}
+	L2PressureWindow(const L2PressureWindow&) = delete;
+	L2PressureWindow& operator=(const L2PressureWindow&) = delete;
 };
 
 // slot ids of the six face neighbours

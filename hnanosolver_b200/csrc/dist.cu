@@ -81,7 +81,8 @@ struct hns_dist {
 		uint64_t region_off = 0;
 		uint8_t* remote_region = nullptr;
 		void* ipc_base = nullptr;
-		void* ipc_p[2] = {nullptr, nullptr};      // the peer's p[red], p[black] arrays mapped into this process
+		void* ipc_pbase = nullptr;                // the peer's pressure allocation mapped into this process
+		void* ipc_p[2] = {nullptr, nullptr};      // the peer's p[red], p[black] inside it
 		std::vector<int32_t> peer_leaf;            // for each entry of my send list: that leaf's id in the PEER's local numbering
 	};
 	std::vector<Peer> peers;
@@ -210,8 +211,7 @@ void hns_dist_destroy(hns_dist* d) {
 	cudaFree(d->d_boundary_nbr), cudaFree(d->d_interior_nbr);
 	for (auto& p : d->peers) {
 		if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base);
-		for (void* q : p.ipc_p)
-			if (q) cudaIpcCloseMemHandle(q);
+		if (p.ipc_pbase) cudaIpcCloseMemHandle(p.ipc_pbase);
 	}
 	cudaFree(d->d_push_off), cudaFree(d->d_push_peer), cudaFree(d->d_push_leaf), cudaFree(d->d_remote_p[0]), cudaFree(d->d_remote_p[1]),
 	    cudaFree(d->d_counter);
@@ -329,10 +329,13 @@ int hns_dist_ipc_prepare(hns_dist* d, uint8_t* handle_out64, uint64_t* region_of
 	cudaIpcMemHandle_t h;
 	HNS_CUDA(cudaIpcGetMemHandle(&h, d->block));
 	std::memcpy(handle_out64, &h, 64);
-	for (int c = 0; c < 2; ++c) {  // handles 1, 2: the red / black pressure arrays (peers store swept ghost values straight into them)
-		HNS_CUDA(cudaIpcGetMemHandle(&h, d->bound_state->p[c]));
-		std::memcpy(handle_out64 + 64 * (1 + c), &h, 64);
-	}
+	// bytes 64..127: the pressure allocation (peers store swept ghost values straight into it); 128..143: byte offsets of the red and
+	// black halves inside it; the rest of the 192 bytes is reserved
+	HNS_CUDA(cudaIpcGetMemHandle(&h, d->bound_state->p[0]));
+	std::memcpy(handle_out64 + 64, &h, 64);
+	std::memset(handle_out64 + 128, 0, 64);
+	const uint64_t off[2] = {0, uint64_t(reinterpret_cast<const uint8_t*>(d->bound_state->p[1]) - reinterpret_cast<const uint8_t*>(d->bound_state->p[0]))};
+	std::memcpy(handle_out64 + 128, off, sizeof(off));
 	return HNS_OK;
 }
 int hns_dist_ipc_connect(hns_dist* d, int peer_index, const uint8_t* peer_handles192, uint64_t my_region_offset_in_peer_block,
@@ -345,11 +348,12 @@ int hns_dist_ipc_connect(hns_dist* d, int peer_index, const uint8_t* peer_handle
 	if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base), p.ipc_base = nullptr;
 	HNS_CUDA(cudaIpcOpenMemHandle(&p.ipc_base, h, cudaIpcMemLazyEnablePeerAccess));
 	p.remote_region = static_cast<uint8_t*>(p.ipc_base) + my_region_offset_in_peer_block;
-	for (int c = 0; c < 2; ++c) {
-		std::memcpy(&h, peer_handles192 + 64 * (1 + c), 64);
-		if (p.ipc_p[c]) cudaIpcCloseMemHandle(p.ipc_p[c]), p.ipc_p[c] = nullptr;
-		HNS_CUDA(cudaIpcOpenMemHandle(&p.ipc_p[c], h, cudaIpcMemLazyEnablePeerAccess));
-	}
+	std::memcpy(&h, peer_handles192 + 64, 64);
+	if (p.ipc_pbase) cudaIpcCloseMemHandle(p.ipc_pbase), p.ipc_pbase = nullptr;
+	HNS_CUDA(cudaIpcOpenMemHandle(&p.ipc_pbase, h, cudaIpcMemLazyEnablePeerAccess));
+	uint64_t off[2];
+	std::memcpy(off, peer_handles192 + 128, sizeof(off));
+	for (int c = 0; c < 2; ++c) p.ipc_p[c] = static_cast<uint8_t*>(p.ipc_pbase) + off[c];
 	p.peer_leaf.assign(peer_leaf_ids, peer_leaf_ids + p.n_send);
 	return HNS_OK;
 }

@@ -216,6 +216,8 @@ template <bool kPush>
 __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __restrict__ div_c, float* __restrict__ p_c, const float* p_o,
                                                     float dx2, int color, float omega, int reverse, RbgsPush push) {
 	RowCtx c;
+	const bool flags_stream_div = (reverse & 2) == 0;  // bit 1 of `reverse`: A/B switch, plain read-only loads of the divergence
+	reverse &= 1;
 	uint32_t i = blockIdx.x * 4u + (threadIdx.x >> 6);
 	const bool active = i < g.count();
 	if (!active && !(kPush && push.counter)) return;
@@ -242,7 +244,9 @@ __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __r
 		const float4 Oxm = (t = c.row(-1, 0)) >= 0 ? ldo(split_idx(uint64_t(t))) : zero4;
 		const float4 Oyp = (t = c.row(0, 1)) >= 0 ? ldo(split_idx(uint64_t(t))) : zero4;
 		const float4 Oym = (t = c.row(0, -1)) >= 0 ? ldo(split_idx(uint64_t(t))) : zero4;
-		const float4 D = ldg4(div_c, q);
+		// the divergence is read once per sweep and not again before 2 x 240 MB of pressure have passed through the L2: load it
+		// with the streaming (evict-first) policy so that it does not displace pressure lines the next, reversed sweep starts on
+		const float4 D = (flags_stream_div) ? __ldcs(reinterpret_cast<const float4*>(div_c + q)) : ldg4(div_c, q);
 		// z neighbours: sc == 0: voxel j (z = 2j) has below = O[j-1] (j = 0: last other-colour voxel of the -z leaf), above = O[j]
 		//               sc == 1: voxel j (z = 2j+1) has below = O[j], above = O[j+1] (j = 3: first other-colour voxel of the +z leaf)
 		float halo = 0.f;
@@ -599,8 +603,10 @@ __device__ __noinline__ float far_weighted(const GridView& g, const LeafFrame& f
 
 template <int kSemantics>
 __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const float* __restrict__ u, const float* __restrict__ v,
-                                                           const float* __restrict__ w, ScalarPtrs sp, int S, float sdt,
+                                                           const float* __restrict__ w, const __grid_constant__ ScalarPtrs sp, int S, float sdt,
                                                            const float* __restrict__ elem0) {
+	// (sp is __grid_constant__: its pointer arrays are indexed with run-time indices, which then read the constant bank directly
+	// instead of a per-thread local-memory copy of the parameter)
 	extern __shared__ __align__(16) float region[];
 	uint32_t first, last;
 	if (!cta_leaf_range(g, first, last)) return;

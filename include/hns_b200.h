@@ -61,6 +61,9 @@ uint64_t hns_launch_count(void);
 void hns_launch_count_reset(void);
 /* Select the CUDA device used by subsequently created grids/states of the calling thread (cudaSetDevice). */
 int hns_set_device(int device);
+/* Size of the L2 set-aside in which a share of the pressure field is kept resident ("persisting" access-policy window) during the
+ * pressure solve; default 64 MB or the environment variable HNS_L2_PERSIST_MB, clamped to the device limit, 0 = off. */
+int hns_set_l2_persist_mb(int megabytes);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Index grid -- replaces CreateIndexGrid (src/Cuda/HNanoSolver.cu:375-390), i.e.
@@ -198,7 +201,8 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 /* Direct peer-memory ghost exchange (CUDA IPC over NVLink/NVSwitch) instead of ncclSend/ncclRecv: bricks are stored straight into
  * the peer's landing block and a flag is raised; in the pressure solve the boundary sweep kernel itself stores every swept quad into
  * the peers' ghost copies (their pressure arrays mapped over NVLink) and raises the flag -- no pack / send / unpack at all.
- * Setup: every rank calls _prepare (three 64-byte IPC handles: landing block, red and black pressure arrays; plus the byte offset of
+ * Setup: every rank calls _prepare (192 opaque bytes: IPC handles of the landing block and of the pressure allocation, offsets of the
+ * red and black halves inside it; plus the byte offset of
  * each peer's region inside the block, in the order of hns_dist_set_plan's peers), the caller all-gathers them together with its recv
  * leaf lists, calls _connect once per peer with that peer's 192 handle bytes, the offset of ITS OWN region inside the peer's block and,
  * for every leaf of its send list to that peer, the leaf's id in the peer's local numbering (= the peer's recv list for this rank),

@@ -25,11 +25,22 @@ stages = [("advect_vector", lambda: sim.advect_velocity(w.dt, st)),
           ("divergence", lambda: sim.divergence(True, st)),
           ("combustion+buoyancy", lambda: sim.combustion_buoyancy(w.dt, st)),
           ("pressure_solve(40)", lambda: sim.pressure_solve(40, omega, 0, st)),
+          ("pressure_solve(40) plain div loads", lambda: sim.pressure_solve(40, omega, 4, st)),
+          ("pressure_solve(40) forward only", lambda: sim.pressure_solve(40, omega, 2, st)),
+          ("pressure_solve(40) again", lambda: sim.pressure_solve(40, omega, 0, st)),
           ("subtract_gradient", lambda: sim.subtract_gradient(True, st)),
           ("advect_scalars(5)", lambda: sim.advect_scalars(w.dt, 0, st))]
+from hnanosolver_b200 import _lib
+pre = {}
+for mb in (0, 32, 48, 64, 80, 96):
+    pre[f"pressure_solve(40) L2 persist {mb} MB"] = (lambda mb=mb: (_lib.lib().hns_set_l2_persist_mb(mb), sim.pressure_solve(2, omega, 0, st)))
+    stages.append((f"pressure_solve(40) L2 persist {mb} MB", lambda: sim.pressure_solve(40, omega, 0, st)))
+stages.append(("advect_scalars(5) after persist", lambda: sim.advect_scalars(w.dt, 0, st)))
 acc = {k: [] for k, _ in stages}
 for r in range(reps + 2):
     for k, fn in stages:
+        if k in pre:
+            pre[k](); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         if r >= 2:
@@ -37,5 +48,5 @@ for r in range(reps + 2):
 tot = 0.0
 for k, v in acc.items():
     m = float(np.median(v)); tot += m
-    print(f"{k:22s} {m:8.3f} ms  (min {min(v):.3f})")
+    print(f"{k:36s} {m:8.3f} ms  (min {min(v):.3f})")
 print(f"{'sum':22s} {tot:8.3f} ms   {w.num_voxels / tot / 1e6:.1f} M voxel-updates/ms-frame -> {w.num_voxels / (tot * 1e-3) / 1e9:.2f} G/s")
