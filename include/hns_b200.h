@@ -62,7 +62,8 @@ void hns_launch_count_reset(void);
 /* Select the CUDA device used by subsequently created grids/states of the calling thread (cudaSetDevice). */
 int hns_set_device(int device);
 /* Size of the L2 set-aside in which a share of the pressure field is kept resident ("persisting" access-policy window) during the
- * pressure solve; default 64 MB or the environment variable HNS_L2_PERSIST_MB, clamped to the device limit, 0 = off. */
+ * pressure solve; default 0 = off (measured slower on B200) or the environment variable HNS_L2_PERSIST_MB, clamped to
+ * the device limit. Experimental. */
 int hns_set_l2_persist_mb(int megabytes);
 
 /* ---------------------------------------------------------------------------------------------------------

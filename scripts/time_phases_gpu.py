@@ -32,10 +32,9 @@ stages = [("advect_vector", lambda: sim.advect_velocity(w.dt, st)),
           ("advect_scalars(5)", lambda: sim.advect_scalars(w.dt, 0, st))]
 from hnanosolver_b200 import _lib
 pre = {}
-for mb in (0, 32, 48, 64, 80, 96):
+for mb in (() if not os.environ.get("L2_SWEEP") else (0, 32, 48, 64, 80, 96, 0)):
     pre[f"pressure_solve(40) L2 persist {mb} MB"] = (lambda mb=mb: (_lib.lib().hns_set_l2_persist_mb(mb), sim.pressure_solve(2, omega, 0, st)))
     stages.append((f"pressure_solve(40) L2 persist {mb} MB", lambda: sim.pressure_solve(40, omega, 0, st)))
-stages.append(("advect_scalars(5) after persist", lambda: sim.advect_scalars(w.dt, 0, st)))
 acc = {k: [] for k, _ in stages}
 for r in range(reps + 2):
     for k, fn in stages:
