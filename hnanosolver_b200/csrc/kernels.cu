@@ -474,12 +474,26 @@ __device__ __forceinline__ LeafFrame leaf_frame(const GridView& g, uint32_t leaf
 	const int4 o = __ldg(g.origin + leaf);
 	return LeafFrame{o.x, o.y, o.z, g.nbr + uint64_t(leaf) * 27u};
 }
-// work items [first, last) of this CTA (indices into the launch's leaf list, see GridView::leaf_at)
-__device__ __forceinline__ bool cta_leaf_range(const GridView& g, uint32_t& first, uint32_t& last) {
-	const uint32_t per = (g.count() + gridDim.x - 1) / gridDim.x;
-	first = blockIdx.x * per;
-	last = min(first + per, g.count());
-	return first < last;
+// Work items of this CTA: item k of the CTA is entry at(k) of the launch's leaf list (GridView::leaf_at). Strided (default): the
+// CTAs advance through the leaf list together, CTA b taking b, b + G, b + 2G, ... -- at any moment the whole grid works inside a
+// window of about G consecutive leaves, so the x-neighbour planes a leaf's region needs (256 leaves away in a lower node) are
+// still in the L2 from the CTAs that staged them a moment ago. Contiguous ranges per CTA (HNS_ADVECT_CONTIGUOUS=1) scatter the grid
+// over the whole list instead: every leaf is then fetched from HBM about three times (ncu: 4.1 GB read by advect_scalars vs 1.3 GB).
+struct CtaItems {
+	uint32_t base, stride, count;
+	__device__ __forceinline__ uint32_t at(uint32_t k) const { return base + k * stride; }
+};
+__device__ __forceinline__ CtaItems cta_items(const GridView& g, int contiguous) {
+	CtaItems it;
+	if (contiguous) {
+		const uint32_t per = (g.count() + gridDim.x - 1) / gridDim.x;
+		it.base = blockIdx.x * per, it.stride = 1;
+		it.count = it.base < g.count() ? min(per, g.count() - it.base) : 0u;
+	} else {
+		it.base = blockIdx.x, it.stride = gridDim.x;
+		it.count = it.base < g.count() ? (g.count() - it.base + gridDim.x - 1) / gridDim.x : 0u;
+	}
+	return it;
 }
 
 // TrilinearSampler<Vec3f>::sample through the staged region when possible
@@ -498,32 +512,32 @@ __device__ __forceinline__ void sample_vec(const GridView& g, const LeafFrame& f
 
 __global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const float* __restrict__ u, const float* __restrict__ v,
                                                           const float* __restrict__ w, float* __restrict__ ou, float* __restrict__ ov,
-                                                          float* __restrict__ ow, float sdt) {
+                                                          float* __restrict__ ow, float sdt, int contiguous) {
 	extern __shared__ __align__(16) float region[];
-	uint32_t first, last;
-	if (!cta_leaf_range(g, first, last)) return;
+	const CtaItems items = cta_items(g, contiguous);
+	if (!items.count) return;
 	const int x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
 	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
 	__shared__ int meta[3][kMetaInts];  // ring over the CTA's leaves: in use / being staged / being prefetched
-	auto issue = [&](uint32_t item, int buf) {
-		const StagePlan plan = make_stage_plan(meta[(item - first) % 3]);
+	auto issue = [&](uint32_t k, int buf) {  // stage item k; its metadata is already in the ring, the next item's rides along
+		const StagePlan plan = make_stage_plan(meta[k % 3]);
 		float* r = region + buf * kStageFloats;
 		stage_region(plan, u, r, 0.f);
 		stage_region(plan, v, r + kRegionFloats, 0.f);
 		stage_region(plan, w, r + 2 * kRegionFloats, 0.f);
-		if (item + 1 < last) meta_prefetch(g, meta[(item + 1 - first) % 3], item + 1);
+		if (k + 1 < items.count) meta_prefetch(g, meta[(k + 1) % 3], items.at(k + 1));
 		cp_async_commit();
 	};
-	meta_load_now(g, meta[0], first);
+	meta_load_now(g, meta[0], items.at(0));
 	__syncthreads();
-	issue(first, 0);
-	for (uint32_t item = first; item < last; ++item) {
-		const int buf = (item - first) & 1;
+	issue(0, 0);
+	for (uint32_t k = 0; k < items.count; ++k) {
+		const int buf = k & 1;
 		cp_async_wait<0>();
 		__syncthreads();  // this item's region (and the next leaf's metadata) has landed for every thread, and every thread is done reading the other buffer
-		if (item + 1 < last) issue(item + 1, buf ^ 1);
+		if (k + 1 < items.count) issue(k + 1, buf ^ 1);
 		const float *ru = region + buf * kStageFloats, *rv = ru + kRegionFloats, *rw = ru + 2 * kRegionFloats;
-		const int* m = meta[(item - first) % 3];
+		const int* m = meta[k % 3];
 		const uint32_t leaf = uint32_t(m[kMetaLeaf]);
 		const LeafFrame f{m[kMetaOrigin], m[kMetaOrigin + 1], m[kMetaOrigin + 2], g.nbr + uint64_t(leaf) * 27u};
 		const uint64_t self = uint64_t(leaf) * 512u + threadIdx.x;
@@ -564,6 +578,13 @@ static int advect_grid(uint32_t num_leaves) {
 	}
 	return int(min(uint32_t(2 * sms), num_leaves));  // num_leaves = work items of the launch
 }
+static int advect_contiguous() {  // A/B switch, see CtaItems
+	static const int v = [] {
+		const char* e = std::getenv("HNS_ADVECT_CONTIGUOUS");
+		return e && std::atoi(e) != 0 ? 1 : 0;
+	}();
+	return v;
+}
 template <typename K>
 static void advect_attrs(K kernel) {
 	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAdvectSmem));
@@ -573,7 +594,8 @@ void launch_advect_vector(const GridView& g, const float* const vel[3], float* c
 	if (!g.count()) return;
 	static bool attr = false;
 	if (!attr) advect_attrs(k_advect_vector), attr = true;
-	HNS_LAUNCH(k_advect_vector, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], dt * inv_dx);
+	HNS_LAUNCH(k_advect_vector, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], dt * inv_dx,
+	           advect_contiguous());
 }
 
 // advect_scalars (Kernel.cu:118-266) [kSemantics 0]: explicit corner weights, fma accumulation in corner order
@@ -604,22 +626,22 @@ __device__ __noinline__ float far_weighted(const GridView& g, const LeafFrame& f
 template <int kSemantics>
 __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const float* __restrict__ u, const float* __restrict__ v,
                                                            const float* __restrict__ w, const __grid_constant__ ScalarPtrs sp, int S, float sdt,
-                                                           const float* __restrict__ elem0) {
+                                                           const float* __restrict__ elem0, int contiguous) {
 	// (sp is __grid_constant__: its pointer arrays are indexed with run-time indices, which then read the constant bank directly
 	// instead of a per-thread local-memory copy of the parameter)
 	extern __shared__ __align__(16) float region[];
-	uint32_t first, last;
-	if (!cta_leaf_range(g, first, last)) return;
+	const CtaItems items = cta_items(g, contiguous);
+	if (!items.count) return;
 	const int x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
 	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
 	// pipeline jobs: per leaf one velocity stage (the shared trace) and ceil(S/3) stages of up to three scalar fields
 	const int jobs_per_leaf = 1 + (S + 2) / 3;
-	const int n_jobs = int(last - first) * jobs_per_leaf;
+	const int n_jobs = int(items.count) * jobs_per_leaf;
 	// (the shared-memory metadata ring of k_advect_vector does not pay here: one decode per 1 + ceil(S/3) jobs, measured +2 %)
 	StagePlan plan{};  // of the leaf whose jobs are being issued; decoded once per leaf
 	auto issue = [&](int job) {
 		const int jj = job % jobs_per_leaf;
-		if (jj == 0) plan = make_stage_plan(g.nbr + uint64_t(g.leaf_at(first + uint32_t(job / jobs_per_leaf))) * 27u);
+		if (jj == 0) plan = make_stage_plan(g.nbr + uint64_t(g.leaf_at(items.at(uint32_t(job / jobs_per_leaf)))) * 27u);
 		float* r = region + (job & 1) * kStageFloats;
 		if (jj == 0) {
 			// advect_scalars samples the velocity with "inactive -> element 0" as well (Kernel.cu:192,204). elem0, when given,
@@ -643,7 +665,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 		cp_async_wait<0>();
 		__syncthreads();  // this job's region has landed for every thread, and every thread is done reading the other buffer
 		if (job + 1 < n_jobs) issue(job + 1);
-		const uint32_t leaf = g.leaf_at(first + uint32_t(job / jobs_per_leaf));
+		const uint32_t leaf = g.leaf_at(items.at(uint32_t(job / jobs_per_leaf)));
 		const int jj = job % jobs_per_leaf;
 		const float* __restrict__ base = region + (job & 1) * kStageFloats;
 		if (jj == 0) {
@@ -733,9 +755,9 @@ void launch_advect_scalars(const GridView& g, const float* const vel[3], const S
 	static bool attr = false;
 	if (!attr) advect_attrs(k_advect_scalars<0>), advect_attrs(k_advect_scalars<1>), attr = true;
 	if (sampler_semantics == 0)
-		HNS_LAUNCH(k_advect_scalars<0>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0);
+		HNS_LAUNCH(k_advect_scalars<0>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0, advect_contiguous());
 	else
-		HNS_LAUNCH(k_advect_scalars<1>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0);
+		HNS_LAUNCH(k_advect_scalars<1>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0, advect_contiguous());
 }
 
 // element 0 of velocity (x,y,z) and of each scalar field -> dst[3 + S]
