@@ -420,6 +420,8 @@ def _load_ref(path: str) -> C.CDLL:
             L.ref_frame_destroy.argtypes = [C.c_void_p]
             L.ref_frame_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, c_f32p]
             L.ref_frame_download.argtypes = [C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, C.POINTER(c_f32p)]
+            if hasattr(L, "ref_frame_collision_stage"):
+                L.ref_frame_collision_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_f32p, C.c_float, C.c_float, c_f32p]
             if hasattr(L, "ref_frame_vorticity"):
                 L.ref_frame_vorticity.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, c_f32p]
         _ref_libs[path] = L
@@ -577,6 +579,17 @@ class RefFrame:
             rc = ref().ref_frame_vorticity(self._h, self.grid._h, dt, voxel_size, scale, factor_scale, out.ctypes.data_as(c_f32p))
         _rcheck(rc)
         return out
+
+    def collision_stage(self, stage, sdf, dt, voxel_size):
+        """one reference kernel of the hasCollision path (see ref_frame_collision_stage); stages 0-2 return (N, 3), stage 3 the
+        advected scalars"""
+        sdf = np.ascontiguousarray(sdf, np.float32)
+        out = np.empty((self.data.n, 3), np.float32)
+        with _Quiet():
+            rc = ref().ref_frame_collision_stage(self._h, self.grid._h, stage, sdf.ctypes.data_as(c_f32p), dt, voxel_size,
+                                                 out.ctypes.data_as(c_f32p))
+        _rcheck(rc)
+        return self.download()["scalars"] if stage == 3 else out
 
     def download(self):
         n = self.data.n

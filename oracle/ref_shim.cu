@@ -213,6 +213,7 @@ struct RefFrame {
 	float *div = nullptr, *p = nullptr;
 	float *in[16] = {}, *out[16] = {};
 	float **dIn = nullptr, **dOut = nullptr;
+	float* sdf = nullptr;  // collision SDF of the collision stages below (allocated on first use)
 };
 
 void* ref_frame_create(void* data_, int S, const char** names) {
@@ -244,7 +245,7 @@ void ref_frame_destroy(void* f_) {
 	auto* f = static_cast<RefFrame*>(f_);
 	cudaFree(f->coords), cudaFree(f->vel), cudaFree(f->adv), cudaFree(f->proj), cudaFree(f->div), cudaFree(f->p);
 	for (int s = 0; s < f->S; ++s) cudaFree(f->in[s]), cudaFree(f->out[s]);
-	cudaFree(f->dIn), cudaFree(f->dOut);
+	cudaFree(f->dIn), cudaFree(f->dOut), cudaFree(f->sdf);
 	delete f;
 }
 // Runs `frames` frames; returns total device ms (CUDA events on the launch stream). State is NOT advanced
@@ -302,6 +303,38 @@ int ref_frame_vorticity(void* f_, void* handle, float dt, float voxelSize, float
 	vorticityConfinement<<<gs, bs>>>(grid, f->coords, f->vel, f->adv, dt, 1.0f / voxelSize, scale, factorScale, f->n);
 	if (cudaDeviceSynchronize() != cudaSuccess) return 2;
 	cudaMemcpy(outHost, f->adv, f->n * 12, cudaMemcpyDeviceToHost);
+	REF_CATCH
+}
+
+// One reference kernel of the collision path (hasCollision = true) on the frame's buffers, launched as Compute() launches it
+// (HNanoSolver.cu:153-157, 164-169, 282-296, 346-348). stage 0: enforceCollisionBoundaries on a copy of the input velocity -> outVec;
+// 1: advect_vector(velocity, sdf) -> outVec; 2: subtractPressureGradient(advected velocity and pressure of the last ref_frame_run,
+// sdf) -> outVec; 3: advect_scalars(projected velocity of the last ref_frame_run, sdf) -> fetch with ref_frame_download.
+int ref_frame_collision_stage(void* f_, void* handle, int stage, const float* sdfHost, float dt, float voxelSize, float* outVec) {
+	REF_TRY
+	auto* f = static_cast<RefFrame*>(f_);
+	auto* grid = static_cast<HandleT*>(handle)->deviceGrid<nanovdb::ValueOnIndex>();
+	const float inv = 1.0f / voxelSize;
+	const int bs = 256;
+	const int gs = int((f->n + bs - 1) / bs);
+	if (!f->sdf) cudaMalloc(&f->sdf, f->n * 4);
+	cudaMemcpy(f->sdf, sdfHost, f->n * 4, cudaMemcpyHostToDevice);
+	nanovdb::Vec3f* tmp = nullptr;
+	cudaMalloc(&tmp, f->n * 12);
+	switch (stage) {
+		case 0:
+			cudaMemcpy(tmp, f->vel, f->n * 12, cudaMemcpyDeviceToDevice);
+			enforceCollisionBoundaries<<<gs, bs>>>(grid, f->coords, tmp, f->sdf, voxelSize, f->n);
+			break;
+		case 1: advect_vector<<<gs, bs>>>(grid, f->coords, f->vel, tmp, f->sdf, true, f->n, dt, inv); break;
+		case 2: subtractPressureGradient<<<gs, bs>>>(grid, f->coords, f->n, f->adv, f->p, tmp, f->sdf, true, inv); break;
+		case 3: advect_scalars<<<gs, bs>>>(grid, f->coords, f->proj, f->dIn, f->dOut, f->S, f->sdf, true, f->n, dt, inv); break;
+		default: cudaFree(tmp); return 1;
+	}
+	const cudaError_t e = cudaDeviceSynchronize();
+	if (outVec && stage != 3) cudaMemcpy(outVec, tmp, f->n * 12, cudaMemcpyDeviceToHost);
+	cudaFree(tmp);
+	if (e != cudaSuccess) return 2;
 	REF_CATCH
 }
 

@@ -36,6 +36,17 @@ def case_inputs(name):
     return w, comb
 
 
+def collision_sdf(w):
+    """a sphere collider in the middle of the active region; 0.05 per voxel, so that the reference's 0.1-wide boundary band
+    (Kernel.cu:99, 438, 814) is two voxels thick and holds plenty of voxels; sidecar element 0 stays 0"""
+    c = w.coords.astype(np.float32)
+    centre = np.round(c.mean(0))
+    r = np.sqrt(((c - centre) ** 2).sum(1))
+    sdf = (0.05 * (r - 6.0)).astype(np.float32)
+    sdf[0] = 0.0
+    return sdf
+
+
 def make(name, iterations):
     w, comb = case_inputs(name)
     out = dict(origins=w.origins, coords=w.coords, velocity=w.velocity, voxel_size=np.float32(w.voxel_size), dt=np.float32(w.dt),
@@ -72,6 +83,14 @@ def make(name, iterations):
     out["vorticity_cases"] = np.array(vc, np.float32)
     for i, (sc, fs) in enumerate(vc):
         out[f"vorticity_{i}"] = f.vorticity(w.dt, w.voxel_size, sc, fs)
+    # the hasCollision path, kernel by kernel (inputs of stages 2 and 3 are frame_adv / frame_p and frame_vel above)
+    sdf = collision_sdf(w)
+    out["collision_sdf"] = sdf
+    out["coll_enforce"] = f.collision_stage(0, sdf, w.dt, w.voxel_size)
+    out["coll_advect_vector"] = f.collision_stage(1, sdf, w.dt, w.voxel_size)
+    out["coll_gradient"] = f.collision_stage(2, sdf, w.dt, w.voxel_size)
+    for i, sc in enumerate(f.collision_stage(3, sdf, w.dt, w.voxel_size)):
+        out[f"coll_scalar{i}"] = sc
     # stand-alone launchers
     d = data(floats=list(zip(w.scalar_names, w.scalars)))
     O.ref_advect_index_grid(d, w.dt, w.voxel_size)
@@ -102,6 +121,14 @@ def make(name, iterations):
     g3 = O.RefGrid(d, w.voxel_size)
     O.ref_compute_sim(d, g3, iterations, w.dt, w.voxel_size, pv, False)
     out["compute_sim_sopdefault_vel"] = d.blocks["vel"].copy()
+    # the all-in-one node with a collision_sdf block and hasCollision = true
+    d = data(floats=fl + [("collision_sdf", sdf)])
+    g4 = O.RefGrid(d, w.voxel_size)
+    O.ref_compute_sim(d, g4, iterations, w.dt, w.voxel_size, PARAMS, True)
+    out["compute_sim_coll_vel"] = d.blocks["vel"].copy()
+    for nm, _ in fl:
+        out[f"compute_sim_coll_{nm}"] = d.blocks[nm].copy()
+    out["compute_sim_coll_sdf_out"] = d.blocks["collision_sdf"].copy()  # what the reference hands back in the collision_sdf block
     np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), **out)
     print(name, "leaves", w.num_leaves, "voxels", w.num_voxels, "->", f"ref_{name}.npz")
 
