@@ -292,7 +292,7 @@ int ref_frame_download(void* f_, float* velProj, float* pressure, float* div, fl
 }
 
 // The reference's vorticityConfinement kernel (Kernel.cu:969-1025) launched OUT OF PLACE on the frame's velocity (input f->vel, output
-// f->adv, downloaded to outHost): Compute() passes one buffer as input and output (HNanoSolver.cu:174), which races; with two buffers
+// a scratch buffer, downloaded to outHost): Compute() passes one buffer as input and output (HNanoSolver.cu:174), which races; with two buffers
 // the same kernel is deterministic, and that is what the oracle's restatement is pinned against.
 int ref_frame_vorticity(void* f_, void* handle, float dt, float voxelSize, float scale, float factorScale, float* outHost) {
 	REF_TRY
@@ -300,9 +300,13 @@ int ref_frame_vorticity(void* f_, void* handle, float dt, float voxelSize, float
 	auto* grid = static_cast<HandleT*>(handle)->deviceGrid<nanovdb::ValueOnIndex>();
 	const int bs = 256;
 	const int gs = int((f->n + bs - 1) / bs);
-	vorticityConfinement<<<gs, bs>>>(grid, f->coords, f->vel, f->adv, dt, 1.0f / voxelSize, scale, factorScale, f->n);
-	if (cudaDeviceSynchronize() != cudaSuccess) return 2;
-	cudaMemcpy(outHost, f->adv, f->n * 12, cudaMemcpyDeviceToHost);
+	nanovdb::Vec3f* tmp = nullptr;  // a scratch output: the frame's own buffers keep the results of the last ref_frame_run
+	cudaMalloc(&tmp, f->n * 12);
+	vorticityConfinement<<<gs, bs>>>(grid, f->coords, f->vel, tmp, dt, 1.0f / voxelSize, scale, factorScale, f->n);
+	const cudaError_t e = cudaDeviceSynchronize();
+	cudaMemcpy(outHost, tmp, f->n * 12, cudaMemcpyDeviceToHost);
+	cudaFree(tmp);
+	if (e != cudaSuccess) return 2;
 	REF_CATCH
 }
 
