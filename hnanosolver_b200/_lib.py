@@ -61,6 +61,9 @@ SIGNATURES = {
     "hns_state_step": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_void_p]),
     "hns_state_advect_velocity": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
     "hns_state_vorticity_confinement": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "hns_state_set_collision": (C.c_int, [C.c_void_p, C.c_int]),
+    "hns_state_collision_active": (C.c_int, [C.c_void_p]),
+    "hns_state_enforce_collision": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hns_state_vorticity_active": (C.c_int, [C.c_void_p]),
     "hns_state_vorticity_mag": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hns_state_vorticity_force": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),

@@ -99,7 +99,9 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
                  cudaEvent_t ev_p1 = nullptr, const FrameDeps* deps = nullptr) {
 	const GridView g = s->view();
 	const float h = voxel_size, inv = 1.0f / h;
-	launch_advect_vector(g, s->vel, s->adv, dt, inv, st);
+	const float* sdf = s->collision_sdf();
+	if (sdf) launch_collision_boundary(g, s->vel, s->vel, sdf, inv, 0.1f, 0, st);  // enforceCollisionBoundaries, HNanoSolver.cu:153-157
+	launch_advect_vector(g, s->vel, s->adv, dt, inv, st, sdf);
 	if (s->comb_enabled) {
 		const int rc = vorticity_pass(s, dt, inv, s->comb.vorticityScale, s->comb.factorScale, st);
 		if (rc) return rc;
@@ -118,6 +120,10 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 	if (rc) return rc;
 	if (ev_p1) cudaEventRecord(ev_p1, st);
 	launch_subtract_gradient(g, s->adv, s->p, s->vel, inv, st);
+	if (sdf) {
+		launch_collision_boundary(g, s->vel, s->vel, sdf, inv, 0.1f, 0, st);  // the tail of subtractPressureGradient, Kernel.cu:808-826
+		launch_collision_boundary(g, s->vel, s->vel, sdf, inv, 0.1f, 0, st);  // enforceCollisionBoundaries again, HNanoSolver.cu:292-296
+	}
 	if (deps && deps->velocity_done) {
 		launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, s->n, st);
 		HNS_CUDA(cudaEventRecord(deps->velocity_done, st));
@@ -131,7 +137,7 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 			sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i];
 			++S;
 		}
-		launch_advect_scalars(g, s->vel, sp, S, dt, inv, 0, s->elem0, st);
+		launch_advect_scalars(g, s->vel, sp, S, dt, inv, 0, s->elem0, st, sdf);
 		for (int i = 0; i < s->n_scalars; ++i)
 			if (i != s->skip_scalar) std::swap(s->sc[i], s->sc_out[i]);
 	}
@@ -296,7 +302,7 @@ int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void*
 }
 int hns_state_advect_velocity(hns_state* s, float dt, void* stream) {
 	HNS_REQUIRE(s, "null state");
-	launch_advect_vector(s->view(), s->vel, s->adv, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream));
+	launch_advect_vector(s->view(), s->vel, s->adv, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream), s->collision_sdf());
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
@@ -367,15 +373,41 @@ int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream) {
 		// in place is safe: every thread reads only its own velocity row (the reference does the same, PressureProjection.cu:64)
 		launch_subtract_gradient(s->view(), s->vel, s->p, s->vel, 1.0f / s->grid->voxel_size, st);
 	}
+	if (const float* sdf = s->collision_sdf())  // the collision tail of the kernel, Kernel.cu:808-826
+		launch_collision_boundary(s->view(), s->vel, s->vel, sdf, 1.0f / s->grid->voxel_size, 0.1f, 0, st);
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+int hns_state_set_collision(hns_state* s, int sdf_scalar_index) {
+	HNS_REQUIRE(s, "null state");
+	HNS_REQUIRE(sdf_scalar_index >= -1 && sdf_scalar_index < s->n_scalars, "sdf scalar index out of range");
+	s->skip_scalar = sdf_scalar_index;
+	s->collision = sdf_scalar_index >= 0;
+	return HNS_OK;
+}
+int hns_state_collision_active(const hns_state* s) { return s && s->collision_sdf() ? 1 : 0; }
+int hns_state_enforce_collision(hns_state* s, void* stream) {
+	HNS_REQUIRE(s, "null state");
+	const float* sdf = s->collision_sdf();
+	if (!sdf) return HNS_OK;
+	++s->vel_version;
+	launch_collision_boundary(s->view(), s->vel, s->vel, sdf, 1.0f / s->grid->voxel_size, 0.1f, 0, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
 int hns_state_advect_scalars(hns_state* s, float dt, int sampler_semantics, void* stream) {
 	HNS_REQUIRE(s, "null state");
 	if (!s->n_scalars || !s->n) return HNS_OK;
-	launch_advect_scalars(s->view(), s->vel, scalar_ptrs(s), s->n_scalars, dt, 1.0f / s->grid->voxel_size, sampler_semantics, s->elem0,
-	                      static_cast<cudaStream_t>(stream));
-	for (int i = 0; i < s->n_scalars; ++i) std::swap(s->sc[i], s->sc_out[i]);
+	// every scalar except the one marked as not advected ("collision_sdf", HNanoSolver.cu:327); a sharded run's elem0 table is indexed
+	// by position in this list, so there the skipped scalar has to be the last one (checked in hns_dist_frame)
+	ScalarPtrs sp{};
+	int S = 0;
+	for (int i = 0; i < s->n_scalars; ++i)
+		if (i != s->skip_scalar) sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i], ++S;
+	launch_advect_scalars(s->view(), s->vel, sp, S, dt, 1.0f / s->grid->voxel_size, sampler_semantics, s->elem0, static_cast<cudaStream_t>(stream),
+	                      s->collision_sdf());
+	for (int i = 0; i < s->n_scalars; ++i)
+		if (i != s->skip_scalar) std::swap(s->sc[i], s->sc_out[i]);
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
@@ -511,7 +543,7 @@ int acquire_scratch(const hns_grid* g, int n_scalars, hns_state** out) {
 		g_scratch_device = dev;
 	}
 	g_scratch->grid = g;
-	g_scratch->comb_enabled = false, g_scratch->skip_scalar = -1, g_scratch->elem0 = nullptr, g_scratch->active = nullptr, g_scratch->n_active = 0;
+	g_scratch->comb_enabled = false, g_scratch->skip_scalar = -1, g_scratch->collision = false, g_scratch->elem0 = nullptr, g_scratch->active = nullptr, g_scratch->n_active = 0;
 	*out = g_scratch;
 	return HNS_OK;
 }
@@ -572,7 +604,6 @@ int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char*
 		if (!std::strcmp(names[i], "flame")) iL = i;
 		if (!std::strcmp(names[i], "collision_sdf")) iSdf = i;
 	}
-	if (has_collision && iSdf >= 0) return fail(HNS_ERR_UNSUPPORTED, "SDF collision handling is not implemented in this build (SURVEY.md 8f rank 2)");
 	for (const char* req : {"fuel", "waste", "temperature", "flame"}) {  // :193-201
 		bool found = false;
 		for (int i = 0; i < n_float; ++i) found |= !std::strcmp(names[i], req);
@@ -585,6 +616,7 @@ int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char*
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if ((rc = hns_state_set_combustion(s, 1, iF, iW, iT, iL, params))) return rc;
 	s->skip_scalar = iSdf;
+	s->collision = has_collision && iSdf >= 0;  // hasCollisionData, HNanoSolver.cu:65-76
 	if ((rc = ensure_aos(s))) return rc;
 	Streams* ss = nullptr;
 	if ((rc = acquire_streams(&ss))) return rc;
@@ -597,11 +629,13 @@ int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char*
 	HNS_CUDA(cudaEventRecord(e_start, st));
 	HNS_CUDA(cudaStreamWaitEvent(cs, e_start, 0));  // everything the caller queued on `stream` before this call stays ordered
 	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, cs));
+	if (s->collision) HNS_CUDA(cudaMemcpyAsync(s->sc[iSdf], fields[iSdf], n * 4, cudaMemcpyHostToDevice, cs));  // the first kernel reads it
 	HNS_CUDA(cudaEventRecord(e_vel_in, cs));
 	for (int i : {iF, iW, iT, iL}) HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, cs));
 	HNS_CUDA(cudaEventRecord(e_comb_in, cs));
 	for (int i = 0; i < n_float; ++i)
-		if (i != iF && i != iW && i != iT && i != iL) HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, cs));
+		if (i != iF && i != iW && i != iT && i != iL && !(s->collision && i == iSdf))
+			HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, cs));
 	HNS_CUDA(cudaEventRecord(e_all_in, cs));
 	HNS_CUDA(cudaStreamWaitEvent(st, e_vel_in, 0));
 	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);

@@ -183,6 +183,8 @@ struct hns_state {
 	int comb_idx[4] = {-1, -1, -1, -1};  // fuel, waste, temperature, flame
 	hns_combustion_params comb{};
 	int skip_scalar = -1;  // scalar that is carried but not advected ("collision_sdf")
+	bool collision = false;  // hasCollision with collision data: scalar `skip_scalar` is the SDF the kernels collide against
+	const float* collision_sdf() const { return collision && skip_scalar >= 0 ? sc[skip_scalar] : nullptr; }
 	const float* elem0 = nullptr;  // device float[3 + n_scalars]: element 0 of the global arrays (sharded runs), else null
 	uint64_t vel_version = 0;  // bumped by every entry point that (may) overwrite the velocity planes; lets a sharded run skip a ghost exchange of unchanged data
 	const int32_t* active = nullptr;  // device list of the leaves the kernels process (sharded runs: the owned leaves), null = all

@@ -571,6 +571,11 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	mark();
 	const int fvel[3] = {0, 1, 2}, fadv[3] = {3, 4, 5}, fred[1] = {6}, fblk[1] = {7};
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (s->skip_scalar >= 0 && s->skip_scalar != s->n_scalars - 1)
+		return fail(HNS_ERR_UNSUPPORTED, "sharded frames need the non-advected scalar (collision_sdf) to be the last scalar field");
+	// collision path: the SDF's ghost leaves arrive with the upload and never change; enforceCollisionBoundaries is per voxel on the
+	// owned leaves (it bumps the velocity version, so the velocity ghosts below are exchanged, never reused)
+	if (hns_state_collision_active(s) && (rc = hns_state_enforce_collision(s, stream))) return rc;
 	// the velocity ghosts are still current when the last thing that wrote the velocity was the previous sharded frame (its final
 	// exchange refreshed them and advect_scalars does not touch the velocity)
 	if (d->vel_exchanged_version != s->vel_version && (rc = exchange_channel(d, s, 0, 3, fvel, st))) return rc;
@@ -678,6 +683,7 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	}
 	mark();
 	if ((rc = hns_state_subtract_gradient(s, 1, stream))) return rc;
+	if (hns_state_collision_active(s) && (rc = hns_state_enforce_collision(s, stream))) return rc;  // HNanoSolver.cu:292-296
 	mark();
 	std::vector<int> last = {0, 1, 2};
 	if (!scalars_early)

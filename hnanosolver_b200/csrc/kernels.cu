@@ -192,6 +192,68 @@ void launch_subtract_gradient(const GridView& g, const float* const vel[3], cons
 }
 
 // =============================================================================================================
+// collision boundary treatment (reference Kernel.cu:77-116 enforceCollisionBoundaries; :432-450 tail of advect_vector; :808-826 tail
+// of subtractPressureGradient): sdf at the voxel < 0 -> velocity 0; sdf < 0.1 -> blend towards the velocity with its normal component
+// removed, blend = 1 - sdf / blend_divisor; normal = normalised central difference of the sdf (inactive neighbour -> 0).
+// Per voxel, so in place is safe. Contraction as compiled in the reference (settled bit for bit against its kernels, see
+// oracle/hns_oracle.c): |g|^2 = fma(gz,gz, fma(gx,gx, rnd(gy*gy))), v.n = fma(vz,nz, fma(vx,nx, rnd(vy*ny))), tangent = fma(-v.n, n, v),
+// result = fma(1-b, v, rnd(b*t)) -- except in advect_vector's tail (mixed_sum), where y and z are fma(b, t, rnd((1-b)*v)).
+// =============================================================================================================
+__global__ void __launch_bounds__(256) k_collision_boundary(GridView g, const float* u, const float* v, const float* w, float* ou, float* ov,
+                                                            float* ow, const float* __restrict__ sdf, float inv_dx, float blend_divisor,
+                                                            int mixed_sum) {
+	RowCtx c;
+	if (!make_row_ctx(g, c)) return;
+	const uint64_t self = c.self();
+	const Row8 sd = ld_row(sdf, self);
+	Row8 a = ld_row_coherent(u, self), b = ld_row_coherent(v, self), d = ld_row_coherent(w, self);
+	bool any = false;
+#pragma unroll
+	for (int z = 0; z < 8; ++z) any |= sd.v[z] < 0.1f;
+	if (any) {
+		int64_t i;
+		const Row8 sxp = (i = c.row(1, 0)) >= 0 ? ld_row(sdf, i) : zero_row(), sxm = (i = c.row(-1, 0)) >= 0 ? ld_row(sdf, i) : zero_row();
+		const Row8 syp = (i = c.row(0, 1)) >= 0 ? ld_row(sdf, i) : zero_row(), sym = (i = c.row(0, -1)) >= 0 ? ld_row(sdf, i) : zero_row();
+		const float szm = (i = c.zminus()) >= 0 ? __ldg(sdf + i) : 0.f, szp = (i = c.zplus()) >= 0 ? __ldg(sdf + i) : 0.f;
+		const float s = 0.5f * inv_dx;
+#pragma unroll
+		for (int z = 0; z < 8; ++z) {
+			const float sv = sd.v[z];
+			if (sv < 0.0f) {
+				a.v[z] = b.v[z] = d.v[z] = 0.0f;
+			} else if (sv < 0.1f) {
+				const float zp = z < 7 ? sd.v[z < 7 ? z + 1 : 7] : szp, zm = z > 0 ? sd.v[z > 0 ? z - 1 : 0] : szm;
+				const float gx = __fmul_rn(s, sxp.v[z] - sxm.v[z]), gy = __fmul_rn(s, syp.v[z] - sym.v[z]), gz = __fmul_rn(s, zp - zm);
+				const float len = sqrtf(fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy))));
+				float nx = 0.f, ny = 0.f, nz = 0.f;
+				if (len > 1e-6f) {
+					const float r = __fdiv_rn(1.0f, len);
+					nx = __fmul_rn(r, gx), ny = __fmul_rn(r, gy), nz = __fmul_rn(r, gz);
+				}
+				const float blend = __fsub_rn(1.0f, __fdiv_rn(sv, blend_divisor)), keep = __fsub_rn(1.0f, blend);
+				const float vx = a.v[z], vy = b.v[z], vz = d.v[z];
+				const float vdotn = fmaf(vz, nz, fmaf(vx, nx, __fmul_rn(vy, ny)));
+				const float tx = fmaf(-vdotn, nx, vx), ty = fmaf(-vdotn, ny, vy), tz = fmaf(-vdotn, nz, vz);
+				a.v[z] = fmaf(keep, vx, __fmul_rn(blend, tx));
+				b.v[z] = mixed_sum ? fmaf(blend, ty, __fmul_rn(keep, vy)) : fmaf(keep, vy, __fmul_rn(blend, ty));
+				d.v[z] = mixed_sum ? fmaf(blend, tz, __fmul_rn(keep, vz)) : fmaf(keep, vz, __fmul_rn(blend, tz));
+			}
+		}
+	}
+	if (any || ou != u) {
+		st_row(ou, self, a);
+		st_row(ov, self, b);
+		st_row(ow, self, d);
+	}
+}
+void launch_collision_boundary(const GridView& g, const float* const vel[3], float* const out[3], const float* sdf, float inv_dx,
+                               float blend_divisor, int mixed_sum, cudaStream_t st) {
+	if (g.count())
+		HNS_LAUNCH(k_collision_boundary, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdf, inv_dx, blend_divisor,
+		           mixed_sum);
+}
+
+// =============================================================================================================
 // red-black Gauss-Seidel / SOR  (reference Kernel.cu:591-623)
 //   s = (pxp + pxm + pyp + pym + pzp + pzm) - div*dx^2 ; pGS = s/6 ; p = pOld + omega*(pGS - pOld)
 //   as compiled in the reference: s = fma(-div, dx2, sum); d = fma(s, 1/6, -pOld); p = fma(d, omega, pOld)
@@ -510,9 +572,13 @@ __device__ __forceinline__ void sample_vec(const GridView& g, const LeafFrame& f
 	}
 }
 
+// kCollision (reference Kernel.cu:377-394): a back-trace that ends inside the collider (trilinear SDF sample < 0, inactive corners 0)
+// stays at the voxel, a forward trace that does falls back to the back-traced position. The SDF is not staged: its two samples per
+// voxel go through the neighbour table (global memory); the boundary treatment of the result (:432-450) is a separate launch.
+template <bool kCollision>
 __global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const float* __restrict__ u, const float* __restrict__ v,
                                                           const float* __restrict__ w, float* __restrict__ ou, float* __restrict__ ov,
-                                                          float* __restrict__ ow, float sdt, int contiguous) {
+                                                          float* __restrict__ ow, float sdt, int contiguous, const float* __restrict__ sdf) {
 	extern __shared__ __align__(16) float region[];
 	const CtaItems items = cta_items(g, contiguous);
 	if (!items.count) return;
@@ -544,10 +610,12 @@ __global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const floa
 		const int ci = f.ox + x, cj = f.oy + y, ck = f.oz + z;
 		const float u0 = ru[c], v0 = rv[c], w0 = rw[c];
 		// backtrace: pos - velOrig * scaled_dt  (Kernel.cu:374)
-		const float bx = fmaf(-sdt, u0, float(ci)), by = fmaf(-sdt, v0, float(cj)), bz = fmaf(-sdt, w0, float(ck));
+		float bx = fmaf(-sdt, u0, float(ci)), by = fmaf(-sdt, v0, float(cj)), bz = fmaf(-sdt, w0, float(ck));
+		if (kCollision && trilinear_f(g, f, sdf, bx, by, bz) < 0.0f) bx = float(ci), by = float(cj), bz = float(ck);  // :377-382
 		float uf, vf, wf, ub, vb, wb;
 		sample_vec(g, f, ru, rv, rw, u, v, w, bx, by, bz, uf, vf, wf);
-		const float fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :387
+		float fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :387
+		if (kCollision && trilinear_f(g, f, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;  // :390-394
 		sample_vec(g, f, ru, rv, rw, u, v, w, fx, fy, fz, ub, vb, wb);
 		const float cu = fmaf(0.5f, u0 - ub, uf), cv = fmaf(0.5f, v0 - vb, vf), cw = fmaf(0.5f, w0 - wb, wf);  // :399-400
 		float mnu = u0, mxu = u0, mnv = v0, mxv = v0, mnw = w0, mxw = w0;
@@ -590,12 +658,19 @@ static void advect_attrs(K kernel) {
 	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAdvectSmem));
 	cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
-void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st) {
+void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st,
+                          const float* sdf) {
 	if (!g.count()) return;
 	static bool attr = false;
-	if (!attr) advect_attrs(k_advect_vector), attr = true;
-	HNS_LAUNCH(k_advect_vector, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], dt * inv_dx,
-	           advect_contiguous());
+	if (!attr) advect_attrs(k_advect_vector<false>), advect_attrs(k_advect_vector<true>), attr = true;
+	if (sdf) {
+		HNS_LAUNCH(k_advect_vector<true>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2],
+		           dt * inv_dx, advect_contiguous(), sdf);
+		launch_collision_boundary(g, out, out, sdf, inv_dx, 1.5f, 1, st);  // Kernel.cu:432-450
+	} else {
+		HNS_LAUNCH(k_advect_vector<false>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2],
+		           dt * inv_dx, advect_contiguous(), sdf);
+	}
 }
 
 // advect_scalars (Kernel.cu:118-266) [kSemantics 0]: explicit corner weights, fma accumulation in corner order
@@ -623,10 +698,10 @@ __device__ __noinline__ float far_weighted(const GridView& g, const LeafFrame& f
 	return acc;
 }
 
-template <int kSemantics>
+template <int kSemantics, bool kCollision>
 __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const float* __restrict__ u, const float* __restrict__ v,
                                                            const float* __restrict__ w, const __grid_constant__ ScalarPtrs sp, int S, float sdt,
-                                                           const float* __restrict__ elem0, int contiguous) {
+                                                           const float* __restrict__ elem0, int contiguous, const float* __restrict__ sdf) {
 	// (sp is __grid_constant__: its pointer arrays are indexed with run-time indices, which then read the constant bank directly
 	// instead of a per-thread local-memory copy of the parameter)
 	extern __shared__ __align__(16) float region[];
@@ -674,6 +749,9 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 			f = leaf_frame(g, leaf);
 			const int ci = f.ox + x, cj = f.oy + y, ck = f.oz + z;
 			bx = fmaf(-sdt, ru[c], float(ci)), by = fmaf(-sdt, rv[c], float(cj)), bz = fmaf(-sdt, rw[c], float(ck));
+			// hasCollision (Kernel.cu:142-155): the reference tests the back-traced position twice; the second test sees either the
+			// same position or the voxel itself and resets to the voxel again, so one test decides
+			if (kCollision && trilinear_f(g, f, sdf, bx, by, bz) < 0.0f) bx = float(ci), by = float(cj), bz = float(ck);
 			float uf, vf, wf;
 			if (kSemantics == 0) {
 				const int i0 = __float2int_rd(bx), j0 = __float2int_rd(by), k0 = __float2int_rd(bz);
@@ -698,6 +776,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 				sample_vec(g, f, ru, rv, rw, u, v, w, bx, by, bz, uf, vf, wf);
 			}
 			fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :208
+			if (kCollision && trilinear_f(g, f, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;  // :211-214
 			bB = region_base(f, __float2int_rd(bx), __float2int_rd(by), __float2int_rd(bz));
 			bF = region_base(f, __float2int_rd(fx), __float2int_rd(fy), __float2int_rd(fz));
 		} else {
@@ -750,14 +829,20 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 	}
 }
 void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx,
-                           int sampler_semantics, const float* elem0, cudaStream_t st) {
+                           int sampler_semantics, const float* elem0, cudaStream_t st, const float* sdf) {
 	if (!g.count() || S <= 0) return;
 	static bool attr = false;
-	if (!attr) advect_attrs(k_advect_scalars<0>), advect_attrs(k_advect_scalars<1>), attr = true;
-	if (sampler_semantics == 0)
-		HNS_LAUNCH(k_advect_scalars<0>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0, advect_contiguous());
-	else
-		HNS_LAUNCH(k_advect_scalars<1>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, dt * inv_dx, elem0, advect_contiguous());
+	if (!attr) {
+		advect_attrs(k_advect_scalars<0, false>), advect_attrs(k_advect_scalars<1, false>);
+		advect_attrs(k_advect_scalars<0, true>), advect_attrs(k_advect_scalars<1, true>);  // (commas inside <> are fine in a function argument)
+		attr = true;
+	}
+	const int grid = advect_grid(g.count());
+	const float sdt = dt * inv_dx;
+	const int cont = advect_contiguous();
+	auto kernel = sampler_semantics == 0 ? (sdf ? k_advect_scalars<0, true> : k_advect_scalars<0, false>)
+	                                     : (sdf ? k_advect_scalars<1, true> : k_advect_scalars<1, false>);
+	HNS_LAUNCH(kernel, grid, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, sdt, elem0, cont, sdf);
 }
 
 // element 0 of velocity (x,y,z) and of each scalar field -> dst[3 + S]

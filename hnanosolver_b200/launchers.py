@@ -253,6 +253,14 @@ class Simulation:
     def advect_velocity(self, dt, stream=None):
         check(_lib.lib().hns_state_advect_velocity(self._h, dt, _stream(stream)))
 
+    def set_collision(self, sdf_scalar_index: int = -1):
+        """scalar `sdf_scalar_index` becomes the collision SDF of the hasCollision path (-1: off)"""
+        check(_lib.lib().hns_state_set_collision(self._h, int(sdf_scalar_index)))
+
+    def enforce_collision(self, stream=None):
+        """enforceCollisionBoundaries (reference Kernel.cu:77-116) on the velocity"""
+        check(_lib.lib().hns_state_enforce_collision(self._h, _stream(stream)))
+
     def vorticity_confinement(self, dt, scale, factor_scale, stream=None):
         """vorticityConfinement (reference Kernel.cu:969-1025) on the advected velocity, out of place"""
         check(_lib.lib().hns_state_vorticity_confinement(self._h, dt, scale, factor_scale, _stream(stream)))

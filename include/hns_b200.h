@@ -99,7 +99,10 @@ int hns_grid_neighbors_download(const hns_grid* g, int32_t* dst_host);
 void hns_release_scratch(void);
 /* Compute_Sim (src/Cuda/HNanoSolver.cu:9-372,393-396): advect velocity -> [vorticity] -> divergence -> combustion ->
  * buoyancy -> iterations x (red, black) -> gradient subtract -> advect all float fields. float_names/float_fields are
- * the float blocks in insertion order (GridData.hpp:136-145); fuel, waste, temperature, flame must be among them. */
+ * the float blocks in insertion order (GridData.hpp:136-145); fuel, waste, temperature, flame must be among them.
+ * A block named "collision_sdf" is never advected and comes back zeroed (the reference copies back an output buffer it never
+ * writes, :361-369); with has_collision != 0 it is the SDF of the collision path (enforceCollisionBoundaries before the advection
+ * and after the projection, collision tests of the traced positions, boundary tails of advect_vector and the gradient subtract). */
 int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char* const* float_names, float* const* float_fields,
                     int iterations, float dt, float voxel_size, const hns_combustion_params* params, int has_collision, void* stream);
 /* AdvectIndexGrid (src/Cuda/Advection.cu:13-112,169-171): BFECC advection of every float block by the velocity block. */
@@ -146,6 +149,13 @@ int hns_state_set_combustion(hns_state* s, int enabled, int i_fuel, int i_waste,
 int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void* stream);
 /* Individual steps on resident state (asynchronous). */
 int hns_state_advect_velocity(hns_state* s, float dt, void* stream);                 /* vel -> adv              */
+/* Collision path (reference hasCollision): scalar `sdf_scalar_index` is the collision SDF (-1 switches the path off). The scalar
+ * is then never advected, hns_state_step / hns_state_advect_velocity / _subtract_gradient / _advect_scalars apply the reference's
+ * collision handling, and hns_state_enforce_collision is enforceCollisionBoundaries (Kernel.cu:77-116) on the velocity, which
+ * hns_state_step runs before the advection and after the projection (HNanoSolver.cu:153-157, 292-296). */
+int hns_state_set_collision(hns_state* s, int sdf_scalar_index);
+int hns_state_collision_active(const hns_state* s);
+int hns_state_enforce_collision(hns_state* s, void* stream);
 int hns_state_vorticity_confinement(hns_state* s, float dt, float scale, float factor_scale, void* stream); /* adv -> adv, out of place */
 /* the same in its two launches (a sharded run exchanges the ghost leaves of field 26 = |curl| in between); _active: does the
  * configured frame (hns_state_set_combustion) contain the pass at all? */

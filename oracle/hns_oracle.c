@@ -425,7 +425,77 @@ float ora_nearest_float(const ora_index* ix, const float* data, int32_t i, int32
 static const int ORA_NBR[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
 
 /* advect_vector (Kernel.cu:354-453) */
-void ora_advect_vector(const ora_index* ix, const int32_t* coords, const float* vel, float* out, uint64_t n, float dt, float inv_dx) {
+/* isInCollision (Kernel.cu:31-37): IndexSampler<float,1> (trilinear, inactive -> 0) of the SDF at a position, < 0 */
+static inline int ora_in_collision(const ora_index* ix, const float* sdf, const float* p) { return ora_trilinear_f(ix, sdf, p[0], p[1], p[2]) < 0.0f; }
+
+/* The collision boundary treatment shared by enforceCollisionBoundaries (Kernel.cu:77-116), the tail of advect_vector (:432-450) and
+ * the tail of subtractPressureGradient (:808-826): inside the collider (sdf < 0) the velocity is zeroed; within 0.1 of it the normal
+ * component is blended out, blend = 1 - sdf / blend_divisor (0.1 in enforce and gradient, 1.5 in advect_vector). sdf is sampled at
+ * the voxel (IndexSampler<float,1>(Coord) = nearest), the normal from central differences of the six neighbours (inactive -> 0).
+ * Contraction knobs (ora_coll_variant) exist because the three call sites are compiled separately and nvcc contracts them differently
+ * (read off the SASS of advect_vector: v.n = fma(v2,n2, fma(v0,n0, rnd(v1*n1))), tangent = fma(-v.n, n, v), and the blend sum is
+ * fma(1-b, v, rnd(b*t)) for x but fma(b, t, rnd((1-b)*v)) for y and z; in enforce and in the gradient all three components take the
+ * first form). The words below reproduce the reference kernels bit for bit on tests/golden (enumerated, then fixed). */
+int ora_coll_variant[3] = {943, 79, 943}; /* [0] enforce, [1] advect_vector tail, [2] gradient tail; words decoded in ora_boundary_voxel */
+/* a*b + c*d + e*f, parsed ((a*b + c*d) + e*f), in the six ways nvcc may contract it: v % 3 picks the first pair
+ * (0: fma(c,d, rnd(a*b)), 1: fma(a,b, rnd(c*d)), 2: both products rounded), v / 3 the last addition (0: fused, 1: rounded product) */
+static inline float ora_dot3(float a, float b, float c, float d, float e, float f, int v) {
+	float t;
+	switch (v % 3) {
+		case 0: t = fmaf(c, d, a * b); break;
+		case 1: t = fmaf(a, b, c * d); break;
+		default: t = a * b + c * d; break;
+	}
+	return (v / 3) ? t + e * f : fmaf(e, f, t);
+}
+/* variant word: digits (base 6) ssq, (base 6) v.n, (base 2) tangent, (base 27 = one base-3 digit per component) blend sum, (base 2) blend factor */
+static void ora_boundary_voxel(const ora_index* ix, const float* sdf, int32_t i, int32_t j, int32_t k, float inv_dx, float blend_divisor,
+                               const float* vin, float* vout, int var) {
+	const int v_ssq = var % 6, v_dot = (var / 6) % 6, v_tan = (var / 36) % 2, v_sum = (var / 72) % 27, v_bl = (var / 1944) % 2;
+	const int sum_c[3] = {v_sum % 3, (v_sum / 3) % 3, v_sum / 9};
+	const float sv = ora_nearest_f(ix, sdf, i, j, k);
+	if (sv < 0.0f) {
+		vout[0] = vout[1] = vout[2] = 0.0f;
+		return;
+	}
+	if (!(sv < 0.1f)) {
+		vout[0] = vin[0], vout[1] = vin[1], vout[2] = vin[2];
+		return;
+	}
+	/* getSDFNormal (:41-48) over gradientSDF (:16-28) */
+	const float s = 0.5f * inv_dx;
+	float g[3] = {s * (ora_nearest_f(ix, sdf, i + 1, j, k) - ora_nearest_f(ix, sdf, i - 1, j, k)),
+	              s * (ora_nearest_f(ix, sdf, i, j + 1, k) - ora_nearest_f(ix, sdf, i, j - 1, k)),
+	              s * (ora_nearest_f(ix, sdf, i, j, k + 1) - ora_nearest_f(ix, sdf, i, j, k - 1))};
+	const float len = sqrtf(ora_dot3(g[0], g[0], g[1], g[1], g[2], g[2], v_ssq));
+	float nrm[3] = {0.0f, 0.0f, 0.0f};
+	if (len > 1e-6f) {
+		const float r = 1.0f / len; /* Vec3::operator/(T) = (T(1)/s) * v, nanovdb/math/Math.h:650 */
+		nrm[0] = r * g[0], nrm[1] = r * g[1], nrm[2] = r * g[2];
+	}
+	const float blend = v_bl ? fmaf(-sv, 1.0f / blend_divisor, 1.0f) : 1.0f - (sv / blend_divisor);
+	/* applyNoSlipBoundary (:58-74): v - n * (v . n) */
+	const float vdotn = ora_dot3(vin[0], nrm[0], vin[1], nrm[1], vin[2], nrm[2], v_dot);
+	const float keep = 1.0f - blend;
+	for (int c = 0; c < 3; ++c) {
+		const float tang = v_tan ? vin[c] - vdotn * nrm[c] : fmaf(-vdotn, nrm[c], vin[c]);
+		switch (sum_c[c]) { /* velocity * (1 - blend) + no_slip * blend */
+			case 0: vout[c] = fmaf(blend, tang, keep * vin[c]); break;
+			case 1: vout[c] = fmaf(keep, vin[c], blend * tang); break;
+			default: vout[c] = keep * vin[c] + blend * tang; break;
+		}
+	}
+}
+void ora_collision_boundary(const ora_index* ix, const int32_t* coords, const float* vel, float* out, const float* sdf, float inv_dx,
+                            float blend_divisor, int site, uint64_t n) {
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t)
+		ora_boundary_voxel(ix, sdf, coords[3 * t], coords[3 * t + 1], coords[3 * t + 2], inv_dx, blend_divisor, vel + 3 * t, out + 3 * t,
+		                   ora_coll_variant[site]);
+}
+
+static void ora_advect_vector_impl(const ora_index* ix, const int32_t* coords, const float* vel, float* out, uint64_t n, float dt, float inv_dx,
+                                   const float* sdf) {
 	const float sdt = dt * inv_dx;
 #pragma omp parallel for schedule(static)
 	for (int64_t t = 0; t < (int64_t)n; ++t) {
@@ -434,8 +504,10 @@ void ora_advect_vector(const ora_index* ix, const int32_t* coords, const float* 
 		float u0[3], uf[3], ub[3], bp[3], fp[3];
 		ora_nearest_v(ix, vel, ci, cj, ck, u0);                       /* velocitySampler(coord) :371 */
 		for (int c = 0; c < 3; ++c) bp[c] = fmaf(-sdt, u0[c], pos[c]); /* pos - velOrig*scaled_dt :374 */
+		if (sdf && ora_in_collision(ix, sdf, bp)) bp[0] = pos[0], bp[1] = pos[1], bp[2] = pos[2]; /* :377-382 */
 		ora_trilinear_v(ix, vel, bp[0], bp[1], bp[2], uf);            /* :384 */
 		for (int c = 0; c < 3; ++c) fp[c] = fmaf(sdt, uf[c], bp[c]);   /* :387 */
+		if (sdf && ora_in_collision(ix, sdf, fp)) fp[0] = bp[0], fp[1] = bp[1], fp[2] = bp[2];    /* :390-394 */
 		ora_trilinear_v(ix, vel, fp[0], fp[1], fp[2], ub);            /* :396 */
 		float mn[3], mx[3], corr[3];
 		for (int c = 0; c < 3; ++c) {
@@ -454,7 +526,19 @@ void ora_advect_vector(const ora_index* ix, const int32_t* coords, const float* 
 			mn[c] = fminf(mn[c], uf[c]), mx[c] = fmaxf(mx[c], uf[c]);
 			out[3 * t + c] = fmaxf(mn[c], fminf(corr[c], mx[c]));
 		}
+		if (sdf) {                                                    /* :432-450 */
+			const float v[3] = {out[3 * t], out[3 * t + 1], out[3 * t + 2]};
+			ora_boundary_voxel(ix, sdf, ci, cj, ck, inv_dx, 1.5f, v, out + 3 * t, ora_coll_variant[1]);
+		}
 	}
+}
+void ora_advect_vector(const ora_index* ix, const int32_t* coords, const float* vel, float* out, uint64_t n, float dt, float inv_dx) {
+	ora_advect_vector_impl(ix, coords, vel, out, n, dt, inv_dx, NULL);
+}
+/* advect_vector with hasCollision (Kernel.cu:377-394, 432-450) */
+void ora_advect_vector_sdf(const ora_index* ix, const int32_t* coords, const float* vel, float* out, uint64_t n, float dt, float inv_dx,
+                           const float* sdf) {
+	ora_advect_vector_impl(ix, coords, vel, out, n, dt, inv_dx, sdf);
 }
 
 /* advect_scalar (Kernel.cu:269-352), the stand-alone node's kernel: samplers everywhere, inactive -> 0 */
@@ -507,8 +591,8 @@ static void ora_setup_interp(const ora_index* ix, const float* p, ora_interp* d)
 		d->idx[q] = off == 0 ? 0 : off - 1;                            /* :191-192: inactive corner reads element 0 */
 	}
 }
-void ora_advect_scalars(const ora_index* ix, const int32_t* coords, const float* vel, const float* const* in, float* const* out, int S,
-                        uint64_t n, float dt, float inv_dx) {
+static void ora_advect_scalars_impl(const ora_index* ix, const int32_t* coords, const float* vel, const float* const* in, float* const* out, int S,
+                                    uint64_t n, float dt, float inv_dx, const float* sdf) {
 	const float sdt = dt * inv_dx;
 #pragma omp parallel for schedule(static)
 	for (int64_t t = 0; t < (int64_t)n; ++t) {
@@ -518,11 +602,15 @@ void ora_advect_scalars(const ora_index* ix, const int32_t* coords, const float*
 		const float pos[3] = {(float)ci, (float)cj, (float)ck};
 		float bp[3], fp[3], uf[3] = {0.0f, 0.0f, 0.0f};
 		for (int c = 0; c < 3; ++c) bp[c] = fmaf(-sdt, vel[3 * orig + c], pos[c]); /* :136-139 */
+		/* :142-155: two checks; the second re-tests the possibly reset position and resets it to the same posCell, so one suffices */
+		if (sdf && ora_in_collision(ix, sdf, bp)) bp[0] = pos[0], bp[1] = pos[1], bp[2] = pos[2];
+		if (sdf && ora_in_collision(ix, sdf, bp)) bp[0] = pos[0], bp[1] = pos[1], bp[2] = pos[2];
 		ora_interp B, F;
 		ora_setup_interp(ix, bp, &B);                                  /* :198 */
 		for (int q = 0; q < 8; ++q)                                    /* :201-206 */
 			for (int c = 0; c < 3; ++c) uf[c] = fmaf(B.w[q], vel[3 * B.idx[q] + c], uf[c]);
 		for (int c = 0; c < 3; ++c) fp[c] = fmaf(sdt, uf[c], bp[c]);    /* :208 */
+		if (sdf && ora_in_collision(ix, sdf, fp)) fp[0] = bp[0], fp[1] = bp[1], fp[2] = bp[2]; /* :211-214 */
 		ora_setup_interp(ix, fp, &F);                                  /* :216 */
 		uint32_t nbr[6];                                               /* :219-226 (uint32_t, sic) */
 		for (int q = 0; q < 6; ++q) {
@@ -547,6 +635,16 @@ void ora_advect_scalars(const ora_index* ix, const int32_t* coords, const float*
 			out[s][t] = fmaxf(mn, fminf(corr, mx));
 		}
 	}
+}
+
+void ora_advect_scalars(const ora_index* ix, const int32_t* coords, const float* vel, const float* const* in, float* const* out, int S,
+                        uint64_t n, float dt, float inv_dx) {
+	ora_advect_scalars_impl(ix, coords, vel, in, out, S, n, dt, inv_dx, NULL);
+}
+/* advect_scalars with hasCollision (Kernel.cu:142-155, 211-214) */
+void ora_advect_scalars_sdf(const ora_index* ix, const int32_t* coords, const float* vel, const float* const* in, float* const* out, int S,
+                            uint64_t n, float dt, float inv_dx, const float* sdf) {
+	ora_advect_scalars_impl(ix, coords, vel, in, out, S, n, dt, inv_dx, sdf);
 }
 
 /* divergence (Kernel.cu:499-519); divergence_opt (:455-496) evaluates the same expression (all *0.5 are exact) */
@@ -736,29 +834,34 @@ void ora_frame(const ora_index* ix, const int32_t* coords, uint64_t n, float* ve
  * out of place: the reference runs it in place, racing, :174) -> divergence -> combustion_oxygen ->
  * temperature_buoyancy -> RBGS -> subtractPressureGradient -> advect_scalars over ALL float blocks in insertion order.
  * names[s] identify fuel / waste / temperature / flame (:193); returns 1 if one is missing (the reference throws). */
-int ora_compute_sim(const ora_index* ix, const int32_t* coords, uint64_t n, float* vel, float* const* scalars, const char* const* names, int S,
-                    int iterations, float dt, float voxelSize, const float* params6) {
-	int iF = -1, iW = -1, iT = -1, iL = -1;
+int ora_compute_sim_collision(const ora_index* ix, const int32_t* coords, uint64_t n, float* vel, float* const* scalars, const char* const* names,
+                              int S, int iterations, float dt, float voxelSize, const float* params6, int hasCollision) {
+	int iF = -1, iW = -1, iT = -1, iL = -1, iSdf = -1;
 	for (int s = 0; s < S; ++s) {
 		if (!strcmp(names[s], "fuel")) iF = s;
 		if (!strcmp(names[s], "waste")) iW = s;
 		if (!strcmp(names[s], "temperature")) iT = s;
 		if (!strcmp(names[s], "flame")) iL = s;
+		if (!strcmp(names[s], "collision_sdf")) iSdf = s;
 	}
 	if (iF < 0 || iW < 0 || iT < 0 || iL < 0) return 1;
+	const float* sdf = (hasCollision && iSdf >= 0) ? scalars[iSdf] : NULL; /* hasCollisionData, HNanoSolver.cu:65-76 */
 	const float expansionRate = params6[0], temperatureRelease = params6[1], buoyancyStrength = params6[2], ambientTemp = params6[3];
 	const float inv = 1.0f / voxelSize;
 	float* adv = (float*)malloc(n * 12);
 	float* div = (float*)malloc(n * 4);
 	float* p = (float*)calloc(n, 4);
-	ora_advect_vector(ix, coords, vel, adv, n, dt, inv);
+	float* tmp = (float*)malloc(n * 12);
+	if (sdf) { /* enforceCollisionBoundaries on the input velocity, :153-157 (per voxel, in place is safe) */
+		ora_collision_boundary(ix, coords, vel, tmp, sdf, 1.0f / voxelSize, 0.1f, 0, n);
+		memcpy(vel, tmp, n * 12);
+	}
+	ora_advect_vector_impl(ix, coords, vel, adv, n, dt, inv, sdf);
 	/* vorticityConfinement (:172-176) on the advected velocity; params6[4] = vorticityScale, [5] = factorScale. A zero scale, or a
 	 * factorScale that truncates to a zero offset (the SOP default 0.5), adds (+-0) * dt to every component: identity for finite inputs */
 	if (params6[4] != 0.0f && (int32_t)params6[5] != 0) {
-		float* conf = (float*)malloc(n * 12);
-		ora_vorticity_confinement(ix, coords, adv, conf, n, dt, inv, params6[4], params6[5]);
-		memcpy(adv, conf, n * 12);
-		free(conf);
+		ora_vorticity_confinement(ix, coords, adv, tmp, n, dt, inv, params6[4], params6[5]);
+		memcpy(adv, tmp, n * 12);
 	}
 	ora_divergence(ix, coords, adv, div, inv, n);
 	float *oF = (float*)malloc(n * 4), *oW = (float*)malloc(n * 4), *oT = (float*)malloc(n * 4), *oL = (float*)malloc(n * 4);
@@ -772,16 +875,33 @@ int ora_compute_sim(const ora_index* ix, const int32_t* coords, uint64_t n, floa
 		ora_rbgs(ix, coords, div, p, voxelSize, n, 1, omega);
 	}
 	ora_subtract_gradient(ix, coords, n, adv, p, vel, inv);
-	float** outs = (float**)malloc(sizeof(float*) * (size_t)S);
-	for (int s = 0; s < S; ++s) outs[s] = (float*)malloc(n * 4);
-	ora_advect_scalars(ix, coords, vel, (const float* const*)scalars, outs, S, n, dt, inv);
-	for (int s = 0; s < S; ++s) {
-		memcpy(scalars[s], outs[s], n * 4);
-		free(outs[s]);
+	if (sdf) {
+		ora_collision_boundary(ix, coords, vel, tmp, sdf, inv, 0.1f, 2, n); /* the tail of subtractPressureGradient, Kernel.cu:808-826 */
+		ora_collision_boundary(ix, coords, tmp, vel, sdf, 1.0f / voxelSize, 0.1f, 0, n); /* enforceCollisionBoundaries again, :292-296 */
 	}
-	free(outs);
-	free(adv), free(div), free(p);
+	/* advect_scalars over every float block except "collision_sdf" (:324-333), in insertion order */
+	const float** ins = (const float**)malloc(sizeof(float*) * (size_t)S);
+	float** outs = (float**)malloc(sizeof(float*) * (size_t)S);
+	int A = 0;
+	for (int s = 0; s < S; ++s)
+		if (s != iSdf) ins[A] = scalars[s], outs[A] = (float*)malloc(n * 4), ++A;
+	ora_advect_scalars_impl(ix, coords, vel, ins, outs, A, n, dt, inv, sdf);
+	A = 0;
+	for (int s = 0; s < S; ++s) {
+		if (s == iSdf) continue;
+		memcpy(scalars[s], outs[A], n * 4);
+		free(outs[A]);
+		++A;
+	}
+	/* the collision_sdf block comes back as the reference's never-written output buffer (:361-369): zeros on a fresh allocation */
+	if (iSdf >= 0) memset(scalars[iSdf], 0, n * 4);
+	free(ins), free(outs);
+	free(adv), free(div), free(p), free(tmp);
 	return 0;
+}
+int ora_compute_sim(const ora_index* ix, const int32_t* coords, uint64_t n, float* vel, float* const* scalars, const char* const* names, int S,
+                    int iterations, float dt, float voxelSize, const float* params6) {
+	return ora_compute_sim_collision(ix, coords, n, vel, scalars, names, S, iterations, dt, voxelSize, params6, 0);
 }
 
 /* pressure_projection_idx (PressureProjection.cu:9-78): divergence_opt -> I x RBGS_opt -> subtractPressureGradient_opt, in place */

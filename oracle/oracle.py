@@ -81,6 +81,13 @@ def lib() -> C.CDLL:
         L.ora_omega_project.argtypes = [C.c_float]
         L.ora_frame.argtypes = [C.c_void_p, c_i32p, C.c_uint64, c_f32p, C.POINTER(c_f32p), C.c_int, C.c_int, C.c_float, C.c_float,
                                 c_f32p, c_f32p, c_f32p]
+        L.ora_compute_sim_collision.restype = C.c_int
+        L.ora_compute_sim_collision.argtypes = [C.c_void_p, c_i32p, C.c_uint64, c_f32p, C.POINTER(c_f32p), C.POINTER(C.c_char_p), C.c_int,
+                                                C.c_int, C.c_float, C.c_float, c_f32p, C.c_int]
+        L.ora_collision_boundary.argtypes = [C.c_void_p, c_i32p, c_f32p, c_f32p, c_f32p, C.c_float, C.c_float, C.c_int, C.c_uint64]
+        L.ora_advect_vector_sdf.argtypes = [C.c_void_p, c_i32p, c_f32p, c_f32p, C.c_uint64, C.c_float, C.c_float, c_f32p]
+        L.ora_advect_scalars_sdf.argtypes = [C.c_void_p, c_i32p, c_f32p, C.POINTER(c_f32p), C.POINTER(c_f32p), C.c_int, C.c_uint64,
+                                             C.c_float, C.c_float, c_f32p]
         L.ora_compute_sim.restype = C.c_int
         L.ora_compute_sim.argtypes = [C.c_void_p, c_i32p, C.c_uint64, c_f32p, C.POINTER(c_f32p), C.POINTER(C.c_char_p), C.c_int,
                                       C.c_int, C.c_float, C.c_float, c_f32p]
@@ -228,14 +235,43 @@ class OracleIndex:
                         iterations, dt, voxel_size, div.ctypes.data_as(c_f32p), p.ctypes.data_as(c_f32p), adv.ctypes.data_as(c_f32p))
         return dict(vel=vel, scalars=sc, div=div, p=p, adv=adv)
 
-    def compute_sim(self, vel, fields: dict, iterations, dt, voxel_size, params6):
+    # ---- the hasCollision path ----
+    SITE_ENFORCE, SITE_ADVECT, SITE_GRADIENT = 0, 1, 2
+
+    def collision_boundary(self, vel, sdf, voxel_size, site):
+        """enforceCollisionBoundaries (site 0), or the boundary tail of advect_vector (1) / subtractPressureGradient (2) applied to `vel`"""
+        vel, vp = _f32(vel)
+        sdf, sp = _f32(sdf)
+        out = np.empty((self.n, 3), np.float32)
+        lib().ora_collision_boundary(self._h, self.coords.ctypes.data_as(c_i32p), vp, out.ctypes.data_as(c_f32p), sp,
+                                     np.float32(1.0) / np.float32(voxel_size), 1.5 if site == 1 else 0.1, site, self.n)
+        return out
+
+    def advect_vector_sdf(self, vel, sdf, dt, voxel_size):
+        vel, vp = _f32(vel)
+        sdf, sp = _f32(sdf)
+        out = np.empty((self.n, 3), np.float32)
+        lib().ora_advect_vector_sdf(self._h, self.coords.ctypes.data_as(c_i32p), vp, out.ctypes.data_as(c_f32p), self.n, dt,
+                                    np.float32(1.0) / np.float32(voxel_size), sp)
+        return out
+
+    def advect_scalars_sdf(self, vel, scalars, sdf, dt, voxel_size):
+        vel, vp = _f32(vel)
+        sdf, sp = _f32(sdf)
+        ins = [np.ascontiguousarray(a, np.float32) for a in scalars]
+        outs = [np.empty(self.n, np.float32) for _ in ins]
+        lib().ora_advect_scalars_sdf(self._h, self.coords.ctypes.data_as(c_i32p), vp, _ptr_array(ins), _ptr_array(outs), len(ins), self.n, dt,
+                                     np.float32(1.0) / np.float32(voxel_size), sp)
+        return outs
+
+    def compute_sim(self, vel, fields: dict, iterations, dt, voxel_size, params6, has_collision=False):
         vel = np.array(vel, np.float32, copy=True)
         names = list(fields.keys())
         sc = [np.array(fields[k], np.float32, copy=True) for k in names]
         cn = (C.c_char_p * len(names))(*[s.encode() for s in names])
         pr = np.asarray(params6, np.float32)
-        rc = lib().ora_compute_sim(self._h, self.coords.ctypes.data_as(c_i32p), self.n, vel.ctypes.data_as(c_f32p), _ptr_array(sc), cn,
-                                   len(sc), iterations, dt, voxel_size, pr.ctypes.data_as(c_f32p))
+        rc = lib().ora_compute_sim_collision(self._h, self.coords.ctypes.data_as(c_i32p), self.n, vel.ctypes.data_as(c_f32p), _ptr_array(sc), cn,
+                                             len(sc), iterations, dt, voxel_size, pr.ctypes.data_as(c_f32p), int(has_collision))
         if rc:
             raise RuntimeError("Missing required input field for combustion")
         return vel, dict(zip(names, sc))

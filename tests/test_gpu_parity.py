@@ -352,6 +352,135 @@ def test_compute_sim_default_sop_vorticity_parameters_match_reference(case):
         assert_close(d.pValues(FLOAT, k), rd.blocks[k], f"Compute_Sim {k}")
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# SDF collision path
+# ------------------------------------------------------------------------------------------------------------------
+def _collision_sdf(w):
+    c = w.coords.astype(np.float32)
+    centre = np.round(c.mean(0))
+    sdf = (0.05 * (np.sqrt(((c - centre) ** 2).sum(1)) - 6.0)).astype(np.float32)
+    sdf[0] = 0.0
+    return sdf
+
+
+def _collision_sim(w, sdf):
+    g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    sim = H.Simulation(g, len(w.scalars) + 1)
+    sim.upload(w.velocity, list(w.scalars) + [sdf])
+    sim.set_collision(len(w.scalars))
+    return sim
+
+
+def test_collision_kernels_match_oracle(case):
+    w = case
+    sdf = _collision_sdf(w)
+    ix = O.OracleIndex(w.coords)
+    sim = _collision_sim(w, sdf)
+    sim.enforce_collision()
+    sim.sync()
+    v1 = ix.collision_boundary(w.velocity, sdf, w.voxel_size, ix.SITE_ENFORCE)
+    assert np.array_equal(sim.velocity(), v1), "enforceCollisionBoundaries"
+    sim.advect_velocity(w.dt)
+    sim.sync()
+    adv = ix.advect_vector_sdf(v1, sdf, w.dt, w.voxel_size)
+    assert np.array_equal(sim.aux(H.Simulation.AUX_ADVECTED), adv), "advect_vector(hasCollision)"
+    sim.divergence(True)
+    sim.pressure_solve(4, H.launchers.omega_compute(w.voxel_size))
+    sim.subtract_gradient(True)
+    sim.sync()
+    div = ix.divergence(adv, w.voxel_size)
+    p = ix.rbgs(div, np.zeros(w.num_voxels, np.float32), w.voxel_size, 4, O.omega_compute(w.voxel_size))
+    proj = ix.collision_boundary(ix.subtract_gradient(adv, p, w.voxel_size), sdf, w.voxel_size, ix.SITE_GRADIENT)
+    assert np.array_equal(sim.velocity(), proj), "subtractPressureGradient(hasCollision)"
+    sim.advect_scalars(w.dt, 0)
+    sim.sync()
+    want = ix.advect_scalars_sdf(proj, w.scalars, sdf, w.dt, w.voxel_size)
+    for i in range(len(w.scalars)):
+        assert np.array_equal(sim.scalar(i), want[i]), f"advect_scalars(hasCollision)[{i}]"
+    assert np.array_equal(sim.scalar(len(w.scalars)), sdf), "the SDF itself is not advected"
+
+
+def _compute_sim_collision(w, has_collision, iterations=5):
+    fields = dict(density=w.scalars[0], **_combustion_fields(w.num_voxels), collision_sdf=_collision_sdf(w))
+    d = _sidecar(w, fields)
+    g = H.CreateIndexGrid(d, w.voxel_size)
+    H.Compute_Sim(d, g, iterations, w.dt, w.voxel_size, H.CombustionParams(*PARAMS6.tolist()), has_collision)
+    return fields, d
+
+
+def test_compute_sim_with_collision_matches_oracle(case):
+    w = case
+    fields, d = _compute_sim_collision(w, True)
+    ix = O.OracleIndex(w.coords)
+    want_vel, want = ix.compute_sim(w.velocity, fields, 5, w.dt, w.voxel_size, PARAMS6, has_collision=True)
+    assert_close(d.pValues(VEC3F, "vel"), want_vel, "Compute_Sim(hasCollision) velocity")
+    for k, v in want.items():
+        assert_close(d.pValues(FLOAT, k), v, f"Compute_Sim(hasCollision) {k}")
+    assert not d.pValues(FLOAT, "collision_sdf").any()
+    # hasCollision = false with the block present: carried, zeroed, no other effect
+    fields0, d0 = _compute_sim_collision(w, False)
+    want_vel0, _ = ix.compute_sim(w.velocity, {k: v for k, v in fields0.items() if k != "collision_sdf"}, 5, w.dt, w.voxel_size, PARAMS6)
+    assert_close(d0.pValues(VEC3F, "vel"), want_vel0, "Compute_Sim velocity, collision_sdf present but hasCollision false")
+    assert not d0.pValues(FLOAT, "collision_sdf").any()
+
+
+@needs_ref
+def test_compute_sim_with_collision_matches_reference(case):
+    w = case
+    fields, d = _compute_sim_collision(w, True, iterations=7)
+    rd = O.RefData(w.coords)
+    rd.add_vec3("vel", w.velocity)
+    for k, v in fields.items():
+        rd.add_float(k, v)
+    rg = O.RefGrid(rd, w.voxel_size)
+    O.ref_compute_sim(rd, rg, 7, w.dt, w.voxel_size, PARAMS6, True)
+    assert_close(d.pValues(VEC3F, "vel"), rd.blocks["vel"], "Compute_Sim(hasCollision) velocity")
+    assert np.array_equal(d.pValues(VEC3F, "vel"), rd.blocks["vel"])
+    for k in fields:
+        if k != "collision_sdf":
+            assert_close(d.pValues(FLOAT, k), rd.blocks[k], f"Compute_Sim(hasCollision) {k}")
+
+
+@pytest.mark.parametrize("name", ["soup", "sphere"])
+def test_collision_against_golden_reference_outputs(name):
+    path = os.path.join(GOLDEN, f"ref_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip("no golden fixture")
+    z = np.load(path)
+    if "collision_sdf" not in z.files:
+        pytest.skip("fixture predates the collision vectors")
+    origins, h, dt, I = z["origins"], float(z["voxel_size"]), float(z["dt"]), int(z["iterations"])
+    S = len(z["scalar_names"])
+    g = H.create_index_grid_from_origins(origins, h)
+    sim = H.Simulation(g, S + 1)
+    sim.upload(z["velocity"], [z[f"scalar{i}"] for i in range(S)] + [z["collision_sdf"]])
+    sim.set_collision(S)
+    sim.enforce_collision()
+    sim.sync()
+    assert np.array_equal(sim.velocity(), z["coll_enforce"])
+    sim.upload(z["velocity"], [z[f"scalar{i}"] for i in range(S)] + [z["collision_sdf"]])
+    sim.advect_velocity(dt)
+    sim.sync()
+    assert np.array_equal(sim.aux(H.Simulation.AUX_ADVECTED), z["coll_advect_vector"])
+    # all-in-one node
+    fields = dict(density=z["scalar0"], fuel=z["comb_fuel"], waste=z["comb_waste"], temperature=z["comb_temperature"], flame=z["comb_flame"],
+                  collision_sdf=z["collision_sdf"])
+    d = H.GridIndexedData()
+    d.allocateCoords(len(z["coords"]))
+    d.pCoords()[:] = z["coords"]
+    d.addValueBlock(VEC3F, "vel")
+    d.pValues(VEC3F, "vel")[:] = z["velocity"]
+    for k, v in fields.items():
+        d.addValueBlock(FLOAT, k)
+        d.pValues(FLOAT, k)[:] = v
+    gh = H.CreateIndexGrid(d, h)
+    H.Compute_Sim(d, gh, I, dt, h, H.CombustionParams(*z["params"].tolist()), True)
+    assert np.array_equal(d.pValues(VEC3F, "vel"), z["compute_sim_coll_vel"])
+    for k in fields:
+        if k != "collision_sdf":
+            assert np.array_equal(d.pValues(FLOAT, k), z[f"compute_sim_coll_{k}"]), k
+
+
 @needs_ref
 def test_standalone_launchers_match_reference_launchers(case):
     w = case

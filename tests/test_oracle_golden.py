@@ -94,3 +94,51 @@ def test_compute_sim_sop_default_vorticity_is_identity(gold):
     p[4], p[5] = 1.0, 0.5
     vel, _ = ix.compute_sim(gold["velocity"], fields, I, dt, h, p)
     assert_close(vel, gold["compute_sim_sopdefault_vel"], "Compute_Sim velocity, SOP default vorticity parameters")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the hasCollision path: reference kernels launched one by one with a sphere-collider SDF
+# ------------------------------------------------------------------------------------------------------------------
+def _needs_collision(gold):
+    if "collision_sdf" not in gold:
+        pytest.skip("fixture predates the collision vectors")
+
+
+def test_collision_kernels(gold):
+    _needs_collision(gold)
+    ix = O.OracleIndex(gold["coords"])
+    h, dt = float(gold["voxel_size"]), float(gold["dt"])
+    sdf = gold["collision_sdf"]
+    assert (sdf < 0).sum() > 100 and ((sdf >= 0) & (sdf < 0.1)).sum() > 100      # the fixture exercises both branches
+    got = ix.collision_boundary(gold["velocity"], sdf, h, ix.SITE_ENFORCE)
+    assert np.array_equal(got, gold["coll_enforce"]), "enforceCollisionBoundaries"
+    assert not np.array_equal(got, gold["velocity"])
+    got = ix.advect_vector_sdf(gold["velocity"], sdf, dt, h)
+    assert np.array_equal(got, gold["coll_advect_vector"]), "advect_vector(hasCollision)"
+    # the tail of subtractPressureGradient acts on the kernel's own result = the collision-free projected velocity
+    got = ix.collision_boundary(gold["frame_vel"], sdf, h, ix.SITE_GRADIENT)
+    assert np.array_equal(got, gold["coll_gradient"]), "subtractPressureGradient(hasCollision)"
+    outs = ix.advect_scalars_sdf(gold["frame_vel"], _scalars(gold), sdf, dt, h)
+    for i, o in enumerate(outs):
+        assert np.array_equal(o, gold[f"coll_scalar{i}"]), f"advect_scalars(hasCollision)[{i}]"
+        assert not np.array_equal(o, gold[f"frame_scalar{i}"])
+
+
+def test_compute_sim_with_collision(gold):
+    _needs_collision(gold)
+    ix = O.OracleIndex(gold["coords"])
+    h, dt, I = float(gold["voxel_size"]), float(gold["dt"]), int(gold["iterations"])
+    fields = dict(density=gold["scalar0"], fuel=gold["comb_fuel"], waste=gold["comb_waste"], temperature=gold["comb_temperature"],
+                  flame=gold["comb_flame"], collision_sdf=gold["collision_sdf"])
+    vel, out = ix.compute_sim(gold["velocity"], fields, I, dt, h, gold["params"], has_collision=True)
+    assert_close(vel, gold["compute_sim_coll_vel"], "Compute_Sim(hasCollision) velocity")
+    assert np.array_equal(vel, gold["compute_sim_coll_vel"])
+    for k, v in out.items():
+        if k == "collision_sdf":
+            assert np.array_equal(v, gold["compute_sim_coll_sdf_out"])          # zeros: the reference's never-written output buffer
+        else:
+            assert np.array_equal(v, gold[f"compute_sim_coll_{k}"]), k
+    # without hasCollision the SDF block is carried (and zeroed) but changes nothing else
+    vel0, out0 = ix.compute_sim(gold["velocity"], fields, I, dt, h, gold["params"], has_collision=False)
+    assert np.array_equal(vel0, gold["compute_sim_vel"])
+    assert not np.array_equal(vel0, vel)
