@@ -301,8 +301,8 @@ class ShardedSimulation:
         s, ex, st = self.sim, self.ex, self._stream()
         from . import _lib
 
-        if _lib.lib().hns_state_vorticity_active(s._h):
-            raise NotImplementedError("vorticity confinement is only wired into the native sharded frame (native=True)")
+        if _lib.lib().hns_state_vorticity_active(s._h) or _lib.lib().hns_state_collision_active(s._h):
+            raise NotImplementedError("vorticity confinement / SDF collision are only wired into the native sharded frame (native=True)")
         ex.exchange(F_VEL)
         s.advect_velocity(dt, st)
         ex.exchange(F_ADV)

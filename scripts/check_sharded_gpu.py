@@ -18,8 +18,17 @@ lo = (np.repeat(plan.local_ids, 512) * 512 + np.tile(np.arange(512), plan.n_loca
 comb = synth.combustion_fields(wg)
 names = ["density", "fuel", "waste", "temperature", "flame"]
 gfields = [wg.scalars[0]] + [comb[k] for k in names[1:]]
-sh = hdist.ShardedSimulation(plan, np.ascontiguousarray(go[plan.local_ids]), wg.voxel_size, 5, torch.device("cuda", lr),
+COLL = int(os.environ.get("COLLISION", "0"))  # COLLISION=1: a sphere collider SDF as the last scalar, hasCollision path on
+if COLL:
+    gc = (np.repeat(go, 512, axis=0) + np.stack(np.unravel_index(np.arange(512), (8, 8, 8)), 1)[np.tile(np.arange(512), go.shape[0])]).astype(np.float32)
+    sdf = (0.05 * (np.sqrt(((gc - np.array([128.0, 64.0, 64.0], np.float32)) ** 2).sum(1)) - 20.0)).astype(np.float32)
+    sdf[0] = 0.0
+    names = names + ["collision_sdf"]
+    gfields = gfields + [sdf]
+NS = len(gfields)
+sh = hdist.ShardedSimulation(plan, np.ascontiguousarray(go[plan.local_ids]), wg.voxel_size, NS, torch.device("cuda", lr),
                              native=not int(os.environ.get("PY_EXCHANGE", "0")))
+if COLL: sh.sim.set_collision(NS - 1)
 VS, VF = (float(x) for x in os.environ.get("VORT", "0,1").split(","))  # vorticityScale, factorScale (VORT="0.8,2" turns the pass on)
 P = H.CombustionParams(0.5, 2.0, 1.5, 0.1, VS, VF)
 if not int(os.environ.get("NO_COMB", "0")): sh.set_combustion(names, P)
@@ -30,18 +39,19 @@ for _ in range(NF):
     sh.frame(I, wg.dt)
 torch.cuda.synchronize()
 m = np.repeat(plan.owned_local, 512)
-mine = [sh.sim.velocity()[m]] + [sh.sim.scalar(i)[m] for i in range(5)] + [sh.sim.aux(1)[m]]
+mine = [sh.sim.velocity()[m]] + [sh.sim.scalar(i)[m] for i in range(NS)] + [sh.sim.aux(1)[m]]
 gathered = [None] * world
 dist.all_gather_object(gathered, mine)
 if rank == 0:
     g = H.create_index_grid_from_origins(go, wg.voxel_size)
-    sim = H.Simulation(g, 5)
+    sim = H.Simulation(g, NS)
     sim.upload(wg.velocity, gfields)
+    if COLL: sim.set_collision(NS - 1)
     if not int(os.environ.get("NO_COMB", "0")): sim.set_combustion(True, 1, 2, 3, 4, P)
     for _ in range(NF):
         sim.step(I, wg.dt)
     sim.sync()
-    ref = [sim.velocity()] + [sim.scalar(i) for i in range(5)] + [sim.aux(1)]
+    ref = [sim.velocity()] + [sim.scalar(i) for i in range(NS)] + [sim.aux(1)]
     ok = True
     for k, nm in enumerate(["velocity"] + names + ["pressure"]):
         got = np.concatenate([gathered[r][k] for r in range(world)])
@@ -50,7 +60,7 @@ if rank == 0:
         bad = np.nonzero((got != ref[k]).reshape(got.shape[0], -1).any(1))[0]
         print(f"  {nm:12s} sharded({world}) == single GPU bitwise: {same}  mismatching voxels {bad.size}/{got.shape[0]} "
               f"max|diff| {np.abs(got.astype(np.float64) - ref[k]).max():.3e} first leaves {np.unique(bad // 512)[:8]}")
-    print("SHARDED PARITY", "OK" if ok else "FAILED", f"leaves={go.shape[0]} exchanges/frame={sh.exchanges // NF} native={sh.native} p2p={getattr(sh, 'p2p', False)} vorticity=({VS},{VF})", flush=True)
+    print("SHARDED PARITY", "OK" if ok else "FAILED", f"leaves={go.shape[0]} exchanges/frame={sh.exchanges // NF} native={sh.native} p2p={getattr(sh, 'p2p', False)} vorticity=({VS},{VF}) collision={COLL}", flush=True)
 sh.check_errors()
 dist.barrier()
 sh.close()
