@@ -664,6 +664,18 @@ def _drive(which, w, fields, iterations):
         out["sim_vel"] = d.blocks["vel"].copy()
         for k in fields:
             out["sim_" + k] = d.blocks[k].copy()
+        # the same node with the SOP's default vorticity parameters and a collision SDF (third SOP input, hasCollision = true)
+        d = O.RefData(w.coords)
+        d.add_vec3("vel", w.velocity)
+        for k, v in fields.items():
+            d.add_float(k, v)
+        d.add_float("collision_sdf", _collision_sdf(w))
+        params = PARAMS6.copy()
+        params[4], params[5] = 1.0, 0.5
+        O.ref_compute_sim(d, g, iterations, w.dt, w.voxel_size, params, True)
+        out["coll_vel"] = d.blocks["vel"].copy()
+        for k in fields:
+            out["coll_" + k] = d.blocks[k].copy()
         d = O.RefData(w.coords)
         d.add_vec3("vel", w.velocity)
         for n, s in zip(w.scalar_names, w.scalars):
