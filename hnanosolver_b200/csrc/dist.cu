@@ -547,6 +547,33 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 
 int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream) { return dist_frame(d, s, iterations, dt, stream, nullptr); }
 
+// The sharded cook on HOST arrays of this rank's local voxels (owned + ghost leaves, local sidecar order), in place and synchronous:
+// the per-rank equivalent of hns_compute_sim. Every rank moves its own shard over its own PCIe link, so the transfers of the N ranks
+// run in parallel; ghost entries of the inputs need not be valid (every field's ghosts are exchanged before they are read) and ghost
+// entries of the outputs are whatever the last exchange left there.
+int hns_dist_cook(hns_dist* d, hns_state* s, float* velocity, int n_float, float* const* fields, int iterations, float dt, void* stream) {
+	if (!d || !s || !velocity || n_float != s->n_scalars || (n_float && !fields)) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	const uint64_t n = s->n;
+	if (!n) return HNS_OK;
+	if (!s->aos) HNS_CUDA(cudaMalloc(&s->aos, n * 3 * sizeof(float)));
+	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
+	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
+	++s->vel_version;
+	for (int i = 0; i < n_float; ++i) {
+		if (!fields[i]) return fail(HNS_ERR_INVALID_ARGUMENT, "null field pointer");
+		HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, st));
+	}
+	int rc = dist_frame(d, s, iterations, dt, stream, nullptr);
+	if (rc) return rc;
+	launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, n, st);
+	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, st));
+	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc[i], n * 4, cudaMemcpyDeviceToHost, st));
+	HNS_CUDA(cudaStreamSynchronize(st));
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+
 // Same frame with CUDA events between the phases; ms_out[8] = exchange velocity, advect_vector, exchange advected, divergence(+combustion),
 // pressure solve incl. its exchanges, gradient, final exchange (+element-0 broadcast), advect_scalars. Synchronises the stream.
 int hns_dist_frame_timed(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, float* ms_out) {

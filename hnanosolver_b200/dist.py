@@ -325,6 +325,23 @@ class ShardedSimulation:
             dist.broadcast(self.elem0, src=0)
         s.advect_scalars(dt, 0, st)
 
+    def cook(self, velocity: np.ndarray, scalars, iterations: int, dt: float) -> None:
+        """One sharded cook on this rank's HOST arrays (local voxels: owned + ghost leaves), in place, synchronous: the per-rank
+        counterpart of Compute_Sim (hns_dist_cook). velocity float32 (n, 3), scalars a list of float32 (n,); pinned memory recommended."""
+        import ctypes as C
+
+        from . import _lib
+
+        if not self.native:
+            raise NotImplementedError("cook() needs the native sharded frame")
+        assert velocity.dtype == np.float32 and velocity.flags.c_contiguous and velocity.size == 3 * self.sim.n
+        ptrs = (_lib.c_f32p * max(1, len(scalars)))()
+        for i, a in enumerate(scalars):
+            assert a.dtype == np.float32 and a.flags.c_contiguous and a.size == self.sim.n
+            ptrs[i] = a.ctypes.data_as(_lib.c_f32p)
+        _lib.check(_lib.lib().hns_dist_cook(self._dist, self.sim._h, velocity.ctypes.data_as(_lib.c_f32p), len(scalars), ptrs, iterations, dt,
+                                            C.c_void_p(self._stream())))
+
     PHASES = ("exch_vel", "advect_vector", "exch_adv", "div+comb", "pressure", "gradient", "exch_final", "advect_scalars")
 
     def frame_timed(self, iterations: int, dt: float) -> dict:
@@ -438,17 +455,13 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
     ms_step = float(ms.item()) / args.steps
     n_owned_total, n_local_total = int(owned[0].item()), int(owned[1].item())
 
-    # end to end: pinned host -> device, frame, device -> pinned host, every step
-    out_vel = torch.empty_like(vel_pinned).pin_memory()
-    out_sc = [torch.empty_like(t).pin_memory() for t in sc_pinned]
+    # end to end: one sharded cook per step on this rank's pinned host arrays, in place (hns_dist_cook: upload, frame, download)
+    restore()
+    torch.cuda.synchronize()
+    vel_np, sc_np = vel_pinned.numpy(), [t.numpy() for t in sc_pinned]
 
     def cook():
-        sh.upload(vel_pinned.numpy(), [t.numpy() for t in sc_pinned])
-        sh.frame(iterations, w.dt)
-        torch.cuda.synchronize()
-        out_vel.numpy()[:] = sh.sim.velocity()
-        for i, t in enumerate(out_sc):
-            t.numpy()[:] = sh.sim.scalar(i)
+        sh.cook(vel_np, sc_np, iterations, w.dt)
 
     cook()
     dist.barrier()
@@ -471,6 +484,6 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
                        "l2": "per-rank fields larger than L2; no flush"},
             "e2e": {"value": n_owned_total / (float(e2e.item()) * 1e-3), "unit": "voxel-updates/s", "ms_per_step": float(e2e.item()),
                     "h2d_bytes_per_step": int(n_local_total * (12 + 4 * S)), "d2h_bytes_per_step": int(n_local_total * (12 + 4 * S)),
-                    "call": "ShardedSimulation.upload + frame + download per rank on pinned host buffers"},
+                    "call": "ShardedSimulation.cook (hns_dist_cook) per rank on pinned host arrays of its shard, in place, synchronous"},
             "gpu_launches": int(launches.item()),
             "halo_bytes_per_frame": int(owned[2].item() / (args.steps + args.warmup + args.e2e_steps + 1))}

@@ -232,6 +232,10 @@ int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields
  * previous sharded frame skips the leading velocity-ghost exchange (those ghosts are still current), and the ranks must agree on
  * that; a disagreement surfaces as a flag time-out in hns_dist_error, not as wrong values. */
 int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream);
+/* the sharded cook on HOST arrays of this rank's local voxels (owned + ghost leaves; velocity float[n][3] and the state's scalar
+ * fields float[n] in index order), in place, synchronous: upload, hns_dist_frame, download. Collective. Pinned host memory lets the
+ * copies run at PCIe rate; the ranks' transfers go over their own links in parallel. */
+int hns_dist_cook(hns_dist* d, hns_state* s, float* velocity, int n_float, float* const* fields, int iterations, float dt, void* stream);
 /* the same frame with CUDA events between its phases (ms_out[8]: exchange velocity, advect_vector, exchange advected velocity,
  * divergence + combustion, pressure solve incl. exchanges, gradient, final exchange, advect_scalars); synchronises the stream */
 int hns_dist_frame_timed(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, float* ms_out);

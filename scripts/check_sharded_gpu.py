@@ -35,11 +35,18 @@ if not int(os.environ.get("NO_COMB", "0")): sh.set_combustion(names, P)
 sh.upload(wg.velocity[lo], [f[lo] for f in gfields])
 I = 12
 NF = int(os.environ.get("NFRAMES", "2"))
-for _ in range(NF):
-    sh.frame(I, wg.dt)
-torch.cuda.synchronize()
+COOK = int(os.environ.get("COOK", "0"))  # COOK=1: drive the frames through the host-buffer entry point (hns_dist_cook), in place
 m = np.repeat(plan.owned_local, 512)
-mine = [sh.sim.velocity()[m]] + [sh.sim.scalar(i)[m] for i in range(NS)] + [sh.sim.aux(1)[m]]
+if COOK:
+    lv = np.ascontiguousarray(wg.velocity[lo]); lf = [np.ascontiguousarray(f[lo]) for f in gfields]
+    for _ in range(NF):
+        sh.cook(lv, lf, I, wg.dt)
+    mine = [lv[m]] + [a[m] for a in lf] + [sh.sim.aux(1)[m]]
+else:
+    for _ in range(NF):
+        sh.frame(I, wg.dt)
+    torch.cuda.synchronize()
+    mine = [sh.sim.velocity()[m]] + [sh.sim.scalar(i)[m] for i in range(NS)] + [sh.sim.aux(1)[m]]
 gathered = [None] * world
 dist.all_gather_object(gathered, mine)
 if rank == 0:
@@ -60,7 +67,7 @@ if rank == 0:
         bad = np.nonzero((got != ref[k]).reshape(got.shape[0], -1).any(1))[0]
         print(f"  {nm:12s} sharded({world}) == single GPU bitwise: {same}  mismatching voxels {bad.size}/{got.shape[0]} "
               f"max|diff| {np.abs(got.astype(np.float64) - ref[k]).max():.3e} first leaves {np.unique(bad // 512)[:8]}")
-    print("SHARDED PARITY", "OK" if ok else "FAILED", f"leaves={go.shape[0]} exchanges/frame={sh.exchanges // NF} native={sh.native} p2p={getattr(sh, 'p2p', False)} vorticity=({VS},{VF}) collision={COLL}", flush=True)
+    print("SHARDED PARITY", "OK" if ok else "FAILED", f"leaves={go.shape[0]} exchanges/frame={sh.exchanges // NF} native={sh.native} p2p={getattr(sh, 'p2p', False)} vorticity=({VS},{VF}) collision={COLL} cook={COOK}", flush=True)
 sh.check_errors()
 dist.barrier()
 sh.close()
