@@ -16,17 +16,6 @@ int fail(int code, const std::string& msg) {
 	return code;
 }
 
-static int ensure_tables() {
-	// once per process and device
-	static thread_local int done_device = -1;
-	int dev = 0;
-	HNS_CUDA(cudaGetDevice(&dev));
-	if (done_device == dev) return HNS_OK;
-	const int rc = upload_tables();
-	if (rc == HNS_OK) done_device = dev;
-	return rc;
-}
-
 // omega exactly as Compute() evaluates it (reference src/Cuda/HNanoSolver.cu:257): float sinf of float(3.14159)*voxelSize
 static inline float omega_compute(float voxelSize) { return 2.0f / (1.0f + sinf(static_cast<float>(3.14159) * voxelSize)); }
 // ... and as pressure_projection_idx does (reference src/Cuda/PressureProjection.cu:53): double sin, narrowed at the kernel call
@@ -176,8 +165,6 @@ int hns_state_create(const hns_grid* g, int n_scalars, hns_state** out) {
 	HNS_REQUIRE(g && out, "null argument");
 	HNS_REQUIRE(n_scalars >= 0 && n_scalars <= 16, "n_scalars must be in [0, 16]");
 	*out = nullptr;
-	int rc = ensure_tables();
-	if (rc) return rc;
 	auto* s = new hns_state();
 	s->grid = g;
 	s->n = g->num_leaves * 512;

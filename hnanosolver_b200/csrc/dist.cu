@@ -94,7 +94,7 @@ struct hns_dist {
 	int32_t *d_boundary_nbr = nullptr, *d_interior_nbr = nullptr;  // GridView::list_nbr of the two pressure work lists
 	uint32_t n_owned = 0, n_boundary = 0, n_interior = 0;
 	cudaStream_t comm_stream = nullptr;  // boundary sweeps + ghost exchange run here, next to the interior sweep on the caller's stream
-	cudaEvent_t ev_boundary = nullptr, ev_exchanged = nullptr;
+	cudaEvent_t ev_exchanged = nullptr;
 	cudaStream_t aux_stream = nullptr;  // the scalars' ghost exchange, hidden behind the pressure solve
 	cudaEvent_t ev_scalars_final = nullptr, ev_scalars_exchanged = nullptr;
 	uint64_t vel_exchanged_version = ~uint64_t(0);  // hns_state::vel_version whose velocity ghosts are current on every rank
@@ -224,7 +224,6 @@ void hns_dist_destroy(hns_dist* d) {
 	if (d->aux_stream) cudaStreamDestroy(d->aux_stream);
 	if (d->ev_scalars_final) cudaEventDestroy(d->ev_scalars_final);
 	if (d->ev_scalars_exchanged) cudaEventDestroy(d->ev_scalars_exchanged);
-	if (d->ev_boundary) cudaEventDestroy(d->ev_boundary);
 	if (d->ev_exchanged) cudaEventDestroy(d->ev_exchanged);
 	if (d->comm) g_nccl.CommDestroy(d->comm);
 	delete d;
@@ -270,7 +269,6 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 			HNS_CUDA(cudaStreamCreateWithFlags(&d->aux_stream, cudaStreamNonBlocking));
 			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_scalars_final, cudaEventDisableTiming));
 			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_scalars_exchanged, cudaEventDisableTiming));
-			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_boundary, cudaEventDisableTiming));
 			HNS_CUDA(cudaEventCreateWithFlags(&d->ev_exchanged, cudaEventDisableTiming));
 			for (auto& e : d->ev_I) HNS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 			for (auto& e : d->ev_B) HNS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

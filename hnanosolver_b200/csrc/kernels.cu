@@ -374,8 +374,6 @@ void launch_gather_nbr_rows(const int32_t* nbr, const int32_t* list, uint32_t n,
 	if (n) HNS_LAUNCH(k_gather_nbr_rows, uint32_t((uint64_t(n) * 27u + 255u) / 256u), 256, 0, st, nbr, list, n, out);
 }
 
-int upload_tables() { return HNS_OK; }
-
 // =============================================================================================================
 // semi-Lagrangian BFECC advection  (reference Kernel.cu:118-453, samplers src/Utils/Stencils.hpp:25-173)
 // =============================================================================================================

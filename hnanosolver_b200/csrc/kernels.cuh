@@ -71,6 +71,4 @@ void launch_unpack_leaves(float* field, const int32_t* ids, uint64_t n_ids, cons
 // colour-split (red, black) -> brick order
 void launch_split_to_brick(const float* const f[2], float* out, uint64_t n, cudaStream_t st);
 
-int upload_tables();  // constant tables of the fused pressure kernel, once per device
-
 }  // namespace hns
