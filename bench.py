@@ -98,6 +98,14 @@ def build_workload(name: str, rank: int, world: int):
     return w, list(w.scalar_names), list(w.scalars), "north_star"
 
 
+def hbm_peak():
+    """(GB/s, where it came from): the driver-measured copy bandwidth when present, else the profiling guide's fallback"""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
 def algorithmic_bytes_per_voxel(S: int, I: int, full: bool) -> int:
     b = 80 + 16 * I + 8 * S                      # BASELINE.md section 3
     if full:
@@ -176,8 +184,23 @@ def main():
     if world > 1:
         from hnanosolver_b200 import dist as hdist
 
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
         res = hdist.run_sharded_bench(w, names, fields, full, args, ITERATIONS, PARAMS6, rank, world, local_rank)
         if rank == 0:
+            t_lo, t_hi = res.pop("_timed_wall")
+            res["clocks"] = sampler.stop(t_lo, t_hi)
+            # roofline of the dominant kernel on the slowest rank: one pressure half-sweep moves 8 B per OWNED voxel of that rank
+            # (interior + boundary sweep together), timed with CUDA events around the pressure phase of one extra frame
+            peak, peak_src = hbm_peak()
+            pressure_ms, owned_voxels = res.pop("_pressure")
+            sweep_ms = pressure_ms / (2 * ITERATIONS)
+            achieved = 8 * owned_voxels / (sweep_ms * 1e-3) / 1e9
+            res["roofline"] = {"bound": "hbm", "kernel": "k_rbgs_split (interior sweep + fused boundary sweep/ghost push of one colour, per rank)",
+                               "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                               "algorithmic_bytes_per_launch": 8 * owned_voxels, "avg_launch_ms": sweep_ms, "launches_timed": 2 * ITERATIONS,
+                               "peak_source": peak_src, "note": "max over ranks of the pressure phase incl. the pipelined ghost exchange"}
             print(json.dumps(res), flush=True)
         return
 
@@ -205,11 +228,7 @@ def main():
     value = N / (ms_step * 1e-3)
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    peak, peak_src = hbm_peak()
     n_sweeps = ITERATIONS * args.steps * 2
     sweep_ms = ms_pressure / n_sweeps
     bytes_per_launch = 8 * N                                           # one colour: read other-colour p, read+write this colour's p, read its div

@@ -435,13 +435,19 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
     _lib.lib().hns_launch_count_reset()
     dist.barrier()
     torch.cuda.synchronize()
+    t_wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
         sh.frame(iterations, w.dt)
     e1.record()
     torch.cuda.synchronize()
+    t_wall1 = time.time()
     dist.barrier()
     phases = sh.frame_timed(iterations, w.dt) if sh.native else {}
+    pr = torch.tensor([float(phases.get("pressure", 0.0)), float(plan.n_owned * 512)], device=dev)
+    pr_all = [torch.zeros_like(pr) for _ in range(world)]
+    dist.all_gather(pr_all, pr)
+    slowest = max(pr_all, key=lambda t: float(t[0]))
     log = __import__("sys").stderr
     print(f"[rank {rank}] owned {plan.n_owned} ghost {plan.n_local - plan.n_owned} peers { {p: len(v) for p, v in plan.send.items()} } "
           f"phases(ms) { {k: (round(v, 3) if isinstance(v, float) else v) for k, v in phases.items()} }", file=log, flush=True)
@@ -486,4 +492,5 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
                     "h2d_bytes_per_step": int(n_local_total * (12 + 4 * S)), "d2h_bytes_per_step": int(n_local_total * (12 + 4 * S)),
                     "call": "ShardedSimulation.cook (hns_dist_cook) per rank on pinned host arrays of its shard, in place, synchronous"},
             "gpu_launches": int(launches.item()),
+            "_timed_wall": (t_wall0, t_wall1), "_pressure": (float(slowest[0]), float(slowest[1])),
             "halo_bytes_per_frame": int(owned[2].item() / (args.steps + args.warmup + args.e2e_steps + 1))}
