@@ -64,9 +64,11 @@ struct RowCtx {
 		return l < 0 ? int64_t(-1) : int64_t(uint64_t(l) * 512u + uint32_t(x * 64 + y * 8));
 	}
 	// The same addresses in a colour-split half-brick field (float index of the row's quad: leaf*256 + x*32 + y*4), computed directly
-	// instead of halving a brick index: the 64-bit (a + b) >> 1 costs six instructions per neighbour row in the hottest kernel.
-	__device__ __forceinline__ uint64_t self_q() const { return uint64_t(leaf) * 256u + uint32_t(x * 32 + y * 4); }
-	__device__ __forceinline__ int64_t row_q(int dx, int dy) const {
+	// and in 32 bits (grids are limited to 2^24 leaves, topology.cu): halving a 64-bit brick index costs six instructions per neighbour
+	// row, a 64-bit index three more per address, in the hottest kernel. kNoRow marks a row in a missing leaf.
+	static constexpr uint32_t kNoRow = 0xffffffffu;
+	__device__ __forceinline__ uint32_t self_q() const { return leaf * 256u + uint32_t(x * 32 + y * 4); }
+	__device__ __forceinline__ uint32_t row_q(int dx, int dy) const {
 		int xx = x + dx, yy = y + dy;
 		int slot = kSlotSelf;
 		if (xx < 0) slot = kSlotXm, xx = 7;
@@ -74,12 +76,12 @@ struct RowCtx {
 		if (yy < 0) slot = kSlotYm, yy = 7;
 		else if (yy > 7) slot = kSlotYp, yy = 0;
 		const int32_t l = slot == kSlotSelf ? int32_t(leaf) : __ldg(nbr + slot);
-		return l < 0 ? int64_t(-1) : int64_t(uint64_t(l) * 256u + uint32_t(xx * 32 + yy * 4));
+		return l < 0 ? kNoRow : uint32_t(l) * 256u + uint32_t(xx * 32 + yy * 4);
 	}
-	// quad of row (x, y) in the -z / +z neighbour leaf, or -1
-	__device__ __forceinline__ int64_t z_q(int slot) const {
+	// quad of row (x, y) in the -z / +z neighbour leaf, or kNoRow
+	__device__ __forceinline__ uint32_t z_q(int slot) const {
 		const int32_t l = __ldg(nbr + slot);
-		return l < 0 ? int64_t(-1) : int64_t(uint64_t(l) * 256u + uint32_t(x * 32 + y * 4));
+		return l < 0 ? kNoRow : uint32_t(l) * 256u + uint32_t(x * 32 + y * 4);
 	}
 };
 __device__ __forceinline__ bool make_row_ctx(const GridView& g, RowCtx& c) {
@@ -312,18 +314,18 @@ __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __r
 			c.leaf = g.leaf_at(i);
 			c.nbr = g.nbr + uint64_t(c.leaf) * 27u;
 		}
-		const uint64_t q = c.self_q();
+		const uint32_t q = c.self_q();
 		const int sc = (c.x + c.y + color) & 1;  // swept voxels of this row are z = 2j + sc
 		const float4 C = ld4(p_c, q);            // old values of the swept colour (only this thread writes them)
 		// other colour: plain (coherent) loads when peers write ghost values into this array, read-only path otherwise
 		auto ldo = [&](uint64_t idx) { return kPush ? ld4(p_o, idx) : ldg4(p_o, idx); };
 		const float4 O = ldo(q);                 // own row: the z neighbours
-		int64_t t;
+		uint32_t t;
 		const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-		const float4 Oxp = (t = c.row_q(1, 0)) >= 0 ? ldo(uint64_t(t)) : zero4;
-		const float4 Oxm = (t = c.row_q(-1, 0)) >= 0 ? ldo(uint64_t(t)) : zero4;
-		const float4 Oyp = (t = c.row_q(0, 1)) >= 0 ? ldo(uint64_t(t)) : zero4;
-		const float4 Oym = (t = c.row_q(0, -1)) >= 0 ? ldo(uint64_t(t)) : zero4;
+		const float4 Oxp = (t = c.row_q(1, 0)) != RowCtx::kNoRow ? ldo(t) : zero4;
+		const float4 Oxm = (t = c.row_q(-1, 0)) != RowCtx::kNoRow ? ldo(t) : zero4;
+		const float4 Oyp = (t = c.row_q(0, 1)) != RowCtx::kNoRow ? ldo(t) : zero4;
+		const float4 Oym = (t = c.row_q(0, -1)) != RowCtx::kNoRow ? ldo(t) : zero4;
 		// the divergence is read once per sweep and not again before 2 x 240 MB of pressure have passed through the L2: load it
 		// with the streaming (evict-first) policy so that it does not displace pressure lines the next, reversed sweep starts on
 		const float4 D = (flags_stream_div) ? __ldcs(reinterpret_cast<const float4*>(div_c + q)) : ldg4(div_c, q);
@@ -331,9 +333,9 @@ __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __r
 		//               sc == 1: voxel j (z = 2j+1) has below = O[j], above = O[j+1] (j = 3: first other-colour voxel of the +z leaf)
 		float halo = 0.f;
 		if (sc == 0) {
-			if ((t = c.z_q(kSlotZm)) >= 0) halo = p_o[uint64_t(t) + 3];
+			if ((t = c.z_q(kSlotZm)) != RowCtx::kNoRow) halo = p_o[t + 3u];
 		} else {
-			if ((t = c.z_q(kSlotZp)) >= 0) halo = p_o[uint64_t(t)];
+			if ((t = c.z_q(kSlotZp)) != RowCtx::kNoRow) halo = p_o[t];
 		}
 		const float b0 = sc ? O.x : halo, b1 = sc ? O.y : O.x, b2 = sc ? O.z : O.y, b3 = sc ? O.w : O.z;  // below (z-1)
 		const float a0 = sc ? O.y : O.x, a1 = sc ? O.z : O.y, a2 = sc ? O.w : O.z, a3 = sc ? halo : O.w;  // above (z+1)
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __r
 		n.w = sor_update(Oxp.w, Oxm.w, Oyp.w, Oym.w, a3, b3, D.w, C.w, dx2, omega);
 		*reinterpret_cast<float4*>(p_c + q) = n;
 		if (kPush) {
-			const uint32_t row4 = uint32_t(q) & 255u;  // quad offset inside the half-brick
+			const uint32_t row4 = q & 255u;  // quad offset inside the half-brick
 			// bit f of this row's face membership: 0 x==0, 1 x==7, 2 y==0, 3 y==7; a z face (bits 4, 5) involves every row
 			const int mine = (c.x == 0 ? 1 : 0) | (c.x == 7 ? 2 : 0) | (c.y == 0 ? 4 : 0) | (c.y == 7 ? 8 : 0) | 0x30;
 			for (uint32_t e = __ldg(push.dst_off + i), e1 = __ldg(push.dst_off + i + 1); e < e1; ++e) {

@@ -198,6 +198,7 @@ static int build_grid(const int32_t* origins, uint64_t L, float voxel_size, hns_
 		if (l == 0 || keys[l].tile != keys[l - 1].tile) ++T;
 		if (l == 0 || keys[l].tile != keys[l - 1].tile || (keys[l].node >> 12) != (keys[l - 1].node >> 12)) ++nLower;
 	}
+	if (L >= (uint64_t(1) << 24)) return fail(HNS_ERR_UNSUPPORTED, "more than 2^24 leaves (8.6 G voxels): the kernels index half-brick fields with 32 bits");
 	auto* g = new hns_grid();
 	cudaGetDevice(&g->device);
 	g->voxel_size = voxel_size;
