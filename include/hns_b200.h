@@ -203,6 +203,9 @@ void* hns_state_field_device_ptr(hns_state* s, int field);
 typedef struct hns_dist hns_dist;
 int hns_dist_unique_id(uint8_t* out128);                                  /* rank 0: ncclGetUniqueId; ship the 128 bytes to all ranks */
 int hns_dist_create(const uint8_t* id128, int rank, int world, hns_dist** out); /* ncclCommInitRank on the current device */
+/* Lifetime: hns_dist_set_plan points the state at work lists owned by the hns_dist (owned leaves, global element 0); after
+ * hns_dist_destroy the state must be destroyed too or re-planned before it launches anything. Synchronise with the peers first:
+ * destroying unmaps memory a peer may still be storing into. */
 void hns_dist_destroy(hns_dist* d);
 /* per peer: LOCAL leaf ids (HOST arrays) of the owned leaves it holds as ghosts (send) and of the ghost leaves it owns (recv),
  * both in ascending global leaf order so that the two sides agree; owned_ids: LOCAL ids of all owned leaves (kernels skip the
