@@ -426,6 +426,7 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
         sh.upload(vel_pinned.numpy(), [t.numpy() for t in sc_pinned])
 
     restore()
+    dist.barrier()  # pinning and uploading take a different time on every rank; a frame's flag waits give up after ~4 s
     for _ in range(args.warmup):
         sh.frame(iterations, w.dt)
     torch.cuda.synchronize()
@@ -444,6 +445,7 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
     t_wall1 = time.time()
     dist.barrier()
     phases = sh.frame_timed(iterations, w.dt) if sh.native else {}
+    sh.check_errors()
     pr = torch.tensor([float(phases.get("pressure", 0.0)), float(plan.n_owned * 512)], device=dev)
     pr_all = [torch.zeros_like(pr) for _ in range(world)]
     dist.all_gather(pr_all, pr)
