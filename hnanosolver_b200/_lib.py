@@ -31,6 +31,10 @@ SIGNATURES = {
     "hns_launch_count_reset": (None, []),
     "hns_set_device": (C.c_int, [C.c_int]),
     "hns_set_l2_persist_mb": (C.c_int, [C.c_int]),
+    "hns_nvdb_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64]),
+    "hns_nvdb_file_grid_bytes": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint64)]),
+    "hns_nvdb_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64]),
+    "hns_nvdb_leaf_origins": (C.c_int, [C.c_void_p, C.c_uint64, c_i32p, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),
     "hns_grid_create_from_coords": (C.c_int, [c_i32p, C.c_uint64, C.c_float, C.c_int, C.POINTER(C.c_void_p)]),
     "hns_grid_create_from_origins": (C.c_int, [c_i32p, C.c_uint64, C.c_float, C.POINTER(C.c_void_p)]),
     "hns_grid_destroy": (None, [C.c_void_p]),

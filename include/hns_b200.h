@@ -91,6 +91,18 @@ int hns_grid_get_values(const hns_grid* g, const int32_t* ijk_host, uint64_t n, 
 int hns_grid_neighbors_download(const hns_grid* g, int32_t* dst_host);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * NanoVDB files (host only, no GPU): the index grid as an uncompressed .nvdb segment -- FileHeader, FileMetaData, name, raw grid;
+ * reference externals/nanovdb/NanoVDB.h:6252-6422 -- readable by stock NanoVDB tools, and back. The sidecar arrays are plain
+ * float arrays in leaf order and are stored by the caller next to it (hnanosolver_b200/io.py uses .npy).
+ * ------------------------------------------------------------------------------------------------------- */
+int hns_nvdb_write(const char* path, const void* nanovdb_buffer, uint64_t bytes);   /* e.g. the bytes of hns_grid_nanovdb_download */
+int hns_nvdb_file_grid_bytes(const char* path, uint64_t* bytes_out);                /* size of the first grid in the file */
+int hns_nvdb_read(const char* path, void* dst, uint64_t capacity);                  /* segment files and raw buffer dumps, codec NONE */
+/* leaf origins (int32[L][3], NanoVDB order; may be NULL to query L) and voxel size of a ValueOnIndex grid buffer on the host:
+ * the arguments of hns_grid_create_from_origins */
+int hns_nvdb_leaf_origins(const void* nanovdb_buffer, uint64_t bytes, int32_t* origins_out, uint64_t* num_leaves_out, float* voxel_size_out);
+
+/* ---------------------------------------------------------------------------------------------------------
  * One-shot launchers on HOST sidecar arrays, in place, synchronous -- the drop-in equivalents of the reference's
  * extern "C" launchers. `stream` is a cudaStream_t passed as void* (may be NULL).
  * ------------------------------------------------------------------------------------------------------- */

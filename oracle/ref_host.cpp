@@ -11,7 +11,9 @@
 // (Stencils.hpp:135-137: a + (b-a)*w), so Vec3f samples can differ from the device path in the last ulp;
 // the float path is a + w*(b-a) on both.
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "../Utils/Stencils.hpp"
 #include "nanovdb/NanoVDB.h"
@@ -67,5 +69,27 @@ void refhost_trilinear_v(void* g_, const float* data, const float* xyz, uint64_t
 		const nanovdb::Vec3f v = f(nanovdb::Vec3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
 		out[3 * i] = v[0], out[3 * i + 1] = v[1], out[3 * i + 2] = v[2];
 	}
+}
+// ---- NanoVDB's own file IO on the CPU (pins hnanosolver_b200/csrc/nvdb_io.cu) ----
+// writeUncompressedGrid / readUncompressedGrids are the dependency-free reference implementations inside NanoVDB.h (:6316-6422).
+struct FileOut {
+	FILE* f;
+	void write(const char* data, size_t n) { fwrite(data, 1, n, f); }
+};
+// buffer (any valid NanoVDB grid) -> file, segment layout (raw = 0) or raw dump (raw = 1)
+int refhost_write_nvdb(const char* path, const void* buffer, int raw) {
+	FileOut os{fopen(path, "wb")};
+	if (!os.f) return 1;
+	nanovdb::io::writeUncompressedGrid(os, static_cast<const nanovdb::GridData*>(buffer), raw != 0);
+	fclose(os.f);
+	return 0;
+}
+// file -> first grid's bytes (returns its size; copies at most `capacity` bytes into dst when dst != null)
+uint64_t refhost_read_nvdb(const char* path, void* dst, uint64_t capacity) {
+	auto handles = nanovdb::io::readUncompressedGrids<nanovdb::GridHandle<nanovdb::HostBuffer>, std::vector>(path);
+	if (handles.empty()) return 0;
+	const uint64_t n = handles[0].buffer().size();
+	if (dst) memcpy(dst, handles[0].data(), n < capacity ? n : capacity);
+	return n;
 }
 }
