@@ -162,13 +162,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: hnanosolver_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if args.impl == "reference":  # rank 0 alone times the reference; the other ranks leave without joining a process group
+        return reference_arm(args, rank, world)
     if world > 1:
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if args.impl == "reference":
-        return reference_arm(args, rank, world)
 
     import hnanosolver_b200 as H
     from hnanosolver_b200 import _lib, synth
