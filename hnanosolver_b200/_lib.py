@@ -97,6 +97,7 @@ SIGNATURES = {
     "hns_dist_ipc_connect": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.c_uint64, c_i32p]),
     "hns_dist_ipc_finish": (C.c_int, [C.c_void_p]),
     "hns_dist_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "hns_dist_reset_error": (C.c_int, [C.c_void_p]),
     "hns_dist_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "hns_dist_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "hns_dist_cook": (C.c_int, [C.c_void_p, C.c_void_p, c_f32p, C.c_int, C.POINTER(c_f32p), C.c_int, C.c_float, C.c_void_p]),

@@ -57,6 +57,9 @@ struct GridView {
 	// optional companion of `list`: the neighbour rows gathered in list order, [num_list][27] with slot 13 = the leaf id itself. One
 	// dependent load then yields the leaf id AND its neighbours (list -> nbr -> data would be three hops; this is two, like no list).
 	const int32_t* list_nbr;
+	// optional (sharded runs): bit 8 is set when a semi-Lagrangian sample leaves the 3x3x3 leaf neighbourhood, i.e. may land beyond
+	// the shard's ghost layer where the local tree knows nothing about leaves other ranks own
+	uint32_t* far_flag;
 	__host__ __device__ uint32_t count() const { return list ? num_list : num_leaves; }
 #ifdef __CUDACC__
 	__device__ __forceinline__ uint32_t leaf_at(uint32_t i) const { return list ? uint32_t(__ldg(list + i)) : i; }
@@ -189,9 +192,10 @@ struct hns_state {
 	uint64_t vel_version = 0;  // bumped by every entry point that (may) overwrite the velocity planes; lets a sharded run skip a ghost exchange of unchanged data
 	const int32_t* active = nullptr;  // device list of the leaves the kernels process (sharded runs: the owned leaves), null = all
 	uint32_t n_active = 0;
+	uint32_t* far_flag = nullptr;  // GridView::far_flag
 	hns::GridView view() const {
 		hns::GridView v = grid->view;
-		v.list = active, v.num_list = n_active;
+		v.list = active, v.num_list = n_active, v.far_flag = far_flag;
 		return v;
 	}
 };

@@ -188,7 +188,13 @@ int hns_dist_unique_id(uint8_t* out128) {
 }
 
 int hns_dist_create(const uint8_t* id128, int rank, int world, hns_dist** out) {
-	if (!id128 || !out || world < 1 || rank < 0 || rank >= world) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	if (!out || world < 1 || rank < 0 || rank >= world) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	if (!id128) {  // peer-memory only: no communicator; every exchange goes through the CUDA IPC path (hns_dist_ipc_*)
+		auto* d = new hns_dist();
+		d->rank = rank, d->world = world;
+		*out = d;
+		return HNS_OK;
+	}
 	int rc = load_nccl();
 	if (rc) return rc;
 	auto* d = new hns_dist();
@@ -292,8 +298,14 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 		}
 		d->peers.push_back(p);
 	}
-	if (!d->d_elem0) HNS_CUDA(cudaMalloc(&d->d_elem0, 32 * sizeof(float)));
-	s->elem0 = d->d_elem0;
+	// advect_scalars' "inactive -> element 0": the plan keeps global leaf 0 on every rank as LOCAL leaf 0 (a ghost fed by rank 0 in the
+	// exchange before advect_scalars), so element 0 of the local arrays is the global one: no override
+	s->elem0 = nullptr;
+	if (!d->d_err) {
+		HNS_CUDA(cudaMalloc(&d->d_err, sizeof(uint32_t)));
+		HNS_CUDA(cudaMemset(d->d_err, 0, sizeof(uint32_t)));
+	}
+	s->far_flag = d->d_err;  // a semi-Lagrangian sample beyond the ghost layer is reported, not silently treated as inactive
 	d->n_scalars = s->n_scalars;
 	d->bound_state = s;
 	d->vel_exchanged_version = ~uint64_t(0);
@@ -370,10 +382,6 @@ int hns_dist_ipc_finish(hns_dist* d) {
 	HNS_CUDA(cudaMalloc(&d->d_local_flags, loc.size() * sizeof(uint32_t*)));
 	HNS_CUDA(cudaMemcpy(d->d_remote_flags, rem.data(), rem.size() * sizeof(uint32_t*), cudaMemcpyHostToDevice));
 	HNS_CUDA(cudaMemcpy(d->d_local_flags, loc.data(), loc.size() * sizeof(uint32_t*), cudaMemcpyHostToDevice));
-	if (!d->d_err) {
-		HNS_CUDA(cudaMalloc(&d->d_err, sizeof(uint32_t)));
-		HNS_CUDA(cudaMemset(d->d_err, 0, sizeof(uint32_t)));
-	}
 	{
 		// CSR over the boundary work list: which peers hold a ghost copy of boundary leaf i, under which leaf id, and which of its
 		// faces touch leaves that peer owns. The 7-point stencil (sweeps, gradient) only ever reads the face layer of a ghost leaf, so
@@ -448,11 +456,26 @@ int hns_dist_ipc_finish(hns_dist* d) {
 	d->p2p = true;
 	return HNS_OK;
 }
-// 0 = no flag wait has timed out so far; otherwise 1 + the channel that did
+// 0 = clean; low byte: 1 + the channel of a flag wait that timed out; bit 8: a semi-Lagrangian sample landed beyond the ghost layer
+// (the leaf may exist on another rank, so the sharded result would differ from the single-GPU one). Sticky until _reset_error.
 int hns_dist_error(hns_dist* d, uint32_t* out) {
 	if (!d || !out) return fail(HNS_ERR_INVALID_ARGUMENT, "null argument");
 	*out = 0;
 	if (d->d_err) HNS_CUDA(cudaMemcpy(out, d->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return HNS_OK;
+}
+int hns_dist_reset_error(hns_dist* d) {
+	if (!d) return fail(HNS_ERR_INVALID_ARGUMENT, "null argument");
+	if (d->d_err) HNS_CUDA(cudaMemset(d->d_err, 0, sizeof(uint32_t)));
+	return HNS_OK;
+}
+// after a stream sync: turn a recorded device-side error into a status
+static int check_device_error(hns_dist* d) {
+	uint32_t e = 0;
+	if (d->d_err) HNS_CUDA(cudaMemcpy(&e, d->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	if (e & 0xffu) return fail(HNS_ERR_RUNTIME, "ghost exchange timed out waiting for a peer on channel " + std::to_string((e & 0xffu) - 1) + ": the frame ran on stale ghosts");
+	if (e & 0x100u)
+		return fail(HNS_ERR_RUNTIME, "a semi-Lagrangian sample landed beyond the one-leaf ghost layer of this shard (CFL too large for a sharded run): the result may differ from the single-GPU frame");
 	return HNS_OK;
 }
 
@@ -505,6 +528,7 @@ static int exchange_channel(hns_dist* d, hns_state* s, int channel, int n_fields
 // pack -> grouped send/recv -> unpack of the given fields' ghost bricks, all on `stream`
 int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields, void* stream) {
 	if (!d || !s || n_fields <= 0 || n_fields > d->max_fields) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	if (!d->comm && d->world > 1) return fail(HNS_ERR_RUNTIME, "no NCCL communicator (hns_dist_create without an id) and the peer-memory exchange is not connected");
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	for (auto& p : d->peers) {
 		uint64_t off = 0;
@@ -569,7 +593,7 @@ int hns_dist_cook(hns_dist* d, hns_state* s, float* velocity, int n_float, float
 	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc[i], n * 4, cudaMemcpyDeviceToHost, st));
 	HNS_CUDA(cudaStreamSynchronize(st));
 	HNS_CUDA(cudaGetLastError());
-	return HNS_OK;
+	return check_device_error(d);
 }
 
 // Same frame with CUDA events between the phases; ms_out[8] = exchange velocity, advect_vector, exchange advected, divergence(+combustion),
@@ -583,7 +607,7 @@ int hns_dist_frame_timed(hns_dist* d, hns_state* s, int iterations, float dt, vo
 	if (rc == HNS_OK)
 		for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
 	for (auto& e : ev) cudaEventDestroy(e);
-	return rc;
+	return rc ? rc : check_device_error(d);
 }
 
 static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, cudaEvent_t* marks) {
@@ -598,9 +622,20 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if (s->skip_scalar >= 0 && s->skip_scalar != s->n_scalars - 1)
 		return fail(HNS_ERR_UNSUPPORTED, "sharded frames need the non-advected scalar (collision_sdf) to be the last scalar field");
-	// collision path: the SDF's ghost leaves arrive with the upload and never change; enforceCollisionBoundaries is per voxel on the
-	// owned leaves (it bumps the velocity version, so the velocity ghosts below are exchanged, never reused)
-	if (hns_state_collision_active(s) && (rc = hns_state_enforce_collision(s, stream))) return rc;
+	// collision path: enforceCollisionBoundaries and the collision tests of advect_vector read the SDF in ghost leaves (neighbour rows
+	// of the normal, trilinear samples at the traced positions), so its ghosts are exchanged first -- the caller's ghost entries need
+	// not be valid (hns_dist_cook's contract). The landing region is the |curl| one (flag 7), free at this point of a frame.
+	// enforceCollisionBoundaries is per voxel on the owned leaves (it bumps the velocity version, so the velocity ghosts below are
+	// exchanged, never reused).
+	if (hns_state_collision_active(s)) {
+		const int fsdf[1] = {10 + s->skip_scalar};
+		if (d->p2p) {
+			if ((rc = exchange_p2p(d, s, 7, 1, fsdf, st, nullptr, 5, 0))) return rc;
+		} else if ((rc = hns_dist_exchange(d, s, 1, fsdf, st))) {
+			return rc;
+		}
+		if ((rc = hns_state_enforce_collision(s, stream))) return rc;
+	}
 	// the velocity ghosts are still current when the last thing that wrote the velocity was the previous sharded frame (its final
 	// exchange refreshed them and advect_scalars does not touch the velocity)
 	if (d->vel_exchanged_version != s->vel_version && (rc = exchange_channel(d, s, 0, 3, fvel, st))) return rc;
@@ -715,9 +750,8 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 		for (int i = 0; i < s->n_scalars; ++i) last.push_back(10 + i);
 	if ((rc = exchange_channel(d, s, 4, int(last.size()), last.data(), st))) return rc;
 	if (scalars_early) HNS_CUDA(cudaStreamWaitEvent(st, d->ev_scalars_exchanged, 0));
-	// advect_scalars' "inactive -> element 0" value is global voxel 0's (reference Kernel.cu:192,225): rank 0 owns it
-	if (d->rank == 0 && (rc = hns_state_gather_element0(s, d->d_elem0, stream))) return rc;
-	if (d->world > 1) HNS_NCCL(g_nccl.Broadcast(d->d_elem0, d->d_elem0, size_t(3 + s->n_scalars), ncclFloat, 0, d->comm, st));
+	// advect_scalars' "inactive -> element 0" value (reference Kernel.cu:192,225) is global voxel 0's = local voxel 0's: that exchange
+	// has just refreshed it on every rank
 	mark();
 	rc = hns_state_advect_scalars(s, dt, 0, stream);
 	d->vel_exchanged_version = s->vel_version;

@@ -408,6 +408,7 @@ __device__ __forceinline__ int64_t voxel_index(const GridView& g, const LeafFram
 	const int dx = rx >> 3, dy = ry >> 3, dz = rz >> 3;
 	int32_t l;
 	if (((dx + 1) | (dy + 1) | (dz + 1)) & ~3 || dx == 2 || dy == 2 || dz == 2) {  // outside the 3x3x3 neighbourhood
+		if (g.far_flag) atomicOr(g.far_flag, 0x100u);
 		l = probe_leaf(g, i, j, k);
 	} else {
 		l = __ldg(f.nbr + (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1));

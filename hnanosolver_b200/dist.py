@@ -63,7 +63,10 @@ class ShardPlan:
 
 
 def make_plan(global_origins: np.ndarray, world: int, rank: int) -> ShardPlan:
-    """Contiguous, count-balanced ranges of the sorted leaf list; ghosts = 26-neighbours owned by another rank."""
+    """Contiguous, count-balanced ranges of the sorted leaf list; ghosts = 26-neighbours owned by another rank, plus global leaf 0
+    on every rank: advect_scalars reads "array element 0" for inactive voxels (reference src/Cuda/Kernel.cu:192,225), and with
+    leaf 0 held as a ghost (it sorts first, so it is LOCAL leaf 0 too) the local element 0 IS the global one after the exchange
+    that precedes advect_scalars -- no broadcast, no special case in the kernels."""
     L = global_origins.shape[0]
     ranges = np.array([(L * r) // world for r in range(world + 1)], np.int64)
     owner = np.searchsorted(ranges, np.arange(L), side="right") - 1
@@ -92,6 +95,14 @@ def make_plan(global_origins: np.ndarray, world: int, rank: int) -> ShardPlan:
                     send.setdefault(int(peer), set()).update(src[sel].tolist())   # my leaves the peer needs
                     recv.setdefault(int(peer), set()).update(nbr[sel].tolist())   # the peer's leaves I need
                 ghost.update(nbr[far].tolist())
+    if L and world > 1:
+        if rank == 0:
+            for peer in range(1, world):
+                if ranges[peer + 1] > ranges[peer]:      # a rank without leaves holds nothing
+                    send.setdefault(peer, set()).add(0)
+        elif hi > lo:
+            recv.setdefault(0, set()).add(0)
+            ghost.add(0)
     local_ids = np.array(sorted(set(mine.tolist()) | ghost), np.int64)
     owned_local = (local_ids >= lo) & (local_ids < hi)
     to_local = {int(g): i for i, g in enumerate(local_ids.tolist())}
@@ -194,15 +205,20 @@ class ShardedSimulation:
         self._dist = None
         if native:
             L = _lib.lib()
-            uid = (C.c_uint8 * 128)()
-            if plan.rank == 0:
-                _lib.check(L.hns_dist_unique_id(uid))
-            box = [bytes(uid)]
-            if plan.world > 1:
-                tdist.broadcast_object_list(box, src=0)
-            uid = (C.c_uint8 * 128).from_buffer_copy(box[0])
+            # NCCL carries the ghost bricks only in the fallback mode (HNS_P2P=0). Without it -- a gloo process group, e.g. two
+            # ranks time-sharing ONE GPU in the tests, which NCCL refuses -- the peer-memory exchange is the only data path.
+            use_nccl = plan.world > 1 and tdist.get_backend() == "nccl" and not bool(int(_os.environ.get("HNS_NO_NCCL", "0")))
             h = C.c_void_p()
-            _lib.check(L.hns_dist_create(uid, plan.rank, plan.world, C.byref(h)))
+            if use_nccl:
+                uid = (C.c_uint8 * 128)()
+                if plan.rank == 0:
+                    _lib.check(L.hns_dist_unique_id(uid))
+                box = [bytes(uid)]
+                tdist.broadcast_object_list(box, src=0)
+                uid = (C.c_uint8 * 128).from_buffer_copy(box[0])
+                _lib.check(L.hns_dist_create(uid, plan.rank, plan.world, C.byref(h)))
+            else:
+                _lib.check(L.hns_dist_create(None, plan.rank, plan.world, C.byref(h)))
             self._dist = h
             peers = sorted(set(plan.send) | set(plan.recv))
             n = len(peers)
@@ -217,7 +233,7 @@ class ShardedSimulation:
                 (_lib.c_i32p * max(n, 1))(*[a.ctypes.data_as(_lib.c_i32p) for a in rcv]), len(owned), owned.ctypes.data_as(_lib.c_i32p)))
             self.ex = None
             self.p2p = False
-            if plan.world > 1 and bool(int(_os.environ.get("HNS_P2P", "1"))):
+            if plan.world > 1 and (not use_nccl or bool(int(_os.environ.get("HNS_P2P", "1")))):
                 # direct peer-memory exchange: all-gather every rank's IPC handle and region offsets, connect to the peers
                 handle = (C.c_uint8 * 192)()
                 offs = (C.c_uint64 * max(n, 1))()
@@ -243,9 +259,6 @@ class ShardedSimulation:
                 self.sim.unpack_leaves(field, ids.data_ptr(), ids.numel(), src.data_ptr(), stream())
 
             self.ex = HaloExchanger(plan, device, pack, unpack, max_fields=3 + n_scalars)
-            # element 0 of the global arrays (the "inactive" value of advect_scalars, reference Kernel.cu:192,225): owned by rank 0
-            self.elem0 = torch.zeros(3 + n_scalars, dtype=torch.float32, device=device)
-            self.sim.set_element0(self.elem0.data_ptr())
 
     def check_errors(self) -> None:
         """raises if a peer-flag wait timed out on the device (the frame then ran on stale ghosts)"""
@@ -256,8 +269,10 @@ class ShardedSimulation:
 
             e = C.c_uint32()
             _lib.check(_lib.lib().hns_dist_error(self._dist, C.byref(e)))
-            if e.value:
-                raise RuntimeError(f"ghost exchange timed out waiting for a peer on channel {e.value - 1}")
+            if e.value & 0xff:
+                raise RuntimeError(f"ghost exchange timed out waiting for a peer on channel {(e.value & 0xff) - 1}: the frame ran on stale ghosts")
+            if e.value & 0x100:
+                raise RuntimeError("a semi-Lagrangian sample landed beyond the shard's one-leaf ghost layer (CFL too large for a sharded run)")
 
     def close(self):
         if self._dist is not None:
@@ -317,13 +332,7 @@ class ShardedSimulation:
             ex.exchange([F_P_BLK])
         s.subtract_gradient(True, st)
         ex.exchange(list(F_VEL) + [F_SCALAR0 + i for i in range(self.n_scalars)])
-        if self.plan.rank == 0:
-            s.gather_element0(self.elem0.data_ptr(), st)
-        if self.plan.world > 1:
-            import torch.distributed as dist
-
-            dist.broadcast(self.elem0, src=0)
-        s.advect_scalars(dt, 0, st)
+        s.advect_scalars(dt, 0, st)   # "inactive -> element 0": global leaf 0 is local leaf 0 on every rank (make_plan)
 
     def cook(self, velocity: np.ndarray, scalars, iterations: int, dt: float) -> None:
         """One sharded cook on this rank's HOST arrays (local voxels: owned + ghost leaves), in place, synchronous: the per-rank
@@ -374,6 +383,95 @@ class ShardedSimulation:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# sharded frame == single-GPU frame, bit for bit (run by tests/test_sharded_gpu.py and by bench.py --gpus N before it times anything)
+# ------------------------------------------------------------------------------------------------------------------
+def sharded_parity_check(rank: int, world: int, device, *, box=(256, 128, 128), fill: float = 0.35, seed: int = 7, iterations: int = 12,
+                         frames: int = 2, collision: bool = False, vorticity=(0.0, 1.0), cook: bool = False, combustion: bool = True,
+                         native: bool = True):
+    """Collective. Runs `frames` sharded frames of a small sparse box and, on rank 0, the same frames on ONE GPU over the whole
+    domain; compares the owned voxels of every rank (velocity, every scalar, pressure) with np.array_equal.
+    Returns (ok, report) on rank 0 and (None, None) elsewhere. Two frames exercise the reuse of the velocity ghosts across frames."""
+    import torch
+    import torch.distributed as tdist
+
+    from . import launchers as H
+
+    go = global_sparse_origins(box, fill, seed)
+    vel, den, tem = synth._swirl_fields(max(box))
+    wg = synth._finish("parity", go, vel, [den, tem], ["density", "temperature"], 40, seed, with_coords=False)
+    plan = make_plan(go, world, rank)
+    lo = np.repeat(plan.local_ids, 512) * 512 + np.tile(np.arange(512), plan.n_local)
+    comb = synth.combustion_fields(wg)
+    names = ["density", "fuel", "waste", "temperature", "flame"]
+    gfields = [wg.scalars[0]] + [comb[k] for k in names[1:]]
+    if collision:  # a sphere collider as the last scalar, hasCollision path on
+        off = np.stack(np.unravel_index(np.arange(512), (8, 8, 8)), 1)
+        gc = (np.repeat(go, 512, axis=0) + off[np.tile(np.arange(512), go.shape[0])]).astype(np.float32)
+        centre = np.array([box[0] / 2, box[1] / 2, box[2] / 2], np.float32)
+        sdf = (0.05 * (np.sqrt(((gc - centre) ** 2).sum(1)) - 20.0)).astype(np.float32)
+        sdf[0] = 0.0
+        names, gfields = names + ["collision_sdf"], gfields + [sdf]
+    NS = len(gfields)
+    P = H.CombustionParams(0.5, 2.0, 1.5, 0.1, float(vorticity[0]), float(vorticity[1]))
+    sh = ShardedSimulation(plan, np.ascontiguousarray(go[plan.local_ids]), wg.voxel_size, NS, device, native=native)
+    try:
+        if collision:
+            sh.sim.set_collision(NS - 1)
+        if combustion:
+            sh.set_combustion(names, P)
+        m = np.repeat(plan.owned_local, 512)
+        lv, lf = np.ascontiguousarray(wg.velocity[lo]), [np.ascontiguousarray(f[lo]) for f in gfields]
+        if cook:
+            # ghost entries of the host inputs are deliberately garbage: hns_dist_cook's contract says they need not be valid
+            lv[~m] = np.float32(1e30)
+            for i, a in enumerate(lf):
+                a[~m] = np.float32(-7.0)
+            for _ in range(frames):
+                sh.cook(lv, lf, iterations, wg.dt)
+            mine = [lv[m]] + [a[m] for a in lf] + [sh.sim.aux(1)[m]]
+        else:
+            sh.upload(lv, lf)
+            for _ in range(frames):
+                sh.frame(iterations, wg.dt)
+            torch.cuda.synchronize()
+            sh.check_errors()
+            mine = [sh.sim.velocity()[m]] + [sh.sim.scalar(i)[m] for i in range(NS)] + [sh.sim.aux(1)[m]]
+        gathered = [None] * world
+        tdist.all_gather_object(gathered, mine)
+        ok, report = None, None
+        if rank == 0:
+            g = H.create_index_grid_from_origins(go, wg.voxel_size)
+            sim = H.Simulation(g, NS)
+            sim.upload(wg.velocity, gfields)
+            if collision:
+                sim.set_collision(NS - 1)
+            if combustion:
+                sim.set_combustion(True, 1, 2, 3, 4, P)
+            for _ in range(frames):
+                sim.step(iterations, wg.dt)
+            sim.sync()
+            ref = [sim.velocity()] + [sim.scalar(i) for i in range(NS)] + [sim.aux(1)]
+            if cook and collision:
+                ref[NS] = gfields[-1]   # the resident state keeps the SDF; hns_dist_cook hands the caller's block back untouched
+            ok, lines = True, []
+            for k, nm in enumerate(["velocity"] + names + ["pressure"]):
+                got = np.concatenate([gathered[r][k] for r in range(world)])
+                same = bool(np.array_equal(got, ref[k]))
+                ok &= same
+                bad = np.nonzero((got != ref[k]).reshape(got.shape[0], -1).any(1))[0]
+                lines.append(f"{nm}: bitwise {'ok' if same else 'MISMATCH'} ({bad.size}/{got.shape[0]} voxels differ"
+                             + (f", max|diff| {np.abs(got.astype(np.float64) - ref[k]).max():.3e}, first leaves {np.unique(bad // 512)[:6].tolist()}" if bad.size else "") + ")")
+            report = dict(ok=ok, leaves=int(go.shape[0]), world=world, frames=frames, iterations=iterations, p2p=bool(getattr(sh, "p2p", False)),
+                          native=native, collision=collision, vorticity=list(vorticity), cook=cook, exchanges_per_frame=sh.exchanges // max(frames, 1),
+                          fields=lines)
+            del sim
+        tdist.barrier()
+        return ok, report
+    finally:
+        sh.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # weak-scaling workload: the bounding box grows with the number of ranks
 # ------------------------------------------------------------------------------------------------------------------
 WEAK_BOX = {1: (512, 512, 512), 2: (1024, 512, 512), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}
@@ -416,6 +514,16 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
 
     plan: ShardPlan = w.meta["plan"]
     dev = torch.device("cuda", local_rank)
+    # Before anything is timed: the sharded frame must equal the single-GPU frame bit for bit on a small box (two frames, full
+    # frame; then the host-buffer cook with vorticity confinement and the collision path on). A mismatch ends the run.
+    parity = []
+    for mode in (dict(), dict(cook=True, collision=True, vorticity=(0.8, 2.0))):
+        ok, report = sharded_parity_check(rank, world, dev, **mode)
+        if rank == 0:
+            print(f"[sharded parity] {report}", file=__import__("sys").stderr, flush=True)
+            parity.append(report)
+            if not ok:
+                raise SystemExit("sharded frame != single-GPU frame: refusing to time a wrong result")
     sh = ShardedSimulation(plan, w.origins, w.voxel_size, len(fields), dev)
     if full:
         sh.set_combustion(names, H.CombustionParams(*params6))
@@ -494,5 +602,7 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
                     "h2d_bytes_per_step": int(n_local_total * (12 + 4 * S)), "d2h_bytes_per_step": int(n_local_total * (12 + 4 * S)),
                     "call": "ShardedSimulation.cook (hns_dist_cook) per rank on pinned host arrays of its shard, in place, synchronous"},
             "gpu_launches": int(launches.item()),
+            "sharded_parity": "bitwise-ok" if parity and all(r["ok"] for r in parity) else None,
+            "sharded_parity_detail": [{k: r[k] for k in ("leaves", "world", "frames", "iterations", "p2p", "collision", "vorticity", "cook")} for r in parity],
             "_timed_wall": (t_wall0, t_wall1), "_pressure": (float(slowest[0]), float(slowest[1])),
             "halo_bytes_per_frame": int(owned[2].item() / (args.steps + args.warmup + args.e2e_steps + 1))}

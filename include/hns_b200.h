@@ -214,7 +214,9 @@ void* hns_state_field_device_ptr(hns_state* s, int field);
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct hns_dist hns_dist;
 int hns_dist_unique_id(uint8_t* out128);                                  /* rank 0: ncclGetUniqueId; ship the 128 bytes to all ranks */
-int hns_dist_create(const uint8_t* id128, int rank, int world, hns_dist** out); /* ncclCommInitRank on the current device */
+/* ncclCommInitRank on the current device. id128 == NULL: no communicator at all -- the peer-memory exchange (hns_dist_ipc_*) is then
+ * the only data path and must be connected before the first frame (this also lets several ranks share one GPU, which NCCL refuses). */
+int hns_dist_create(const uint8_t* id128, int rank, int world, hns_dist** out);
 /* Lifetime: hns_dist_set_plan points the state at work lists owned by the hns_dist (owned leaves, global element 0); after
  * hns_dist_destroy the state must be destroyed too or re-planned before it launches anything. Synchronise with the peers first:
  * destroying unmaps memory a peer may still be storing into. */
@@ -237,7 +239,13 @@ int hns_dist_ipc_prepare(hns_dist* d, uint8_t* handle_out64, uint64_t* region_of
 int hns_dist_ipc_connect(hns_dist* d, int peer_index, const uint8_t* peer_handles192, uint64_t my_region_offset_in_peer_block,
                          const int32_t* peer_leaf_ids);
 int hns_dist_ipc_finish(hns_dist* d);
+/* device-side error word, sticky until reset: 0 = clean; low byte = 1 + the channel of a peer-flag wait that gave up after ~4 s (the
+ * frame then ran on stale ghosts); bit 8 = a semi-Lagrangian sample of advect_vector / advect_scalars landed outside the 3x3x3 leaf
+ * neighbourhood of its leaf, i.e. possibly beyond the shard's one-leaf ghost layer (more than ~8 voxels of back-trace), where the
+ * sharded result can differ from the single-GPU one. hns_dist_cook and hns_dist_frame_timed return HNS_ERR_RUNTIME when it is set;
+ * after the asynchronous hns_dist_frame the caller polls it at its next synchronisation point. */
 int hns_dist_error(hns_dist* d, uint32_t* out);
+int hns_dist_reset_error(hns_dist* d);
 /* ghost exchange of the given fields (ids as for hns_state_pack_leaves): pack, grouped ncclSend/ncclRecv, unpack; asynchronous */
 int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields, void* stream);
 /* the whole sharded frame (same steps as hns_state_step) with its 3 + 2*iterations ghost exchanges; the exchange of a swept
@@ -249,7 +257,8 @@ int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields
 int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream);
 /* the sharded cook on HOST arrays of this rank's local voxels (owned + ghost leaves; velocity float[n][3] and the state's scalar
  * fields float[n] in index order), in place, synchronous: upload, hns_dist_frame, download. Collective. Pinned host memory lets the
- * copies run at PCIe rate; the ranks' transfers go over their own links in parallel. */
+ * copies run at PCIe rate; the ranks' transfers go over their own links in parallel. Ghost entries of the inputs need not be valid
+ * (every field's ghosts, the collision SDF's included, are exchanged before they are read). */
 int hns_dist_cook(hns_dist* d, hns_state* s, float* velocity, int n_float, float* const* fields, int iterations, float dt, void* stream);
 /* the same frame with CUDA events between its phases (ms_out[8]: exchange velocity, advect_vector, exchange advected velocity,
  * divergence + combustion, pressure solve incl. exchanges, gradient, final exchange, advect_scalars); synchronises the stream */

@@ -37,6 +37,9 @@ def test_plan_partitions_and_ghosts_are_consistent():
                         m = lut.get((o[0] + dx, o[1] + dy, o[2] + dz))
                         if m is not None and m not in mine:
                             want.add(m)
+        if p.rank > 0:
+            want.add(0)                                                           # + global leaf 0 ("element 0" of advect_scalars)
+            assert p.local_ids[0] == 0 and 0 in p.local_ids[p.recv[0]]
         assert set(p.local_ids[~p.owned_local].tolist()) == want                 # ghosts == 26-neighbours owned elsewhere
         assert np.all(np.diff(p.local_ids) > 0)                                   # local order == global NanoVDB order
         for q, ids in p.send.items():                                             # my send list == the peer's recv list
