@@ -104,6 +104,19 @@ SIGNATURES = {
     "hns_dist_frame_timed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, c_f32p]),
     "hns_dist_debug_step": (C.c_int, [C.c_void_p, c_f32p]),
     "hns_dist_time_sweeps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, c_f32p]),
+    "hns_dist_allreduce_sum": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_void_p]),
+    "hns_state_residual_sums": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    "hns_state_divergence_sum_squares": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
+    "hns_mg_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "hns_mg_destroy": (None, [C.c_void_p]),
+    "hns_mg_num_levels": (C.c_int, [C.c_void_p]),
+    "hns_mg_level_leaves": (C.c_uint64, [C.c_void_p, C.c_int]),
+    "hns_mg_level_cells": (C.c_uint64, [C.c_void_p, C.c_int]),
+    "hns_mg_set_coarsest_iterations": (C.c_int, [C.c_void_p, C.c_int]),
+    "hns_state_pressure_solve_mg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "hns_mg_last_cycles": (C.c_int, [C.c_void_p]),
+    "hns_mg_last_relative_residual": (C.c_double, [C.c_void_p]),
+    "hns_state_set_pressure_solver": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]),
     "hns_dist_bytes_sent": (C.c_uint64, [C.c_void_p]),
     "hns_dist_exchanges": (C.c_uint64, [C.c_void_p]),
 }

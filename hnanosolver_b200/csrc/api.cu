@@ -105,7 +105,9 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 		for (int i : {iF, iW, iT, iL}) std::swap(s->sc[i], s->sc_out[i]);  // HNanoSolver.cu:239-246
 	}
 	if (ev_p0) cudaEventRecord(ev_p0, st);
-	int rc = pressure_solve(s, iterations, h, omega_compute(h), flags, st);
+	// the reference's solve, or -- opted in with hns_state_set_pressure_solver -- a fixed number of multigrid V-cycles
+	int rc = s->mg ? mg_pressure_solve(s, s->mg, s->mg_cycles, 0.0, s->mg_nu[0], s->mg_nu[1], s->mg_omega, st)
+	               : pressure_solve(s, iterations, h, omega_compute(h), flags, st);
 	if (rc) return rc;
 	if (ev_p1) cudaEventRecord(ev_p1, st);
 	launch_subtract_gradient(g, s->adv, s->p, s->vel, inv, st);
@@ -206,6 +208,7 @@ void hns_state_destroy(hns_state* s) {
 	cudaFree(s->div[0]), cudaFree(s->div[1]), cudaFree(s->p[0]);  // p[1] lives in p[0]'s allocation
 	for (int i = 0; i < 16; ++i) cudaFree(s->sc[i]), cudaFree(s->sc_out[i]);
 	cudaFree(s->aos);
+	cudaFree(s->d_sums);
 	for (float* v : s->vort) cudaFree(v);
 	delete s;
 }
@@ -530,6 +533,7 @@ int acquire_scratch(const hns_grid* g, int n_scalars, hns_state** out) {
 		g_scratch_device = dev;
 	}
 	g_scratch->grid = g;
+	g_scratch->mg = nullptr;
 	g_scratch->comb_enabled = false, g_scratch->skip_scalar = -1, g_scratch->collision = false, g_scratch->elem0 = nullptr, g_scratch->active = nullptr, g_scratch->n_active = 0;
 	*out = g_scratch;
 	return HNS_OK;

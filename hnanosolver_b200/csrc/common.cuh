@@ -157,6 +157,11 @@ __device__ __forceinline__ int probe_leaf(const GridView& g, int x, int y, int z
 
 }  // namespace hns
 
+struct hns_mg;
+struct hns_state;
+namespace hns {
+int mg_pressure_solve(hns_state* s, hns_mg* mg, int max_cycles, double rel_tol, int nu_pre, int nu_post, float omega, cudaStream_t st);  // multigrid.cu
+}
 // ---- opaque handle definitions ----------------------------------------------------------------------------
 struct hns_grid {
 	int device = 0;
@@ -193,6 +198,11 @@ struct hns_state {
 	const int32_t* active = nullptr;  // device list of the leaves the kernels process (sharded runs: the owned leaves), null = all
 	uint32_t n_active = 0;
 	uint32_t* far_flag = nullptr;  // GridView::far_flag
+	// optional multigrid pressure solve of the frame (hns_state_set_pressure_solver); null = the reference's fixed-count red-black SOR
+	struct hns_mg* mg = nullptr;
+	int mg_cycles = 0, mg_nu[2] = {2, 2};
+	float mg_omega = 1.0f;
+	double* d_sums = nullptr;  // device double[2] of the norm reductions, allocated on first use
 	hns::GridView view() const {
 		hns::GridView v = grid->view;
 		v.list = active, v.num_list = n_active, v.far_flag = far_flag;

@@ -24,7 +24,8 @@ struct ncclUniqueId {
 	char internal[128];
 };
 enum { ncclSuccess = 0 };
-enum { ncclFloat = 7 };  // ncclFloat32
+enum { ncclFloat = 7, ncclDouble = 8 };  // ncclFloat32, ncclFloat64
+enum { ncclSum = 0 };
 struct Nccl {
 	void* lib = nullptr;
 	int (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -33,6 +34,7 @@ struct Nccl {
 	int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	int (*GroupStart)() = nullptr;
 	int (*GroupEnd)() = nullptr;
 	const char* (*GetErrorString)(int) = nullptr;
@@ -52,6 +54,7 @@ static int load_nccl() {
 	HNS_SYM(Send, "ncclSend")
 	HNS_SYM(Recv, "ncclRecv")
 	HNS_SYM(Broadcast, "ncclBroadcast")
+	HNS_SYM(AllReduce, "ncclAllReduce")
 	HNS_SYM(GroupStart, "ncclGroupStart")
 	HNS_SYM(GroupEnd, "ncclGroupEnd")
 	HNS_SYM(GetErrorString, "ncclGetErrorString")
@@ -88,6 +91,7 @@ struct hns_dist {
 	std::vector<Peer> peers;
 	int max_fields = 0;
 	float* d_elem0 = nullptr;
+	double* d_reduce = nullptr;  // staging of hns_dist_allreduce_sum
 	uint64_t bytes_sent = 0, exchanges = 0;
 	// work lists (local leaf ids, device): owned = boundary (sent to some peer) + interior
 	int32_t *d_owned = nullptr, *d_boundary = nullptr, *d_interior = nullptr;
@@ -213,6 +217,7 @@ int hns_dist_create(const uint8_t* id128, int rank, int world, hns_dist** out) {
 void hns_dist_destroy(hns_dist* d) {
 	if (!d) return;
 	for (auto& p : d->peers) cudaFree(p.d_send), cudaFree(p.d_recv), cudaFree(p.buf_send), cudaFree(p.buf_recv);
+	cudaFree(d->d_reduce);
 	cudaFree(d->d_elem0), cudaFree(d->d_owned), cudaFree(d->d_boundary), cudaFree(d->d_interior);
 	cudaFree(d->d_boundary_nbr), cudaFree(d->d_interior_nbr);
 	for (auto& p : d->peers) {
@@ -813,6 +818,19 @@ int hns_dist_time_sweeps(hns_dist* d, hns_state* s, int mode, int n, void* strea
 	cudaEventElapsedTime(ms_out, e0, e1);
 	cudaEventDestroy(e0), cudaEventDestroy(e1);
 	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+// global sums of the ranks' fp64 partial sums (residual / divergence norms): ncclAllReduce(sum, fp64), SURVEY.md 8e
+int hns_dist_allreduce_sum(hns_dist* d, double* inout_host, int n, void* stream) {
+	if (!d || !inout_host || n <= 0 || n > 16) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
+	if (d->world == 1) return HNS_OK;
+	if (!d->comm) return fail(HNS_ERR_UNSUPPORTED, "no NCCL communicator (hns_dist_create without an id): reduce the sums with the caller's own collective");
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (!d->d_reduce) HNS_CUDA(cudaMalloc(&d->d_reduce, 16 * sizeof(double)));
+	HNS_CUDA(cudaMemcpyAsync(d->d_reduce, inout_host, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, st));
+	HNS_NCCL(g_nccl.AllReduce(d->d_reduce, d->d_reduce, size_t(n), ncclDouble, ncclSum, d->comm, st));
+	HNS_CUDA(cudaMemcpyAsync(inout_host, d->d_reduce, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, st));
+	HNS_CUDA(cudaStreamSynchronize(st));
 	return HNS_OK;
 }
 uint64_t hns_dist_bytes_sent(const hns_dist* d) { return d ? d->bytes_sent : 0; }

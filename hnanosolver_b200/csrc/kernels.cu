@@ -285,6 +285,13 @@ __device__ __forceinline__ float sor_update(float pxp, float pxm, float pyp, flo
 	return fmaf(d, omega, pOld);
 }
 
+// the same relaxation with a per-cell diagonal (coarse multigrid levels): pGS = s / diag
+__device__ __forceinline__ float sor_update_diag(float pxp, float pxm, float pyp, float pym, float pzp, float pzm, float dv, float pOld, float dx2,
+                                                 float omega, float diag) {
+	const float s = fmaf(-dv, dx2, ((((pxp + pxm) + pyp) + pym) + pzp) + pzm);
+	return fmaf(__fdiv_rn(s, diag) - pOld, omega, pOld);
+}
+
 // One colour per launch, in place, on the colour-split layout. Thread per row (x,y): the four voxels of the swept colour are
 // one float4; their x/y neighbours are the same-index float4 of the other colour in the four adjacent rows, their z neighbours
 // the other-colour quad of the own row shifted by one, plus one scalar from the leaf above/below. Per half-sweep the HBM
@@ -294,9 +301,14 @@ __device__ __forceinline__ float sor_update(float pxp, float pxm, float pyp, flo
 // kPush: the sharded run's boundary sweep -- every freshly swept quad is also stored straight into the ghost copy of the leaf on
 // each peer GPU that holds one (NVLink peer memory, CUDA IPC), and the last block to finish raises the peers' arrival flags:
 // compute and ghost exchange are one kernel, nothing is packed, sent or unpacked afterwards.
-template <bool kPush>
+// kMask: a coarse level of the multigrid solve -- `diag_c` holds the operator's diagonal of every cell of the swept colour: 6 plus a
+// boundary term per face neighbour outside the domain (multigrid.cu), 0 for a cell that is itself outside. Such cells keep the value 0
+// they were initialised with, which is the Dirichlet condition of the reference's solve (inactive -> 0); the update divides by the
+// diagonal instead of multiplying by the reference's 0.166666667f.
+template <bool kPush, bool kMask = false>
 __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __restrict__ div_c, float* __restrict__ p_c, const float* p_o,
-                                                    float dx2, int color, float omega, int reverse, RbgsPush push) {
+                                                    float dx2, int color, float omega, int reverse, RbgsPush push,
+                                                    const float* __restrict__ diag_c = nullptr) {
 	RowCtx c;
 	const bool flags_stream_div = (reverse & 2) == 0;  // bit 1 of `reverse`: A/B switch, plain read-only loads of the divergence
 	reverse &= 1;
@@ -344,6 +356,13 @@ __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __r
 		n.y = sor_update(Oxp.y, Oxm.y, Oyp.y, Oym.y, a1, b1, D.y, C.y, dx2, omega);
 		n.z = sor_update(Oxp.z, Oxm.z, Oyp.z, Oym.z, a2, b2, D.z, C.z, dx2, omega);
 		n.w = sor_update(Oxp.w, Oxm.w, Oyp.w, Oym.w, a3, b3, D.w, C.w, dx2, omega);
+		if (kMask) {
+			const float4 W = ldg4(diag_c, q);
+			n.x = W.x != 0.f ? sor_update_diag(Oxp.x, Oxm.x, Oyp.x, Oym.x, a0, b0, D.x, C.x, dx2, omega, W.x) : 0.f;
+			n.y = W.y != 0.f ? sor_update_diag(Oxp.y, Oxm.y, Oyp.y, Oym.y, a1, b1, D.y, C.y, dx2, omega, W.y) : 0.f;
+			n.z = W.z != 0.f ? sor_update_diag(Oxp.z, Oxm.z, Oyp.z, Oym.z, a2, b2, D.z, C.z, dx2, omega, W.z) : 0.f;
+			n.w = W.w != 0.f ? sor_update_diag(Oxp.w, Oxm.w, Oyp.w, Oym.w, a3, b3, D.w, C.w, dx2, omega, W.w) : 0.f;
+		}
 		*reinterpret_cast<float4*>(p_c + q) = n;
 		if (kPush) {
 			const uint32_t row4 = q & 255u;  // quad offset inside the half-brick
@@ -375,6 +394,12 @@ void launch_rbgs_color(const GridView& g, const float* const div[2], float* cons
 	if (g.count())
 		HNS_LAUNCH(k_rbgs_split<false>, (g.count() + 3) / 4, 256, 0, st, g, div[color], p[color], p[color ^ 1], dx * dx, color, omega, reverse,
 		           RbgsPush{});
+}
+void launch_rbgs_color_masked(const GridView& g, const float* const rhs[2], float* const p[2], float dx, int color, float omega,
+                              const float* const diag[2], cudaStream_t st) {
+	if (g.count())
+		HNS_LAUNCH((k_rbgs_split<false, true>), (g.count() + 3) / 4, 256, 0, st, g, rhs[color], p[color], p[color ^ 1], dx * dx, color, omega, 0, RbgsPush{},
+		           diag[color]);
 }
 void launch_rbgs_color_push(const GridView& g, const float* const div[2], float* const p[2], float dx, int color, float omega, int reverse,
                             const RbgsPush& push, cudaStream_t st) {
@@ -1097,6 +1122,233 @@ void launch_vorticity_force(const GridView& g, const float* const vel[3], const 
 	if (g.count())
 		HNS_LAUNCH(k_vorticity_force, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], mag, out[0], out[1], out[2], 0.5f * inv_dx, inv_dx, scale,
 		           dt, fs);
+}
+
+// =============================================================================================================
+// multigrid V-cycle pieces. The reference only sketches them: restrict_to_4x4x4 / restrict_to_2x2x2 / prolongate / compute_residual
+// are declared (src/Cuda/Kernels.cuh:38-49) and called from a commented-out v_cycle (src/Cuda/HNanoSolver.cu:399-507), never defined.
+// Built here on the same bricks: level k+1 has cells of twice the size, its leaves are 2x2x2 leaves of level k, cell-centred
+// coarsening (8 children -> 1 parent), the same 7-point operator and red-black sweep on every level, p = 0 outside the domain.
+//   residual   r = rhs - (sum of the 6 neighbours - 6 p) / dx^2          (the equation the reference's sweep relaxes, Kernel.cu:621)
+//   restrict   parent rhs = mean of the 8 children's residuals           (summed z pair, then y pair, then x pair)
+//   prolong    p += trilinear interpolation of the parents' correction   (weights 3/4, 1/4 per axis; z, then y, then x)
+// =============================================================================================================
+// kNorm: also accumulates sum r^2 and sum rhs^2 in fp64 (per-thread partial sums, warp shuffles, one atomic per warp).
+template <bool kMask, bool kRestrict, bool kNorm>
+__global__ void __launch_bounds__(256) k_mg_residual(GridView g, const float* __restrict__ p_red, const float* __restrict__ p_blk,
+                                                     const float* __restrict__ rhs_red, const float* __restrict__ rhs_blk, float inv_dx2,
+                                                     const float* __restrict__ diag_red, const float* __restrict__ diag_blk,
+                                                     const int32_t* __restrict__ parent,
+                                                     float* __restrict__ crhs_red, float* __restrict__ crhs_blk, double* __restrict__ sums) {
+	RowCtx c;
+	if (!make_row_ctx(g, c)) return;
+	const uint64_t self = c.self();
+	const bool s = (c.x + c.y) & 1;
+	const Row8 cp = ld_split_row(p_red, p_blk, self, s);
+	int64_t i;
+	const Row8 pxp = (i = c.row(1, 0)) >= 0 ? ld_split_row(p_red, p_blk, i, !s) : zero_row();
+	const Row8 pxm = (i = c.row(-1, 0)) >= 0 ? ld_split_row(p_red, p_blk, i, !s) : zero_row();
+	const Row8 pyp = (i = c.row(0, 1)) >= 0 ? ld_split_row(p_red, p_blk, i, !s) : zero_row();
+	const Row8 pym = (i = c.row(0, -1)) >= 0 ? ld_split_row(p_red, p_blk, i, !s) : zero_row();
+	const float pzm = (i = c.zminus()) >= 0 ? __ldg((s ? p_red : p_blk) + (split_idx(uint64_t(i) & ~uint64_t(7)) + 3)) : 0.f;
+	const float pzp = (i = c.zplus()) >= 0 ? __ldg((s ? p_blk : p_red) + split_idx(uint64_t(i))) : 0.f;
+	const Row8 f = ld_split_row(rhs_red, rhs_blk, self, s);
+	Row8 dg;
+	if (kMask) dg = ld_split_row(diag_red, diag_blk, self, s);
+	float r[8];
+	double a = 0.0, b = 0.0;
+#pragma unroll
+	for (int z = 0; z < 8; ++z) {
+		const float zp = z < 7 ? cp.v[z < 7 ? z + 1 : 7] : pzp;
+		const float zm = z > 0 ? cp.v[z > 0 ? z - 1 : 0] : pzm;
+		const float sum = ((((pxp.v[z] + pxm.v[z]) + pyp.v[z]) + pym.v[z]) + zp) + zm;
+		const float lap = fmaf(kMask ? -dg.v[z] : -6.0f, cp.v[z], sum);
+		r[z] = fmaf(-lap, inv_dx2, f.v[z]);
+		if (kMask && dg.v[z] == 0.f) r[z] = 0.f;
+		if (kNorm) a = fma(double(r[z]), double(r[z]), a), b = fma(double(f.v[z]), double(f.v[z]), b);
+	}
+	if (kNorm) {
+#pragma unroll
+		for (int o = 16; o; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o), b += __shfl_down_sync(0xffffffffu, b, o);
+		if ((threadIdx.x & 31) == 0) atomicAdd(sums, a), atomicAdd(sums + 1, b);
+	}
+	if (kRestrict) {
+		float q[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			q[k] = r[2 * k] + r[2 * k + 1];
+			q[k] += __shfl_xor_sync(0xffffffffu, q[k], 1);  // the row at y ^ 1
+			q[k] += __shfl_xor_sync(0xffffffffu, q[k], 8);  // the rows at x ^ 1
+			q[k] *= 0.125f;
+		}
+		if (!((c.x | c.y) & 1)) {
+			const int4 o = __ldg(g.origin + c.leaf);
+			const int X = ((o.x >> 3) & 1) * 4 + (c.x >> 1), Y = ((o.y >> 3) & 1) * 4 + (c.y >> 1), oz = (o.z >> 3) & 1;
+			const uint32_t base = uint32_t(__ldg(parent + c.leaf)) * 256u + uint32_t(X * 32 + Y * 4 + 2 * oz);
+			const bool sp = (X + Y) & 1;  // parent cells z = 4 oz + k have colour (X + Y + k) & 1
+			*reinterpret_cast<float2*>((sp ? crhs_blk : crhs_red) + base) = make_float2(q[0], q[2]);
+			*reinterpret_cast<float2*>((sp ? crhs_red : crhs_blk) + base) = make_float2(q[1], q[3]);
+		}
+	}
+}
+void launch_mg_residual(const GridView& g, const float* const p[2], const float* const rhs[2], float dx, const float* const diag[2], const int32_t* parent,
+                        float* const coarse_rhs[2], double* sums, cudaStream_t st) {
+	if (!g.count()) return;
+	const float inv_dx2 = 1.0f / (dx * dx);
+	const unsigned grid = (g.count() + 3) / 4;
+	float* cr = coarse_rhs ? coarse_rhs[0] : nullptr;
+	float* cb = coarse_rhs ? coarse_rhs[1] : nullptr;
+	const float* dr = diag ? diag[0] : nullptr;
+	const float* db = diag ? diag[1] : nullptr;
+#define HNS_MG_RES(M, R, N) HNS_LAUNCH((k_mg_residual<M, R, N>), grid, 256, 0, st, g, p[0], p[1], rhs[0], rhs[1], inv_dx2, dr, db, parent, cr, cb, sums)
+	const bool R = coarse_rhs != nullptr, N = sums != nullptr;
+	if (diag) {
+		if (R && N) HNS_MG_RES(true, true, true);
+		else if (R) HNS_MG_RES(true, true, false);
+		else HNS_MG_RES(true, false, true);
+	} else {
+		if (R && N) HNS_MG_RES(false, true, true);
+		else if (R) HNS_MG_RES(false, true, false);
+		else HNS_MG_RES(false, false, true);
+	}
+#undef HNS_MG_RES
+}
+
+// sum of squares of a colour-split field over the listed leaves (fp64)
+__global__ void __launch_bounds__(256) k_sum_squares(GridView g, const float* __restrict__ red, const float* __restrict__ blk, double* __restrict__ sum) {
+	RowCtx c;
+	if (!make_row_ctx(g, c)) return;
+	const uint32_t q = c.self_q();
+	const float4 r = ldg4(red, q), k = ldg4(blk, q);
+	double a = 0.0;
+	a = fma(double(r.x), double(r.x), a), a = fma(double(r.y), double(r.y), a), a = fma(double(r.z), double(r.z), a), a = fma(double(r.w), double(r.w), a);
+	a = fma(double(k.x), double(k.x), a), a = fma(double(k.y), double(k.y), a), a = fma(double(k.z), double(k.z), a), a = fma(double(k.w), double(k.w), a);
+#pragma unroll
+	for (int o = 16; o; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+	if ((threadIdx.x & 31) == 0) atomicAdd(sum, a);
+}
+void launch_sum_squares(const GridView& g, const float* const f[2], double* sum, cudaStream_t st) {
+	if (g.count()) HNS_LAUNCH(k_sum_squares, (g.count() + 3) / 4, 256, 0, st, g, f[0], f[1], sum);
+}
+
+// p_fine += P e_coarse. Four leaves per CTA; each stages the 6^3 parent cells around its octant of the parent leaf (4^3 + one cell of
+// halo, fetched through the parent grid's neighbour table; cells outside the domain hold 0) in shared memory.
+template <bool kMask>
+__global__ void __launch_bounds__(256) k_mg_prolong(GridView g, float* __restrict__ p_red, float* __restrict__ p_blk, const float* __restrict__ diag_red,
+                                                    const float* __restrict__ diag_blk, const int32_t* __restrict__ parent, const int32_t* __restrict__ cnbr,
+                                                    const float* __restrict__ e_red, const float* __restrict__ e_blk) {
+	__shared__ float tile[4][216];
+	const int slot = threadIdx.x >> 6, r = threadIdx.x & 63;
+	const uint32_t i = blockIdx.x * 4u + slot;
+	const bool active = i < g.count();
+	uint32_t leaf = 0;
+	if (active) {
+		leaf = g.leaf_at(i);
+		const int4 o = __ldg(g.origin + leaf);
+		const int bx = ((o.x >> 3) & 1) * 4 - 1, by = ((o.y >> 3) & 1) * 4 - 1, bz = ((o.z >> 3) & 1) * 4 - 1;
+		const int32_t cl = __ldg(parent + leaf);
+		for (int t = r; t < 216; t += 64) {
+			const int X = bx + t / 36, Y = by + (t / 6) % 6, Z = bz + t % 6;  // parent-leaf-local, in [-1, 8]
+			const int sl = ((X >> 3) + 1) * 9 + ((Y >> 3) + 1) * 3 + ((Z >> 3) + 1);
+			const int32_t l = sl == kSlotSelf ? cl : __ldg(cnbr + uint64_t(cl) * 27u + sl);
+			float v = 0.f;
+			if (l >= 0) v = __ldg((((X + Y + Z) & 1) ? e_blk : e_red) + (uint32_t(l) * 256u + uint32_t((X & 7) * 32 + (Y & 7) * 4 + ((Z & 7) >> 1))));
+			tile[slot][t] = v;
+		}
+	}
+	__syncthreads();
+	if (!active) return;
+	const int x = r >> 3, y = r & 7;
+	const float* T = tile[slot];
+	const int X0 = (x >> 1) + 1, X1 = X0 + ((x & 1) ? 1 : -1), Y0 = (y >> 1) + 1, Y1 = Y0 + ((y & 1) ? 1 : -1);
+	float v[8];
+#pragma unroll
+	for (int z = 0; z < 8; ++z) {
+		const int Z0 = (z >> 1) + 1, Z1 = Z0 + ((z & 1) ? 1 : -1);
+		auto zl = [&](int X, int Y) { return fmaf(0.25f, T[X * 36 + Y * 6 + Z1], 0.75f * T[X * 36 + Y * 6 + Z0]); };
+		const float a0 = fmaf(0.25f, zl(X0, Y1), 0.75f * zl(X0, Y0)), a1 = fmaf(0.25f, zl(X1, Y1), 0.75f * zl(X1, Y0));
+		v[z] = fmaf(0.25f, a1, 0.75f * a0);
+	}
+	const uint32_t q = leaf * 256u + uint32_t(x * 32 + y * 4);
+	const bool s = (x + y) & 1;  // red cells of this row are z = 2j + s
+	float4 R = *reinterpret_cast<const float4*>(p_red + q), B = *reinterpret_cast<const float4*>(p_blk + q);
+	float4 dR = make_float4(v[s ? 1 : 0], v[s ? 3 : 2], v[s ? 5 : 4], v[s ? 7 : 6]), dB = make_float4(v[s ? 0 : 1], v[s ? 2 : 3], v[s ? 4 : 5], v[s ? 6 : 7]);
+	if (kMask) {  // cells outside the domain stay 0
+		const float4 WR = ldg4(diag_red, q), WB = ldg4(diag_blk, q);
+		dR.x = WR.x != 0.f ? dR.x : 0.f, dR.y = WR.y != 0.f ? dR.y : 0.f, dR.z = WR.z != 0.f ? dR.z : 0.f, dR.w = WR.w != 0.f ? dR.w : 0.f;
+		dB.x = WB.x != 0.f ? dB.x : 0.f, dB.y = WB.y != 0.f ? dB.y : 0.f, dB.z = WB.z != 0.f ? dB.z : 0.f, dB.w = WB.w != 0.f ? dB.w : 0.f;
+	}
+	R.x += dR.x, R.y += dR.y, R.z += dR.z, R.w += dR.w;
+	B.x += dB.x, B.y += dB.y, B.z += dB.z, B.w += dB.w;
+	*reinterpret_cast<float4*>(p_red + q) = R;
+	*reinterpret_cast<float4*>(p_blk + q) = B;
+}
+void launch_mg_prolong(const GridView& g, float* const p[2], const float* const diag[2], const int32_t* parent, const GridView& coarse,
+                       const float* const e[2], cudaStream_t st) {
+	if (!g.count()) return;
+	if (diag) HNS_LAUNCH(k_mg_prolong<true>, (g.count() + 3) / 4, 256, 0, st, g, p[0], p[1], diag[0], diag[1], parent, coarse.nbr, e[0], e[1]);
+	else HNS_LAUNCH(k_mg_prolong<false>, (g.count() + 3) / 4, 256, 0, st, g, p[0], p[1], nullptr, nullptr, parent, coarse.nbr, e[0], e[1]);
+}
+
+// Diagonal of the operator on a coarse level from its row masks (one byte per row (x, y), bit z = cell inside the domain): 6 + extra for
+// every face neighbour outside the domain, 0 for a cell outside. Why `extra`: the fine level puts p = 0 at the centre of the first
+// outside voxel, i.e. one voxel beyond the last inside centre. Seen from level k that plane lies theta_k = 1/2 + 2^-(k+1) cells beyond
+// the last inside centre, not one cell; a ghost value extrapolated linearly through p = 0 at that distance is p_own (1 - 1/theta_k),
+// which moves extra = 1/theta_k - 1 onto the diagonal. Without it the coarse problems solve for a domain that is too large and the
+// V-cycle converges at 0.5 per cycle instead of 0.05 (measured).
+__global__ void __launch_bounds__(256) k_mg_diag(GridView g, const uint8_t* __restrict__ mask, float extra, float* __restrict__ diag_red,
+                                                 float* __restrict__ diag_blk) {
+	RowCtx c;
+	if (!make_row_ctx(g, c)) return;
+	auto row_mask = [&](int dx, int dy) -> uint32_t {
+		const int64_t i = c.row(dx, dy);
+		return i < 0 ? 0u : uint32_t(__ldg(mask + (i >> 3)));
+	};
+	const uint32_t m = row_mask(0, 0), mxp = row_mask(1, 0), mxm = row_mask(-1, 0), myp = row_mask(0, 1), mym = row_mask(0, -1);
+	int64_t i;
+	const uint32_t mzm = (i = c.zminus()) >= 0 ? (uint32_t(__ldg(mask + (i >> 3))) >> 7) & 1u : 0u;
+	const uint32_t mzp = (i = c.zplus()) >= 0 ? uint32_t(__ldg(mask + (i >> 3))) & 1u : 0u;
+	const uint32_t up = (m >> 1) | (mzp << 7), down = ((m << 1) & 0xffu) | mzm;  // bit z: the cell above / below z is inside
+	Row8 o;
+#pragma unroll
+	for (int z = 0; z < 8; ++z) {
+		const int outside = 6 - int(((mxp >> z) & 1u) + ((mxm >> z) & 1u) + ((myp >> z) & 1u) + ((mym >> z) & 1u) + ((up >> z) & 1u) + ((down >> z) & 1u));
+		o.v[z] = ((m >> z) & 1u) ? __fadd_rn(6.0f, __fmul_rn(float(outside), extra)) : 0.f;
+	}
+	st_split(diag_red, diag_blk, c, o);
+}
+void launch_mg_diag(const GridView& g, const uint8_t* mask, float extra, float* const diag[2], cudaStream_t st) {
+	if (g.count()) HNS_LAUNCH(k_mg_diag, (g.count() + 3) / 4, 256, 0, st, g, mask, extra, diag[0], diag[1]);
+}
+
+// The coarsest level when it is a single leaf: `iterations` red-black sweeps in one CTA, the brick in shared memory with a one-cell
+// rim of zeros (nothing lies outside a one-leaf level). Same update as k_rbgs_split.
+__global__ void __launch_bounds__(512) k_mg_coarsest(float* __restrict__ p_red, float* __restrict__ p_blk, const float* __restrict__ rhs_red,
+                                                     const float* __restrict__ rhs_blk, const float* __restrict__ diag_red,
+                                                     const float* __restrict__ diag_blk, float dx2, float omega, int iterations) {
+	__shared__ float P[10][10][10];
+	const int t = threadIdx.x, x = t >> 6, y = (t >> 3) & 7, z = t & 7;
+	for (int k = t; k < 1000; k += 512) (&P[0][0][0])[k] = 0.f;
+	__syncthreads();
+	const int color = (x + y + z) & 1;
+	const uint32_t q = uint32_t(x * 32 + y * 4 + (z >> 1));
+	const float f = color ? rhs_blk[q] : rhs_red[q];
+	const float dg = color ? diag_blk[q] : diag_red[q];
+	const bool on = dg != 0.f;
+	P[x + 1][y + 1][z + 1] = color ? p_blk[q] : p_red[q];
+	__syncthreads();
+	for (int it = 0; it < 2 * iterations; ++it) {
+		if (on && color == (it & 1)) {
+			const float v = sor_update_diag(P[x + 2][y + 1][z + 1], P[x][y + 1][z + 1], P[x + 1][y + 2][z + 1], P[x + 1][y][z + 1], P[x + 1][y + 1][z + 2],
+			                                P[x + 1][y + 1][z], f, P[x + 1][y + 1][z + 1], dx2, omega, dg);
+			P[x + 1][y + 1][z + 1] = v;
+		}
+		__syncthreads();
+	}
+	(color ? p_blk : p_red)[q] = P[x + 1][y + 1][z + 1];
+}
+void launch_mg_coarsest(float* const p[2], const float* const rhs[2], const float* const diag[2], float dx, float omega, int iterations, cudaStream_t st) {
+	HNS_LAUNCH(k_mg_coarsest, 1, 512, 0, st, p[0], p[1], rhs[0], rhs[1], diag[0], diag[1], dx * dx, omega, iterations);
 }
 
 // =============================================================================================================

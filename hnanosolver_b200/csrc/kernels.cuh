@@ -50,6 +50,19 @@ struct RbgsPush {
 };
 void launch_rbgs_color_push(const GridView& g, const float* const div[2], float* const p[2], float dx, int color, float omega, int reverse,
                             const RbgsPush& push, cudaStream_t st);
+// multigrid pieces (kernels.cu, "multigrid V-cycle pieces"). Coarse levels carry `diag`, the colour-split diagonal of their operator
+// (0 = cell outside the domain; launch_mg_diag builds it from row masks); diag == null means the fine level (diagonal 6, every cell
+// of a leaf inside). Residual: optionally restricted into the parent level's right-hand side and/or summed in fp64 into
+// sums[0..1] = {sum r^2, sum rhs^2}.
+void launch_rbgs_color_masked(const GridView& g, const float* const rhs[2], float* const p[2], float dx, int color, float omega,
+                              const float* const diag[2], cudaStream_t st);
+void launch_mg_residual(const GridView& g, const float* const p[2], const float* const rhs[2], float dx, const float* const diag[2], const int32_t* parent,
+                        float* const coarse_rhs[2], double* sums, cudaStream_t st);
+void launch_sum_squares(const GridView& g, const float* const f[2], double* sum, cudaStream_t st);
+void launch_mg_prolong(const GridView& g, float* const p[2], const float* const diag[2], const int32_t* parent, const GridView& coarse,
+                       const float* const e[2], cudaStream_t st);
+void launch_mg_diag(const GridView& g, const uint8_t* mask, float extra, float* const diag[2], cudaStream_t st);
+void launch_mg_coarsest(float* const p[2], const float* const rhs[2], const float* const diag[2], float dx, float omega, int iterations, cudaStream_t st);
 // subtractPressureGradient (Kernel.cu:765-829)
 void launch_subtract_gradient(const GridView& g, const float* const vel[3], const float* const p[2], float* const out[3], float inv_dx,
                               cudaStream_t st);

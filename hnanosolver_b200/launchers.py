@@ -25,7 +25,7 @@ from ._lib import CombustionParams, HnsError, check, c_f32p, c_i32p, c_u64p
 from .grid_data import FLOAT, VEC3F, GridIndexedData
 
 __all__ = ["CreateIndexGrid", "Compute_Sim", "AdvectIndexGrid", "AdvectIndexGridVelocity", "ProjectNonDivergent", "Divergence",
-           "CombustionKernel", "IndexGridHandle", "Simulation", "CombustionParams"]
+           "CombustionKernel", "IndexGridHandle", "Simulation", "Multigrid", "CombustionParams"]
 
 
 def _fp(a: np.ndarray):
@@ -193,6 +193,40 @@ def CombustionKernel(data: GridIndexedData, handle: IndexGridHandle, dt: float, 
     check(_lib.lib().hns_combustion_kernel(handle._h, _fp(data.pValues(VEC3F, vec[0])), data.size(), dt, voxelSize, _stream(stream)))
 
 
+class Multigrid:
+    """Coarse-level hierarchy over an index grid (hns_mg_create): level k+1 has cells twice the size, 2x2x2 leaves -> one leaf."""
+
+    def __init__(self, grid: IndexGridHandle, max_levels: int = 0):
+        self.grid = grid
+        h = C.c_void_p()
+        check(_lib.lib().hns_mg_create(grid._h, max_levels, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().hns_mg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_levels(self) -> int:
+        return int(_lib.lib().hns_mg_num_levels(self._h))
+
+    def level_leaves(self, k: int) -> int:
+        return int(_lib.lib().hns_mg_level_leaves(self._h, k))
+
+    def level_cells(self, k: int) -> int:
+        return int(_lib.lib().hns_mg_level_cells(self._h, k))
+
+    def set_coarsest_iterations(self, iterations: int):
+        check(_lib.lib().hns_mg_set_coarsest_iterations(self._h, iterations))
+
+
 class Simulation:
     """Device-resident state of one simulation: velocity + n_scalars float fields on an index grid."""
 
@@ -288,6 +322,35 @@ class Simulation:
 
     def sync(self, stream=None):
         check(_lib.lib().hns_state_sync(self._h, _stream(stream)))
+
+    # --- device-side norms and the multigrid solve (the reference declares compute_residual / restrict / prolongate but never
+    #     defines them, src/Cuda/Kernels.cuh:38-49) ------------------------------------------------------------------------
+    def residual_sums(self, stream=None) -> tuple[float, float]:
+        """(sum (div - L p)^2, sum div^2) of the current pressure and divergence, fp64 on the device"""
+        out = (C.c_double * 2)()
+        check(_lib.lib().hns_state_residual_sums(self._h, out, _stream(stream)))
+        return float(out[0]), float(out[1])
+
+    def relative_residual(self, stream=None) -> float:
+        a, b = self.residual_sums(stream)
+        return float(np.sqrt(a / b)) if b > 0 else 0.0
+
+    def divergence_sum_squares(self, of_advected=False, stream=None) -> float:
+        """sum of squares of the divergence of the (advected) velocity; overwrites the state's divergence field"""
+        out = C.c_double()
+        check(_lib.lib().hns_state_divergence_sum_squares(self._h, int(of_advected), C.byref(out), _stream(stream)))
+        return float(out.value)
+
+    def pressure_solve_mg(self, mg: "Multigrid", max_cycles: int, rel_tol: float = 0.0, nu_pre: int = 2, nu_post: int = 2,
+                          omega_smooth: float = 1.15, stream=None) -> tuple[int, float]:
+        """p = 0, then V-cycles until the relative residual <= rel_tol (or exactly max_cycles when rel_tol <= 0); (cycles, residual or -1)"""
+        check(_lib.lib().hns_state_pressure_solve_mg(self._h, mg._h, max_cycles, rel_tol, nu_pre, nu_post, omega_smooth, _stream(stream)))
+        return int(_lib.lib().hns_mg_last_cycles(mg._h)), float(_lib.lib().hns_mg_last_relative_residual(mg._h))
+
+    def set_pressure_solver(self, mg: "Multigrid | None", cycles: int = 2, nu_pre: int = 2, nu_post: int = 2, omega_smooth: float = 1.15):
+        """step()/time_frames() then run `cycles` V-cycles instead of the reference's red-black SOR sweeps (None switches back)"""
+        check(_lib.lib().hns_state_set_pressure_solver(self._h, mg._h if mg is not None else None, cycles, nu_pre, nu_post, omega_smooth))
+        self._mg = mg
 
     def time_frames(self, frames: int, iterations: int, dt: float, flags: int = 0, stream=None) -> tuple[float, float]:
         """(total ms, ms inside the pressure solve) over `frames` identical frames, CUDA events on the launch stream."""

@@ -191,6 +191,41 @@ int hns_state_sync(hns_state* s, void* stream);
 int hns_state_time_frames(hns_state* s, int frames, int iterations, float dt, unsigned flags, void* stream, float* ms_total,
                           float* ms_pressure);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Device-side norms (fp64; per-thread partial sums, warp shuffles, one atomic per warp) and the multigrid pressure solve.
+ * Reference: compute_residual, restrict_to_4x4x4, restrict_to_2x2x2, prolongate are declared but never defined
+ * (src/Cuda/Kernels.cuh:38-49) and their caller v_cycle is commented out (src/Cuda/HNanoSolver.cu:399-507): the reference never
+ * evaluates a residual. These entry points provide what that sketch intends, on the same equation as its red-black sweep
+ * (src/Cuda/Kernel.cu:591-623): (sum of the 6 neighbours - 6 p) / dx^2 = div, p = 0 outside the domain.
+ * ------------------------------------------------------------------------------------------------------- */
+/* out2[0] = sum over voxels of (div - L p)^2, out2[1] = sum of div^2, for the state's current pressure and divergence; over the leaves the
+ * state's kernels process (all of them, or the owned leaves of a shard: add the ranks' sums with hns_dist_allreduce_sum). Synchronous. */
+int hns_state_residual_sums(hns_state* s, double* out2, void* stream);
+/* *out = sum of squares of the divergence (reference kernel `divergence`, src/Cuda/Kernel.cu:499-519) of the current velocity
+ * (of_advected = 0) or of the advected velocity (1). OVERWRITES the state's divergence field. Synchronous. */
+int hns_state_divergence_sum_squares(hns_state* s, int of_advected, double* out, void* stream);
+/* Multigrid hierarchy over an index grid: level k+1 has cells twice the size of level k, a cell belongs to the domain iff one of its 8
+ * children does, leaves of level k+1 are 2x2x2 leaves of level k; coarsening stops at a single leaf (or after max_levels; <= 0: no cap).
+ * The grid must outlive the hierarchy. */
+typedef struct hns_mg hns_mg;
+int hns_mg_create(const hns_grid* g, int max_levels, hns_mg** out);
+void hns_mg_destroy(hns_mg* mg);
+int hns_mg_num_levels(const hns_mg* mg);
+uint64_t hns_mg_level_leaves(const hns_mg* mg, int level);
+uint64_t hns_mg_level_cells(const hns_mg* mg, int level);   /* cells inside the domain on that level */
+int hns_mg_set_coarsest_iterations(hns_mg* mg, int iterations); /* red-black iterations on the last level (default 32) */
+/* p = 0, then V(nu_pre, nu_post) cycles (red-black sweeps with relaxation factor omega_smooth on every level, full-weighting
+ * restriction of the residual, trilinear prolongation of the correction) until the relative residual
+ * sqrt(sum (div - L p)^2 / sum div^2) <= rel_tol or max_cycles cycles have run; rel_tol <= 0: exactly max_cycles cycles and no residual
+ * evaluation (asynchronous). Single-GPU states only. */
+int hns_state_pressure_solve_mg(hns_state* s, hns_mg* mg, int max_cycles, double rel_tol, int nu_pre, int nu_post, float omega_smooth, void* stream);
+int hns_mg_last_cycles(const hns_mg* mg);
+double hns_mg_last_relative_residual(const hns_mg* mg);     /* -1 when the last solve did not evaluate it */
+/* Makes hns_state_step / hns_state_time_frames solve the pressure with `cycles` V-cycles instead of the reference's `iterations`
+ * red-black SOR sweeps (mg = NULL switches back). Not the reference's arithmetic: results then differ from Compute_Sim's by the
+ * difference in how far the two solves converge. */
+int hns_state_set_pressure_solver(hns_state* s, hns_mg* mg, int cycles, int nu_pre, int nu_post, float omega_smooth);
+
 /* Ghost-leaf exchange support for spatially sharded runs (one process per GPU): pack/unpack whole bricks of one
  * internal field by leaf id list into/from a contiguous device buffer (float[n_ids][512]).
  * field: 0..2 velocity components, 3..5 advected velocity components, 6/7 pressure red/black half, 8/9 divergence red/black half,
@@ -267,6 +302,10 @@ int hns_dist_debug_step(hns_dist* d, float* out7); /* sub-step timing of one pre
 /* diagnostic: n exchange-free pressure half-sweeps over (mode) 0 all local leaves, 1 owned, 2 interior, 3 boundary, 4 interior and
  * boundary pipelined on two streams; *ms_out = elapsed milliseconds */
 int hns_dist_time_sweeps(hns_dist* d, hns_state* s, int mode, int n, void* stream, float* ms_out);
+/* in-place sum over all ranks of n <= 16 HOST doubles (ncclAllReduce, fp64): the global residual / divergence norms of a sharded solve
+ * from the ranks' hns_state_residual_sums / hns_state_divergence_sum_squares. Synchronous, collective. HNS_ERR_UNSUPPORTED without a
+ * communicator (hns_dist_create with a NULL id). */
+int hns_dist_allreduce_sum(hns_dist* d, double* inout_host, int n, void* stream);
 uint64_t hns_dist_bytes_sent(const hns_dist* d);
 uint64_t hns_dist_exchanges(const hns_dist* d);
 

@@ -735,6 +735,105 @@ void ora_rbgs(const ora_index* ix, const int32_t* coords, const float* div, floa
 	}
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Multigrid pieces and residual norms. PARITY UNPINNED against the reference for this block: v_cycle is commented out
+ * (src/Cuda/HNanoSolver.cu:399-507) and restrict_to_4x4x4 / restrict_to_2x2x2 / prolongate / compute_residual are
+ * declared but never defined (src/Cuda/Kernels.cuh:38-49), so the reference produces no output to compare with. What is
+ * restated is the equation of its sweep (Kernel.cu:621: (sum of the 6 neighbours - 6 p) / dx^2 = div, inactive -> 0) and
+ * the transfer operators of hnanosolver_b200/csrc/kernels.cu in the same operation order; the acceptance checks are the
+ * Poisson residual in fp64 and the divergence of the projected velocity.
+ * A level is a plain voxel list (only the cells inside the domain), so no masks are needed here.
+ * ---------------------------------------------------------------------------------------------- */
+/* Coarse levels: the diagonal of the operator is 6 + extra per face neighbour outside the domain (extra = 1/theta - 1: the fine level's
+ * p = 0 plane lies theta = 1/2 + 2^-(level+1) coarse cells beyond the last inside centre; kernels.cu k_mg_diag). */
+void ora_mg_diag(const ora_index* ix, const int32_t* coords, uint64_t n, float extra, float* diag) {
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const int32_t i = coords[3 * t], j = coords[3 * t + 1], k = coords[3 * t + 2];
+		const int inside = (ora_get_value(ix, i + 1, j, k) != 0) + (ora_get_value(ix, i - 1, j, k) != 0) + (ora_get_value(ix, i, j + 1, k) != 0) +
+		                   (ora_get_value(ix, i, j - 1, k) != 0) + (ora_get_value(ix, i, j, k + 1) != 0) + (ora_get_value(ix, i, j, k - 1) != 0);
+		diag[t] = 6.0f + (float)(6 - inside) * extra;
+	}
+}
+/* red-black relaxation with a per-cell diagonal: s = fma(-rhs, dx^2, sum6); p += omega (s / diag - p), as sor_update_diag */
+void ora_mg_rbgs(const ora_index* ix, const int32_t* coords, const float* rhs, float* p, const float* diag, float dx, uint64_t n, int color, float omega) {
+	const float dx2 = dx * dx;
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const int32_t i = coords[3 * t], j = coords[3 * t + 1], k = coords[3 * t + 2];
+		if (((i + j + k) & 1) != color) continue;
+		const float pxp = ora_nearest_f(ix, p, i + 1, j, k), pxm = ora_nearest_f(ix, p, i - 1, j, k);
+		const float pyp = ora_nearest_f(ix, p, i, j + 1, k), pym = ora_nearest_f(ix, p, i, j - 1, k);
+		const float pzp = ora_nearest_f(ix, p, i, j, k + 1), pzm = ora_nearest_f(ix, p, i, j, k - 1);
+		const float pOld = p[t];
+		const float s = fmaf(-rhs[t], dx2, ((((pxp + pxm) + pyp) + pym) + pzp) + pzm);
+		p[t] = fmaf(s / diag[t] - pOld, omega, pOld);
+	}
+}
+/* r = rhs - (sum6 - diag p) / dx^2, fp32, as k_mg_residual: lap = fma(-diag, p, sum); r = fma(-lap, 1/(dx*dx), rhs); diag == NULL: 6 */
+void ora_mg_residual(const ora_index* ix, const int32_t* coords, uint64_t n, const float* p, const float* rhs, const float* diag, float dx, float* r) {
+	const float inv_dx2 = 1.0f / (dx * dx);
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const int32_t i = coords[3 * t], j = coords[3 * t + 1], k = coords[3 * t + 2];
+		const float pxp = ora_nearest_f(ix, p, i + 1, j, k), pxm = ora_nearest_f(ix, p, i - 1, j, k);
+		const float pyp = ora_nearest_f(ix, p, i, j + 1, k), pym = ora_nearest_f(ix, p, i, j - 1, k);
+		const float pzp = ora_nearest_f(ix, p, i, j, k + 1), pzm = ora_nearest_f(ix, p, i, j, k - 1);
+		const float sum = ((((pxp + pxm) + pyp) + pym) + pzp) + pzm;
+		const float lap = fmaf(diag ? -diag[t] : -6.0f, p[t], sum);
+		r[t] = fmaf(-lap, inv_dx2, rhs[t]);
+	}
+}
+/* the fine level's residual in fp64 from the fp32 fields: out2 = {sum r^2, sum rhs^2} */
+void ora_residual_sums_f64(const ora_index* ix, const int32_t* coords, uint64_t n, const float* p, const float* rhs, double dx, double* out2) {
+	double a = 0.0, b = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : a, b)
+	for (int64_t t = 0; t < (int64_t)n; ++t) {
+		const int32_t i = coords[3 * t], j = coords[3 * t + 1], k = coords[3 * t + 2];
+		const double sum = (double)ora_nearest_f(ix, p, i + 1, j, k) + (double)ora_nearest_f(ix, p, i - 1, j, k) + (double)ora_nearest_f(ix, p, i, j + 1, k) +
+		                   (double)ora_nearest_f(ix, p, i, j - 1, k) + (double)ora_nearest_f(ix, p, i, j, k + 1) + (double)ora_nearest_f(ix, p, i, j, k - 1);
+		const double r = (double)rhs[t] - (sum - 6.0 * (double)p[t]) / (dx * dx);
+		a += r * r, b += (double)rhs[t] * (double)rhs[t];
+	}
+	out2[0] = a, out2[1] = b;
+}
+/* parent rhs = mean of the 8 children's residuals (children outside the domain count 0): z pair, then y pair, then x pair, * 0.125 */
+void ora_mg_restrict(const ora_index* fine, const float* r, const int32_t* ccoords, uint64_t nc, float* out) {
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)nc; ++t) {
+		const int32_t I = 2 * ccoords[3 * t], J = 2 * ccoords[3 * t + 1], K = 2 * ccoords[3 * t + 2];
+		float sx[2];
+		for (int a = 0; a < 2; ++a) {
+			float sy[2];
+			for (int b = 0; b < 2; ++b) sy[b] = ora_nearest_f(fine, r, I + a, J + b, K) + ora_nearest_f(fine, r, I + a, J + b, K + 1);
+			sx[a] = sy[0] + sy[1];
+		}
+		out[t] = (sx[0] + sx[1]) * 0.125f;
+	}
+}
+/* p += trilinear (cell-centred: 3/4 own parent, 1/4 the parent on the child's side) interpolation of the parents' correction e;
+ * parents outside the domain count 0; z, then y, then x, each fma(0.25, far, 0.75 * near) */
+void ora_mg_prolong_add(const ora_index* coarse, const float* e, const int32_t* fcoords, uint64_t nf, float* p) {
+#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < (int64_t)nf; ++t) {
+		const int32_t i = fcoords[3 * t], j = fcoords[3 * t + 1], k = fcoords[3 * t + 2];
+		const int32_t X0 = i >> 1, Y0 = j >> 1, Z0 = k >> 1;
+		const int32_t X1 = X0 + ((i & 1) ? 1 : -1), Y1 = Y0 + ((j & 1) ? 1 : -1), Z1 = Z0 + ((k & 1) ? 1 : -1);
+#define ORA_ZL(X, Y) fmaf(0.25f, ora_nearest_f(coarse, e, (X), (Y), Z1), 0.75f * ora_nearest_f(coarse, e, (X), (Y), Z0))
+		const float a0 = fmaf(0.25f, ORA_ZL(X0, Y1), 0.75f * ORA_ZL(X0, Y0));
+		const float a1 = fmaf(0.25f, ORA_ZL(X1, Y1), 0.75f * ORA_ZL(X1, Y0));
+#undef ORA_ZL
+		p[t] += fmaf(0.25f, a1, 0.75f * a0);
+	}
+}
+/* sum of squares in fp64 */
+double ora_sum_squares_f64(const float* a, uint64_t n) {
+	double s = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : s)
+	for (int64_t t = 0; t < (int64_t)n; ++t) s += (double)a[t] * (double)a[t];
+	return s;
+}
+
 /* subtractPressureGradient (Kernel.cu:765-829) / _opt (:694-762): u - ((p+ - p-) * 0.5) * inv_dx, last mul+sub fused */
 void ora_subtract_gradient(const ora_index* ix, const int32_t* coords, uint64_t n, const float* vel, const float* p, float* out,
                            float inv_dx) {

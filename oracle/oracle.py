@@ -93,6 +93,15 @@ def lib() -> C.CDLL:
                                       C.c_int, C.c_float, C.c_float, c_f32p]
         L.ora_project_non_divergent.argtypes = [C.c_void_p, c_i32p, C.c_uint64, c_f32p, C.c_int, C.c_float, c_f32p, c_f32p]
         L.ora_num_threads.restype = C.c_int
+        c_f64p = C.POINTER(C.c_double)
+        L.ora_mg_residual.argtypes = [C.c_void_p, c_i32p, C.c_uint64, c_f32p, c_f32p, c_f32p, C.c_float, c_f32p]
+        L.ora_mg_diag.argtypes = [C.c_void_p, c_i32p, C.c_uint64, C.c_float, c_f32p]
+        L.ora_mg_rbgs.argtypes = [C.c_void_p, c_i32p, c_f32p, c_f32p, c_f32p, C.c_float, C.c_uint64, C.c_int, C.c_float]
+        L.ora_residual_sums_f64.argtypes = [C.c_void_p, c_i32p, C.c_uint64, c_f32p, c_f32p, C.c_double, c_f64p]
+        L.ora_mg_restrict.argtypes = [C.c_void_p, c_f32p, c_i32p, C.c_uint64, c_f32p]
+        L.ora_mg_prolong_add.argtypes = [C.c_void_p, c_f32p, c_i32p, C.c_uint64, c_f32p]
+        L.ora_sum_squares_f64.restype = C.c_double
+        L.ora_sum_squares_f64.argtypes = [c_f32p, C.c_uint64]
         _lib = L
     return _lib
 
@@ -283,6 +292,116 @@ class OracleIndex:
         lib().ora_project_non_divergent(self._h, self.coords.ctypes.data_as(c_i32p), self.n, vel.ctypes.data_as(c_f32p), iterations,
                                         voxel_size, div.ctypes.data_as(c_f32p), p.ctypes.data_as(c_f32p))
         return vel, div, p
+
+
+def sum_squares(a) -> float:
+    a, ap = _f32(np.asarray(a).reshape(-1))
+    return float(lib().ora_sum_squares_f64(ap, a.size))
+
+
+def nanovdb_value_order(coords: np.ndarray) -> np.ndarray:
+    """permutation that puts a voxel list into NanoVDB ValueOnIndex order (root tile, upper offset, lower offset, voxel offset;
+    externals/nanovdb/tools/cuda/PointsToGrid.cuh:596-645): the order in which the oracle's samplers index a sidecar array"""
+    c = np.asarray(coords, np.int64).reshape(-1, 3)
+    b = c + (1 << 31)
+    tile = ((b[:, 0] >> 12) << 42) | ((b[:, 1] >> 12) << 21) | (b[:, 2] >> 12)
+    up = (((c[:, 0] & 4095) >> 7) << 10) | (((c[:, 1] & 4095) >> 7) << 5) | ((c[:, 2] & 4095) >> 7)
+    lo = (((c[:, 0] & 127) >> 3) << 8) | (((c[:, 1] & 127) >> 3) << 4) | ((c[:, 2] & 127) >> 3)
+    vox = ((c[:, 0] & 7) << 6) | ((c[:, 1] & 7) << 3) | (c[:, 2] & 7)
+    return np.lexsort((vox, lo, up, tile))
+
+
+class OracleMultigrid:
+    """CPU restatement of the product's multigrid pressure solve (hnanosolver_b200/csrc/multigrid.cu), level by level on plain voxel
+    lists. PARITY UNPINNED against the reference (its v_cycle is dead code, src/Cuda/HNanoSolver.cu:399-507); the checks are the fp64
+    Poisson residual and the divergence of the projected velocity."""
+
+    def __init__(self, coords, voxel_size: float, max_levels: int = 16, coarsest_iterations: int = 32, coarsest_omega: float = 1.5):
+        self.levels = []            # (OracleIndex, dx)
+        self.diag = []              # per level: None (fine level: 6 everywhere) or the operator's diagonal
+        c = np.ascontiguousarray(np.asarray(coords, np.int32).reshape(-1, 3))
+        dx = np.float32(voxel_size)
+        while True:
+            ix = OracleIndex(c)
+            k = len(self.levels)
+            self.levels.append((ix, dx))
+            if k == 0:
+                self.diag.append(None)
+            else:
+                d = np.empty(ix.n, np.float32)
+                theta = 0.5 + 2.0 ** (-(k + 1))
+                lib().ora_mg_diag(ix._h, ix.coords.ctypes.data_as(c_i32p), ix.n, np.float32(1.0 / theta - 1.0), d.ctypes.data_as(c_f32p))
+                self.diag.append(d)
+            leaves = np.unique(c >> 3, axis=0).shape[0]
+            if leaves <= 1 or len(self.levels) >= max_levels:
+                break
+            c = np.unique(c >> 1, axis=0).astype(np.int32)
+            c = np.ascontiguousarray(c[nanovdb_value_order(c)])  # sidecar order == index order, as every kernel assumes
+            dx = np.float32(dx * np.float32(2.0))
+        self.coarsest_iterations, self.coarsest_omega = coarsest_iterations, np.float32(coarsest_omega)
+
+    def _smooth(self, k, rhs, p, iters, omega):
+        ix, dx = self.levels[k]
+        for _ in range(iters):
+            for color in (0, 1):
+                if k == 0:
+                    ix.rbgs_color(rhs, p, dx, color, omega)      # the reference's update (src/Cuda/Kernel.cu:591-623)
+                else:
+                    lib().ora_mg_rbgs(ix._h, ix.coords.ctypes.data_as(c_i32p), rhs.ctypes.data_as(c_f32p), p.ctypes.data_as(c_f32p),
+                                      self.diag[k].ctypes.data_as(c_f32p), dx, ix.n, color, omega)
+
+    def residual(self, k, p, rhs):
+        ix, dx = self.levels[k]
+        r = np.empty(ix.n, np.float32)
+        lib().ora_mg_residual(ix._h, ix.coords.ctypes.data_as(c_i32p), ix.n, p.ctypes.data_as(c_f32p), rhs.ctypes.data_as(c_f32p),
+                              self.diag[k].ctypes.data_as(c_f32p) if k else None, dx, r.ctypes.data_as(c_f32p))
+        return r
+
+    def v_cycle(self, p, rhs, nu_pre, nu_post, omega):
+        n = len(self.levels)
+        P, F = [p] + [None] * (n - 1), [rhs] + [None] * (n - 1)
+        for k in range(n - 1):
+            self._smooth(k, F[k], P[k], nu_pre, omega)
+            r = self.residual(k, P[k], F[k])
+            ixc = self.levels[k + 1][0]
+            F[k + 1] = np.empty(ixc.n, np.float32)
+            lib().ora_mg_restrict(self.levels[k][0]._h, r.ctypes.data_as(c_f32p), ixc.coords.ctypes.data_as(c_i32p), ixc.n,
+                                  F[k + 1].ctypes.data_as(c_f32p))
+            P[k + 1] = np.zeros(ixc.n, np.float32)
+        if n > 1:
+            one_leaf = np.unique(self.levels[-1][0].coords >> 3, axis=0).shape[0] == 1
+            self._smooth(n - 1, F[-1], P[-1], self.coarsest_iterations, self.coarsest_omega if one_leaf else omega)
+        else:
+            self._smooth(0, F[0], P[0], nu_pre + nu_post, omega)
+        for k in range(n - 2, -1, -1):
+            ixf = self.levels[k][0]
+            lib().ora_mg_prolong_add(self.levels[k + 1][0]._h, P[k + 1].ctypes.data_as(c_f32p), ixf.coords.ctypes.data_as(c_i32p), ixf.n,
+                                     P[k].ctypes.data_as(c_f32p))
+            self._smooth(k, F[k], P[k], nu_post, omega)
+
+    def residual_sums(self, p, rhs):
+        """{sum (rhs - L p)^2, sum rhs^2} of the fine level, fp64 arithmetic on the fp32 fields"""
+        ix, dx = self.levels[0]
+        p, pp = _f32(p)
+        rhs, rp = _f32(rhs)
+        out = np.zeros(2, np.float64)
+        lib().ora_residual_sums_f64(ix._h, ix.coords.ctypes.data_as(c_i32p), ix.n, pp, rp, float(dx), out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def solve(self, div, cycles, nu_pre=2, nu_post=2, omega=1.0, rel_tol=0.0):
+        div = np.ascontiguousarray(div, np.float32)
+        p = np.zeros_like(div)
+        rel = None
+        done = 0
+        for _ in range(cycles):
+            self.v_cycle(p, div, nu_pre, nu_post, np.float32(omega))
+            done += 1
+            if rel_tol > 0:
+                a, b = self.residual_sums(p, div)
+                rel = float(np.sqrt(a / b)) if b > 0 else 0.0
+                if rel <= rel_tol:
+                    break
+        return p, done, rel
 
 
 def omega_compute(voxel_size: float) -> float:
