@@ -37,6 +37,8 @@ struct hns_mg {
 	std::vector<Level> lv;
 	double* d_sums = nullptr;         // device double[2]
 	double* h_sums = nullptr;         // pinned
+	uint64_t last_nonempty_count = 0;  // of the last level: non-empty leaves, and (when that is 1) which one
+	int64_t last_nonempty_leaf = -1;
 	int coarsest_iterations = 32;
 	float coarsest_omega = 1.5f;      // a one-leaf last level is solved, not smoothed: SOR near its optimum for 8 cells per axis
 	// statistics of the last solve
@@ -111,7 +113,8 @@ int hns_mg_create(const hns_grid* fine, int max_levels, hns_mg** out) {
 	std::vector<std::array<int32_t, 3>> org(L);
 	for (uint64_t l = 0; l < L; ++l) org[l] = {org4[l].x, org4[l].y, org4[l].z};
 	std::vector<uint8_t> mask(L * 64, 0xff);
-	while (L > 1 && int(mg->lv.size()) < max_levels) {
+	uint64_t non_empty = L;  // leaves of the current level that hold at least one cell of the domain
+	while (non_empty > 1 && int(mg->lv.size()) < max_levels) {
 		// parents of this level's leaves, in NanoVDB order
 		std::map<std::array<int32_t, 3>, int32_t, KeyLess> ids;
 		auto parent_origin = [](const std::array<int32_t, 3>& o) { return std::array<int32_t, 3>{(o[0] >> 4) * 8, (o[1] >> 4) * 8, (o[2] >> 4) * 8}; };
@@ -127,16 +130,22 @@ int hns_mg_create(const hns_grid* fine, int max_levels, hns_mg** out) {
 			const int32_t pl = ids[parent_origin(org[l])];
 			parent[l] = pl;
 			const int bx = ((org[l][0] >> 3) & 1) * 4, by = ((org[l][1] >> 3) & 1) * 4, bz = ((org[l][2] >> 3) & 1) * 4;
-			for (int x = 0; x < 8; ++x)
-				for (int y = 0; y < 8; ++y) {
-					const uint8_t m = mask[l * 64 + x * 8 + y];
+			// A cell belongs to the next level iff ALL 8 of its children belong to this one (they lie in this one leaf). Levels 1-3
+			// then cover the domain exactly (a leaf is 8^3 voxels); deeper levels keep only what is fully covered. The opposite rule
+			// ("any child") makes the coarse domains too large around thin features: the coarse correction overshoots there and
+			// V(1,1) cycles diverge on the 512^3 sparse smoke (measured; the "all" rule converges at ~0.1 per V(2,2) cycle).
+			for (int X = 0; X < 4; ++X)
+				for (int Y = 0; Y < 4; ++Y) {
+					const uint8_t m = mask[l * 64 + (2 * X) * 8 + 2 * Y] & mask[l * 64 + (2 * X) * 8 + 2 * Y + 1] & mask[l * 64 + (2 * X + 1) * 8 + 2 * Y] &
+					                  mask[l * 64 + (2 * X + 1) * 8 + 2 * Y + 1];
 					uint8_t pm = 0;  // children z = 2k, 2k + 1 -> parent cell bz + k
 					for (int k = 0; k < 4; ++k)
-						if (m & (3u << (2 * k))) pm |= uint8_t(1u << (bz + k));
-					cmask[uint64_t(pl) * 64 + (bx + (x >> 1)) * 8 + (by + (y >> 1))] |= pm;
+						if (((m >> (2 * k)) & 3u) == 3u) pm |= uint8_t(1u << (bz + k));
+					cmask[uint64_t(pl) * 64 + (bx + X) * 8 + (by + Y)] |= pm;
 				}
 		}
 		for (uint8_t b : cmask) cells += uint64_t(__builtin_popcount(b));
+		if (!cells) break;  // nothing is fully covered any more: the current level is the last
 		// upload: parent table of the current level, then the new level
 		hns_mg::Level& cur = mg->lv.back();
 		if (cudaMalloc(&cur.parent, L * sizeof(int32_t)) != cudaSuccess || cudaMemcpy(cur.parent, parent.data(), L * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -167,6 +176,13 @@ int hns_mg_create(const hns_grid* fine, int max_levels, hns_mg** out) {
 			if (e != cudaSuccess) return bail(fail(HNS_ERR_CUDA, std::string("k_mg_diag: ") + cudaGetErrorString(e)));
 		}
 		L = Lc, org.swap(corg), mask.swap(cmask);
+		non_empty = 0;
+		for (uint64_t l = 0; l < L; ++l) {
+			bool any = false;
+			for (int r = 0; r < 64 && !any; ++r) any = mask[l * 64 + r] != 0;
+			if (any) ++non_empty, mg->last_nonempty_leaf = int64_t(l);
+		}
+		mg->last_nonempty_count = non_empty;
 	}
 	if (cudaMalloc(&mg->d_sums, 2 * sizeof(double)) != cudaSuccess || cudaMallocHost(&mg->h_sums, 2 * sizeof(double)) != cudaSuccess)
 		return bail(fail(HNS_ERR_CUDA, "cudaMalloc(norm sums)"));
@@ -220,7 +236,14 @@ static void v_cycle(hns_mg* mg, hns_state* s, int nu_pre, int nu_post, float ome
 	}
 	{  // coarsest
 		hns_mg::Level& c = mg->lv[n - 1];
-		if (n > 1 && c.grid->num_leaves == 1) launch_mg_coarsest(c.p, c.rhs, c.diag, c.dx, mg->coarsest_omega, mg->coarsest_iterations, st);
+		if (n > 1 && mg->last_nonempty_count == 1) {
+			// the whole level is one brick (its other leaves, if any, hold no cell of the domain and stay 0): solved inside one CTA
+			const uint64_t off = uint64_t(mg->last_nonempty_leaf) * 256u;
+			float* const p1[2] = {c.p[0] + off, c.p[1] + off};
+			const float* const f1[2] = {c.rhs[0] + off, c.rhs[1] + off};
+			const float* const d1[2] = {c.diag[0] + off, c.diag[1] + off};
+			launch_mg_coarsest(p1, f1, d1, c.dx, mg->coarsest_omega, mg->coarsest_iterations, st);
+		}
 		else smooth(n - 1, n > 1 ? mg->coarsest_iterations : nu_pre + nu_post);
 	}
 	for (int k = n - 2; k >= 0; --k) {  // up

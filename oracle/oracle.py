@@ -316,7 +316,8 @@ class OracleMultigrid:
     lists. PARITY UNPINNED against the reference (its v_cycle is dead code, src/Cuda/HNanoSolver.cu:399-507); the checks are the fp64
     Poisson residual and the divergence of the projected velocity."""
 
-    def __init__(self, coords, voxel_size: float, max_levels: int = 16, coarsest_iterations: int = 32, coarsest_omega: float = 1.5):
+    def __init__(self, coords, voxel_size: float, max_levels: int = 16, coarsest_iterations: int = 32, coarsest_omega: float = 1.5,
+                 rule: str = "all"):
         self.levels = []            # (OracleIndex, dx)
         self.diag = []              # per level: None (fine level: 6 everywhere) or the operator's diagonal
         c = np.ascontiguousarray(np.asarray(coords, np.int32).reshape(-1, 3))
@@ -335,7 +336,13 @@ class OracleMultigrid:
             leaves = np.unique(c >> 3, axis=0).shape[0]
             if leaves <= 1 or len(self.levels) >= max_levels:
                 break
-            c = np.unique(c >> 1, axis=0).astype(np.int32)
+            # a cell belongs to the next level iff all 8 of its children belong to this one ("any": iff one of them does -- kept for
+            # the record: it makes coarse domains too large around thin features and the cycle overshoots there)
+            c, cnt = np.unique(c >> 1, axis=0, return_counts=True)
+            c = c[cnt == 8] if rule == "all" else c
+            if c.shape[0] == 0:
+                break
+            c = c.astype(np.int32)
             c = np.ascontiguousarray(c[nanovdb_value_order(c)])  # sidecar order == index order, as every kernel assumes
             dx = np.float32(dx * np.float32(2.0))
         self.coarsest_iterations, self.coarsest_omega = coarsest_iterations, np.float32(coarsest_omega)

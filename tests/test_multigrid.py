@@ -113,7 +113,7 @@ def test_v_cycles_match_the_cpu_restatement(oracle_mod, name):
 
 
 @pytest.mark.gpu
-def test_config3_multigrid_reaches_1e_4_and_a_smaller_divergence_than_rbgs_100(oracle_mod):
+def test_config3_multigrid_reaches_1e_4_and_the_converged_divergence(oracle_mod):
     """BASELINE.json config 3: 256^3-bounded sparse plume, V-cycles to a relative Poisson residual of 1e-4."""
     import hnanosolver_b200 as H
 
@@ -127,17 +127,28 @@ def test_config3_multigrid_reaches_1e_4_and_a_smaller_divergence_than_rbgs_100(o
     div0 = sim.divergence_sum_squares(of_advected=True)
     mg = H.Multigrid(grid)
     cycles, rel = sim.pressure_solve_mg(mg, 20, 1e-4, 2, 2, 1.15)
-    assert rel <= 1e-4 and cycles <= 12, (cycles, rel)
+    assert rel <= 1e-4 and cycles <= 8, (cycles, rel)
     sim.subtract_gradient(True)
     div_mg = sim.divergence_sum_squares(of_advected=False)
-    # the reference's solve at the top of the SOP's iteration range (I = 100) on the same input
-    sim.divergence(True)
-    sim.pressure_solve(100, O.omega_compute(w.voxel_size))
-    rel_rbgs = sim.relative_residual()
-    sim.subtract_gradient(True)
-    div_rbgs = sim.divergence_sum_squares(of_advected=False)
-    assert rel < rel_rbgs
-    assert div_mg <= div_rbgs * (1 + 1e-6) and div_mg < div0, (div0, div_mg, div_rbgs)
+
+    def rbgs(iterations):
+        sim.divergence(True)
+        sim.pressure_solve(iterations, O.omega_compute(w.voxel_size))
+        r = sim.relative_residual()
+        sim.subtract_gradient(True)
+        return r, sim.divergence_sum_squares(of_advected=False)
+
+    # the reference's solve at the top of the SOP's iteration range (I = 100) on the same input, and run far beyond it
+    rel_100, div_100 = rbgs(100)
+    rel_inf, div_inf = rbgs(3000)
+    assert rel < rel_100 and div_mg < div0
+    # The divergence and the gradient are 2h central differences while the operator is the compact 7-point Laplacian,
+    # so ||div(u_new)|| does not go to zero: it goes to the value the CONVERGED pressure gives, which the reference's own sweep
+    # approaches from below as I grows (an under-converged pressure leaves a slightly smaller central-difference divergence).
+    # Gate: the multigrid result sits at that converged value (0.3 %), and within 2 % of the reference's I = 100 result.
+    assert rel_inf < 5e-3
+    assert abs(np.sqrt(div_mg) - np.sqrt(div_inf)) <= 3e-3 * np.sqrt(div_inf), (div_mg, div_inf)
+    assert np.sqrt(div_mg) <= 1.02 * np.sqrt(div_100), (div0, div_mg, div_100)
 
 
 @pytest.mark.gpu
