@@ -1,0 +1,546 @@
+// Semi-Lagrangian BFECC advection, second generation (reference src/Cuda/Kernel.cu:118-266 advect_scalars, :269-352 advect_scalar,
+// :354-453 advect_vector; samplers src/Utils/Stencils.hpp:25-173).
+//
+// Same data flow as the first generation in kernels.cu -- persistent CTAs of 512 threads (one per voxel of a leaf), two per SM, the
+// 14 x 14 x 16 region around the leaf staged into a double-buffered shared-memory tile with 16-byte cp.async one stage ahead -- but
+// the per-voxel instruction stream is cut to what the arithmetic needs (ncu of the first generation: 1535 instructions per voxel in
+// advect_scalars at S = 5, issue slots 63 % busy, i.e. instruction bound):
+//   * the staging plan of a thread (which two quads of the region it copies, from which neighbour slot and leaf offset) depends on
+//     the thread only: decoded once per kernel instead of once per leaf (it contained an integer division);
+//   * a leaf's metadata (27 neighbour ids, origin, id) travels through a shared-memory ring one leaf ahead, so no stage starts with a
+//     dependent chain of global loads;
+//   * the values "inactive" cells take (0, or array element 0 for advect_scalars) are read once per kernel, not once per stage;
+//   * the shared trace of advect_scalars keeps 6 weight factors per sample (4 xy products, 2 z factors) instead of recomputing all 8
+//     corner weights from the fractions for every field; a corner weight is one more multiply, rounded exactly like the reference's
+//     two-step product (Kernel.cu:169-183);
+//   * scalar stages are compiled for 1, 2 and 3 fields (no run-time loop over fields, no run-time-indexed pointer tables);
+//   * there is NO cold path inside the hot kernels: a voxel whose sample footprint leaves the region (back-trace longer than 3 voxels;
+//     the reference has no CFL limit) only raises its leaf's flag, and a second kernel redoes flagged leaves voxel by voxel through
+//     the neighbour table / tree walk (sampling.cuh). With CFL <= 2.5 no leaf is flagged and that kernel is a few microseconds of
+//     flag reads. Results do not depend on which kernel produced a voxel: both evaluate the reference's expressions in its order.
+// The hasCollision variants keep their two SDF samples per voxel as global gathers (sampling.cuh), as before.
+#include <cstdlib>
+
+#include "kernels.cuh"
+#include "sampling.cuh"
+
+namespace hns {
+namespace {
+
+__device__ __forceinline__ void cp16(float* smem_dst, const float* gsrc) {
+	const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp4(int* smem_dst, const int* gsrc) {
+	const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+constexpr int kMeta = 32, kMetaOx = 27, kMetaLeaf = 30;  // ring slot: nbr[27], origin x y z, leaf id
+
+// metadata of work item `w` into a ring slot: asynchronously (rides in the caller's cp.async group) or right now
+__device__ __forceinline__ void meta_fetch(const GridView& g, int* slot, uint32_t w, bool async) {
+	const int t = threadIdx.x;
+	if (t < 31) {
+		const uint32_t leaf = g.leaf_at(w);
+		if (t < 27) {
+			if (async) cp4(slot + t, g.nbr + uint64_t(leaf) * 27u + t);
+			else slot[t] = __ldg(g.nbr + uint64_t(leaf) * 27u + t);
+		} else if (t < 30) {
+			if (async) cp4(slot + t, reinterpret_cast<const int*>(g.origin + leaf) + (t - 27));
+			else slot[t] = __ldg(reinterpret_cast<const int*>(g.origin + leaf) + (t - 27));
+		} else {
+			slot[kMetaLeaf] = int(leaf);
+		}
+	}
+}
+
+// Thread-constant staging plan: quads `threadIdx.x` and `threadIdx.x + 512` of the 784 the region has per field. The quads are dealt so
+// that 8 consecutive lanes cover 4 rows x 2 quads: with the 24-float row pitch their eight 16-byte stores hit 32 distinct banks.
+struct Stager {
+	int dst[2];   // float offset in the region; -1: nothing to copy
+	int slot[2];  // neighbour slot of the source leaf
+	int src[2];   // float offset inside the source leaf
+};
+__device__ __forceinline__ Stager make_stager() {
+	Stager p;
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		const int it = threadIdx.x + 512 * k;
+		p.dst[k] = -1, p.slot[k] = kSlotSelf, p.src[k] = 0;
+		if (it < kRegionQuads) {
+			const int sub = it & 15, row = (it >> 4) * 4 + (sub & 3), q = ((sub >> 3) << 1) | ((sub >> 2) & 1);
+			const int rx = row / kRX, ry = row - rx * kRX;
+			const int lx = rx - kHaloXY, ly = ry - kHaloXY;  // leaf-local x, y in [-3, 11)
+			const int dz = q == 0 ? -1 : (q == 3 ? 1 : 0);   // z in [-4,0) | [0,4) | [4,8) | [8,12)
+			p.dst[k] = rx * kPlane + ry * kPitch + q * 4;
+			p.slot[k] = ((lx >> 3) + 1) * 9 + ((ly >> 3) + 1) * 3 + dz + 1;
+			p.src[k] = ((lx & 7) << 6) | ((ly & 7) << 3) | ((q == 1 || q == 3) ? 0 : 4);
+		}
+	}
+	return p;
+}
+// starts the fill of NF regions (consecutive in shared memory) from NF brick fields; cells of missing leaves get fill[k]
+template <int NF>
+__device__ __forceinline__ void stage(const Stager& p, const int* __restrict__ meta, const float* const (&f)[NF], float* __restrict__ dst,
+                                      const float* __restrict__ fill) {
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		if (p.dst[k] < 0) continue;
+		const int l = meta[p.slot[k]];
+		float* d = dst + p.dst[k];
+		if (l >= 0) {
+			const uint32_t s = uint32_t(l) * 512u + uint32_t(p.src[k]);
+#pragma unroll
+			for (int i = 0; i < NF; ++i) cp16(d + i * kRegionFloats, f[i] + s);
+		} else {
+#pragma unroll
+			for (int i = 0; i < NF; ++i) {
+				const float v = fill[i];
+				*reinterpret_cast<float4*>(d + i * kRegionFloats) = make_float4(v, v, v, v);
+			}
+		}
+	}
+}
+
+// region offset of the cell (i,j,k) given relative to the leaf origin, or -1 when the 2x2x2 footprint starting there leaves the region
+__device__ __forceinline__ int footprint(int ri, int rj, int rk) {
+	const int rx = ri + kHaloXY, ry = rj + kHaloXY, rz = rk + kHaloZ;
+	if (unsigned(rx) >= unsigned(kRX - 1) || unsigned(ry) >= unsigned(kRX - 1) || unsigned(rz) >= unsigned(kRZ - 1)) return -1;
+	return rx * kPlane + ry * kPitch + rz;
+}
+// TrilinearSampler: lerp z, then y, then x (Stencils.hpp:144-152); r points at the footprint's first cell
+__device__ __forceinline__ float tri_lerp(const float* __restrict__ r, float fx, float fy, float fz) {
+	const float z0 = lerpf(r[0], r[1], fz), z1 = lerpf(r[kPitch], r[kPitch + 1], fz);
+	const float z2 = lerpf(r[kPlane], r[kPlane + 1], fz), z3 = lerpf(r[kPlane + kPitch], r[kPlane + kPitch + 1], fz);
+	return lerpf(lerpf(z0, z1, fy), lerpf(z2, z3, fy), fx);
+}
+// advect_scalars' weighted sum (Kernel.cu:186-206, 239-243): corners in the order (i0j0k0),(i1j0k0),(i0j1k0),(i1j1k0),(i0j0k1),...;
+// wxy = {itx*ity, tx*ity, itx*ty, tx*ty}, wz = {itz, tz}; corner weight = wxy * wz, one rounding each like the reference's products
+struct Weights {
+	float xy[4], z[2];
+};
+__device__ __forceinline__ Weights make_weights(float tx, float ty, float tz) {
+	const float itx = 1.0f - tx, ity = 1.0f - ty;
+	return Weights{{itx * ity, tx * ity, itx * ty, tx * ty}, {1.0f - tz, tz}};
+}
+__device__ __forceinline__ float tri_weighted(const float* __restrict__ r, const Weights& w) {
+	float acc = 0.f;
+	acc = fmaf(r[0], w.xy[0] * w.z[0], acc);
+	acc = fmaf(r[kPlane], w.xy[1] * w.z[0], acc);
+	acc = fmaf(r[kPitch], w.xy[2] * w.z[0], acc);
+	acc = fmaf(r[kPlane + kPitch], w.xy[3] * w.z[0], acc);
+	acc = fmaf(r[1], w.xy[0] * w.z[1], acc);
+	acc = fmaf(r[kPlane + 1], w.xy[1] * w.z[1], acc);
+	acc = fmaf(r[kPitch + 1], w.xy[2] * w.z[1], acc);
+	acc = fmaf(r[kPlane + kPitch + 1], w.xy[3] * w.z[1], acc);
+	return acc;
+}
+// min / max over the cell and its six face neighbours (Kernel.cu:250-258, 402-421)
+__device__ __forceinline__ void clamp_range(const float* __restrict__ r, float own, float& mn, float& mx) {
+	const float a = r[-kPlane], b = r[kPlane], c = r[-kPitch], d = r[kPitch], e = r[-1], f = r[1];
+	mn = fminf(fminf(fminf(own, a), fminf(b, c)), fminf(fminf(d, e), f));
+	mx = fmaxf(fmaxf(fmaxf(own, a), fmaxf(b, c)), fmaxf(fmaxf(d, e), f));
+}
+
+struct Items {
+	uint32_t base, stride, count;
+	__device__ __forceinline__ uint32_t at(uint32_t k) const { return base + k * stride; }
+};
+// CTA b takes work items b, b + G, b + 2G, ...: the whole grid advances through the leaf list together, so the x-neighbour planes a
+// region needs are still in the L2 from the CTAs that staged them a moment ago (kernels.cu CtaItems has the measurement)
+__device__ __forceinline__ Items cta_items2(const GridView& g) {
+	Items it;
+	it.base = blockIdx.x, it.stride = gridDim.x;
+	it.count = it.base < g.count() ? (g.count() - it.base + gridDim.x - 1) / gridDim.x : 0u;
+	return it;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// advect_vector
+// ---------------------------------------------------------------------------------------------------------------------------------
+template <bool kCollision>
+__global__ void __launch_bounds__(512, 2) k_advect_vector2(GridView g, const float* __restrict__ u, const float* __restrict__ v,
+                                                           const float* __restrict__ w, float* __restrict__ ou, float* __restrict__ ov,
+                                                           float* __restrict__ ow, float sdt, const float* __restrict__ sdf,
+                                                           uint8_t* __restrict__ cold) {
+	extern __shared__ __align__(16) float region[];
+	__shared__ int meta[3][kMeta];
+	__shared__ float fill[3];
+	const Items items = cta_items2(g);
+	if (!items.count) return;
+	const int tid = threadIdx.x;
+	const int x = tid >> 6, y = (tid >> 3) & 7, z = tid & 7;
+	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
+	const Stager stg = make_stager();
+	const float* const fields[3] = {u, v, w};
+	if (tid < 3) fill[tid] = 0.f;
+	meta_fetch(g, meta[0], items.at(0), false);
+	__syncthreads();
+	auto issue = [&](uint32_t k) {  // stage item k (its metadata is in the ring); the next item's metadata rides along
+		stage<3>(stg, meta[k % 3], fields, region + (k & 1) * kStageFloats, fill);
+		if (k + 1 < items.count) meta_fetch(g, meta[(k + 1) % 3], items.at(k + 1), true);
+		cp_commit();
+	};
+	issue(0);
+	for (uint32_t k = 0; k < items.count; ++k) {
+		cp_wait_all();
+		__syncthreads();  // item k's region and item k+1's metadata have landed for every thread; nobody reads the other buffer any more
+		if (k + 1 < items.count) issue(k + 1);
+		const float* __restrict__ ru = region + (k & 1) * kStageFloats + c;
+		const float* __restrict__ rv = ru + kRegionFloats;
+		const float* __restrict__ rw = rv + kRegionFloats;
+		const int* m = meta[k % 3];
+		const uint32_t leaf = uint32_t(m[kMetaLeaf]);
+		const float u0 = ru[0], v0 = rv[0], w0 = rw[0];
+		// positions relative to the leaf origin are exact in fp32 only for the fractions; keep the reference's absolute arithmetic
+		const int ox = m[kMetaOx], oy = m[kMetaOx + 1], oz = m[kMetaOx + 2];
+		const float px = float(ox + x), py = float(oy + y), pz = float(oz + z);
+		float bx = fmaf(-sdt, u0, px), by = fmaf(-sdt, v0, py), bz = fmaf(-sdt, w0, pz);  // Kernel.cu:374
+		LeafFrame lf{ox, oy, oz, g.nbr + uint64_t(leaf) * 27u};
+		if (kCollision && trilinear_f(g, lf, sdf, bx, by, bz) < 0.0f) bx = px, by = py, bz = pz;  // :377-382
+		const int bi = __float2int_rd(bx), bj = __float2int_rd(by), bk = __float2int_rd(bz);
+		const int fb = footprint(bi - ox, bj - oy, bk - oz);
+		if (fb < 0) {
+			cold[leaf] = 1;
+			continue;
+		}
+		const int db = fb - c;
+		const float tx = bx - float(bi), ty = by - float(bj), tz = bz - float(bk);
+		const float uf = tri_lerp(ru + db, tx, ty, tz), vf = tri_lerp(rv + db, tx, ty, tz), wf = tri_lerp(rw + db, tx, ty, tz);
+		float fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :387
+		if (kCollision && trilinear_f(g, lf, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;  // :390-394
+		const int fi = __float2int_rd(fx), fj = __float2int_rd(fy), fk = __float2int_rd(fz);
+		const int ff = footprint(fi - ox, fj - oy, fk - oz);
+		if (ff < 0) {
+			cold[leaf] = 1;
+			continue;
+		}
+		const int df = ff - c;
+		const float sx = fx - float(fi), sy = fy - float(fj), sz = fz - float(fk);
+		const float ub = tri_lerp(ru + df, sx, sy, sz), vb = tri_lerp(rv + df, sx, sy, sz), wb = tri_lerp(rw + df, sx, sy, sz);
+		const float cu = fmaf(0.5f, u0 - ub, uf), cv = fmaf(0.5f, v0 - vb, vf), cw = fmaf(0.5f, w0 - wb, wf);  // :399-400
+		float mn, mx;
+		const uint32_t self = leaf * 512u + uint32_t(tid);
+		clamp_range(ru, u0, mn, mx);
+		ou[self] = fmaxf(fminf(mn, uf), fminf(cu, fmaxf(mx, uf)));  // :402-429
+		clamp_range(rv, v0, mn, mx);
+		ov[self] = fmaxf(fminf(mn, vf), fminf(cv, fmaxf(mx, vf)));
+		clamp_range(rw, w0, mn, mx);
+		ow[self] = fmaxf(fminf(mn, wf), fminf(cw, fmaxf(mx, wf)));
+	}
+}
+
+// Flagged leaves again, voxel by voxel through the neighbour table / tree walk: the reference's expressions with IndexSampler
+// semantics (inactive -> 0). One CTA per flagged leaf, grid-stride over the work list.
+template <bool kCollision>
+__global__ void __launch_bounds__(512) k_advect_vector_cold(GridView g, const float* __restrict__ u, const float* __restrict__ v,
+                                                            const float* __restrict__ w, float* __restrict__ ou, float* __restrict__ ov,
+                                                            float* __restrict__ ow, float sdt, const float* __restrict__ sdf, uint8_t* cold) {
+	const int tid = threadIdx.x;
+	const int x = tid >> 6, y = (tid >> 3) & 7, z = tid & 7;
+	for (uint32_t i = blockIdx.x; i < g.count(); i += gridDim.x) {
+		const uint32_t leaf = g.leaf_at(i);
+		if (!cold[leaf]) continue;
+		const int4 o = __ldg(g.origin + leaf);
+		const LeafFrame f{o.x, o.y, o.z, g.nbr + uint64_t(leaf) * 27u};
+		const uint64_t self = uint64_t(leaf) * 512u + uint32_t(tid);
+		const int ci = o.x + x, cj = o.y + y, ck = o.z + z;
+		const float u0 = __ldg(u + self), v0 = __ldg(v + self), w0 = __ldg(w + self);
+		float bx = fmaf(-sdt, u0, float(ci)), by = fmaf(-sdt, v0, float(cj)), bz = fmaf(-sdt, w0, float(ck));
+		if (kCollision && trilinear_f(g, f, sdf, bx, by, bz) < 0.0f) bx = float(ci), by = float(cj), bz = float(ck);
+		float uf, vf, wf, ub, vb, wb;
+		trilinear_vec(g, f, u, v, w, bx, by, bz, uf, vf, wf);
+		float fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);
+		if (kCollision && trilinear_f(g, f, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;
+		trilinear_vec(g, f, u, v, w, fx, fy, fz, ub, vb, wb);
+		const float cu = fmaf(0.5f, u0 - ub, uf), cv = fmaf(0.5f, v0 - vb, vf), cw = fmaf(0.5f, w0 - wb, wf);
+		float mnu = u0, mxu = u0, mnv = v0, mxv = v0, mnw = w0, mxw = w0;
+#pragma unroll 1
+		for (int q = 0; q < 6; ++q) {
+			const int d = (q & 1) ? 1 : -1;
+			const int64_t t = voxel_index(g, f, ci + (q < 2 ? d : 0), cj + ((q >> 1) == 1 ? d : 0), ck + (q >= 4 ? d : 0));
+			const float nu = t < 0 ? 0.f : __ldg(u + t), nv = t < 0 ? 0.f : __ldg(v + t), nw = t < 0 ? 0.f : __ldg(w + t);
+			mnu = fminf(mnu, nu), mxu = fmaxf(mxu, nu), mnv = fminf(mnv, nv), mxv = fmaxf(mxv, nv), mnw = fminf(mnw, nw), mxw = fmaxf(mxw, nw);
+		}
+		ou[self] = fmaxf(fminf(mnu, uf), fminf(cu, fmaxf(mxu, uf)));
+		ov[self] = fmaxf(fminf(mnv, vf), fminf(cv, fmaxf(mxv, vf)));
+		ow[self] = fmaxf(fminf(mnw, wf), fminf(cw, fmaxf(mxw, wf)));
+		__syncthreads();  // every thread has read the flag before it is cleared for the next launch
+		if (tid == 0) cold[leaf] = 0;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// advect_scalars (kSem 0: Kernel.cu:118-266, inactive -> array element 0) / advect_scalar per field (kSem 1: :269-352, inactive -> 0)
+// ---------------------------------------------------------------------------------------------------------------------------------
+struct Trace {  // of one voxel, shared by all its scalar fields
+	int db, df;     // footprint offsets of the back-traced / forward-traced sample relative to the voxel's own cell; db == INT_MIN: cold
+	Weights wb, wf;  // kSem 0
+	float tb[3], tf[3];  // kSem 1: fractions
+};
+
+template <int kSem, int NS>
+__device__ __forceinline__ void scalar_fields(const float* __restrict__ base, const Trace& t, float* const (&out)[NS], uint32_t self) {
+#pragma unroll
+	for (int k = 0; k < NS; ++k) {
+		const float* __restrict__ r = base + k * kRegionFloats;
+		const float phi0 = r[0];
+		float phiF, phiB;
+		if (kSem == 0) {
+			phiF = tri_weighted(r + t.db, t.wb);  // Kernel.cu:239-243
+			phiB = tri_weighted(r + t.df, t.wf);
+		} else {
+			phiF = tri_lerp(r + t.db, t.tb[0], t.tb[1], t.tb[2]);
+			phiB = tri_lerp(r + t.df, t.tf[0], t.tf[1], t.tf[2]);
+		}
+		const float corr = fmaf(0.5f, phi0 - phiB, phiF);  // :246-247
+		float mn, mx;
+		clamp_range(r, phi0, mn, mx);  // :253-258
+		out[k][self] = fmaxf(fminf(mn, phiF), fminf(corr, fmaxf(mx, phiF)));  // :264
+	}
+}
+
+template <int kSem, bool kCollision>
+__global__ void __launch_bounds__(512, 2) k_advect_scalars2(GridView g, const float* __restrict__ u, const float* __restrict__ v,
+                                                            const float* __restrict__ w, const __grid_constant__ ScalarPtrs sp, int S, float sdt,
+                                                            const float* __restrict__ elem0, const float* __restrict__ sdf,
+                                                            uint8_t* __restrict__ cold) {
+	extern __shared__ __align__(16) float region[];
+	__shared__ int meta[3][kMeta];
+	__shared__ float fill[3 + 16];
+	const Items items = cta_items2(g);
+	if (!items.count) return;
+	const int tid = threadIdx.x;
+	const int x = tid >> 6, y = (tid >> 3) & 7, z = tid & 7;
+	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
+	const Stager stg = make_stager();
+	// what inactive cells hold: advect_scalars reads array element 0 (of the GLOBAL arrays: elem0 when given), advect_scalar reads 0
+	if (tid < 3 + S) {
+		float f = 0.f;
+		if (kSem == 0) f = elem0 ? __ldg(elem0 + tid) : (tid == 0 ? __ldg(u) : tid == 1 ? __ldg(v) : tid == 2 ? __ldg(w) : __ldg(sp.in[tid - 3]));
+		fill[tid] = f;
+	}
+	const int groups = (S + 2) / 3, jobs_per_leaf = 1 + groups;
+	const uint32_t n_jobs = items.count * uint32_t(jobs_per_leaf);
+	meta_fetch(g, meta[0], items.at(0), false);
+	__syncthreads();
+	uint32_t issue_item = 0;
+	int issue_jj = 0;  // the job to issue next: (item, stage within the item)
+	auto issue = [&](uint32_t job) {
+		float* dst = region + (job & 1) * kStageFloats;
+		const int* m = meta[issue_item % 3];
+		if (issue_jj == 0) {
+			const float* const f3[3] = {u, v, w};
+			stage<3>(stg, m, f3, dst, fill);
+			if (issue_item + 1 < items.count) meta_fetch(g, meta[(issue_item + 1) % 3], items.at(issue_item + 1), true);
+		} else {
+			const int s0 = 3 * (issue_jj - 1), ns = min(3, S - s0);
+			if (ns == 3) {
+				const float* const f3[3] = {sp.in[s0], sp.in[s0 + 1], sp.in[s0 + 2]};
+				stage<3>(stg, m, f3, dst, fill + 3 + s0);
+			} else if (ns == 2) {
+				const float* const f2[2] = {sp.in[s0], sp.in[s0 + 1]};
+				stage<2>(stg, m, f2, dst, fill + 3 + s0);
+			} else {
+				const float* const f1[1] = {sp.in[s0]};
+				stage<1>(stg, m, f1, dst, fill + 3 + s0);
+			}
+		}
+		cp_commit();
+		if (++issue_jj == jobs_per_leaf) issue_jj = 0, ++issue_item;
+	};
+	Trace t;
+	t.db = t.df = 0;
+	bool is_cold = false;
+	uint32_t item = 0;
+	int jj = 0;
+	issue(0);
+	for (uint32_t job = 0; job < n_jobs; ++job) {
+		cp_wait_all();
+		__syncthreads();
+		if (job + 1 < n_jobs) issue(job + 1);
+		const float* __restrict__ base = region + (job & 1) * kStageFloats + c;
+		const int* m = meta[item % 3];
+		const uint32_t leaf = uint32_t(m[kMetaLeaf]);
+		if (jj == 0) {
+			// ---- the shared trace through the staged velocity (Kernel.cu:126-214) ----
+			const float *ru = base, *rv = base + kRegionFloats, *rw = base + 2 * kRegionFloats;
+			const int ox = m[kMetaOx], oy = m[kMetaOx + 1], oz = m[kMetaOx + 2];
+			const float px = float(ox + x), py = float(oy + y), pz = float(oz + z);
+			float bx = fmaf(-sdt, ru[0], px), by = fmaf(-sdt, rv[0], py), bz = fmaf(-sdt, rw[0], pz);
+			LeafFrame lf{ox, oy, oz, g.nbr + uint64_t(leaf) * 27u};
+			// hasCollision (:142-155): the reference tests the back-traced position twice; the second test sees either the same position
+			// or the voxel itself and resets to the voxel again, so one test decides
+			if (kCollision && trilinear_f(g, lf, sdf, bx, by, bz) < 0.0f) bx = px, by = py, bz = pz;
+			const int bi = __float2int_rd(bx), bj = __float2int_rd(by), bk = __float2int_rd(bz);
+			const int fb = footprint(bi - ox, bj - oy, bk - oz);
+			is_cold = fb < 0;
+			if (!is_cold) {
+				t.db = fb - c;
+				const float tx = bx - float(bi), ty = by - float(bj), tz = bz - float(bk);
+				float uf, vf, wf;
+				if (kSem == 0) {
+					t.wb = make_weights(tx, ty, tz);
+					uf = tri_weighted(ru + t.db, t.wb), vf = tri_weighted(rv + t.db, t.wb), wf = tri_weighted(rw + t.db, t.wb);  // :201-206
+				} else {
+					t.tb[0] = tx, t.tb[1] = ty, t.tb[2] = tz;
+					uf = tri_lerp(ru + t.db, tx, ty, tz), vf = tri_lerp(rv + t.db, tx, ty, tz), wf = tri_lerp(rw + t.db, tx, ty, tz);
+				}
+				float fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :208
+				if (kCollision && trilinear_f(g, lf, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;  // :211-214
+				const int fi = __float2int_rd(fx), fj = __float2int_rd(fy), fk = __float2int_rd(fz);
+				const int ff = footprint(fi - ox, fj - oy, fk - oz);
+				is_cold = ff < 0;
+				t.df = ff - c;
+				const float sx = fx - float(fi), sy = fy - float(fj), sz = fz - float(fk);
+				if (kSem == 0) t.wf = make_weights(sx, sy, sz);
+				else t.tf[0] = sx, t.tf[1] = sy, t.tf[2] = sz;
+			}
+			if (is_cold) cold[leaf] = 1;
+		} else if (!is_cold) {
+			const int s0 = 3 * (jj - 1), ns = min(3, S - s0);
+			const uint32_t self = leaf * 512u + uint32_t(tid);
+			if (ns == 3) {
+				float* const o3[3] = {sp.out[s0], sp.out[s0 + 1], sp.out[s0 + 2]};
+				scalar_fields<kSem, 3>(base, t, o3, self);
+			} else if (ns == 2) {
+				float* const o2[2] = {sp.out[s0], sp.out[s0 + 1]};
+				scalar_fields<kSem, 2>(base, t, o2, self);
+			} else {
+				float* const o1[1] = {sp.out[s0]};
+				scalar_fields<kSem, 1>(base, t, o1, self);
+			}
+		}
+		if (++jj == jobs_per_leaf) jj = 0, ++item;
+	}
+}
+
+template <int kSem, bool kCollision>
+__global__ void __launch_bounds__(512) k_advect_scalars_cold(GridView g, const float* __restrict__ u, const float* __restrict__ v,
+                                                             const float* __restrict__ w, const __grid_constant__ ScalarPtrs sp, int S, float sdt,
+                                                             const float* __restrict__ elem0, const float* __restrict__ sdf, uint8_t* cold) {
+	const int tid = threadIdx.x;
+	const int x = tid >> 6, y = (tid >> 3) & 7, z = tid & 7;
+	for (uint32_t i = blockIdx.x; i < g.count(); i += gridDim.x) {
+		const uint32_t leaf = g.leaf_at(i);
+		if (!cold[leaf]) continue;
+		const int4 o = __ldg(g.origin + leaf);
+		const LeafFrame f{o.x, o.y, o.z, g.nbr + uint64_t(leaf) * 27u};
+		const uint64_t self = uint64_t(leaf) * 512u + uint32_t(tid);
+		const int ci = o.x + x, cj = o.y + y, ck = o.z + z;
+		const float *eu = elem0 ? elem0 : u, *ev = elem0 ? elem0 + 1 : v, *ew = elem0 ? elem0 + 2 : w;
+		float bx = fmaf(-sdt, __ldg(u + self), float(ci)), by = fmaf(-sdt, __ldg(v + self), float(cj)), bz = fmaf(-sdt, __ldg(w + self), float(ck));
+		if (kCollision && trilinear_f(g, f, sdf, bx, by, bz) < 0.0f) bx = float(ci), by = float(cj), bz = float(ck);
+		const int bi = __float2int_rd(bx), bj = __float2int_rd(by), bk = __float2int_rd(bz);
+		const float btx = bx - float(bi), bty = by - float(bj), btz = bz - float(bk);
+		float uf, vf, wf;
+		if (kSem == 0) {
+			uf = far_weighted(g, f, u, eu, bi, bj, bk, btx, bty, btz);
+			vf = far_weighted(g, f, v, ev, bi, bj, bk, btx, bty, btz);
+			wf = far_weighted(g, f, w, ew, bi, bj, bk, btx, bty, btz);
+		} else {
+			trilinear_vec(g, f, u, v, w, bx, by, bz, uf, vf, wf);
+		}
+		float fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);
+		if (kCollision && trilinear_f(g, f, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;
+		const int fi = __float2int_rd(fx), fj = __float2int_rd(fy), fk = __float2int_rd(fz);
+		const float ftx = fx - float(fi), fty = fy - float(fj), ftz = fz - float(fk);
+		int64_t nb[6];
+#pragma unroll
+		for (int q = 0; q < 6; ++q) {
+			const int d = (q & 1) ? 1 : -1;
+			nb[q] = voxel_index(g, f, ci + (q < 2 ? d : 0), cj + ((q >> 1) == 1 ? d : 0), ck + (q >= 4 ? d : 0));
+		}
+#pragma unroll 1
+		for (int k = 0; k < S; ++k) {
+			const float* __restrict__ a = sp.in[k];
+			const float* e0 = elem0 ? elem0 + 3 + k : a;
+			const float phi0 = __ldg(a + self);
+			float phiF, phiB;
+			if (kSem == 0) {
+				phiF = far_weighted(g, f, a, e0, bi, bj, bk, btx, bty, btz);
+				phiB = far_weighted(g, f, a, e0, fi, fj, fk, ftx, fty, ftz);
+			} else {
+				phiF = trilinear_f(g, f, a, bx, by, bz);
+				phiB = trilinear_f(g, f, a, fx, fy, fz);
+			}
+			const float corr = fmaf(0.5f, phi0 - phiB, phiF);
+			float mn = phi0, mx = phi0;
+#pragma unroll
+			for (int q = 0; q < 6; ++q) {
+				const float val = nb[q] < 0 ? (kSem == 0 ? __ldg(e0) : 0.f) : __ldg(a + nb[q]);
+				mn = fminf(mn, val), mx = fmaxf(mx, val);
+			}
+			sp.out[k][self] = fmaxf(fminf(mn, phiF), fminf(corr, fmaxf(mx, phiF)));
+		}
+		__syncthreads();
+		if (tid == 0) cold[leaf] = 0;
+	}
+}
+
+// ---- launch plumbing -------------------------------------------------------------------------------------------------------------
+struct DeviceInfo {
+	int sms = 0;
+	bool attrs = false;
+};
+DeviceInfo& device_info() {  // per device: function attributes and the SM count belong to a device, not to the process
+	static DeviceInfo info[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	DeviceInfo& d = info[dev & 63];
+	if (!d.sms) {
+		cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+		if (d.sms <= 0) d.sms = 148;
+	}
+	return d;
+}
+template <typename K>
+void opt_in(K kernel) {
+	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAdvectSmem));
+	cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+void ensure_attrs(DeviceInfo& d) {
+	if (d.attrs) return;
+	opt_in(k_advect_vector2<false>), opt_in(k_advect_vector2<true>);
+	opt_in(k_advect_scalars2<0, false>), opt_in(k_advect_scalars2<1, false>);
+	opt_in(k_advect_scalars2<0, true>), opt_in(k_advect_scalars2<1, true>);
+	d.attrs = true;
+}
+
+}  // namespace
+
+void launch_advect_vector2(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st, const float* sdf,
+                           uint8_t* cold) {
+	if (!g.count()) return;
+	DeviceInfo& d = device_info();
+	ensure_attrs(d);
+	const int grid = int(std::min<uint32_t>(uint32_t(2 * d.sms), g.count()));
+	const float sdt = dt * inv_dx;
+	if (sdf) {
+		HNS_LAUNCH(k_advect_vector2<true>, grid, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
+		HNS_LAUNCH(k_advect_vector_cold<true>, grid, 512, 0, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
+	} else {
+		HNS_LAUNCH(k_advect_vector2<false>, grid, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
+		HNS_LAUNCH(k_advect_vector_cold<false>, grid, 512, 0, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
+	}
+}
+
+void launch_advect_scalars2(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx, int sampler_semantics,
+                            const float* elem0, cudaStream_t st, const float* sdf, uint8_t* cold) {
+	if (!g.count() || S <= 0) return;
+	DeviceInfo& d = device_info();
+	ensure_attrs(d);
+	const int grid = int(std::min<uint32_t>(uint32_t(2 * d.sms), g.count()));
+	const float sdt = dt * inv_dx;
+	auto hot = sampler_semantics == 0 ? (sdf ? k_advect_scalars2<0, true> : k_advect_scalars2<0, false>)
+	                                  : (sdf ? k_advect_scalars2<1, true> : k_advect_scalars2<1, false>);
+	auto cold_k = sampler_semantics == 0 ? (sdf ? k_advect_scalars_cold<0, true> : k_advect_scalars_cold<0, false>)
+	                                     : (sdf ? k_advect_scalars_cold<1, true> : k_advect_scalars_cold<1, false>);
+	HNS_LAUNCH(hot, grid, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, sdt, elem0, sdf, cold);
+	HNS_LAUNCH(cold_k, grid, 512, 0, st, g, vel[0], vel[1], vel[2], sp, S, sdt, elem0, sdf, cold);
+}
+
+}  // namespace hns

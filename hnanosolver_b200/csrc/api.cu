@@ -90,7 +90,7 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 	const float h = voxel_size, inv = 1.0f / h;
 	const float* sdf = s->collision_sdf();
 	if (sdf) launch_collision_boundary(g, s->vel, s->vel, sdf, inv, 0.1f, 0, st);  // enforceCollisionBoundaries, HNanoSolver.cu:153-157
-	launch_advect_vector(g, s->vel, s->adv, dt, inv, st, sdf);
+	launch_advect_vector(g, s->vel, s->adv, dt, inv, st, sdf, s->cold);
 	if (s->comb_enabled) {
 		const int rc = vorticity_pass(s, dt, inv, s->comb.vorticityScale, s->comb.factorScale, st);
 		if (rc) return rc;
@@ -128,7 +128,7 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 			sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i];
 			++S;
 		}
-		launch_advect_scalars(g, s->vel, sp, S, dt, inv, 0, s->elem0, st, sdf);
+		launch_advect_scalars(g, s->vel, sp, S, dt, inv, 0, s->elem0, st, sdf, s->cold);
 		for (int i = 0; i < s->n_scalars; ++i)
 			if (i != s->skip_scalar) std::swap(s->sc[i], s->sc_out[i]);
 	}
@@ -188,6 +188,14 @@ int hns_state_create(const hns_grid* g, int n_scalars, hns_state** out) {
 			cudaMemset(*p, 0, bytes);
 		}
 	{
+		const size_t nb = std::max<size_t>(g->num_leaves, 1);
+		if (cudaMalloc(&s->cold, nb) != cudaSuccess) {
+			hns_state_destroy(s);
+			return fail(HNS_ERR_CUDA, "cudaMalloc(leaf flags)");
+		}
+		cudaMemset(s->cold, 0, nb);
+	}
+	{
 		// red and black pressure halves in ONE allocation: a single L2 access-policy window (and a single IPC handle) covers both
 		const cudaError_t e = cudaMalloc(&s->p[0], fb);
 		if (e != cudaSuccess) {
@@ -208,6 +216,7 @@ void hns_state_destroy(hns_state* s) {
 	cudaFree(s->div[0]), cudaFree(s->div[1]), cudaFree(s->p[0]);  // p[1] lives in p[0]'s allocation
 	for (int i = 0; i < 16; ++i) cudaFree(s->sc[i]), cudaFree(s->sc_out[i]);
 	cudaFree(s->aos);
+	cudaFree(s->cold);
 	cudaFree(s->d_sums);
 	for (float* v : s->vort) cudaFree(v);
 	delete s;
@@ -292,7 +301,7 @@ int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void*
 }
 int hns_state_advect_velocity(hns_state* s, float dt, void* stream) {
 	HNS_REQUIRE(s, "null state");
-	launch_advect_vector(s->view(), s->vel, s->adv, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream), s->collision_sdf());
+	launch_advect_vector(s->view(), s->vel, s->adv, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream), s->collision_sdf(), s->cold);
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
@@ -395,7 +404,7 @@ int hns_state_advect_scalars(hns_state* s, float dt, int sampler_semantics, void
 	for (int i = 0; i < s->n_scalars; ++i)
 		if (i != s->skip_scalar) sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i], ++S;
 	launch_advect_scalars(s->view(), s->vel, sp, S, dt, 1.0f / s->grid->voxel_size, sampler_semantics, s->elem0, static_cast<cudaStream_t>(stream),
-	                      s->collision_sdf());
+	                      s->collision_sdf(), s->cold);
 	for (int i = 0; i < s->n_scalars; ++i)
 		if (i != s->skip_scalar) std::swap(s->sc[i], s->sc_out[i]);
 	HNS_CUDA(cudaGetLastError());
@@ -672,7 +681,7 @@ int hns_advect_index_grid(const int32_t* coords, uint64_t n, const float* veloci
 		if (!fields[i]) return fail(HNS_ERR_RUNTIME, "Block not found or type mismatch");
 		HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, st));
 	}
-	launch_advect_scalars(sc.grid->view, s->vel, scalar_ptrs(s), n_float, dt, 1.0f / voxel_size, 1, nullptr, st);  // advect_scalar semantics (Advection.cu:89)
+	launch_advect_scalars(sc.grid->view, s->vel, scalar_ptrs(s), n_float, dt, 1.0f / voxel_size, 1, nullptr, st, nullptr, s->cold);  // advect_scalar semantics (Advection.cu:89)
 	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc_out[i], n * 4, cudaMemcpyDeviceToHost, st));
 	HNS_CUDA(cudaStreamSynchronize(st));
 	HNS_CUDA(cudaGetLastError());
@@ -690,7 +699,7 @@ int hns_advect_index_grid_velocity(const int32_t* coords, uint64_t n, float* vel
 	if ((rc = ensure_aos(s))) return rc;
 	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
 	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
-	launch_advect_vector(sc.grid->view, s->vel, s->adv, dt, 1.0f / voxel_size, st);
+	launch_advect_vector(sc.grid->view, s->vel, s->adv, dt, 1.0f / voxel_size, st, nullptr, s->cold);
 	launch_soa_to_aos(s->adv[0], s->adv[1], s->adv[2], s->aos, n, st);
 	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, st));
 	HNS_CUDA(cudaStreamSynchronize(st));

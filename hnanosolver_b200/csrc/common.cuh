@@ -185,6 +185,7 @@ struct hns_state {
 	float* sc[16] = {};   // scalar fields (current)
 	float* sc_out[16] = {};
 	float* aos = nullptr; // staging float[N][3] for host <-> device velocity transfers
+	uint8_t* cold = nullptr;  // [L] leaf flags of the advection kernels (advect.cu), zero between launches
 	float* vort[4] = {nullptr, nullptr, nullptr, nullptr};  // vorticity confinement scratch, allocated on first use: output planes u, v, w and |curl|
 	// optional combustion + buoyancy stage of the all-in-one frame
 	bool comb_enabled = false;

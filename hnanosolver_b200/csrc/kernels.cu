@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "kernels.cuh"
+#include "sampling.cuh"
 
 namespace hns {
 
@@ -422,56 +423,6 @@ void launch_gather_nbr_rows(const int32_t* nbr, const int32_t* list, uint32_t n,
 // =============================================================================================================
 // semi-Lagrangian BFECC advection  (reference Kernel.cu:118-453, samplers src/Utils/Stencils.hpp:25-173)
 // =============================================================================================================
-// Resolves voxel (i,j,k) (global coordinates) to a sidecar index, or -1 when inactive. The 3x3x3 leaf neighbourhood of the
-// current leaf comes from its 27-entry table; anything farther away walks the NanoVDB buffer. Cold path only.
-struct LeafFrame {
-	int ox, oy, oz;
-	const int32_t* nbr;  // this leaf's row of the neighbour table (global memory)
-};
-__device__ __forceinline__ int64_t voxel_index(const GridView& g, const LeafFrame& f, int i, int j, int k) {
-	const int rx = i - f.ox, ry = j - f.oy, rz = k - f.oz;
-	const int dx = rx >> 3, dy = ry >> 3, dz = rz >> 3;
-	int32_t l;
-	if (((dx + 1) | (dy + 1) | (dz + 1)) & ~3 || dx == 2 || dy == 2 || dz == 2) {  // outside the 3x3x3 neighbourhood
-		if (g.far_flag) atomicOr(g.far_flag, 0x100u);
-		l = probe_leaf(g, i, j, k);
-	} else {
-		l = __ldg(f.nbr + (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1));
-	}
-	return l < 0 ? int64_t(-1) : int64_t(uint64_t(l) * 512u + uint32_t(((rx & 7) << 6) | ((ry & 7) << 3) | (rz & 7)));
-}
-__device__ __forceinline__ float lerpf(float a, float b, float w) { return fmaf(w, b - a, a); }
-
-// TrilinearSampler<Vec3f>::sample: Floor (round down, fractional part in place), 8 nearest fetches (inactive -> 0),
-// lerp z, then y, then x (Stencils.hpp:96-157)
-__device__ __noinline__ void trilinear_vec(const GridView& g, const LeafFrame& f, const float* __restrict__ u, const float* __restrict__ v,
-                                              const float* __restrict__ w, float px, float py, float pz, float& ru, float& rv, float& rw) {
-	const int i = __float2int_rd(px), j = __float2int_rd(py), k = __float2int_rd(pz);
-	const float fx = px - float(i), fy = py - float(j), fz = pz - float(k);
-	float cu[8], cv[8], cw[8];
-#pragma unroll
-	for (int q = 0; q < 8; ++q) {  // q = a*4 + b*2 + c  <->  v[a][b][c]
-		const int64_t idx = voxel_index(g, f, i + (q >> 2), j + ((q >> 1) & 1), k + (q & 1));
-		cu[q] = idx < 0 ? 0.f : __ldg(u + idx);
-		cv[q] = idx < 0 ? 0.f : __ldg(v + idx);
-		cw[q] = idx < 0 ? 0.f : __ldg(w + idx);
-	}
-	ru = lerpf(lerpf(lerpf(cu[0], cu[1], fz), lerpf(cu[2], cu[3], fz), fy), lerpf(lerpf(cu[4], cu[5], fz), lerpf(cu[6], cu[7], fz), fy), fx);
-	rv = lerpf(lerpf(lerpf(cv[0], cv[1], fz), lerpf(cv[2], cv[3], fz), fy), lerpf(lerpf(cv[4], cv[5], fz), lerpf(cv[6], cv[7], fz), fy), fx);
-	rw = lerpf(lerpf(lerpf(cw[0], cw[1], fz), lerpf(cw[2], cw[3], fz), fy), lerpf(lerpf(cw[4], cw[5], fz), lerpf(cw[6], cw[7], fz), fy), fx);
-}
-__device__ __noinline__ float trilinear_f(const GridView& g, const LeafFrame& f, const float* __restrict__ a, float px, float py, float pz) {
-	const int i = __float2int_rd(px), j = __float2int_rd(py), k = __float2int_rd(pz);
-	const float fx = px - float(i), fy = py - float(j), fz = pz - float(k);
-	float c[8];
-#pragma unroll
-	for (int q = 0; q < 8; ++q) {
-		const int64_t idx = voxel_index(g, f, i + (q >> 2), j + ((q >> 1) & 1), k + (q & 1));
-		c[q] = idx < 0 ? 0.f : __ldg(a + idx);
-	}
-	return lerpf(lerpf(lerpf(c[0], c[1], fz), lerpf(c[2], c[3], fz), fy), lerpf(lerpf(c[4], c[5], fz), lerpf(c[6], c[7], fz), fy), fx);
-}
-
 // ---- shared-memory staging of a leaf neighbourhood -------------------------------------------------------------------
 // Persistent CTAs of 512 threads (two per SM), each walking a contiguous range of leaves, one thread per voxel. For every
 // leaf the CTA needs the field values of the region
@@ -485,14 +436,6 @@ __device__ __noinline__ float trilinear_f(const GridView& g, const LeafFrame& f,
 // Row pitch is 24 floats (96 B): keeps 16-byte alignment and maps the 4 (y) x 8 (z) lanes of a warp to 32 distinct banks.
 // (Padding the x-plane pitch to a multiple of 32 floats would also keep lanes whose samples straddle an integer x on disjoint
 // banks, but 2 buffers x 3 fields x 19.25 KB no longer fits two CTAs per SM; measured trade-off in DESIGN.md.)
-constexpr int kRX = 14, kRZ = 16, kPitch = 24, kHaloXY = 3, kHaloZ = 4;
-constexpr int kPlane = kRX * kPitch;                              // 336 floats per x-plane
-constexpr int kRegionFloats = kRX * kPlane;                       // 4704 floats = 18.4 KB per field
-constexpr int kRegionQuads = kRX * kRX * (kRZ / 4);               // 16-byte quads per field
-constexpr int kStageFloats = 3 * kRegionFloats;                   // one pipeline stage: three fields
-constexpr size_t kAdvectSmem = 2 * kStageFloats * sizeof(float);  // double buffer: 110.25 KB per CTA, two CTAs per SM
-static_assert(2 * (kAdvectSmem + 1024) <= 233472, "two CTAs of the advection pipeline must fit one SM's shared memory");
-
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 	const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
@@ -702,9 +645,21 @@ static void advect_attrs(K kernel) {
 	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAdvectSmem));
 	cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
+static int advect_v1() {  // A/B switch: HNS_ADVECT_V1=1 runs the first-generation kernels of this file instead of advect.cu's
+	static const int v = [] {
+		const char* e = std::getenv("HNS_ADVECT_V1");
+		return e && std::atoi(e) != 0 ? 1 : 0;
+	}();
+	return v;
+}
 void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st,
-                          const float* sdf) {
+                          const float* sdf, uint8_t* cold) {
 	if (!g.count()) return;
+	if (cold && !advect_v1()) {
+		launch_advect_vector2(g, vel, out, dt, inv_dx, st, sdf, cold);
+		if (sdf) launch_collision_boundary(g, out, out, sdf, inv_dx, 1.5f, 1, st);  // Kernel.cu:432-450
+		return;
+	}
 	static bool attr = false;
 	if (!attr) advect_attrs(k_advect_vector<false>), advect_attrs(k_advect_vector<true>), attr = true;
 	if (sdf) {
@@ -720,28 +675,6 @@ void launch_advect_vector(const GridView& g, const float* const vel[3], float* c
 // advect_scalars (Kernel.cu:118-266) [kSemantics 0]: explicit corner weights, fma accumulation in corner order
 // (i0j0k0),(i1j0k0),(i0j1k0),(i1j1k0),(i0j0k1),...; inactive corner / neighbour -> array element 0 (:192,:225).
 // advect_scalar (Kernel.cu:269-352) [kSemantics 1]: IndexSampler<float,1> everywhere, inactive -> 0, z-y-x lerps.
-__device__ __forceinline__ void corner_weights(float tx, float ty, float tz, float (&w)[8]) {  // :169-183
-	const float itx = 1.0f - tx, ity = 1.0f - ty, itz = 1.0f - tz;
-	const float w00 = itx * ity, w10 = tx * ity, w01 = itx * ty, w11 = tx * ty;
-	w[0] = w00 * itz, w[1] = w10 * itz, w[2] = w01 * itz, w[3] = w11 * itz;
-	w[4] = w00 * tz, w[5] = w10 * tz, w[6] = w01 * tz, w[7] = w11 * tz;
-}
-// region offsets of the eight corners in the reference's accumulation order: bit0 -> i, bit1 -> j, bit2 -> k
-__device__ __forceinline__ int corner_off(int q) { return (q & 1) * kPlane + ((q >> 1) & 1) * kPitch + (q >> 2); }
-// cold path: weighted 8-corner sums through the leaf table / tree walk, for samples outside the staged region
-__device__ __noinline__ float far_weighted(const GridView& g, const LeafFrame& f, const float* __restrict__ a, const float* __restrict__ e0, int i0,
-                                           int j0, int k0, float tx, float ty, float tz) {
-	float wt[8];
-	corner_weights(tx, ty, tz, wt);
-	float acc = 0.f;
-#pragma unroll 1
-	for (int q = 0; q < 8; ++q) {
-		const int64_t t = voxel_index(g, f, i0 + (q & 1), j0 + ((q >> 1) & 1), k0 + (q >> 2));
-		acc = fmaf(t < 0 ? __ldg(e0) : __ldg(a + t), wt[q], acc);
-	}
-	return acc;
-}
-
 template <int kSemantics, bool kCollision>
 __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const float* __restrict__ u, const float* __restrict__ v,
                                                            const float* __restrict__ w, const __grid_constant__ ScalarPtrs sp, int S, float sdt,
@@ -873,8 +806,12 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const flo
 	}
 }
 void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx,
-                           int sampler_semantics, const float* elem0, cudaStream_t st, const float* sdf) {
+                           int sampler_semantics, const float* elem0, cudaStream_t st, const float* sdf, uint8_t* cold) {
 	if (!g.count() || S <= 0) return;
+	if (cold && !advect_v1()) {
+		launch_advect_scalars2(g, vel, sp, S, dt, inv_dx, sampler_semantics, elem0, st, sdf, cold);
+		return;
+	}
 	static bool attr = false;
 	if (!attr) {
 		advect_attrs(k_advect_scalars<0, false>), advect_attrs(k_advect_scalars<1, false>);
