@@ -1,10 +1,14 @@
-// Semi-Lagrangian BFECC advection, second generation (reference src/Cuda/Kernel.cu:118-266 advect_scalars, :269-352 advect_scalar,
-// :354-453 advect_vector; samplers src/Utils/Stencils.hpp:25-173).
+// Semi-Lagrangian BFECC advection (reference src/Cuda/Kernel.cu:118-266 advect_scalars, :269-352 advect_scalar, :354-453
+// advect_vector; samplers src/Utils/Stencils.hpp:25-173).
 //
-// Same data flow as the first generation in kernels.cu -- persistent CTAs of 512 threads (one per voxel of a leaf), two per SM, the
-// 14 x 14 x 16 region around the leaf staged into a double-buffered shared-memory tile with 16-byte cp.async one stage ahead -- but
-// the per-voxel instruction stream is cut to what the arithmetic needs (ncu of the first generation: 1535 instructions per voxel in
-// advect_scalars at S = 5, issue slots 63 % busy, i.e. instruction bound):
+// Persistent CTAs of 512 threads (one per voxel of a leaf), two per SM, walk the leaf list. For every leaf the CTA needs the field
+// values of the region x, y in [-3, 11), z in [-4, 12) (leaf-local; 14 x 14 rows of 16 floats, from up to 27 leaves) in shared memory:
+// every trilinear / nearest fetch whose 2x2x2 footprint lies inside it is then a shared-memory read -- no per-sample leaf lookup, no
+// scattered global loads. The region of the NEXT stage is copied with 16-byte cp.async into the second half of a double buffer while
+// the current one is sampled. Row pitch 24 floats: keeps 16-byte alignment and maps the 4 (y) x 8 (z) lanes of a warp to 32 distinct
+// banks. This is the second generation of these kernels; the first (round 1, profiles/r1e_advect_ncu.txt: 1535 instructions per
+// voxel in advect_scalars at S = 5, issue slots 63 % busy) was instruction bound, so the per-voxel instruction stream was cut to what
+// the arithmetic needs (profiles/r2a_*: 2.65 -> 2.21 ms and 1.13 -> 0.97 ms, now bound by shared-memory wavefronts):
 //   * the staging plan of a thread (which two quads of the region it copies, from which neighbour slot and leaf offset) depends on
 //     the thread only: decoded once per kernel instead of once per leaf (it contained an integer division);
 //   * a leaf's metadata (27 neighbour ids, origin, id) travels through a shared-memory ring one leaf ahead, so no stage starts with a
@@ -233,6 +237,22 @@ __global__ void __launch_bounds__(512, 2) k_advect_vector2(GridView g, const flo
 	}
 }
 
+// The flagged leaves among work items [chunk, chunk + 512) into todo[0 .. n_todo), their flags cleared for the next launch: one flag per
+// thread (coalesced), so an unflagged grid costs one load per leaf, not one dependent round trip per leaf and CTA.
+__device__ __forceinline__ void collect_flagged(const GridView& g, uint8_t* cold, uint32_t chunk, uint32_t* todo, uint32_t& n_todo) {
+	if (threadIdx.x == 0) n_todo = 0;
+	__syncthreads();
+	const uint32_t i = chunk + threadIdx.x;
+	if (i < g.count()) {
+		const uint32_t leaf = g.leaf_at(i);
+		if (cold[leaf]) {
+			cold[leaf] = 0;
+			todo[atomicAdd(&n_todo, 1u)] = leaf;
+		}
+	}
+	__syncthreads();
+}
+
 // Flagged leaves again, voxel by voxel through the neighbour table / tree walk: the reference's expressions with IndexSampler
 // semantics (inactive -> 0). One CTA per flagged leaf, grid-stride over the work list.
 template <bool kCollision>
@@ -241,9 +261,11 @@ __global__ void __launch_bounds__(512) k_advect_vector_cold(GridView g, const fl
                                                             float* __restrict__ ow, float sdt, const float* __restrict__ sdf, uint8_t* cold) {
 	const int tid = threadIdx.x;
 	const int x = tid >> 6, y = (tid >> 3) & 7, z = tid & 7;
-	for (uint32_t i = blockIdx.x; i < g.count(); i += gridDim.x) {
-		const uint32_t leaf = g.leaf_at(i);
-		if (!cold[leaf]) continue;
+	__shared__ uint32_t todo[512], n_todo;
+	for (uint32_t chunk = blockIdx.x * 512u; chunk < g.count(); chunk += gridDim.x * 512u) {
+	collect_flagged(g, cold, chunk, todo, n_todo);
+	for (uint32_t q = 0; q < n_todo; ++q) {
+		const uint32_t leaf = todo[q];
 		const int4 o = __ldg(g.origin + leaf);
 		const LeafFrame f{o.x, o.y, o.z, g.nbr + uint64_t(leaf) * 27u};
 		const uint64_t self = uint64_t(leaf) * 512u + uint32_t(tid);
@@ -268,8 +290,8 @@ __global__ void __launch_bounds__(512) k_advect_vector_cold(GridView g, const fl
 		ou[self] = fmaxf(fminf(mnu, uf), fminf(cu, fmaxf(mxu, uf)));
 		ov[self] = fmaxf(fminf(mnv, vf), fminf(cv, fmaxf(mxv, vf)));
 		ow[self] = fmaxf(fminf(mnw, wf), fminf(cw, fmaxf(mxw, wf)));
-		__syncthreads();  // every thread has read the flag before it is cleared for the next launch
-		if (tid == 0) cold[leaf] = 0;
+	}
+	__syncthreads();  // the list is rebuilt for the next chunk
 	}
 }
 
@@ -424,9 +446,11 @@ __global__ void __launch_bounds__(512) k_advect_scalars_cold(GridView g, const f
                                                              const float* __restrict__ elem0, const float* __restrict__ sdf, uint8_t* cold) {
 	const int tid = threadIdx.x;
 	const int x = tid >> 6, y = (tid >> 3) & 7, z = tid & 7;
-	for (uint32_t i = blockIdx.x; i < g.count(); i += gridDim.x) {
-		const uint32_t leaf = g.leaf_at(i);
-		if (!cold[leaf]) continue;
+	__shared__ uint32_t todo[512], n_todo;
+	for (uint32_t chunk = blockIdx.x * 512u; chunk < g.count(); chunk += gridDim.x * 512u) {
+	collect_flagged(g, cold, chunk, todo, n_todo);
+	for (uint32_t q = 0; q < n_todo; ++q) {
+		const uint32_t leaf = todo[q];
 		const int4 o = __ldg(g.origin + leaf);
 		const LeafFrame f{o.x, o.y, o.z, g.nbr + uint64_t(leaf) * 27u};
 		const uint64_t self = uint64_t(leaf) * 512u + uint32_t(tid);
@@ -476,8 +500,8 @@ __global__ void __launch_bounds__(512) k_advect_scalars_cold(GridView g, const f
 			}
 			sp.out[k][self] = fmaxf(fminf(mn, phiF), fminf(corr, fmaxf(mx, phiF)));
 		}
-		__syncthreads();
-		if (tid == 0) cold[leaf] = 0;
+	}
+	__syncthreads();
 	}
 }
 
@@ -512,35 +536,38 @@ void ensure_attrs(DeviceInfo& d) {
 
 }  // namespace
 
-void launch_advect_vector2(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st, const float* sdf,
-                           uint8_t* cold) {
+void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st, const float* sdf,
+                          uint8_t* cold) {
 	if (!g.count()) return;
 	DeviceInfo& d = device_info();
 	ensure_attrs(d);
 	const int grid = int(std::min<uint32_t>(uint32_t(2 * d.sms), g.count()));
 	const float sdt = dt * inv_dx;
+	const int cold_grid = int(std::min<uint32_t>(uint32_t(4 * d.sms), (g.count() + 511u) / 512u));
 	if (sdf) {
 		HNS_LAUNCH(k_advect_vector2<true>, grid, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
-		HNS_LAUNCH(k_advect_vector_cold<true>, grid, 512, 0, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
+		HNS_LAUNCH(k_advect_vector_cold<true>, cold_grid, 512, 0, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
+		launch_collision_boundary(g, out, out, sdf, inv_dx, 1.5f, 1, st);  // the boundary tail of the kernel, Kernel.cu:432-450
 	} else {
 		HNS_LAUNCH(k_advect_vector2<false>, grid, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
-		HNS_LAUNCH(k_advect_vector_cold<false>, grid, 512, 0, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
+		HNS_LAUNCH(k_advect_vector_cold<false>, cold_grid, 512, 0, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
 	}
 }
 
-void launch_advect_scalars2(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx, int sampler_semantics,
-                            const float* elem0, cudaStream_t st, const float* sdf, uint8_t* cold) {
+void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx, int sampler_semantics,
+                           const float* elem0, cudaStream_t st, const float* sdf, uint8_t* cold) {
 	if (!g.count() || S <= 0) return;
 	DeviceInfo& d = device_info();
 	ensure_attrs(d);
 	const int grid = int(std::min<uint32_t>(uint32_t(2 * d.sms), g.count()));
 	const float sdt = dt * inv_dx;
+	const int cold_grid = int(std::min<uint32_t>(uint32_t(4 * d.sms), (g.count() + 511u) / 512u));
 	auto hot = sampler_semantics == 0 ? (sdf ? k_advect_scalars2<0, true> : k_advect_scalars2<0, false>)
 	                                  : (sdf ? k_advect_scalars2<1, true> : k_advect_scalars2<1, false>);
 	auto cold_k = sampler_semantics == 0 ? (sdf ? k_advect_scalars_cold<0, true> : k_advect_scalars_cold<0, false>)
 	                                     : (sdf ? k_advect_scalars_cold<1, true> : k_advect_scalars_cold<1, false>);
 	HNS_LAUNCH(hot, grid, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, sdt, elem0, sdf, cold);
-	HNS_LAUNCH(cold_k, grid, 512, 0, st, g, vel[0], vel[1], vel[2], sp, S, sdt, elem0, sdf, cold);
+	HNS_LAUNCH(cold_k, cold_grid, 512, 0, st, g, vel[0], vel[1], vel[2], sp, S, sdt, elem0, sdf, cold);
 }
 
 }  // namespace hns

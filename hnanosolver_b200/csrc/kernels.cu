@@ -420,411 +420,7 @@ void launch_gather_nbr_rows(const int32_t* nbr, const int32_t* list, uint32_t n,
 	if (n) HNS_LAUNCH(k_gather_nbr_rows, uint32_t((uint64_t(n) * 27u + 255u) / 256u), 256, 0, st, nbr, list, n, out);
 }
 
-// =============================================================================================================
-// semi-Lagrangian BFECC advection  (reference Kernel.cu:118-453, samplers src/Utils/Stencils.hpp:25-173)
-// =============================================================================================================
-// ---- shared-memory staging of a leaf neighbourhood -------------------------------------------------------------------
-// Persistent CTAs of 512 threads (two per SM), each walking a contiguous range of leaves, one thread per voxel. For every
-// leaf the CTA needs the field values of the region
-//   x, y in [-3, 11), z in [-4, 12)   (leaf-local voxel coordinates; 14 x 14 rows of 16 floats, from up to 27 leaves)
-// in shared memory; every trilinear / nearest fetch whose 2x2x2 footprint lies inside the region is then a shared-memory read:
-// no per-sample leaf lookup, no scattered global loads. The region of the NEXT leaf (or next group of scalar fields) is copied
-// with 16-byte cp.async into the second half of a double buffer while the current one is being sampled, so HBM/L2 latency is
-// hidden behind the gathers instead of being exposed once per leaf. With the benchmark's CFL <= 2.5 every back-trace lands
-// inside the region; a sample that leaves it (the reference has no CFL limit) falls back to the leaf-table / tree-walk path
-// above, so results do not depend on the region size.
-// Row pitch is 24 floats (96 B): keeps 16-byte alignment and maps the 4 (y) x 8 (z) lanes of a warp to 32 distinct banks.
-// (Padding the x-plane pitch to a multiple of 32 floats would also keep lanes whose samples straddle an integer x on disjoint
-// banks, but 2 buffers x 3 fields x 19.25 KB no longer fits two CTAs per SM; measured trade-off in DESIGN.md.)
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
-	const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-	asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-__device__ __forceinline__ void cp_async4(int* smem_dst, const int* gsrc) {
-	const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-// Per-leaf metadata of the pipeline (27 neighbour ids, origin, leaf id) travels through shared memory one leaf ahead of its
-// use, so that neither the staging plan nor the back-trace starts with a dependent global load (list -> neighbour row -> address).
-constexpr int kMetaInts = 32, kMetaOrigin = 27, kMetaLeaf = 30;
-__device__ __forceinline__ void meta_prefetch(const GridView& g, int* __restrict__ slot, uint32_t work_index) {
-	const int t = threadIdx.x;
-	if (t < 31) {
-		const uint32_t leaf = g.leaf_at(work_index);
-		if (t < 27) cp_async4(slot + t, g.nbr + uint64_t(leaf) * 27u + t);
-		else if (t < 30) cp_async4(slot + t, reinterpret_cast<const int*>(g.origin + leaf) + (t - 27));
-		else slot[kMetaLeaf] = int(leaf);
-	}
-}
-__device__ __forceinline__ void meta_load_now(const GridView& g, int* __restrict__ slot, uint32_t work_index) {
-	const int t = threadIdx.x;
-	if (t < 31) {
-		const uint32_t leaf = g.leaf_at(work_index);
-		slot[t] = t < 27 ? __ldg(g.nbr + uint64_t(leaf) * 27u + t) : (t < 30 ? __ldg(reinterpret_cast<const int*>(g.origin + leaf) + (t - 27)) : int(leaf));
-	}
-}
-
-// Staging plan of one thread: which two 16-byte quads of the region it copies (the same for every field, so it is decoded once
-// per CTA and kept in registers). The 784 quads of a field are dealt so that every group of 8 consecutive lanes covers 4 rows x
-// 2 quads: with the 24-float row pitch those eight 16-byte shared-memory stores hit 32 distinct banks.
-struct StagePlan {
-	uint32_t src[2];  // float index of the quad in a brick field, 0xffffffff: leaf missing / nothing to do
-	int dst[2];       // float offset in the region, -1: nothing to do
-};
-__device__ __forceinline__ StagePlan make_stage_plan(const int32_t* nbr) {  // nbr: a leaf's 27 neighbour ids (shared or global memory)
-	StagePlan p;
-#pragma unroll
-	for (int k = 0; k < 2; ++k) {
-		const int it = threadIdx.x + 512 * k;
-		p.src[k] = 0xffffffffu, p.dst[k] = -1;
-		if (it < kRegionQuads) {
-			const int sub = it & 15, row = (it >> 4) * 4 + (sub & 3), q = ((sub >> 3) << 1) | ((sub >> 2) & 1);
-			const int rx = row / kRX, ry = row - rx * kRX;
-			const int lx = rx - kHaloXY, ly = ry - kHaloXY;       // leaf-local x, y in [-3, 11)
-			const int dz = q == 0 ? -1 : (q == 3 ? 1 : 0);        // z in [-4,0) | [0,4) | [4,8) | [8,12)
-			const int32_t l = nbr[((lx >> 3) + 1) * 9 + ((ly >> 3) + 1) * 3 + dz + 1];
-			p.dst[k] = rx * kPlane + ry * kPitch + q * 4;
-			if (l >= 0) p.src[k] = uint32_t(l) * 512u + uint32_t(((lx & 7) << 6) | ((ly & 7) << 3)) + ((q == 1 || q == 3) ? 0u : 4u);
-		}
-	}
-	return p;
-}
-// starts the asynchronous fill of region `dst` with field `f`; cells of missing leaves get `fill` (stored directly)
-__device__ __forceinline__ void stage_region(const StagePlan& p, const float* __restrict__ f, float* __restrict__ dst, float fill) {
-#pragma unroll
-	for (int k = 0; k < 2; ++k) {
-		if (p.dst[k] < 0) continue;
-		if (p.src[k] != 0xffffffffu)
-			cp_async16(dst + p.dst[k], f + p.src[k]);
-		else
-			*reinterpret_cast<float4*>(dst + p.dst[k]) = make_float4(fill, fill, fill, fill);
-	}
-}
-// region offset of global voxel (i,j,k), or -1 if the 2x2x2 footprint starting there is not fully inside the region
-__device__ __forceinline__ int region_base(const LeafFrame& fr, int i, int j, int k) {
-	const int rx = i - fr.ox + kHaloXY, ry = j - fr.oy + kHaloXY, rz = k - fr.oz + kHaloZ;
-	if (unsigned(rx) >= unsigned(kRX - 1) || unsigned(ry) >= unsigned(kRX - 1) || unsigned(rz) >= unsigned(kRZ - 1)) return -1;
-	return rx * kPlane + ry * kPitch + rz;
-}
-__device__ __forceinline__ float tri8(const float* __restrict__ r, int b, float fx, float fy, float fz) {
-	// v[a][b][c] = r[base + a*kPlane + b*kPitch + c]; lerp z, then y, then x (Stencils.hpp:144-152)
-	const float z0 = lerpf(r[b], r[b + 1], fz), z1 = lerpf(r[b + kPitch], r[b + kPitch + 1], fz);
-	const float z2 = lerpf(r[b + kPlane], r[b + kPlane + 1], fz), z3 = lerpf(r[b + kPlane + kPitch], r[b + kPlane + kPitch + 1], fz);
-	return lerpf(lerpf(z0, z1, fy), lerpf(z2, z3, fy), fx);
-}
-
-__device__ __forceinline__ LeafFrame leaf_frame(const GridView& g, uint32_t leaf) {
-	const int4 o = __ldg(g.origin + leaf);
-	return LeafFrame{o.x, o.y, o.z, g.nbr + uint64_t(leaf) * 27u};
-}
-// Work items of this CTA: item k of the CTA is entry at(k) of the launch's leaf list (GridView::leaf_at). Strided (default): the
-// CTAs advance through the leaf list together, CTA b taking b, b + G, b + 2G, ... -- at any moment the whole grid works inside a
-// window of about G consecutive leaves, so the x-neighbour planes a leaf's region needs (256 leaves away in a lower node) are
-// still in the L2 from the CTAs that staged them a moment ago. Contiguous ranges per CTA (HNS_ADVECT_CONTIGUOUS=1) scatter the grid
-// over the whole list instead: every leaf is then fetched from HBM about three times (ncu: 4.1 GB read by advect_scalars vs 1.3 GB).
-struct CtaItems {
-	uint32_t base, stride, count;
-	__device__ __forceinline__ uint32_t at(uint32_t k) const { return base + k * stride; }
-};
-__device__ __forceinline__ CtaItems cta_items(const GridView& g, int contiguous) {
-	CtaItems it;
-	if (contiguous) {
-		const uint32_t per = (g.count() + gridDim.x - 1) / gridDim.x;
-		it.base = blockIdx.x * per, it.stride = 1;
-		it.count = it.base < g.count() ? min(per, g.count() - it.base) : 0u;
-	} else {
-		it.base = blockIdx.x, it.stride = gridDim.x;
-		it.count = it.base < g.count() ? (g.count() - it.base + gridDim.x - 1) / gridDim.x : 0u;
-	}
-	return it;
-}
-
-// TrilinearSampler<Vec3f>::sample through the staged region when possible
-__device__ __forceinline__ void sample_vec(const GridView& g, const LeafFrame& f, const float* __restrict__ ru, const float* __restrict__ rv,
-                                           const float* __restrict__ rw, const float* __restrict__ u, const float* __restrict__ v,
-                                           const float* __restrict__ w, float px, float py, float pz, float& ou, float& ov, float& ow) {
-	const int i = __float2int_rd(px), j = __float2int_rd(py), k = __float2int_rd(pz);
-	const int b = region_base(f, i, j, k);
-	if (b >= 0) {
-		const float fx = px - float(i), fy = py - float(j), fz = pz - float(k);
-		ou = tri8(ru, b, fx, fy, fz), ov = tri8(rv, b, fx, fy, fz), ow = tri8(rw, b, fx, fy, fz);
-	} else {
-		trilinear_vec(g, f, u, v, w, px, py, pz, ou, ov, ow);
-	}
-}
-
-// kCollision (reference Kernel.cu:377-394): a back-trace that ends inside the collider (trilinear SDF sample < 0, inactive corners 0)
-// stays at the voxel, a forward trace that does falls back to the back-traced position. The SDF is not staged: its two samples per
-// voxel go through the neighbour table (global memory); the boundary treatment of the result (:432-450) is a separate launch.
-template <bool kCollision>
-__global__ void __launch_bounds__(512, 2) k_advect_vector(GridView g, const float* __restrict__ u, const float* __restrict__ v,
-                                                          const float* __restrict__ w, float* __restrict__ ou, float* __restrict__ ov,
-                                                          float* __restrict__ ow, float sdt, int contiguous, const float* __restrict__ sdf) {
-	extern __shared__ __align__(16) float region[];
-	const CtaItems items = cta_items(g, contiguous);
-	if (!items.count) return;
-	const int x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
-	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
-	__shared__ int meta[3][kMetaInts];  // ring over the CTA's leaves: in use / being staged / being prefetched
-	auto issue = [&](uint32_t k, int buf) {  // stage item k; its metadata is already in the ring, the next item's rides along
-		const StagePlan plan = make_stage_plan(meta[k % 3]);
-		float* r = region + buf * kStageFloats;
-		stage_region(plan, u, r, 0.f);
-		stage_region(plan, v, r + kRegionFloats, 0.f);
-		stage_region(plan, w, r + 2 * kRegionFloats, 0.f);
-		if (k + 1 < items.count) meta_prefetch(g, meta[(k + 1) % 3], items.at(k + 1));
-		cp_async_commit();
-	};
-	meta_load_now(g, meta[0], items.at(0));
-	__syncthreads();
-	issue(0, 0);
-	for (uint32_t k = 0; k < items.count; ++k) {
-		const int buf = k & 1;
-		cp_async_wait<0>();
-		__syncthreads();  // this item's region (and the next leaf's metadata) has landed for every thread, and every thread is done reading the other buffer
-		if (k + 1 < items.count) issue(k + 1, buf ^ 1);
-		const float *ru = region + buf * kStageFloats, *rv = ru + kRegionFloats, *rw = ru + 2 * kRegionFloats;
-		const int* m = meta[k % 3];
-		const uint32_t leaf = uint32_t(m[kMetaLeaf]);
-		const LeafFrame f{m[kMetaOrigin], m[kMetaOrigin + 1], m[kMetaOrigin + 2], g.nbr + uint64_t(leaf) * 27u};
-		const uint64_t self = uint64_t(leaf) * 512u + threadIdx.x;
-		const int ci = f.ox + x, cj = f.oy + y, ck = f.oz + z;
-		const float u0 = ru[c], v0 = rv[c], w0 = rw[c];
-		// backtrace: pos - velOrig * scaled_dt  (Kernel.cu:374)
-		float bx = fmaf(-sdt, u0, float(ci)), by = fmaf(-sdt, v0, float(cj)), bz = fmaf(-sdt, w0, float(ck));
-		if (kCollision && trilinear_f(g, f, sdf, bx, by, bz) < 0.0f) bx = float(ci), by = float(cj), bz = float(ck);  // :377-382
-		float uf, vf, wf, ub, vb, wb;
-		sample_vec(g, f, ru, rv, rw, u, v, w, bx, by, bz, uf, vf, wf);
-		float fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :387
-		if (kCollision && trilinear_f(g, f, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;  // :390-394
-		sample_vec(g, f, ru, rv, rw, u, v, w, fx, fy, fz, ub, vb, wb);
-		const float cu = fmaf(0.5f, u0 - ub, uf), cv = fmaf(0.5f, v0 - vb, vf), cw = fmaf(0.5f, w0 - wb, wf);  // :399-400
-		float mnu = u0, mxu = u0, mnv = v0, mxv = v0, mnw = w0, mxw = w0;
-		const int d6[6] = {-kPlane, kPlane, -kPitch, kPitch, -1, 1};  // -x, +x, -y, +y, -z, +z  (:410-421)
-#pragma unroll
-		for (int q = 0; q < 6; ++q) {
-			const float nu = ru[c + d6[q]], nv = rv[c + d6[q]], nw = rw[c + d6[q]];
-			mnu = fminf(mnu, nu), mxu = fmaxf(mxu, nu);
-			mnv = fminf(mnv, nv), mxv = fmaxf(mxv, nv);
-			mnw = fminf(mnw, nw), mxw = fmaxf(mxw, nw);
-		}
-		mnu = fminf(mnu, uf), mxu = fmaxf(mxu, uf);
-		mnv = fminf(mnv, vf), mxv = fmaxf(mxv, vf);
-		mnw = fminf(mnw, wf), mxw = fmaxf(mxw, wf);
-		ou[self] = fmaxf(mnu, fminf(cu, mxu));  // :429
-		ov[self] = fmaxf(mnv, fminf(cv, mxv));
-		ow[self] = fmaxf(mnw, fminf(cw, mxw));
-	}
-}
-// persistent launch: two CTAs per SM
-static int advect_grid(uint32_t num_leaves) {
-	static int sms = 0;
-	if (!sms) {
-		int dev = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		if (sms <= 0) sms = 148;
-	}
-	return int(min(uint32_t(2 * sms), num_leaves));  // num_leaves = work items of the launch
-}
-static int advect_contiguous() {  // A/B switch, see CtaItems
-	static const int v = [] {
-		const char* e = std::getenv("HNS_ADVECT_CONTIGUOUS");
-		return e && std::atoi(e) != 0 ? 1 : 0;
-	}();
-	return v;
-}
-template <typename K>
-static void advect_attrs(K kernel) {
-	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAdvectSmem));
-	cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-}
-static int advect_v1() {  // A/B switch: HNS_ADVECT_V1=1 runs the first-generation kernels of this file instead of advect.cu's
-	static const int v = [] {
-		const char* e = std::getenv("HNS_ADVECT_V1");
-		return e && std::atoi(e) != 0 ? 1 : 0;
-	}();
-	return v;
-}
-void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st,
-                          const float* sdf, uint8_t* cold) {
-	if (!g.count()) return;
-	if (cold && !advect_v1()) {
-		launch_advect_vector2(g, vel, out, dt, inv_dx, st, sdf, cold);
-		if (sdf) launch_collision_boundary(g, out, out, sdf, inv_dx, 1.5f, 1, st);  // Kernel.cu:432-450
-		return;
-	}
-	static bool attr = false;
-	if (!attr) advect_attrs(k_advect_vector<false>), advect_attrs(k_advect_vector<true>), attr = true;
-	if (sdf) {
-		HNS_LAUNCH(k_advect_vector<true>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2],
-		           dt * inv_dx, advect_contiguous(), sdf);
-		launch_collision_boundary(g, out, out, sdf, inv_dx, 1.5f, 1, st);  // Kernel.cu:432-450
-	} else {
-		HNS_LAUNCH(k_advect_vector<false>, advect_grid(g.count()), 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2],
-		           dt * inv_dx, advect_contiguous(), sdf);
-	}
-}
-
-// advect_scalars (Kernel.cu:118-266) [kSemantics 0]: explicit corner weights, fma accumulation in corner order
-// (i0j0k0),(i1j0k0),(i0j1k0),(i1j1k0),(i0j0k1),...; inactive corner / neighbour -> array element 0 (:192,:225).
-// advect_scalar (Kernel.cu:269-352) [kSemantics 1]: IndexSampler<float,1> everywhere, inactive -> 0, z-y-x lerps.
-template <int kSemantics, bool kCollision>
-__global__ void __launch_bounds__(512, 2) k_advect_scalars(GridView g, const float* __restrict__ u, const float* __restrict__ v,
-                                                           const float* __restrict__ w, const __grid_constant__ ScalarPtrs sp, int S, float sdt,
-                                                           const float* __restrict__ elem0, int contiguous, const float* __restrict__ sdf) {
-	// (sp is __grid_constant__: its pointer arrays are indexed with run-time indices, which then read the constant bank directly
-	// instead of a per-thread local-memory copy of the parameter)
-	extern __shared__ __align__(16) float region[];
-	const CtaItems items = cta_items(g, contiguous);
-	if (!items.count) return;
-	const int x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
-	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
-	// pipeline jobs: per leaf one velocity stage (the shared trace) and ceil(S/3) stages of up to three scalar fields
-	const int jobs_per_leaf = 1 + (S + 2) / 3;
-	const int n_jobs = int(items.count) * jobs_per_leaf;
-	// (the shared-memory metadata ring of k_advect_vector does not pay here: one decode per 1 + ceil(S/3) jobs, measured +2 %)
-	StagePlan plan{};  // of the leaf whose jobs are being issued; decoded once per leaf
-	auto issue = [&](int job) {
-		const int jj = job % jobs_per_leaf;
-		if (jj == 0) plan = make_stage_plan(g.nbr + uint64_t(g.leaf_at(items.at(uint32_t(job / jobs_per_leaf)))) * 27u);
-		float* r = region + (job & 1) * kStageFloats;
-		if (jj == 0) {
-			// advect_scalars samples the velocity with "inactive -> element 0" as well (Kernel.cu:192,204). elem0, when given,
-			// holds element 0 of the GLOBAL arrays (velocity x,y,z then the S scalars): on a shard the local element 0 is another voxel.
-			stage_region(plan, u, r, kSemantics == 0 ? __ldg(elem0 ? elem0 : u) : 0.f);
-			stage_region(plan, v, r + kRegionFloats, kSemantics == 0 ? __ldg(elem0 ? elem0 + 1 : v) : 0.f);
-			stage_region(plan, w, r + 2 * kRegionFloats, kSemantics == 0 ? __ldg(elem0 ? elem0 + 2 : w) : 0.f);
-		} else {
-			const int s0 = 3 * (jj - 1), ns = min(3, S - s0);
-			for (int k = 0; k < ns; ++k)
-				stage_region(plan, sp.in[s0 + k], r + k * kRegionFloats, kSemantics == 0 ? __ldg(elem0 ? elem0 + 3 + s0 + k : sp.in[s0 + k]) : 0.f);
-		}
-		cp_async_commit();
-	};
-	// the trace of the current leaf, shared by all its scalar jobs
-	LeafFrame f{};
-	float bx = 0.f, by = 0.f, bz = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
-	int bB = -1, bF = -1;
-	issue(0);
-	for (int job = 0; job < n_jobs; ++job) {
-		cp_async_wait<0>();
-		__syncthreads();  // this job's region has landed for every thread, and every thread is done reading the other buffer
-		if (job + 1 < n_jobs) issue(job + 1);
-		const uint32_t leaf = g.leaf_at(items.at(uint32_t(job / jobs_per_leaf)));
-		const int jj = job % jobs_per_leaf;
-		const float* __restrict__ base = region + (job & 1) * kStageFloats;
-		if (jj == 0) {
-			// ---- the shared trace through the staged velocity ----
-			const float *ru = base, *rv = base + kRegionFloats, *rw = base + 2 * kRegionFloats;
-			f = leaf_frame(g, leaf);
-			const int ci = f.ox + x, cj = f.oy + y, ck = f.oz + z;
-			bx = fmaf(-sdt, ru[c], float(ci)), by = fmaf(-sdt, rv[c], float(cj)), bz = fmaf(-sdt, rw[c], float(ck));
-			// hasCollision (Kernel.cu:142-155): the reference tests the back-traced position twice; the second test sees either the
-			// same position or the voxel itself and resets to the voxel again, so one test decides
-			if (kCollision && trilinear_f(g, f, sdf, bx, by, bz) < 0.0f) bx = float(ci), by = float(cj), bz = float(ck);
-			float uf, vf, wf;
-			if (kSemantics == 0) {
-				const int i0 = __float2int_rd(bx), j0 = __float2int_rd(by), k0 = __float2int_rd(bz);
-				const int b = region_base(f, i0, j0, k0);
-				const float tx = bx - float(i0), ty = by - float(j0), tz = bz - float(k0);
-				uf = vf = wf = 0.f;
-				if (b >= 0) {
-					float wt[8];
-					corner_weights(tx, ty, tz, wt);
-#pragma unroll
-					for (int q = 0; q < 8; ++q) {  // :201-206
-						uf = fmaf(wt[q], ru[b + corner_off(q)], uf);
-						vf = fmaf(wt[q], rv[b + corner_off(q)], vf);
-						wf = fmaf(wt[q], rw[b + corner_off(q)], wf);
-					}
-				} else {
-					uf = far_weighted(g, f, u, elem0 ? elem0 : u, i0, j0, k0, tx, ty, tz);
-					vf = far_weighted(g, f, v, elem0 ? elem0 + 1 : v, i0, j0, k0, tx, ty, tz);
-					wf = far_weighted(g, f, w, elem0 ? elem0 + 2 : w, i0, j0, k0, tx, ty, tz);
-				}
-			} else {
-				sample_vec(g, f, ru, rv, rw, u, v, w, bx, by, bz, uf, vf, wf);
-			}
-			fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :208
-			if (kCollision && trilinear_f(g, f, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;  // :211-214
-			bB = region_base(f, __float2int_rd(bx), __float2int_rd(by), __float2int_rd(bz));
-			bF = region_base(f, __float2int_rd(fx), __float2int_rd(fy), __float2int_rd(fz));
-		} else {
-			// ---- up to three scalar fields ----
-			const int s0 = 3 * (jj - 1), ns = min(3, S - s0);
-			const uint64_t self = uint64_t(leaf) * 512u + threadIdx.x;
-			const int bi = __float2int_rd(bx), bj = __float2int_rd(by), bk = __float2int_rd(bz);
-			const int fi = __float2int_rd(fx), fj = __float2int_rd(fy), fk = __float2int_rd(fz);
-			const float btx = bx - float(bi), bty = by - float(bj), btz = bz - float(bk);
-			const float ftx = fx - float(fi), fty = fy - float(fj), ftz = fz - float(fk);
-			const int d6[6] = {-kPlane, kPlane, -kPitch, kPitch, -1, 1};
-			for (int k = 0; k < ns; ++k) {
-				const float* __restrict__ r = base + k * kRegionFloats;
-				const float* __restrict__ a = sp.in[s0 + k];
-				const float phi0 = r[c];
-				float phiF, phiB;
-				if (kSemantics == 0) {
-					phiF = phiB = 0.f;
-					if (bB >= 0) {
-						float wB[8];
-						corner_weights(btx, bty, btz, wB);
-#pragma unroll
-						for (int q = 0; q < 8; ++q) phiF = fmaf(r[bB + corner_off(q)], wB[q], phiF);  // :239-243
-					} else {
-						phiF = far_weighted(g, f, a, elem0 ? elem0 + 3 + s0 + k : a, bi, bj, bk, btx, bty, btz);
-					}
-					if (bF >= 0) {
-						float wF[8];
-						corner_weights(ftx, fty, ftz, wF);
-#pragma unroll
-						for (int q = 0; q < 8; ++q) phiB = fmaf(r[bF + corner_off(q)], wF[q], phiB);
-					} else {
-						phiB = far_weighted(g, f, a, elem0 ? elem0 + 3 + s0 + k : a, fi, fj, fk, ftx, fty, ftz);
-					}
-				} else {
-					phiF = bB >= 0 ? tri8(r, bB, btx, bty, btz) : trilinear_f(g, f, a, bx, by, bz);
-					phiB = bF >= 0 ? tri8(r, bF, ftx, fty, ftz) : trilinear_f(g, f, a, fx, fy, fz);
-				}
-				const float corr = fmaf(0.5f, phi0 - phiB, phiF);  // :246-247
-				float mn = phi0, mx = phi0;
-#pragma unroll
-				for (int q = 0; q < 6; ++q) {  // :253-258
-					const float val = r[c + d6[q]];
-					mn = fminf(mn, val), mx = fmaxf(mx, val);
-				}
-				mn = fminf(mn, phiF), mx = fmaxf(mx, phiF);
-				sp.out[s0 + k][self] = fmaxf(mn, fminf(corr, mx));  // :264
-			}
-		}
-	}
-}
-void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx,
-                           int sampler_semantics, const float* elem0, cudaStream_t st, const float* sdf, uint8_t* cold) {
-	if (!g.count() || S <= 0) return;
-	if (cold && !advect_v1()) {
-		launch_advect_scalars2(g, vel, sp, S, dt, inv_dx, sampler_semantics, elem0, st, sdf, cold);
-		return;
-	}
-	static bool attr = false;
-	if (!attr) {
-		advect_attrs(k_advect_scalars<0, false>), advect_attrs(k_advect_scalars<1, false>);
-		advect_attrs(k_advect_scalars<0, true>), advect_attrs(k_advect_scalars<1, true>);  // (commas inside <> are fine in a function argument)
-		attr = true;
-	}
-	const int grid = advect_grid(g.count());
-	const float sdt = dt * inv_dx;
-	const int cont = advect_contiguous();
-	auto kernel = sampler_semantics == 0 ? (sdf ? k_advect_scalars<0, true> : k_advect_scalars<0, false>)
-	                                     : (sdf ? k_advect_scalars<1, true> : k_advect_scalars<1, false>);
-	HNS_LAUNCH(kernel, grid, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], sp, S, sdt, elem0, cont, sdf);
-}
+// (the advection kernels live in advect.cu)
 
 // element 0 of velocity (x,y,z) and of each scalar field -> dst[3 + S]
 __global__ void k_gather_element0(const float* u, const float* v, const float* w, ScalarPtrs sp, int S, float* __restrict__ dst) {

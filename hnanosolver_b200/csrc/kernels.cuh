@@ -20,10 +20,7 @@ void launch_soa_to_aos(const float* u, const float* v, const float* w, float* ao
 // left its shared-memory region; a follow-up kernel redoes those leaves through the neighbour table and clears the flags (advect.cu)
 void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st,
                           const float* sdf, uint8_t* cold);  // sdf != null: the hasCollision variant incl. its boundary tail
-void launch_advect_vector2(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st, const float* sdf,
-                           uint8_t* cold);
-void launch_advect_scalars2(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx, int sampler_semantics,
-                            const float* elem0, cudaStream_t st, const float* sdf, uint8_t* cold);
+
 // advect_scalars (Kernel.cu:118-266) when sampler_semantics == 0; advect_scalar (Kernel.cu:269-352) per field when == 1
 // elem0 (device, float[3 + S], may be null): element 0 of the GLOBAL velocity / scalar arrays, the value advect_scalars reads for
 // inactive voxels; null = element 0 of the arrays passed in (single-GPU runs).

@@ -641,7 +641,8 @@ def test_every_launch_is_counted():
     _lib.lib().hns_launch_count_reset()
     sim.step(10, w.dt)
     sim.sync()
-    assert _lib.lib().hns_launch_count() == 1 + 1 + 2 * 10 + 1 + 1  # advect_vector, divergence, 10 x (red, black), gradient, advect_scalars
+    # advect_vector (+ its pass over flagged leaves), divergence, 10 x (red, black), gradient, advect_scalars (+ flagged leaves)
+    assert _lib.lib().hns_launch_count() == 2 + 1 + 2 * 10 + 1 + 2
 
 
 # ------------------------------------------------------------------------------------------------------------------
