@@ -46,6 +46,11 @@ SIGNATURES = {
     "hns_grid_nanovdb_download": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hns_grid_get_values": (C.c_int, [C.c_void_p, c_i32p, C.c_uint64, c_u64p]),
     "hns_grid_neighbors_download": (C.c_int, [C.c_void_p, c_i32p]),
+    "hns_domain_build": (C.c_int, [c_i32p, c_u64p, C.c_uint64, C.c_int, c_i32p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "hns_domain_destroy": (None, [C.c_void_p]),
+    "hns_domain_num_leaves": (C.c_uint64, [C.c_void_p]),
+    "hns_domain_origins": (C.c_int, [C.c_void_p, c_i32p]),
+    "hns_domain_create_grid": (C.c_int, [C.c_void_p, C.c_float, C.POINTER(C.c_void_p)]),
     "hns_release_scratch": (None, []),
     "hns_compute_sim": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_f32p), C.c_int, C.c_float, C.c_float,
                                   C.POINTER(CombustionParams), C.c_int, C.c_void_p]),

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libhns_b200.so")
-SOURCES = ["topology.cu", "kernels.cu", "api.cu", "dist.cu", "nvdb_io.cu", "multigrid.cu", "advect.cu"]
+SOURCES = ["topology.cu", "kernels.cu", "api.cu", "dist.cu", "nvdb_io.cu", "multigrid.cu", "advect.cu", "domain.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "sampling.cuh", os.path.join("..", "..", "include", "hns_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -25,7 +25,7 @@ from ._lib import CombustionParams, HnsError, check, c_f32p, c_i32p, c_u64p
 from .grid_data import FLOAT, VEC3F, GridIndexedData
 
 __all__ = ["CreateIndexGrid", "Compute_Sim", "AdvectIndexGrid", "AdvectIndexGridVelocity", "ProjectNonDivergent", "Divergence",
-           "CombustionKernel", "IndexGridHandle", "Simulation", "Multigrid", "CombustionParams"]
+           "CombustionKernel", "IndexGridHandle", "Simulation", "Multigrid", "build_domain", "CombustionParams"]
 
 
 def _fp(a: np.ndarray):
@@ -191,6 +191,27 @@ def CombustionKernel(data: GridIndexedData, handle: IndexGridHandle, dt: float, 
     if len(vec) != 1:
         raise HnsError(-2, "Expected exactly one Vec3f block (velocity)")
     check(_lib.lib().hns_combustion_kernel(handle._h, _fp(data.pValues(VEC3F, vec[0])), data.size(), dt, voxelSize, _stream(stream)))
+
+
+def build_domain(vel_origins, vel_masks=None, padding: int = 0, sdf_origins=None) -> np.ndarray:
+    """The simulation domain's leaf origins (NanoVDB order), built on the device: leaf nodes of the velocity grid, leaves its active
+    voxels reach when dilated `padding` times (26-neighbourhood), leaf nodes of the collision SDF grid -- what
+    SOP_HNanoSolverVerb::cook computes with OpenVDB every cook (src/SOP/HNanoSolver/SOP_HNanoSolver.cpp:188-199).
+    vel_masks: uint64 (n, 8) voxel masks of the velocity leaves (word x, bit y*8+z) or None = all voxels active."""
+    vo = np.ascontiguousarray(np.asarray(vel_origins, np.int32).reshape(-1, 3))
+    vm = None if vel_masks is None else np.ascontiguousarray(np.asarray(vel_masks, np.uint64).reshape(-1, 8))
+    assert vm is None or vm.shape[0] == vo.shape[0]
+    so = np.zeros((0, 3), np.int32) if sdf_origins is None else np.ascontiguousarray(np.asarray(sdf_origins, np.int32).reshape(-1, 3))
+    h = C.c_void_p()
+    L = _lib.lib()
+    check(L.hns_domain_build(_ip(vo) if len(vo) else None, vm.ctypes.data_as(c_u64p) if vm is not None and len(vo) else None, vo.shape[0], int(padding),
+                             _ip(so) if len(so) else None, so.shape[0], C.byref(h)))
+    try:
+        out = np.empty((L.hns_domain_num_leaves(h), 3), np.int32)
+        check(L.hns_domain_origins(h, _ip(out) if len(out) else None))
+    finally:
+        L.hns_domain_destroy(h)
+    return out
 
 
 class Multigrid:

@@ -91,6 +91,24 @@ int hns_grid_get_values(const hns_grid* g, const int32_t* ijk_host, uint64_t n, 
 int hns_grid_neighbors_download(const hns_grid* g, int32_t* dst_host);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Domain construction on the device -- replaces the per-cook OpenVDB pass of SOP_HNanoSolverVerb::cook
+ * (src/SOP/HNanoSolver/SOP_HNanoSolver.cpp:188-199): topologyUnion(velocity tree), dilateVoxels(padding, NN_FACE_EDGE_VERTEX),
+ * topologyUnion(sdf tree); the leaf nodes of the result are the bricks of the sidecar (src/Utils/GridBuilder.hpp:221-239).
+ * vel_origins: HOST int32[n_vel][3] leaf origins of the velocity grid (any order); vel_masks: HOST uint64[n_vel][8] active-voxel masks
+ * of those leaves (bit x<<6 | y<<3 | z, i.e. word x, bit y*8+z -- the leaf mask layout of OpenVDB and NanoVDB) or NULL = every voxel
+ * active; padding in voxels (0..64); sdf_origins: HOST int32[n_sdf][3] leaf origins of the collision SDF grid (n_sdf = 0 without one).
+ * Result: the domain's leaf origins in NanoVDB order = the `origins` argument of hns_grid_create_from_origins.
+ * Coordinates must lie within +-(2^23 - 128) voxels.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct hns_domain hns_domain;
+int hns_domain_build(const int32_t* vel_origins, const uint64_t* vel_masks, uint64_t n_vel, int padding, const int32_t* sdf_origins, uint64_t n_sdf,
+                     hns_domain** out);
+void hns_domain_destroy(hns_domain* d);
+uint64_t hns_domain_num_leaves(const hns_domain* d);
+int hns_domain_origins(const hns_domain* d, int32_t* origins_out);       /* HOST int32[num_leaves][3] */
+int hns_domain_create_grid(const hns_domain* d, float voxel_size, hns_grid** out);
+
+/* ---------------------------------------------------------------------------------------------------------
  * NanoVDB files (host only, no GPU): the index grid as an uncompressed .nvdb segment -- FileHeader, FileMetaData, name, raw grid;
  * reference externals/nanovdb/NanoVDB.h:6252-6422 -- readable by stock NanoVDB tools, and back. The sidecar arrays are plain
  * float arrays in leaf order and are stored by the caller next to it (hnanosolver_b200/io.py uses .npy).

@@ -294,6 +294,43 @@ class OracleIndex:
         return vel, div, p
 
 
+def domain_leaves(vel_origins, vel_masks, padding: int, sdf_origins=None) -> np.ndarray:
+    """Host set-based restatement of the domain construction of SOP_HNanoSolverVerb::cook (reference
+    src/SOP/HNanoSolver/SOP_HNanoSolver.cpp:188-199): topologyUnion(velocity tree) -> every leaf node of the velocity grid;
+    dilateVoxels(padding, NN_FACE_EDGE_VERTEX) -> every leaf an active voxel reaches within `padding` voxels in the Chebyshev metric
+    (`padding` rounds of 26-neighbour dilation); topologyUnion(sdf tree) -> every leaf node of the SDF grid. Returns the leaf origins in
+    NanoVDB order. PARITY UNPINNED against OpenVDB itself (an un-vendored dependency): this restates its documented
+    semantics voxel by voxel.  vel_masks: uint64 (n, 8), word x, bit y*8+z; None = all active."""
+    vo = np.asarray(vel_origins, np.int64).reshape(-1, 3)
+    leaves = {tuple(o) for o in vo.tolist()}
+    if sdf_origins is not None:
+        leaves |= {tuple(o) for o in np.asarray(sdf_origins, np.int64).reshape(-1, 3).tolist()}
+    p = int(padding)
+    for l in range(vo.shape[0]):
+        if vel_masks is None:
+            bits = np.ones(512, bool)
+        else:
+            words = np.asarray(vel_masks[l], np.uint64)
+            bits = ((words[:, None] >> np.arange(64, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool).reshape(512)
+        n = np.nonzero(bits)[0]
+        if n.size == 0:
+            continue
+        v = vo[l][None, :] + np.stack([n >> 6, (n >> 3) & 7, n & 7], 1)          # active voxels, global coordinates
+        lo, hi = (v - p) >> 3, (v + p) >> 3                                       # leaf range the dilated voxel touches, per axis
+        for a, b in {(tuple(x), tuple(y)) for x, y in zip(lo.tolist(), hi.tolist())}:
+            for X in range(a[0], b[0] + 1):
+                for Y in range(a[1], b[1] + 1):
+                    for Z in range(a[2], b[2] + 1):
+                        leaves.add((8 * X, 8 * Y, 8 * Z))
+    out = np.array(sorted(leaves), np.int32).reshape(-1, 3)
+    c = out.astype(np.int64)
+    b = c + (1 << 31)
+    tile = ((b[:, 0] >> 12) << 42) | ((b[:, 1] >> 12) << 21) | (b[:, 2] >> 12)
+    up = (((c[:, 0] & 4095) >> 7) << 10) | (((c[:, 1] & 4095) >> 7) << 5) | ((c[:, 2] & 4095) >> 7)
+    lo_ = (((c[:, 0] & 127) >> 3) << 8) | (((c[:, 1] & 127) >> 3) << 4) | ((c[:, 2] & 127) >> 3)
+    return np.ascontiguousarray(out[np.lexsort((lo_, up, tile))])
+
+
 def sum_squares(a) -> float:
     a, ap = _f32(np.asarray(a).reshape(-1))
     return float(lib().ora_sum_squares_f64(ap, a.size))
