@@ -35,6 +35,12 @@ SIGNATURES = {
     "hns_nvdb_file_grid_bytes": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint64)]),
     "hns_nvdb_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64]),
     "hns_nvdb_leaf_origins": (C.c_int, [C.c_void_p, C.c_uint64, c_i32p, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),
+    "hns_nvdb_grid_info": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_float),
+                                     C.c_char_p]),
+    "hns_nvdb_leaf_topology": (C.c_int, [C.c_void_p, C.c_uint64, c_i32p, c_u64p, C.POINTER(C.c_uint64)]),
+    "hns_sidecar_from_nanovdb": (C.c_int, [C.c_void_p, C.c_uint64, c_i32p, C.c_uint64, C.c_int, C.c_void_p]),
+    "hns_sidecar_nanovdb_bytes": (C.c_uint64, [c_i32p, C.c_uint64, C.c_int]),
+    "hns_sidecar_to_nanovdb": (C.c_int, [c_i32p, C.c_uint64, c_u64p, C.c_void_p, C.c_int, C.c_float, C.c_char_p, C.c_void_p, C.c_uint64]),
     "hns_grid_create_from_coords": (C.c_int, [c_i32p, C.c_uint64, C.c_float, C.c_int, C.POINTER(C.c_void_p)]),
     "hns_grid_create_from_origins": (C.c_int, [c_i32p, C.c_uint64, C.c_float, C.POINTER(C.c_void_p)]),
     "hns_grid_destroy": (None, [C.c_void_p]),

@@ -74,3 +74,89 @@ def load_cache(directory: str):
         data.addValueBlock(kind, b["name"])
         data.pValues(kind, b["name"])[:] = arr
     return origins, h, data
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# value grids <-> sidecar blocks: IndexGridBuilder::build / writeIndexGrid (reference src/Utils/GridBuilder.hpp:87-216) over NanoVDB
+# float / Vec3f grids (OpenVDB is not vendored with the reference; NanoVDB grids carry the same 512-value leaf buffers)
+# ------------------------------------------------------------------------------------------------------------------
+GRID_TYPE_FLOAT, GRID_TYPE_VEC3F, GRID_TYPE_ONINDEX = 1, 6, 20
+GRID_CLASS_FOG_VOLUME, GRID_CLASS_STAGGERED = 2, 3
+
+
+def _buf(a):
+    a = np.ascontiguousarray(a, np.uint8)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def grid_info(nanovdb_buffer: np.ndarray) -> dict:
+    buf, p = _buf(nanovdb_buffer)
+    t, c, n, h = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_float()
+    name = C.create_string_buffer(256)
+    _lib.check(_lib.lib().hns_nvdb_grid_info(p, buf.size, C.byref(t), C.byref(c), C.byref(n), C.byref(h), name))
+    return {"grid_type": t.value, "grid_class": c.value, "num_leaves": n.value, "voxel_size": float(h.value), "name": name.value.decode()}
+
+
+def leaf_topology(nanovdb_buffer: np.ndarray):
+    """(leaf origins int32 (L, 3), active-voxel masks uint64 (L, 8)) of a float / Vec3f / index grid: the inputs of build_domain"""
+    buf, p = _buf(nanovdb_buffer)
+    n = C.c_uint64()
+    L = _lib.lib()
+    _lib.check(L.hns_nvdb_leaf_topology(p, buf.size, None, None, C.byref(n)))
+    origins, masks = np.empty((n.value, 3), np.int32), np.empty((n.value, 8), np.uint64)
+    _lib.check(L.hns_nvdb_leaf_topology(p, buf.size, origins.ctypes.data_as(_lib.c_i32p), masks.ctypes.data_as(_lib.c_u64p), C.byref(n)))
+    return origins, masks
+
+
+def sidecar_from_grid(nanovdb_buffer: np.ndarray, domain_origins: np.ndarray, fill_byte: int = 0) -> np.ndarray:
+    """One block of IndexGridBuilder::build: float32 (N,) for a float grid, (N, 3) for a Vec3f grid, N = 512 per domain leaf; leaves
+    the grid does not have are filled with bytes `fill_byte` (1 for the collision SDF, GridBuilder.hpp:108)."""
+    buf, p = _buf(nanovdb_buffer)
+    o = np.ascontiguousarray(np.asarray(domain_origins, np.int32).reshape(-1, 3))
+    comps = 3 if grid_info(buf)["grid_type"] == GRID_TYPE_VEC3F else 1
+    out = np.empty((o.shape[0] * 512, 3) if comps == 3 else o.shape[0] * 512, np.float32)
+    _lib.check(_lib.lib().hns_sidecar_from_nanovdb(p, buf.size, o.ctypes.data_as(_lib.c_i32p), o.shape[0], int(fill_byte), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def grid_from_sidecar(domain_origins: np.ndarray, values: np.ndarray, voxel_size: float, name: str, masks=None) -> np.ndarray:
+    """writeIndexGrid: the block as a NanoVDB float (FogVolume) or Vec3f (Staggered) grid over the domain's leaves -> uint8 buffer"""
+    o = np.ascontiguousarray(np.asarray(domain_origins, np.int32).reshape(-1, 3))
+    v = np.ascontiguousarray(values, np.float32)
+    comps = 3 if v.ndim == 2 else 1
+    assert v.shape[0] == o.shape[0] * 512
+    m = None if masks is None else np.ascontiguousarray(np.asarray(masks, np.uint64).reshape(-1, 8))
+    L = _lib.lib()
+    n = L.hns_sidecar_nanovdb_bytes(o.ctypes.data_as(_lib.c_i32p), o.shape[0], comps)
+    out = np.empty(n, np.uint8)
+    _lib.check(L.hns_sidecar_to_nanovdb(o.ctypes.data_as(_lib.c_i32p), o.shape[0], m.ctypes.data_as(_lib.c_u64p) if m is not None else None,
+                                        v.ctypes.data_as(C.c_void_p), comps, voxel_size, name.encode(), out.ctypes.data_as(C.c_void_p), out.size))
+    return out
+
+
+def build_sidecar(domain_origins: np.ndarray, grids) -> GridIndexedData:
+    """IndexGridBuilder over a domain: grids = [(name, nanovdb buffer, is_sdf)], blocks added in that order (GridBuilder.hpp:58-166)"""
+    from . import synth
+
+    o = np.ascontiguousarray(np.asarray(domain_origins, np.int32).reshape(-1, 3))
+    data = GridIndexedData()
+    data.allocateCoords(o.shape[0] * 512)
+    if o.shape[0]:
+        data.pCoords()[:] = synth.dense_coords(o)
+    for name, buf, is_sdf in grids:
+        block = sidecar_from_grid(buf, o, 1 if is_sdf else 0)
+        kind = VEC3F if block.ndim == 2 else FLOAT
+        data.addValueBlock(kind, name)
+        data.pValues(kind, name)[:] = block
+    return data
+
+
+def write_index_grids(directory: str, domain_origins: np.ndarray, data: GridIndexedData, voxel_size: float) -> list:
+    """writeIndexGrid for every block of the sidecar: one <name>.nvdb per block; returns the paths"""
+    os.makedirs(directory, exist_ok=True)
+    paths = []
+    for name, kind, arr in data._blocks:
+        path = os.path.join(directory, f"{name}.nvdb")
+        write_nvdb(path, grid_from_sidecar(domain_origins, arr, voxel_size, name))
+        paths.append(path)
+    return paths

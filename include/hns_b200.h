@@ -120,6 +120,24 @@ int hns_nvdb_read(const char* path, void* dst, uint64_t capacity);              
  * the arguments of hns_grid_create_from_origins */
 int hns_nvdb_leaf_origins(const void* nanovdb_buffer, uint64_t bytes, int32_t* origins_out, uint64_t* num_leaves_out, float* voxel_size_out);
 
+/* Value grids <-> sidecar blocks (host only): what IndexGridBuilder::build / writeIndexGrid do over OpenVDB grids
+ * (src/Utils/GridBuilder.hpp:87-166, 168-216), over NanoVDB float (GridType 1) and Vec3f (GridType 6) grids, which carry the same
+ * 512-value leaf buffers. `buffer` is a host copy of one grid (hns_nvdb_read). */
+int hns_nvdb_grid_info(const void* buffer, uint64_t bytes, uint32_t* grid_type, uint32_t* grid_class, uint64_t* num_leaves, float* voxel_size,
+                       char* name256);
+/* leaf origins (int32[L][3]) and active-voxel masks (uint64[L][8], bit x<<6|y<<3|z) in the buffer's leaf order: the topology inputs of
+ * hns_domain_build; either may be NULL */
+int hns_nvdb_leaf_topology(const void* buffer, uint64_t bytes, int32_t* origins_out, uint64_t* masks_out, uint64_t* num_leaves_out);
+/* build(): per domain leaf the grid's whole leaf buffer at that origin, or 512 values whose bytes are `fill_byte` where the grid has no
+ * leaf (0 for float / vector blocks; 1 for the collision SDF, GridBuilder.hpp:108). out: float[n_leaves*512] or float[n_leaves*512][3] */
+int hns_sidecar_from_nanovdb(const void* buffer, uint64_t bytes, const int32_t* domain_origins, uint64_t n_leaves, int fill_byte, void* out);
+/* writeIndexGrid(): a float grid of class FogVolume (components 1) or a Vec3f grid of class Staggered (components 3) named `name` with
+ * a leaf at every domain origin (NanoVDB order) holding the block's values; masks: uint64[n_leaves][8] or NULL = every voxel active.
+ * out_buf must hold hns_sidecar_nanovdb_bytes(...) bytes; write it with hns_nvdb_write. */
+uint64_t hns_sidecar_nanovdb_bytes(const int32_t* domain_origins, uint64_t n_leaves, int components);
+int hns_sidecar_to_nanovdb(const int32_t* domain_origins, uint64_t n_leaves, const uint64_t* masks, const void* values, int components,
+                           float voxel_size, const char* name, void* out_buf, uint64_t capacity);
+
 /* ---------------------------------------------------------------------------------------------------------
  * One-shot launchers on HOST sidecar arrays, in place, synchronous -- the drop-in equivalents of the reference's
  * extern "C" launchers. `stream` is a cudaStream_t passed as void* (may be NULL).

@@ -93,3 +93,73 @@ uint64_t refhost_read_nvdb(const char* path, void* dst, uint64_t capacity) {
 	return n;
 }
 }
+
+// ---- NanoVDB's own float / Vec3f grids on the CPU (pins the product's value-grid IO, hnanosolver_b200/csrc/nvdb_io.cu) ----
+// a grid built by NanoVDB's host builder from (coords, values): components 1 -> float, 3 -> Vec3f
+struct RefValueGrid {
+	nanovdb::GridHandle<nanovdb::HostBuffer> handle;
+};
+extern "C" {
+void* refhost_value_grid_create(const int32_t* coords, const float* values, uint64_t n, int components, double voxel_size, const char* name, int grid_class) {
+	auto* out = new RefValueGrid();
+	const auto cls = static_cast<nanovdb::GridClass>(grid_class);
+	if (components == 1) {
+		nanovdb::tools::build::Grid<float> src(0.0f, name, cls);
+		src.setTransform(voxel_size);
+		auto acc = src.getAccessor();
+		for (uint64_t i = 0; i < n; ++i) acc.setValue(nanovdb::Coord(coords[3 * i], coords[3 * i + 1], coords[3 * i + 2]), values[i]);
+		out->handle = nanovdb::tools::createNanoGrid(src);
+	} else {
+		nanovdb::tools::build::Grid<nanovdb::Vec3f> src(nanovdb::Vec3f(0.0f), name, cls);
+		src.setTransform(voxel_size);
+		auto acc = src.getAccessor();
+		for (uint64_t i = 0; i < n; ++i)
+			acc.setValue(nanovdb::Coord(coords[3 * i], coords[3 * i + 1], coords[3 * i + 2]), nanovdb::Vec3f(values[3 * i], values[3 * i + 1], values[3 * i + 2]));
+		out->handle = nanovdb::tools::createNanoGrid(src);
+	}
+	return out;
+}
+void refhost_value_grid_destroy(void* g) { delete static_cast<RefValueGrid*>(g); }
+uint64_t refhost_value_grid_bytes(void* g) { return static_cast<RefValueGrid*>(g)->handle.buffer().size(); }
+const void* refhost_value_grid_data(void* g) { return static_cast<RefValueGrid*>(g)->handle.data(); }
+
+// a grid buffer (e.g. written by the product) read through NanoVDB's own classes: values + active states at n coordinates
+// returns 0 on success, 1 when the buffer is not a valid grid of the expected type
+int refhost_query_grid(const void* buffer, const int32_t* ijk, uint64_t n, int components, float* values_out, uint8_t* active_out) {
+	const auto* gd = static_cast<const nanovdb::GridData*>(buffer);
+	if (!gd->isValid()) return 1;
+	if (components == 1) {
+		if (gd->mGridType != nanovdb::GridType::Float) return 1;
+		const auto* grid = static_cast<const nanovdb::NanoGrid<float>*>(buffer);
+		auto acc = grid->getAccessor();
+		for (uint64_t i = 0; i < n; ++i) {
+			const nanovdb::Coord c(ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2]);
+			values_out[i] = acc.getValue(c), active_out[i] = acc.isActive(c);
+		}
+	} else {
+		if (gd->mGridType != nanovdb::GridType::Vec3f) return 1;
+		const auto* grid = static_cast<const nanovdb::NanoGrid<nanovdb::Vec3f>*>(buffer);
+		auto acc = grid->getAccessor();
+		for (uint64_t i = 0; i < n; ++i) {
+			const nanovdb::Coord c(ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2]);
+			const nanovdb::Vec3f v = acc.getValue(c);
+			values_out[3 * i] = v[0], values_out[3 * i + 1] = v[1], values_out[3 * i + 2] = v[2], active_out[i] = acc.isActive(c);
+		}
+	}
+	return 0;
+}
+// what NanoVDB reports about a grid buffer: out[0] grid class, [1] grid type, [2] leaf count, [3] lower count, [4] upper count, [5] active voxels
+int refhost_grid_meta(const void* buffer, uint64_t* out6, char* name256, double* voxel_size, int32_t* index_bbox6) {
+	const auto* gd = static_cast<const nanovdb::GridData*>(buffer);
+	if (!gd->isValid()) return 1;
+	const auto* grid = static_cast<const nanovdb::NanoGrid<float>*>(buffer);  // GridData / TreeData accessors do not depend on the value type
+	out6[0] = uint64_t(gd->mGridClass), out6[1] = uint64_t(gd->mGridType);
+	const auto* tree = reinterpret_cast<const nanovdb::TreeData*>(static_cast<const uint8_t*>(buffer) + sizeof(nanovdb::GridData));
+	out6[2] = tree->mNodeCount[0], out6[3] = tree->mNodeCount[1], out6[4] = tree->mNodeCount[2], out6[5] = tree->mVoxelCount;
+	strncpy(name256, gd->mGridName, 255);
+	*voxel_size = gd->mVoxelSize[0];
+	const auto bbox = grid->indexBBox();
+	for (int a = 0; a < 3; ++a) index_bbox6[a] = bbox.min()[a], index_bbox6[3 + a] = bbox.max()[a];
+	return 0;
+}
+}

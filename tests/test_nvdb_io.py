@@ -124,3 +124,129 @@ def test_cache_round_trip(w, tmp_path):
     assert np.array_equal(back.pValues(VEC3F, "vel"), w.velocity)
     for n, s in zip(w.scalar_names, w.scalars):
         assert np.array_equal(back.pValues(FLOAT, n), s)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# value grids <-> sidecar blocks (IndexGridBuilder::build / writeIndexGrid, reference src/Utils/GridBuilder.hpp:87-216) over NanoVDB
+# float / Vec3f grids, against NanoVDB's own host builder, accessor and file IO
+# ------------------------------------------------------------------------------------------------------------------
+def _refvalue():
+    L = _refhost()
+    L.refhost_value_grid_create.restype = C.c_void_p
+    L.refhost_value_grid_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_double, C.c_char_p, C.c_int]
+    L.refhost_value_grid_destroy.argtypes = [C.c_void_p]
+    L.refhost_value_grid_bytes.restype = C.c_uint64
+    L.refhost_value_grid_bytes.argtypes = [C.c_void_p]
+    L.refhost_value_grid_data.restype = C.c_void_p
+    L.refhost_value_grid_data.argtypes = [C.c_void_p]
+    L.refhost_query_grid.restype = C.c_int
+    L.refhost_query_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    L.refhost_grid_meta.restype = C.c_int
+    L.refhost_grid_meta.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_void_p]
+    return L
+
+
+def _nanovdb_grid(coords, values, comps, h, name, cls):
+    """a float / Vec3f grid made by NanoVDB's own builder (tools::build::Grid + createNanoGrid) -> uint8 buffer"""
+    L = _refvalue()
+    c = np.ascontiguousarray(coords, np.int32)
+    v = np.ascontiguousarray(values, np.float32)
+    g = L.refhost_value_grid_create(c.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), c.shape[0], comps, float(h), name.encode(), cls)
+    try:
+        n = L.refhost_value_grid_bytes(g)
+        return np.ctypeslib.as_array(C.cast(L.refhost_value_grid_data(g), C.POINTER(C.c_uint8)), shape=(n,)).copy()
+    finally:
+        L.refhost_value_grid_destroy(g)
+
+
+@needs_refhost
+@pytest.mark.parametrize("comps", [1, 3])
+def test_sidecar_block_from_a_nanovdb_grid_is_indexgridbuilder_build(w, comps, tmp_path):
+    """build(): leaves the grid has are copied whole, the others filled with bytes 0 (or 1 for the SDF)"""
+    rng = np.random.default_rng(5)
+    keep = rng.random(w.num_leaves) < 0.7 if w.num_leaves > 1 else np.ones(1, bool)      # the grid lacks some of the domain's leaves
+    leaf_of_voxel = np.repeat(np.arange(w.num_leaves), 512)
+    active = keep[leaf_of_voxel] & (rng.random(w.num_voxels) < 0.6)                      # ... and has inactive voxels inside its leaves
+    active[np.nonzero(keep)[0] * 512] = True                                             # every kept leaf exists
+    vals = rng.standard_normal((w.num_voxels, comps) if comps == 3 else w.num_voxels).astype(np.float32)
+    buf = _nanovdb_grid(w.coords[active], vals[active], comps, w.voxel_size, "density", hio.GRID_CLASS_FOG_VOLUME)
+    path = str(tmp_path / "in.nvdb")
+    assert _refhost().refhost_write_nvdb(path.encode(), buf.ctypes.data_as(C.c_void_p), 0) == 0      # NanoVDB writes the file ...
+    got_buf = hio.read_nvdb(path)                                                                    # ... the product reads it
+    info = hio.grid_info(got_buf)
+    assert info["name"] == "density" and info["grid_type"] == (hio.GRID_TYPE_VEC3F if comps == 3 else hio.GRID_TYPE_FLOAT)
+    assert info["num_leaves"] == int(keep.sum()) and info["voxel_size"] == np.float32(w.voxel_size)
+    for fill in (0, 1):
+        block = hio.sidecar_from_grid(got_buf, w.origins, fill)
+        want = np.where(active.reshape(-1, *([1] * (vals.ndim - 1))), vals, np.float32(0))           # inactive voxels of a NanoVDB leaf hold the background
+        missing = ~keep[leaf_of_voxel]
+        want[missing] = np.frombuffer(bytes([fill]) * 4, np.float32)[0]
+        assert np.array_equal(block.view(np.uint32), want.astype(np.float32).view(np.uint32))
+    origins, masks = hio.leaf_topology(got_buf)
+    assert np.array_equal(origins, w.origins[keep])
+    bits = ((masks[:, :, None] >> np.arange(64, dtype=np.uint64)[None, None, :]) & np.uint64(1)).astype(bool).reshape(-1, 512)
+    assert np.array_equal(bits, active.reshape(-1, 512)[keep])
+
+
+@needs_refhost
+@pytest.mark.parametrize("comps", [1, 3])
+def test_grid_written_from_a_sidecar_block_is_read_by_nanovdb(w, comps, tmp_path):
+    """writeIndexGrid(): FogVolume float / Staggered Vec3f grid over the domain's leaves, values = the block, readable by stock NanoVDB"""
+    L = _refvalue()
+    rng = np.random.default_rng(6)
+    vals = rng.standard_normal((w.num_voxels, 3) if comps == 3 else w.num_voxels).astype(np.float32)
+    name = "vel" if comps == 3 else "temperature"
+    buf = hio.grid_from_sidecar(w.origins, vals, w.voxel_size, name)
+    path = str(tmp_path / "out.nvdb")
+    hio.write_nvdb(path, buf)
+    n = L.refhost_read_nvdb(path.encode(), None, 0)                                                  # NanoVDB's reader accepts the file
+    assert n == buf.size
+    back = np.empty(n, np.uint8)
+    L.refhost_read_nvdb(path.encode(), back.ctypes.data_as(C.c_void_p), n)
+    assert np.array_equal(back, buf)
+    meta, nm, h, bbox = np.zeros(6, np.uint64), C.create_string_buffer(256), C.c_double(), np.zeros(6, np.int32)
+    assert L.refhost_grid_meta(back.ctypes.data_as(C.c_void_p), meta.ctypes.data_as(C.c_void_p), nm, C.byref(h), bbox.ctypes.data_as(C.c_void_p)) == 0
+    assert nm.value.decode() == name and h.value == float(np.float32(w.voxel_size))
+    assert meta[0] == (hio.GRID_CLASS_STAGGERED if comps == 3 else hio.GRID_CLASS_FOG_VOLUME)        # GridBuilder.hpp:181-186
+    assert meta[1] == (hio.GRID_TYPE_VEC3F if comps == 3 else hio.GRID_TYPE_FLOAT)
+    assert meta[2] == w.num_leaves and meta[5] == w.num_voxels
+    assert bbox[:3].tolist() == w.origins.min(0).tolist() and bbox[3:].tolist() == (w.origins.max(0) + 7).tolist()
+    # every voxel of the domain through NanoVDB's accessor, plus probes outside it
+    probe = np.concatenate([w.coords, w.coords[:: max(1, w.num_voxels // 500)] + np.array([4096, -64, 9])]).astype(np.int32)
+    got = np.empty((probe.shape[0], comps) if comps == 3 else probe.shape[0], np.float32)
+    act = np.empty(probe.shape[0], np.uint8)
+    assert L.refhost_query_grid(back.ctypes.data_as(C.c_void_p), np.ascontiguousarray(probe).ctypes.data_as(C.c_void_p), probe.shape[0], comps,
+                                got.ctypes.data_as(C.c_void_p), act.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(got[:w.num_voxels], vals) and act[:w.num_voxels].all()
+    inside = O.OracleIndex(w.coords).get_values(probe[w.num_voxels:]) != 0
+    assert not act[w.num_voxels:][~inside].any() and not got[w.num_voxels:][~inside].any()
+    # and back into a block through the product's reader: the round trip is the identity
+    assert np.array_equal(hio.sidecar_from_grid(back, w.origins), vals)
+
+
+def test_sidecar_round_trip_without_nanovdb(w, tmp_path):
+    """build_sidecar(write_index_grids(data)) == data, collision SDF fill included; runs without the reference build"""
+    data = GridIndexedData()
+    data.allocateCoords(w.num_voxels)
+    data.pCoords()[:] = w.coords
+    data.addValueBlock(VEC3F, "vel")
+    data.pValues(VEC3F, "vel")[:] = w.velocity
+    for nm, a in zip(w.scalar_names, w.scalars):
+        data.addValueBlock(FLOAT, nm)
+        data.pValues(FLOAT, nm)[:] = a
+    paths = hio.write_index_grids(str(tmp_path), w.origins, data, w.voxel_size)
+    grids = [(os.path.basename(p)[:-5], hio.read_nvdb(p), False) for p in paths]
+    back = hio.build_sidecar(w.origins, grids)
+    assert back.getBlocksOfType(VEC3F) == ["vel"] and back.getBlocksOfType(FLOAT) == list(w.scalar_names)
+    assert np.array_equal(back.pValues(VEC3F, "vel"), w.velocity)
+    for nm, a in zip(w.scalar_names, w.scalars):
+        assert np.array_equal(back.pValues(FLOAT, nm), a)
+    assert np.array_equal(back.pCoords(), w.coords)
+    # an SDF grid that covers only part of the domain: the rest reads as bytes 0x01 (GridBuilder.hpp:108)
+    half = max(1, w.num_leaves // 2)
+    sdf = hio.grid_from_sidecar(w.origins[:half], np.full(half * 512, 0.25, np.float32), w.voxel_size, "collision_sdf")
+    block = hio.build_sidecar(w.origins, [("collision_sdf", sdf, True)]).pValues(FLOAT, "collision_sdf")
+    assert np.all(block[:half * 512] == np.float32(0.25))
+    assert np.all(block[half * 512:].view(np.uint32) == 0x01010101)
+    with pytest.raises(Exception):
+        hio.grid_from_sidecar(w.origins[::-1] if w.num_leaves > 1 else np.array([[1, 0, 0]], np.int32), np.zeros(w.num_leaves * 512, np.float32), 0.1, "x")
