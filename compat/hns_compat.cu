@@ -91,7 +91,9 @@ const int32_t* coords_of(const HNS::GridIndexedData& d) { return reinterpret_cas
 
 extern "C" void CreateIndexGrid(HNS::GridIndexedData& data, HandleT& handle, const float voxelSize) {
 	hns_grid* g = nullptr;
-	check(hns_grid_create_from_coords(coords_of(data), data.size(), voxelSize, 0, &g));
+	// validate = 2: eight voxels of every 512-block are checked against the dense-brick order the kernels assume (O(leaves)); anything
+	// else is refused with a std::runtime_error instead of being simulated wrongly
+	check(hns_grid_create_from_coords(coords_of(data), data.size(), voxelSize, 2, &g));
 	const uint64_t bytes = hns_grid_nanovdb_bytes(g);
 	auto buffer = nanovdb::cuda::DeviceBuffer::create(bytes, nullptr, false);  // device only, like voxelsToGrid (PointsToGrid.cuh:763)
 	if (cudaMemcpy(buffer.deviceData(), hns_grid_nanovdb_device_ptr(g), bytes, cudaMemcpyDeviceToDevice) != cudaSuccess) {
@@ -122,7 +124,7 @@ extern "C" void Compute_Sim(HNS::GridIndexedData& data, const HandleT& handle, i
 	hns_grid* g = lookup(handle.deviceData(), data.size());
 	hns_grid* temp = nullptr;
 	if (!g) {  // a handle that did not come from our CreateIndexGrid (e.g. a real voxelsToGrid): rebuild the leaf tables from the coords
-		check(hns_grid_create_from_coords(coords_of(data), data.size(), voxelSize, 0, &temp));
+		check(hns_grid_create_from_coords(coords_of(data), data.size(), voxelSize, 2, &temp));
 		g = temp;
 	}
 	hns_combustion_params p{params.expansionRate, params.temperatureRelease, params.buoyancyStrength, params.ambientTemp, params.vorticityScale,
@@ -171,7 +173,7 @@ extern "C" void CombustionKernel(HNS::GridIndexedData& data, const HandleT& hand
 	hns_grid* g = lookup(handle.deviceData(), data.size());
 	hns_grid* temp = nullptr;
 	if (!g) {
-		check(hns_grid_create_from_coords(coords_of(data), data.size(), voxelSize, 0, &temp));
+		check(hns_grid_create_from_coords(coords_of(data), data.size(), voxelSize, 2, &temp));
 		g = temp;
 	}
 	const int rc = hns_combustion_kernel(g, reinterpret_cast<float*>(data.pValues<openvdb::Vec3f>(vec[0])), data.size(), dt, voxelSize, stream);

@@ -71,8 +71,9 @@ int hns_set_l2_persist_mb(int megabytes);
  * nanovdb::tools::cuda::voxelsToGrid<ValueOnIndex>(coords, N, voxelSize) for HNS's dense-leaf sidecar.
  * ------------------------------------------------------------------------------------------------------- */
 /* coords: HOST int32[n_voxels][3] exactly as HNS::GridIndexedData::pCoords() holds them. Only the first coord of
- * every 512-block is needed to build the grid; validate != 0 additionally checks on the device that every block
- * is the dense brick in offset order (the reference silently produces inconsistent results otherwise). */
+ * every 512-block is needed to build the grid. validate = 1 additionally checks (on the host) that every block is the dense brick in
+ * offset order, validate = 2 spot-checks eight voxels per block (O(leaves): the drop-in CreateIndexGrid does this on every cook);
+ * a violation is HNS_ERR_TOPOLOGY (the reference silently produces inconsistent results for such input). */
 int hns_grid_create_from_coords(const int32_t* coords, uint64_t n_voxels, float voxel_size, int validate, hns_grid** out);
 /* origins: HOST int32[n_leaves][3], multiples of 8, in NanoVDB order. */
 int hns_grid_create_from_origins(const int32_t* origins, uint64_t n_leaves, float voxel_size, hns_grid** out);

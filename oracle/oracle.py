@@ -29,6 +29,8 @@ def build(ref: bool | None = None) -> None:
         ref = os.path.isdir("/root/reference/src/Cuda")
     if ref:
         subprocess.check_call(["make", "-s", "-j4", "-C", _HERE, "ref"])
+        if os.path.exists(os.path.join(os.path.dirname(_HERE), "compat", "libhns_compat.so")):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "_ref/libcompat_driver.so"])
 
 
 def _f32(a):

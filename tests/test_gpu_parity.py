@@ -592,6 +592,52 @@ def test_config4_full_frame_matches_reference_kernels(c4):
         assert_close(got["scalars"][i], want["scalars"][i], f"scalar {i}")
 
 
+@needs_ref
+def test_config4_all_in_one_frame_matches_reference_compute_sim(c4):
+    """What bench.py times: the FULL HNanoSolver frame (combustion + buoyancy, S = 5 float blocks, I = 40) on the 512^3 sparse smoke,
+    through the launcher pair CreateIndexGrid + Compute_Sim, against the unmodified reference's own CreateIndexGrid + Compute_Sim on
+    the same GPU."""
+    w = c4
+    fields = dict(density=w.scalars[0], **synth.combustion_fields(w))
+    coords = synth.dense_coords(w.origins)
+    rd = O.RefData(coords)
+    rd.add_vec3("vel", w.velocity)
+    for k, v in fields.items():
+        rd.add_float(k, v)
+    O.ref_cook_frame(rd, 40, w.dt, w.voxel_size, PARAMS6)
+    d = GridIndexedData.from_arrays(coords, w.velocity.copy(), "vel", **{k: v.copy() for k, v in fields.items()})
+    g = H.CreateIndexGrid(d, w.voxel_size)
+    H.Compute_Sim(d, g, 40, w.dt, w.voxel_size, H.CombustionParams(*PARAMS6.tolist()), False)
+    assert_close(d.pValues(VEC3F, "vel"), rd.blocks["vel"], "Compute_Sim velocity")
+    for k in fields:
+        assert_close(d.pValues(FLOAT, k), rd.blocks[k], f"Compute_Sim {k}")
+
+
+def test_config1_reference_host_path_case():
+    """BASELINE.json config 1 at its stated size: 64^3 smoke sphere, one density advection (the stand-alone advect_scalar semantics of
+    AdvectIndexGrid) + one divergence, against the oracle and -- when present -- the reference's own launchers."""
+    w = synth.WORKLOADS["c1"]()
+    assert w.origins.max() + 8 <= 64 + 16
+    ix = O.OracleIndex(w.coords)
+    d = GridIndexedData.from_arrays(w.coords, w.velocity.copy(), "vel", density=w.scalars[0].copy(), divergence=np.zeros(w.num_voxels, np.float32))
+    H.Divergence(d, w.voxel_size)
+    assert_close(d.pValues(FLOAT, "divergence"), ix.divergence(w.velocity, w.voxel_size), "divergence")
+    d2 = GridIndexedData.from_arrays(w.coords, w.velocity.copy(), "vel", density=w.scalars[0].copy())
+    H.AdvectIndexGrid(d2, w.dt, w.voxel_size)
+    assert_close(d2.pValues(FLOAT, "density"), ix.advect_scalar(w.velocity, w.scalars[0], w.dt, w.voxel_size), "advect_scalar")
+    if O.ref_gpu_available():
+        rd = O.RefData(w.coords)
+        rd.add_vec3("vel", w.velocity)
+        rd.add_float("density", w.scalars[0])
+        O.ref_advect_index_grid(rd, w.dt, w.voxel_size)
+        assert_close(d2.pValues(FLOAT, "density"), rd.blocks["density"], "AdvectIndexGrid vs the reference launcher")
+        rd = O.RefData(w.coords)
+        rd.add_vec3("vel", w.velocity)
+        rd.add_float("divergence", np.zeros(w.num_voxels, np.float32))
+        O.ref_divergence(rd, w.voxel_size)
+        assert_close(d.pValues(FLOAT, "divergence"), rd.blocks["divergence"], "Divergence vs the reference launcher")
+
+
 def test_config4_size_independent_properties(c4):
     w = c4
     g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
@@ -726,3 +772,35 @@ def test_compat_library_throws_the_reference_exception_types():
             O.ref_compute_sim(d, g, 4, w.dt, w.voxel_size, PARAMS6, False)
         with pytest.raises(RuntimeError, match="voxelSize must be positive"):
             O.ref_compute_sim(d, g, 4, w.dt, 0.0, PARAMS6, False)
+        # a sidecar whose 512-blocks are not dense bricks in offset order is refused by the drop-in CreateIndexGrid (C++ exception through
+        # the reference's own signature), not simulated wrongly; the reference itself accepts it silently
+        c = w.coords.copy()
+        c[512 + 64] += np.array([1, 0, 0], np.int32)
+        bad = O.RefData(c)
+        bad.add_vec3("vel", w.velocity)
+        with pytest.raises(RuntimeError, match="not a dense leaf"):
+            O.RefGrid(bad, w.voxel_size)
+
+
+def test_two_devices_in_one_process():
+    """hns_set_device: function attributes (the >48 KB dynamic shared memory opt-in of the advection kernels) and the SM count belong
+    to a device, not to the process."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from hnanosolver_b200 import _lib
+
+    w = synth.smoke_sphere(32, 1)
+    want = None
+    try:
+        for dev in (0, 1, 0):
+            _lib.check(_lib.lib().hns_set_device(dev))
+            got = run_product_frame(w, 4)
+            if want is None:
+                want = got
+            for k in ("adv", "p", "vel"):
+                assert np.array_equal(got[k], want[k]), (dev, k)
+    finally:
+        _lib.lib().hns_set_device(0)
+
