@@ -82,7 +82,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------------------------
-def build_workload(name: str, rank: int, world: int):
+def build_workload(name: str, rank: int, world: int, scaling: str = "weak"):
     """Returns (workload, field_names, fields, frame_kind). N > 1: weak scaling, the bounding box grows with N
     (512^3 -> 1024x512x512 -> 1024x1024x512 -> 1024^3) and each rank generates and owns one contiguous leaf range."""
     from hnanosolver_b200 import synth
@@ -90,7 +90,7 @@ def build_workload(name: str, rank: int, world: int):
     if world > 1:
         from hnanosolver_b200 import dist
 
-        return dist.build_sharded_workload(name, rank, world)
+        return dist.build_sharded_workload(name, rank, world, scaling)
     w = synth.WORKLOADS[name](with_coords=False)
     if name in ("c4", "c5"):
         fields = dict(density=w.scalars[0], **synth.combustion_fields(w))
@@ -202,6 +202,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--forward-only", action="store_true", help="no back-to-front black sweeps (disables the L2 reuse between launches)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="multi-GPU c4: weak = 512^3 of sparse smoke per GPU (the box grows), strong = BASELINE.json config 4 as stated, the 512^3 box "
+                         "split over the GPUs. c5 (1024^3 narrow band, ~2e8 voxels) is always a fixed total")
     ap.add_argument("--solver", default=None, choices=["rbgs", "mg"],
                     help="pressure solve of the timed frame: the reference's I red-black SOR iterations (default; bit-exact with the reference) or "
                          "multigrid V-cycles to a relative Poisson residual of 1e-4 (default for --workload c3, BASELINE.json config 3)")
@@ -230,7 +233,7 @@ def main():
 
     _lib.lib().hns_set_device(local_rank)
     t0 = time.time()
-    w, names, fields, kind = build_workload(args.workload, rank, world)
+    w, names, fields, kind = build_workload(args.workload, rank, world, args.scaling)
     full = kind == "full"
     S = len(fields)
     log(f"[rank {rank}] workload {w.name}: {w.num_leaves} leaves, {w.num_voxels} voxels, S={S}, frame={kind}, generated in {time.time()-t0:.1f}s")
@@ -358,14 +361,19 @@ def main():
                 e2e_names.append(nm)
     params = H.CombustionParams(*PARAMS6)
 
+    t_grid = [0.0]
+
     def cook():
+        t = time.perf_counter()
         g = H.CreateIndexGrid(data, w.voxel_size)                      # per cook, like SOP_HNanoSolverVerb::cook (SOP_HNanoSolver.cpp:231)
+        t_grid[0] += time.perf_counter() - t                           # synchronous: host build, upload, neighbour-table kernel
         H.Compute_Sim(data, g, ITERATIONS, w.dt, w.voxel_size, params, False)
         g.reset()
 
     for _ in range(2):
         cook()
     torch.cuda.synchronize()
+    t_grid[0] = 0.0
     te = time.perf_counter()
     for _ in range(args.e2e_steps):
         cook()
@@ -373,6 +381,7 @@ def main():
     e2e_ms = (time.perf_counter() - te) * 1e3 / args.e2e_steps
     Se = len(e2e_names)
     e2e = {"value": N / (e2e_ms * 1e-3), "unit": "voxel-updates/s", "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+           "create_index_grid_ms": t_grid[0] * 1e3 / args.e2e_steps,
            "h2d_bytes_per_step": int(N * (12 + 4 * Se) + grid.nanovdb_buffer().size + w.num_leaves * 16),
            "d2h_bytes_per_step": int(N * (12 + 4 * Se)),
            "call": "CreateIndexGrid + Compute_Sim on a pinned GridIndexedData (velocity + %d float blocks), in place, synchronous" % Se}

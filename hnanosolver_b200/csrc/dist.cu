@@ -129,6 +129,10 @@ struct hns_dist {
 	uint64_t push_bytes_per_sweep = 0;
 	bool fused_push = true;         // HNS_FUSED_PUSH=0: pack / push / signal / wait / unpack kernels instead (A/B switch)
 	bool signal_in_kernel = false;  // HNS_SIGNAL_IN_KERNEL=1: the boundary sweep raises the arrival flags itself (A/B switch)
+	cudaStream_t copy_stream = nullptr;  // hns_dist_cook: host <-> device transfers overlapping the frame
+	cudaEvent_t ev_copy[6] = {};
+	bool cook_overlap = true;       // HNS_COOK_OVERLAP=0: transfers and frame one after the other on the caller's stream (A/B switch)
+	bool wait_in_kernel = true;     // HNS_WAIT_IN_KERNEL=0: a one-warp kernel in front of the boundary sweep waits for the peers' flags (A/B switch)
 };
 
 // ---- layout of one peer region: [flags 128 B][ch0 velocity 3 x 512n][ch1 advected velocity 3 x 512n][ch2 red p 256n][ch3 black p 256n]
@@ -231,6 +235,9 @@ void hns_dist_destroy(hns_dist* d) {
 		if (e) cudaEventDestroy(e);
 	for (auto& e : d->ev_B)
 		if (e) cudaEventDestroy(e);
+	if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+	for (auto& e : d->ev_copy)
+		if (e) cudaEventDestroy(e);
 	if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
 	if (d->aux_stream) cudaStreamDestroy(d->aux_stream);
 	if (d->ev_scalars_final) cudaEventDestroy(d->ev_scalars_final);
@@ -316,6 +323,8 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 	d->vel_exchanged_version = ~uint64_t(0);
 	if (const char* e = std::getenv("HNS_SIGNAL_IN_KERNEL")) d->signal_in_kernel = std::atoi(e) != 0;
 	if (const char* e = std::getenv("HNS_FUSED_PUSH")) d->fused_push = std::atoi(e) != 0;
+	if (const char* e = std::getenv("HNS_WAIT_IN_KERNEL")) d->wait_in_kernel = std::atoi(e) != 0;
+	if (const char* e = std::getenv("HNS_COOK_OVERLAP")) d->cook_overlap = std::atoi(e) != 0;
 	if (const char* e = std::getenv("HNS_AUX_BLOCKS")) d->aux_blocks = std::atoi(e);
 	if (const char* e = std::getenv("HNS_PUSH_WHOLE_LEAVES")) d->push_whole_leaves = std::atoi(e) != 0;
 	return HNS_OK;
@@ -570,7 +579,13 @@ int hns_dist_exchange(hns_dist* d, hns_state* s, int n_fields, const int* fields
 
 // The sharded frame: Compute()'s step order (reference src/Cuda/HNanoSolver.cu:159-356) with a ghost exchange in front of every step
 // that reads a neighbour leaf. Asynchronous on `stream`.
-static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, cudaEvent_t* marks);
+// optional stream dependencies of a frame whose inputs arrive / outputs leave on a copy stream while it runs (hns_dist_cook): waited for
+// before the combustion stage / before the scalars are first read by a ghost exchange; recorded once the projected velocity (ghosts
+// included) is final and converted to the host layout
+struct DistDeps {
+	cudaEvent_t combustion_inputs = nullptr, scalar_inputs = nullptr, velocity_done = nullptr;
+};
+static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, cudaEvent_t* marks, const DistDeps* deps = nullptr);
 
 int hns_dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream) { return dist_frame(d, s, iterations, dt, stream, nullptr); }
 
@@ -583,19 +598,46 @@ int hns_dist_cook(hns_dist* d, hns_state* s, float* velocity, int n_float, float
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	const uint64_t n = s->n;
 	if (!n) return HNS_OK;
+	for (int i = 0; i < n_float; ++i)
+		if (!fields[i]) return fail(HNS_ERR_INVALID_ARGUMENT, "null field pointer");
 	if (!s->aos) HNS_CUDA(cudaMalloc(&s->aos, n * 3 * sizeof(float)));
-	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, st));
+	if (!d->copy_stream) {
+		HNS_CUDA(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+		for (auto& e : d->ev_copy) HNS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	}
+	// Like hns_compute_sim (api.cu): the shard crosses PCIe on a copy stream while the kernels run. Velocity (and the collision SDF) first
+	// -- advect_vector and the divergence start as soon as they have landed --, the four combustion inputs next, the remaining scalars
+	// behind them (they are needed by the scalars' ghost exchange behind the pressure solve); the projected velocity goes back while
+	// advect_scalars runs, the scalars when it is done. HNS_COOK_OVERLAP=0: everything on the caller's stream, one after the other.
+	cudaStream_t cs = d->cook_overlap ? d->copy_stream : st;
+	cudaEvent_t e_start = d->ev_copy[0], e_vel_in = d->ev_copy[1], e_comb_in = d->ev_copy[2], e_all_in = d->ev_copy[3], e_vel_out = d->ev_copy[4],
+	            e_done = d->ev_copy[5];
+	HNS_CUDA(cudaEventRecord(e_start, st));
+	HNS_CUDA(cudaStreamWaitEvent(cs, e_start, 0));
+	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, cs));
+	const bool coll = hns_state_collision_active(s);
+	if (coll) HNS_CUDA(cudaMemcpyAsync(s->sc[s->skip_scalar], fields[s->skip_scalar], n * 4, cudaMemcpyHostToDevice, cs));
+	HNS_CUDA(cudaEventRecord(e_vel_in, cs));
+	auto is_comb = [&](int i) { return s->comb_enabled && (i == s->comb_idx[0] || i == s->comb_idx[1] || i == s->comb_idx[2] || i == s->comb_idx[3]); };
+	for (int i = 0; i < n_float; ++i)
+		if (is_comb(i)) HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, cs));
+	HNS_CUDA(cudaEventRecord(e_comb_in, cs));
+	for (int i = 0; i < n_float; ++i)
+		if (!is_comb(i) && !(coll && i == s->skip_scalar)) HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, cs));
+	HNS_CUDA(cudaEventRecord(e_all_in, cs));
+	HNS_CUDA(cudaStreamWaitEvent(st, e_vel_in, 0));
 	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
 	++s->vel_version;
-	for (int i = 0; i < n_float; ++i) {
-		if (!fields[i]) return fail(HNS_ERR_INVALID_ARGUMENT, "null field pointer");
-		HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, st));
-	}
-	int rc = dist_frame(d, s, iterations, dt, stream, nullptr);
+	DistDeps deps;
+	deps.combustion_inputs = e_comb_in, deps.scalar_inputs = e_all_in, deps.velocity_done = e_vel_out;
+	int rc = dist_frame(d, s, iterations, dt, stream, nullptr, &deps);
 	if (rc) return rc;
-	launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, n, st);
-	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, st));
-	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc[i], n * 4, cudaMemcpyDeviceToHost, st));
+	HNS_CUDA(cudaStreamWaitEvent(cs, e_vel_out, 0));
+	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, cs));
+	HNS_CUDA(cudaEventRecord(e_done, st));
+	HNS_CUDA(cudaStreamWaitEvent(cs, e_done, 0));
+	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc[i], n * 4, cudaMemcpyDeviceToHost, cs));
+	HNS_CUDA(cudaStreamSynchronize(cs));
 	HNS_CUDA(cudaStreamSynchronize(st));
 	HNS_CUDA(cudaGetLastError());
 	return check_device_error(d);
@@ -615,7 +657,7 @@ int hns_dist_frame_timed(hns_dist* d, hns_state* s, int iterations, float dt, vo
 	return rc ? rc : check_device_error(d);
 }
 
-static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, cudaEvent_t* marks) {
+static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, cudaEvent_t* marks, const DistDeps* deps) {
 	if (!d || !s || iterations <= 0 || dt < 0.f) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
 	int rc;
 	int mark_i = 0;
@@ -666,7 +708,9 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	}
 	mark();
 	if ((rc = hns_state_divergence(s, 1, stream))) return rc;
+	if (deps && deps->combustion_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->combustion_inputs, 0));
 	if (s->comb_enabled && (rc = hns_state_combustion_buoyancy(s, dt, stream))) return rc;
+	if (deps && deps->scalar_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->scalar_inputs, 0));
 	// The scalars are final until advect_scalars: exchange their ghosts now, on a third stream, behind the pressure solve.
 	const bool scalars_early = d->p2p && s->n_scalars > 0;
 	if (scalars_early) {
@@ -754,6 +798,10 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	if (!scalars_early)
 		for (int i = 0; i < s->n_scalars; ++i) last.push_back(10 + i);
 	if ((rc = exchange_channel(d, s, 4, int(last.size()), last.data(), st))) return rc;
+	if (deps && deps->velocity_done) {
+		launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, s->n, st);
+		HNS_CUDA(cudaEventRecord(deps->velocity_done, st));
+	}
 	if (scalars_early) HNS_CUDA(cudaStreamWaitEvent(st, d->ev_scalars_exchanged, 0));
 	// advect_scalars' "inactive -> element 0" value (reference Kernel.cu:192,225) is global voxel 0's = local voxel 0's: that exchange
 	// has just refreshed it on every rank

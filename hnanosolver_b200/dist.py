@@ -486,19 +486,30 @@ def global_sparse_origins(box, fill: float = 0.30, seed: int = 4) -> np.ndarray:
     return synth.origins_from_mask(mask)
 
 
-def build_sharded_workload(name: str, rank: int, world: int):
-    """(workload of the LOCAL leaves, field names, fields, frame kind); the plan is attached as workload.meta['plan']."""
-    if name not in ("c4", "c5"):
-        raise SystemExit("multi-GPU bench: use --workload c4 (weak scaling of the 512^3 sparse smoke box per GPU)")
-    box = WEAK_BOX.get(world)
-    if box is None:
-        raise SystemExit(f"no weak-scaling box defined for {world} ranks (1, 2, 4, 8)")
-    gorigins = global_sparse_origins(box)
+def build_sharded_workload(name: str, rank: int, world: int, scaling: str = "weak"):
+    """(workload of the LOCAL leaves, field names, fields, frame kind); the plan is attached as workload.meta['plan'].
+    c4, scaling "weak": the sparse-smoke box grows with the number of ranks (512^3 per GPU); c4, "strong": BASELINE.json config 4 as
+    stated -- the 512^3 box split over the ranks; c5: the 1024^3 narrow band (~2e8 voxels) split over the ranks (a fixed total)."""
+    if name == "c5":
+        R = 1024
+        gorigins, half_width = synth.narrow_band_origins(R, 2.0e8)
+        box, label, scaling = (R, R, R), f"c5 narrow band (half width {half_width:.1f} voxels) in a {R}^3 box", "strong"
+    elif name == "c4":
+        if scaling == "strong":
+            box = (512, 512, 512)
+        else:
+            box = WEAK_BOX.get(world)
+            if box is None:
+                raise SystemExit(f"no weak-scaling box defined for {world} ranks (1, 2, 4, 8)")
+        gorigins = global_sparse_origins(box)
+        label = f"c4 {scaling} scaling: sparse smoke ~30% of a {box[0]}x{box[1]}x{box[2]} box"
+    else:
+        raise SystemExit("multi-GPU bench: --workload c4 (weak: 512^3 of sparse smoke per GPU; --scaling strong: the 512^3 box split) or c5")
     plan = make_plan(gorigins, world, rank)
     local = np.ascontiguousarray(gorigins[plan.local_ids])
     vel, density, temperature = synth._swirl_fields(max(box))
-    w = synth._finish(f"sparse{box[0]}x{box[1]}x{box[2]}/rank{rank}", local, vel, [density, temperature], ["density", "temperature"], 40, 4,
-                      with_coords=False, meta=dict(box=box, global_leaves=int(gorigins.shape[0])))
+    w = synth._finish(f"{name}/{box[0]}x{box[1]}x{box[2]}/rank{rank}", local, vel, [density, temperature], ["density", "temperature"], 40, 4,
+                      with_coords=False, meta=dict(box=box, global_leaves=int(gorigins.shape[0]), label=label, scaling=scaling))
     w.meta["plan"] = plan
     fields = dict(density=w.scalars[0], **synth.combustion_fields(w))
     return w, list(fields), list(fields.values()), "full"
@@ -589,18 +600,40 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
     dist.barrier()
     e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.e2e_steps], device=dev)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    # the floor of that call contract: the same bytes up and down over every rank's PCIe link at the same time, no kernels in between
+    dev_bufs = [torch.empty_like(t, device=dev) for t in [vel_pinned] + sc_pinned]
+    host_bufs = [vel_pinned] + sc_pinned
+
+    def copies():
+        for dbuf, hbuf in zip(dev_bufs, host_bufs):
+            dbuf.copy_(hbuf, non_blocking=True)
+        for dbuf, hbuf in zip(dev_bufs, host_bufs):
+            hbuf.copy_(dbuf, non_blocking=True)
+
+    copies()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        copies()
+    torch.cuda.synchronize()
+    floor = torch.tensor([(time.perf_counter() - t0) * 1e3 / 3], device=dev)
+    dist.all_reduce(floor, op=dist.ReduceOp.MAX)
+    del dev_bufs
     S = len(fields)
     box = w.meta["box"]
     return {"metric": "active voxel-updates/s per advect+project frame", "value": n_owned_total / (ms_step * 1e-3), "unit": "voxel-updates/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": w.meta["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"c4 weak scaling: sparse smoke ~30% of a {box[0]}x{box[1]}x{box[2]} box, {n_owned_total} active voxels over "
+            "config": {"workload": f"{w.meta['label']}, {n_owned_total} active voxels over "
                                    f"{world} GPUs (+{n_local_total - n_owned_total} ghost voxels), frame=full, I={iterations}, S={S}",
                        "parallelism": f"spatial leaf-range sharding x{world}, ghost-leaf exchange by " + ("direct peer-memory stores + flags over NVLink (CUDA IPC)" if getattr(sh, "p2p", False) else "ncclSend/ncclRecv") + f", issued from C++, boundary sweeps + exchange pipelined against interior sweeps ({sh.exchanges // (args.steps + args.warmup + args.e2e_steps + 1)} exchanges/frame)",
                        "l2": "per-rank fields larger than L2; no flush"},
             "e2e": {"value": n_owned_total / (float(e2e.item()) * 1e-3), "unit": "voxel-updates/s", "ms_per_step": float(e2e.item()),
                     "h2d_bytes_per_step": int(n_local_total * (12 + 4 * S)), "d2h_bytes_per_step": int(n_local_total * (12 + 4 * S)),
-                    "call": "ShardedSimulation.cook (hns_dist_cook) per rank on pinned host arrays of its shard, in place, synchronous"},
+                    "copy_floor_ms": float(floor.item()),
+                    "call": "ShardedSimulation.cook (hns_dist_cook) per rank on pinned host arrays of its shard, in place, synchronous; "
+                            "copy_floor_ms = the same bytes up then down on all ranks at once without any kernel"},
             "gpu_launches": int(launches.item()),
             "sharded_parity": "bitwise-ok" if parity and all(r["ok"] for r in parity) else None,
             "sharded_parity_detail": [{k: r[k] for k in ("leaves", "world", "frames", "iterations", "p2p", "collision", "vorticity", "cook")} for r in parity],

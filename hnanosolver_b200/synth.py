@@ -253,8 +253,8 @@ def sparse_smoke(R: int = 512, fill: float = 0.30, seed: int = 4, with_coords=Tr
                    meta=dict(R=R, fill=fill, active_leaf_fraction=float(mask.mean())))
 
 
-def narrow_band(R: int = 1024, target_voxels: float = 2.0e8, seed: int = 5, with_coords=False, x_range=None) -> Workload:
-    """C5: R^3-bounded spherical shell | |x - c| - 0.39 R | < w with w chosen for ~target_voxels active voxels."""
+def narrow_band_origins(R: int = 1024, target_voxels: float = 2.0e8, x_range=None):
+    """leaf origins (NanoVDB order) of the C5 shell and its half width in voxels"""
     n = R // 8
     c = R / 2.0
     g = np.arange(n) * 8 + 3.5
@@ -267,7 +267,12 @@ def narrow_band(R: int = 1024, target_voxels: float = 2.0e8, seed: int = 5, with
         keep = np.zeros_like(mask)
         keep[x_range[0]:x_range[1]] = True
         mask &= keep
-    origins = origins_from_mask(mask)
+    return origins_from_mask(mask), float(w)
+
+
+def narrow_band(R: int = 1024, target_voxels: float = 2.0e8, seed: int = 5, with_coords=False, x_range=None) -> Workload:
+    """C5: R^3-bounded spherical shell | |x - c| - 0.39 R | < w with w chosen for ~target_voxels active voxels."""
+    origins, w = narrow_band_origins(R, target_voxels, x_range)
     vel, density, temperature = _swirl_fields(R)
     return _finish(f"band{R}", origins, vel, [density, temperature], ["density", "temperature"], 40, seed, with_coords,
                    meta=dict(R=R, half_width_voxels=float(w)))
