@@ -5,8 +5,7 @@
 // values of the region x, y in [-3, 11), z in [-4, 12) (leaf-local; 14 x 14 rows of 16 floats, from up to 27 leaves) in shared memory:
 // every trilinear / nearest fetch whose 2x2x2 footprint lies inside it is then a shared-memory read -- no per-sample leaf lookup, no
 // scattered global loads. The region of the NEXT stage is copied with 16-byte cp.async into the second half of a double buffer while
-// the current one is sampled. Row pitch 24 floats: keeps 16-byte alignment and maps the 4 (y) x 8 (z) lanes of a warp to 32 distinct
-// banks. This is the second generation of these kernels; the first (round 1, profiles/r1e_advect_ncu.txt: 1535 instructions per
+// the current one is sampled ("the staged region" below has the shared-memory layout). This is the second generation of these kernels; the first (round 1, profiles/r1e_advect_ncu.txt: 1535 instructions per
 // voxel in advect_scalars at S = 5, issue slots 63 % busy) was instruction bound, so the per-voxel instruction stream was cut to what
 // the arithmetic needs (profiles/r2a_*: 2.65 -> 2.21 ms and 1.13 -> 0.97 ms, now bound by shared-memory wavefronts):
 //   * the staging plan of a thread (which two quads of the region it copies, from which neighbour slot and leaf offset) depends on
@@ -61,8 +60,29 @@ __device__ __forceinline__ void meta_fetch(const GridView& g, int* slot, uint32_
 	}
 }
 
-// Thread-constant staging plan: quads `threadIdx.x` and `threadIdx.x + 512` of the 784 the region has per field. The quads are dealt so
-// that 8 consecutive lanes cover 4 rows x 2 quads: with the 24-float row pitch their eight 16-byte stores hit 32 distinct banks.
+// ---- the staged region --------------------------------------------------------------------------------------------------------------
+// x, y in [-3, 11), z in [-4, 12) around the leaf: 14 x 14 rows of 16 floats per field. Row pitch 16 floats with NO padding; instead the
+// two 8-float halves of a row trade places in every other pair of rows (physical z = z ^ 8 when bit 1 of the row index is set):
+//   * the 4 (y) x 8 (z) lanes of a warp still hit 32 distinct banks when they read one displaced copy of their own cells -- rows y and
+//     y + 1 use different 16-bank halves, rows y and y + 2 use complementary 8-bank halves of the same half;
+//   * an x-plane is 14 * 16 = 224 floats = 7 * 32 banks, so a lane whose sample straddles an integer x reads the SAME bank one plane
+//     further: lanes of one warp that disagree about floor(x) no longer conflict (with the padded 24-float pitch of the first version the
+//     plane pitch was 16 banks off and every such warp paid two wavefronts per gather; ncu: 33-38 % of all shared wavefronts were
+//     conflicts);
+//   * a field takes 12.25 KB instead of 18.4 KB, so a stage holds FOUR fields in less shared memory than three took: the shared trace of
+//     advect_scalars rides with the first scalar field and the remaining fields go four at a time (S = 5: two stages per leaf, not three).
+constexpr int kRX = 14, kRZ = 16, kHaloXY = 3, kHaloZ = 4;
+constexpr int kPitch = 16, kPlane = kRX * kPitch, kRegionFloats = kRX * kPlane;  // 224 floats per x-plane, 3136 per field
+constexpr int kStageFields = 4, kStageFloats = kStageFields * kRegionFloats;     // 49 KB per pipeline stage
+constexpr size_t kAdvectSmem = 2 * kStageFloats * sizeof(float);                 // double buffer: 98 KB per CTA, two CTAs per SM
+static_assert(2 * (kAdvectSmem + 2048) <= 233472, "two CTAs of the advection pipeline must fit one SM's shared memory");
+
+__device__ __forceinline__ int swz(int ry) { return (ry & 2) << 2; }  // 8 for rows 2, 3, 6, 7, 10, 11
+__device__ __forceinline__ int cell(int rx, int ry, int rz) { return rx * kPlane + ry * kPitch + (rz ^ swz(ry)); }
+
+// Thread-constant staging plan. The region has 14 planes x 4 groups of (up to) 4 rows x 4 quads; item `it` = group * 16 + sub copies quad
+// ((sub >> 3) << 1 | (sub >> 2) & 1) of row (sub & 3) of its group, so that 8 consecutive lanes cover 4 rows x 2 quads: eight 16-byte
+// stores on 32 distinct banks. A thread handles items threadIdx.x and threadIdx.x + 512 (896 items, 784 of them real).
 struct Stager {
 	int dst[2];   // float offset in the region; -1: nothing to copy
 	int slot[2];  // neighbour slot of the source leaf
@@ -73,13 +93,13 @@ __device__ __forceinline__ Stager make_stager() {
 #pragma unroll
 	for (int k = 0; k < 2; ++k) {
 		const int it = threadIdx.x + 512 * k;
+		const int group = it >> 4, sub = it & 15;
+		const int rx = group >> 2, ry = (group & 3) * 4 + (sub & 3), q = ((sub >> 3) << 1) | ((sub >> 2) & 1);
 		p.dst[k] = -1, p.slot[k] = kSlotSelf, p.src[k] = 0;
-		if (it < kRegionQuads) {
-			const int sub = it & 15, row = (it >> 4) * 4 + (sub & 3), q = ((sub >> 3) << 1) | ((sub >> 2) & 1);
-			const int rx = row / kRX, ry = row - rx * kRX;
+		if (rx < kRX && ry < kRX) {
 			const int lx = rx - kHaloXY, ly = ry - kHaloXY;  // leaf-local x, y in [-3, 11)
 			const int dz = q == 0 ? -1 : (q == 3 ? 1 : 0);   // z in [-4,0) | [0,4) | [4,8) | [8,12)
-			p.dst[k] = rx * kPlane + ry * kPitch + q * 4;
+			p.dst[k] = rx * kPlane + ry * kPitch + ((q * 4) ^ swz(ry));
 			p.slot[k] = ((lx >> 3) + 1) * 9 + ((ly >> 3) + 1) * 3 + dz + 1;
 			p.src[k] = ((lx & 7) << 6) | ((ly & 7) << 3) | ((q == 1 || q == 3) ? 0 : 4);
 		}
@@ -109,16 +129,23 @@ __device__ __forceinline__ void stage(const Stager& p, const int* __restrict__ m
 	}
 }
 
-// region offset of the cell (i,j,k) given relative to the leaf origin, or -1 when the 2x2x2 footprint starting there leaves the region
-__device__ __forceinline__ int footprint(int ri, int rj, int rk) {
+// The 2x2x2 footprint of a sample whose first cell is (ri, rj, rk) relative to the leaf origin: region offsets of its four (y, z) corners
+// in the plane x (the plane x + 1 is kPlane further). false when the footprint leaves the region.
+struct Foot {
+	int a00, a01, a10, a11;  // (y, z), (y, z+1), (y+1, z), (y+1, z+1)
+};
+__device__ __forceinline__ bool footprint(int ri, int rj, int rk, Foot& f) {
 	const int rx = ri + kHaloXY, ry = rj + kHaloXY, rz = rk + kHaloZ;
-	if (unsigned(rx) >= unsigned(kRX - 1) || unsigned(ry) >= unsigned(kRX - 1) || unsigned(rz) >= unsigned(kRZ - 1)) return -1;
-	return rx * kPlane + ry * kPitch + rz;
+	if (unsigned(rx) >= unsigned(kRX - 1) || unsigned(ry) >= unsigned(kRX - 1) || unsigned(rz) >= unsigned(kRZ - 1)) return false;
+	const int r0 = rx * kPlane + ry * kPitch, s0 = swz(ry), s1 = swz(ry + 1);
+	f.a00 = r0 + (rz ^ s0), f.a01 = r0 + ((rz + 1) ^ s0);
+	f.a10 = r0 + kPitch + (rz ^ s1), f.a11 = r0 + kPitch + ((rz + 1) ^ s1);
+	return true;
 }
-// TrilinearSampler: lerp z, then y, then x (Stencils.hpp:144-152); r points at the footprint's first cell
-__device__ __forceinline__ float tri_lerp(const float* __restrict__ r, float fx, float fy, float fz) {
-	const float z0 = lerpf(r[0], r[1], fz), z1 = lerpf(r[kPitch], r[kPitch + 1], fz);
-	const float z2 = lerpf(r[kPlane], r[kPlane + 1], fz), z3 = lerpf(r[kPlane + kPitch], r[kPlane + kPitch + 1], fz);
+// TrilinearSampler: lerp z, then y, then x (Stencils.hpp:144-152)
+__device__ __forceinline__ float tri_lerp(const float* __restrict__ r, const Foot& f, float fx, float fy, float fz) {
+	const float z0 = lerpf(r[f.a00], r[f.a01], fz), z1 = lerpf(r[f.a10], r[f.a11], fz);
+	const float z2 = lerpf(r[f.a00 + kPlane], r[f.a01 + kPlane], fz), z3 = lerpf(r[f.a10 + kPlane], r[f.a11 + kPlane], fz);
 	return lerpf(lerpf(z0, z1, fy), lerpf(z2, z3, fy), fx);
 }
 // advect_scalars' weighted sum (Kernel.cu:186-206, 239-243): corners in the order (i0j0k0),(i1j0k0),(i0j1k0),(i1j1k0),(i0j0k1),...;
@@ -130,21 +157,29 @@ __device__ __forceinline__ Weights make_weights(float tx, float ty, float tz) {
 	const float itx = 1.0f - tx, ity = 1.0f - ty;
 	return Weights{{itx * ity, tx * ity, itx * ty, tx * ty}, {1.0f - tz, tz}};
 }
-__device__ __forceinline__ float tri_weighted(const float* __restrict__ r, const Weights& w) {
+__device__ __forceinline__ float tri_weighted(const float* __restrict__ r, const Foot& f, const Weights& w) {
 	float acc = 0.f;
-	acc = fmaf(r[0], w.xy[0] * w.z[0], acc);
-	acc = fmaf(r[kPlane], w.xy[1] * w.z[0], acc);
-	acc = fmaf(r[kPitch], w.xy[2] * w.z[0], acc);
-	acc = fmaf(r[kPlane + kPitch], w.xy[3] * w.z[0], acc);
-	acc = fmaf(r[1], w.xy[0] * w.z[1], acc);
-	acc = fmaf(r[kPlane + 1], w.xy[1] * w.z[1], acc);
-	acc = fmaf(r[kPitch + 1], w.xy[2] * w.z[1], acc);
-	acc = fmaf(r[kPlane + kPitch + 1], w.xy[3] * w.z[1], acc);
+	acc = fmaf(r[f.a00], w.xy[0] * w.z[0], acc);
+	acc = fmaf(r[f.a00 + kPlane], w.xy[1] * w.z[0], acc);
+	acc = fmaf(r[f.a10], w.xy[2] * w.z[0], acc);
+	acc = fmaf(r[f.a10 + kPlane], w.xy[3] * w.z[0], acc);
+	acc = fmaf(r[f.a01], w.xy[0] * w.z[1], acc);
+	acc = fmaf(r[f.a01 + kPlane], w.xy[1] * w.z[1], acc);
+	acc = fmaf(r[f.a11], w.xy[2] * w.z[1], acc);
+	acc = fmaf(r[f.a11 + kPlane], w.xy[3] * w.z[1], acc);
 	return acc;
 }
+// a voxel's own cell and its y / z neighbours in the region (the x neighbours are +-kPlane): thread constants
+struct Own {
+	int c, ym, yp, zm, zp;
+};
+__device__ __forceinline__ Own make_own(int x, int y, int z) {
+	const int rx = x + kHaloXY, ry = y + kHaloXY, rz = z + kHaloZ;
+	return Own{cell(rx, ry, rz), cell(rx, ry - 1, rz), cell(rx, ry + 1, rz), cell(rx, ry, rz - 1), cell(rx, ry, rz + 1)};
+}
 // min / max over the cell and its six face neighbours (Kernel.cu:250-258, 402-421)
-__device__ __forceinline__ void clamp_range(const float* __restrict__ r, float own, float& mn, float& mx) {
-	const float a = r[-kPlane], b = r[kPlane], c = r[-kPitch], d = r[kPitch], e = r[-1], f = r[1];
+__device__ __forceinline__ void clamp_range(const float* __restrict__ r, const Own& o, float own, float& mn, float& mx) {
+	const float a = r[o.c - kPlane], b = r[o.c + kPlane], c = r[o.ym], d = r[o.yp], e = r[o.zm], f = r[o.zp];
 	mn = fminf(fminf(fminf(own, a), fminf(b, c)), fminf(fminf(d, e), f));
 	mx = fmaxf(fmaxf(fmaxf(own, a), fmaxf(b, c)), fmaxf(fmaxf(d, e), f));
 }
@@ -154,7 +189,8 @@ struct Items {
 	__device__ __forceinline__ uint32_t at(uint32_t k) const { return base + k * stride; }
 };
 // CTA b takes work items b, b + G, b + 2G, ...: the whole grid advances through the leaf list together, so the x-neighbour planes a
-// region needs are still in the L2 from the CTAs that staged them a moment ago (kernels.cu CtaItems has the measurement)
+// region needs are still in the L2 from the CTAs that staged them a moment ago (measured in round 1: with one contiguous range per CTA
+// every leaf was fetched from HBM about three times)
 __device__ __forceinline__ Items cta_items2(const GridView& g) {
 	Items it;
 	it.base = blockIdx.x, it.stride = gridDim.x;
@@ -177,7 +213,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_vector2(GridView g, const flo
 	if (!items.count) return;
 	const int tid = threadIdx.x;
 	const int x = tid >> 6, y = (tid >> 3) & 7, z = tid & 7;
-	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
+	const Own own = make_own(x, y, z);
 	const Stager stg = make_stager();
 	const float* const fields[3] = {u, v, w};
 	if (tid < 3) fill[tid] = 0.f;
@@ -193,51 +229,47 @@ __global__ void __launch_bounds__(512, 2) k_advect_vector2(GridView g, const flo
 		cp_wait_all();
 		__syncthreads();  // item k's region and item k+1's metadata have landed for every thread; nobody reads the other buffer any more
 		if (k + 1 < items.count) issue(k + 1);
-		const float* __restrict__ ru = region + (k & 1) * kStageFloats + c;
+		const float* __restrict__ ru = region + (k & 1) * kStageFloats;
 		const float* __restrict__ rv = ru + kRegionFloats;
 		const float* __restrict__ rw = rv + kRegionFloats;
 		const int* m = meta[k % 3];
 		const uint32_t leaf = uint32_t(m[kMetaLeaf]);
-		const float u0 = ru[0], v0 = rv[0], w0 = rw[0];
-		// positions relative to the leaf origin are exact in fp32 only for the fractions; keep the reference's absolute arithmetic
+		const float u0 = ru[own.c], v0 = rv[own.c], w0 = rw[own.c];
 		const int ox = m[kMetaOx], oy = m[kMetaOx + 1], oz = m[kMetaOx + 2];
 		const float px = float(ox + x), py = float(oy + y), pz = float(oz + z);
 		float bx = fmaf(-sdt, u0, px), by = fmaf(-sdt, v0, py), bz = fmaf(-sdt, w0, pz);  // Kernel.cu:374
 		LeafFrame lf{ox, oy, oz, g.nbr + uint64_t(leaf) * 27u};
 		if (kCollision && trilinear_f(g, lf, sdf, bx, by, bz) < 0.0f) bx = px, by = py, bz = pz;  // :377-382
 		const int bi = __float2int_rd(bx), bj = __float2int_rd(by), bk = __float2int_rd(bz);
-		const int fb = footprint(bi - ox, bj - oy, bk - oz);
-		if (fb < 0) {
+		Foot fb;
+		if (!footprint(bi - ox, bj - oy, bk - oz, fb)) {
 			cold[leaf] = 1;
 			continue;
 		}
-		const int db = fb - c;
 		const float tx = bx - float(bi), ty = by - float(bj), tz = bz - float(bk);
-		const float uf = tri_lerp(ru + db, tx, ty, tz), vf = tri_lerp(rv + db, tx, ty, tz), wf = tri_lerp(rw + db, tx, ty, tz);
+		const float uf = tri_lerp(ru, fb, tx, ty, tz), vf = tri_lerp(rv, fb, tx, ty, tz), wf = tri_lerp(rw, fb, tx, ty, tz);
 		float fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :387
 		if (kCollision && trilinear_f(g, lf, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;  // :390-394
 		const int fi = __float2int_rd(fx), fj = __float2int_rd(fy), fk = __float2int_rd(fz);
-		const int ff = footprint(fi - ox, fj - oy, fk - oz);
-		if (ff < 0) {
+		Foot ff;
+		if (!footprint(fi - ox, fj - oy, fk - oz, ff)) {
 			cold[leaf] = 1;
 			continue;
 		}
-		const int df = ff - c;
 		const float sx = fx - float(fi), sy = fy - float(fj), sz = fz - float(fk);
-		const float ub = tri_lerp(ru + df, sx, sy, sz), vb = tri_lerp(rv + df, sx, sy, sz), wb = tri_lerp(rw + df, sx, sy, sz);
+		const float ub = tri_lerp(ru, ff, sx, sy, sz), vb = tri_lerp(rv, ff, sx, sy, sz), wb = tri_lerp(rw, ff, sx, sy, sz);
 		const float cu = fmaf(0.5f, u0 - ub, uf), cv = fmaf(0.5f, v0 - vb, vf), cw = fmaf(0.5f, w0 - wb, wf);  // :399-400
 		float mn, mx;
 		const uint32_t self = leaf * 512u + uint32_t(tid);
-		clamp_range(ru, u0, mn, mx);
+		clamp_range(ru, own, u0, mn, mx);
 		ou[self] = fmaxf(fminf(mn, uf), fminf(cu, fmaxf(mx, uf)));  // :402-429
-		clamp_range(rv, v0, mn, mx);
+		clamp_range(rv, own, v0, mn, mx);
 		ov[self] = fmaxf(fminf(mn, vf), fminf(cv, fmaxf(mx, vf)));
-		clamp_range(rw, w0, mn, mx);
+		clamp_range(rw, own, w0, mn, mx);
 		ow[self] = fmaxf(fminf(mn, wf), fminf(cw, fmaxf(mx, wf)));
 	}
 }
 
-// The flagged leaves among work items [chunk, chunk + 512) into todo[0 .. n_todo), their flags cleared for the next launch: one flag per
 // thread (coalesced), so an unflagged grid costs one load per leaf, not one dependent round trip per leaf and CTA.
 __device__ __forceinline__ void collect_flagged(const GridView& g, uint8_t* cold, uint32_t chunk, uint32_t* todo, uint32_t& n_todo) {
 	if (threadIdx.x == 0) n_todo = 0;
@@ -299,32 +331,33 @@ __global__ void __launch_bounds__(512) k_advect_vector_cold(GridView g, const fl
 // advect_scalars (kSem 0: Kernel.cu:118-266, inactive -> array element 0) / advect_scalar per field (kSem 1: :269-352, inactive -> 0)
 // ---------------------------------------------------------------------------------------------------------------------------------
 struct Trace {  // of one voxel, shared by all its scalar fields
-	int db, df;     // footprint offsets of the back-traced / forward-traced sample relative to the voxel's own cell; db == INT_MIN: cold
-	Weights wb, wf;  // kSem 0
+	Foot fb, ff;         // footprints of the back-traced / forward-traced sample
+	Weights wb, wf;      // kSem 0
 	float tb[3], tf[3];  // kSem 1: fractions
 };
 
 template <int kSem, int NS>
-__device__ __forceinline__ void scalar_fields(const float* __restrict__ base, const Trace& t, float* const (&out)[NS], uint32_t self) {
+__device__ __forceinline__ void scalar_fields(const float* __restrict__ base, const Own& own, const Trace& t, float* const (&out)[NS], uint32_t self) {
 #pragma unroll
 	for (int k = 0; k < NS; ++k) {
 		const float* __restrict__ r = base + k * kRegionFloats;
-		const float phi0 = r[0];
+		const float phi0 = r[own.c];
 		float phiF, phiB;
 		if (kSem == 0) {
-			phiF = tri_weighted(r + t.db, t.wb);  // Kernel.cu:239-243
-			phiB = tri_weighted(r + t.df, t.wf);
+			phiF = tri_weighted(r, t.fb, t.wb);  // Kernel.cu:239-243
+			phiB = tri_weighted(r, t.ff, t.wf);
 		} else {
-			phiF = tri_lerp(r + t.db, t.tb[0], t.tb[1], t.tb[2]);
-			phiB = tri_lerp(r + t.df, t.tf[0], t.tf[1], t.tf[2]);
+			phiF = tri_lerp(r, t.fb, t.tb[0], t.tb[1], t.tb[2]);
+			phiB = tri_lerp(r, t.ff, t.tf[0], t.tf[1], t.tf[2]);
 		}
 		const float corr = fmaf(0.5f, phi0 - phiB, phiF);  // :246-247
 		float mn, mx;
-		clamp_range(r, phi0, mn, mx);  // :253-258
+		clamp_range(r, own, phi0, mn, mx);  // :253-258
 		out[k][self] = fmaxf(fminf(mn, phiF), fminf(corr, fmaxf(mx, phiF)));  // :264
 	}
 }
 
+// Stages of a leaf: A = the velocity (the shared trace) + scalar field 0; then the remaining fields four at a time.
 template <int kSem, bool kCollision>
 __global__ void __launch_bounds__(512, 2) k_advect_scalars2(GridView g, const float* __restrict__ u, const float* __restrict__ v,
                                                             const float* __restrict__ w, const __grid_constant__ ScalarPtrs sp, int S, float sdt,
@@ -337,7 +370,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars2(GridView g, const fl
 	if (!items.count) return;
 	const int tid = threadIdx.x;
 	const int x = tid >> 6, y = (tid >> 3) & 7, z = tid & 7;
-	const int c = (x + kHaloXY) * kPlane + (y + kHaloXY) * kPitch + z + kHaloZ;
+	const Own own = make_own(x, y, z);
 	const Stager stg = make_stager();
 	// what inactive cells hold: advect_scalars reads array element 0 (of the GLOBAL arrays: elem0 when given), advect_scalar reads 0
 	if (tid < 3 + S) {
@@ -345,7 +378,7 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars2(GridView g, const fl
 		if (kSem == 0) f = elem0 ? __ldg(elem0 + tid) : (tid == 0 ? __ldg(u) : tid == 1 ? __ldg(v) : tid == 2 ? __ldg(w) : __ldg(sp.in[tid - 3]));
 		fill[tid] = f;
 	}
-	const int groups = (S + 2) / 3, jobs_per_leaf = 1 + groups;
+	const int jobs_per_leaf = 1 + (S - 1 + 3) / 4;
 	const uint32_t n_jobs = items.count * uint32_t(jobs_per_leaf);
 	meta_fetch(g, meta[0], items.at(0), false);
 	__syncthreads();
@@ -355,12 +388,15 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars2(GridView g, const fl
 		float* dst = region + (job & 1) * kStageFloats;
 		const int* m = meta[issue_item % 3];
 		if (issue_jj == 0) {
-			const float* const f3[3] = {u, v, w};
-			stage<3>(stg, m, f3, dst, fill);
+			const float* const f4[4] = {u, v, w, sp.in[0]};
+			stage<4>(stg, m, f4, dst, fill);
 			if (issue_item + 1 < items.count) meta_fetch(g, meta[(issue_item + 1) % 3], items.at(issue_item + 1), true);
 		} else {
-			const int s0 = 3 * (issue_jj - 1), ns = min(3, S - s0);
-			if (ns == 3) {
+			const int s0 = 1 + 4 * (issue_jj - 1), ns = min(4, S - s0);
+			if (ns == 4) {
+				const float* const f4[4] = {sp.in[s0], sp.in[s0 + 1], sp.in[s0 + 2], sp.in[s0 + 3]};
+				stage<4>(stg, m, f4, dst, fill + 3 + s0);
+			} else if (ns == 3) {
 				const float* const f3[3] = {sp.in[s0], sp.in[s0 + 1], sp.in[s0 + 2]};
 				stage<3>(stg, m, f3, dst, fill + 3 + s0);
 			} else if (ns == 2) {
@@ -375,7 +411,6 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars2(GridView g, const fl
 		if (++issue_jj == jobs_per_leaf) issue_jj = 0, ++issue_item;
 	};
 	Trace t;
-	t.db = t.df = 0;
 	bool is_cold = false;
 	uint32_t item = 0;
 	int jj = 0;
@@ -384,56 +419,60 @@ __global__ void __launch_bounds__(512, 2) k_advect_scalars2(GridView g, const fl
 		cp_wait_all();
 		__syncthreads();
 		if (job + 1 < n_jobs) issue(job + 1);
-		const float* __restrict__ base = region + (job & 1) * kStageFloats + c;
+		const float* __restrict__ base = region + (job & 1) * kStageFloats;
 		const int* m = meta[item % 3];
 		const uint32_t leaf = uint32_t(m[kMetaLeaf]);
+		const uint32_t self = leaf * 512u + uint32_t(tid);
 		if (jj == 0) {
-			// ---- the shared trace through the staged velocity (Kernel.cu:126-214) ----
+			// ---- the shared trace through the staged velocity (Kernel.cu:126-214), then the first scalar field ----
 			const float *ru = base, *rv = base + kRegionFloats, *rw = base + 2 * kRegionFloats;
 			const int ox = m[kMetaOx], oy = m[kMetaOx + 1], oz = m[kMetaOx + 2];
 			const float px = float(ox + x), py = float(oy + y), pz = float(oz + z);
-			float bx = fmaf(-sdt, ru[0], px), by = fmaf(-sdt, rv[0], py), bz = fmaf(-sdt, rw[0], pz);
+			float bx = fmaf(-sdt, ru[own.c], px), by = fmaf(-sdt, rv[own.c], py), bz = fmaf(-sdt, rw[own.c], pz);
 			LeafFrame lf{ox, oy, oz, g.nbr + uint64_t(leaf) * 27u};
 			// hasCollision (:142-155): the reference tests the back-traced position twice; the second test sees either the same position
 			// or the voxel itself and resets to the voxel again, so one test decides
 			if (kCollision && trilinear_f(g, lf, sdf, bx, by, bz) < 0.0f) bx = px, by = py, bz = pz;
 			const int bi = __float2int_rd(bx), bj = __float2int_rd(by), bk = __float2int_rd(bz);
-			const int fb = footprint(bi - ox, bj - oy, bk - oz);
-			is_cold = fb < 0;
+			is_cold = !footprint(bi - ox, bj - oy, bk - oz, t.fb);
 			if (!is_cold) {
-				t.db = fb - c;
 				const float tx = bx - float(bi), ty = by - float(bj), tz = bz - float(bk);
 				float uf, vf, wf;
 				if (kSem == 0) {
 					t.wb = make_weights(tx, ty, tz);
-					uf = tri_weighted(ru + t.db, t.wb), vf = tri_weighted(rv + t.db, t.wb), wf = tri_weighted(rw + t.db, t.wb);  // :201-206
+					uf = tri_weighted(ru, t.fb, t.wb), vf = tri_weighted(rv, t.fb, t.wb), wf = tri_weighted(rw, t.fb, t.wb);  // :201-206
 				} else {
 					t.tb[0] = tx, t.tb[1] = ty, t.tb[2] = tz;
-					uf = tri_lerp(ru + t.db, tx, ty, tz), vf = tri_lerp(rv + t.db, tx, ty, tz), wf = tri_lerp(rw + t.db, tx, ty, tz);
+					uf = tri_lerp(ru, t.fb, tx, ty, tz), vf = tri_lerp(rv, t.fb, tx, ty, tz), wf = tri_lerp(rw, t.fb, tx, ty, tz);
 				}
 				float fx = fmaf(sdt, uf, bx), fy = fmaf(sdt, vf, by), fz = fmaf(sdt, wf, bz);  // :208
 				if (kCollision && trilinear_f(g, lf, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;  // :211-214
 				const int fi = __float2int_rd(fx), fj = __float2int_rd(fy), fk = __float2int_rd(fz);
-				const int ff = footprint(fi - ox, fj - oy, fk - oz);
-				is_cold = ff < 0;
-				t.df = ff - c;
+				is_cold = !footprint(fi - ox, fj - oy, fk - oz, t.ff);
 				const float sx = fx - float(fi), sy = fy - float(fj), sz = fz - float(fk);
 				if (kSem == 0) t.wf = make_weights(sx, sy, sz);
 				else t.tf[0] = sx, t.tf[1] = sy, t.tf[2] = sz;
 			}
-			if (is_cold) cold[leaf] = 1;
+			if (is_cold) {
+				cold[leaf] = 1;
+			} else {
+				float* const o1[1] = {sp.out[0]};
+				scalar_fields<kSem, 1>(base + 3 * kRegionFloats, own, t, o1, self);
+			}
 		} else if (!is_cold) {
-			const int s0 = 3 * (jj - 1), ns = min(3, S - s0);
-			const uint32_t self = leaf * 512u + uint32_t(tid);
-			if (ns == 3) {
+			const int s0 = 1 + 4 * (jj - 1), ns = min(4, S - s0);
+			if (ns == 4) {
+				float* const o4[4] = {sp.out[s0], sp.out[s0 + 1], sp.out[s0 + 2], sp.out[s0 + 3]};
+				scalar_fields<kSem, 4>(base, own, t, o4, self);
+			} else if (ns == 3) {
 				float* const o3[3] = {sp.out[s0], sp.out[s0 + 1], sp.out[s0 + 2]};
-				scalar_fields<kSem, 3>(base, t, o3, self);
+				scalar_fields<kSem, 3>(base, own, t, o3, self);
 			} else if (ns == 2) {
 				float* const o2[2] = {sp.out[s0], sp.out[s0 + 1]};
-				scalar_fields<kSem, 2>(base, t, o2, self);
+				scalar_fields<kSem, 2>(base, own, t, o2, self);
 			} else {
 				float* const o1[1] = {sp.out[s0]};
-				scalar_fields<kSem, 1>(base, t, o1, self);
+				scalar_fields<kSem, 1>(base, own, t, o1, self);
 			}
 		}
 		if (++jj == jobs_per_leaf) jj = 0, ++item;

@@ -7,16 +7,6 @@
 
 namespace hns {
 
-// staged region of the advection kernels (kernels.cu / advect.cu explain the layout)
-constexpr int kRX = 14, kRZ = 16, kPitch = 24, kHaloXY = 3, kHaloZ = 4;
-constexpr int kPlane = kRX * kPitch;                              // 336 floats per x-plane
-constexpr int kRegionFloats = kRX * kPlane;                       // 4704 floats = 18.4 KB per field
-constexpr int kRegionQuads = kRX * kRX * (kRZ / 4);               // 16-byte quads per field
-constexpr int kStageFloats = 3 * kRegionFloats;                   // one pipeline stage: three fields
-constexpr size_t kAdvectSmem = 2 * kStageFloats * sizeof(float);  // double buffer: 110.25 KB per CTA, two CTAs per SM
-static_assert(2 * (kAdvectSmem + 1024) <= 233472, "two CTAs of the advection pipeline must fit one SM's shared memory");
-
-
 // Resolves voxel (i,j,k) (global coordinates) to a sidecar index, or -1 when inactive. The 3x3x3 leaf neighbourhood of the
 // current leaf comes from its 27-entry table; anything farther away walks the NanoVDB buffer. Cold path only.
 struct LeafFrame {
@@ -74,8 +64,6 @@ __device__ __forceinline__ void corner_weights(float tx, float ty, float tz, flo
 	w[0] = w00 * itz, w[1] = w10 * itz, w[2] = w01 * itz, w[3] = w11 * itz;
 	w[4] = w00 * tz, w[5] = w10 * tz, w[6] = w01 * tz, w[7] = w11 * tz;
 }
-// region offsets of the eight corners in the reference's accumulation order: bit0 -> i, bit1 -> j, bit2 -> k
-__device__ __forceinline__ int corner_off(int q) { return (q & 1) * kPlane + ((q >> 1) & 1) * kPitch + (q >> 2); }
 // cold path: weighted 8-corner sums through the leaf table / tree walk, for samples outside the staged region
 static __device__ __noinline__ float far_weighted(const GridView& g, const LeafFrame& f, const float* __restrict__ a, const float* __restrict__ e0, int i0,
                                            int j0, int k0, float tx, float ty, float tz) {
