@@ -156,6 +156,35 @@ def mg_frame_bytes_per_voxel(S: int, full: bool, info: dict) -> float:
     return 80 + 8 * S + (52 if full else 0) + 4 + per_cycle * info["cycles"]      # + 4: p zeroed once per solve
 
 
+def stage_breakdown(H, sim, w, S: int, full: bool, peak: float, reps: int = 5) -> dict:
+    """Every stage of the frame on its own (CUDA events on the launch stream, median of `reps`), with its algorithmic bytes per voxel
+    (SURVEY.md 8d / BASELINE.md section 3) and the fraction of the measured HBM copy rate that makes."""
+    import torch
+
+    omega = H.launchers.omega_compute(w.voxel_size)
+    stages = [("advect_vector", 24, lambda: sim.advect_velocity(w.dt)), ("divergence", 16, lambda: sim.divergence(True))]
+    if full:
+        stages.append(("combustion+buoyancy", 52, lambda: sim.combustion_buoyancy(w.dt)))
+    stages += [(f"pressure_solve({ITERATIONS})", 16 * ITERATIONS, lambda: sim.pressure_solve(ITERATIONS, omega)),
+               ("subtract_gradient", 28, lambda: sim.subtract_gradient(True)), (f"advect_scalars({S})", 12 + 8 * S, lambda: sim.advect_scalars(w.dt, 0))]
+    acc = {k: [] for k, _, _ in stages}
+    for r in range(reps + 1):
+        for k, _, fn in stages:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if r:
+                acc[k].append(e0.elapsed_time(e1))
+    out = {}
+    for k, b, _ in stages:
+        ms = float(np.median(acc[k]))
+        gbs = b * w.num_voxels / (ms * 1e-3) / 1e9
+        out[k] = {"ms": ms, "algorithmic_bytes_per_voxel": b, "algorithmic_GBps": gbs, "frac_of_peak": gbs / peak}
+    return out
+
+
 def frame_quality(sim) -> dict:
     """of the frame the state just ran: relative Poisson residual of its pressure and ||div(u_new)||_2 (rms), both reduced on the device"""
     a, b = sim.residual_sums()
@@ -309,12 +338,13 @@ def main():
         n_sweeps, sweep_ms = 40, e0.elapsed_time(e1) / 40
     bytes_per_launch = 8 * N                                           # one colour: read other-colour p, read+write this colour's p, read its div
     achieved = bytes_per_launch / (sweep_ms * 1e-3) / 1e9
+    # dram__bytes_read + dram__bytes_write of the kernel per launch from the committed `ncu --set full` capture of THIS kernel on the
+    # config-4 workload (profiles/kernel_traffic.json says which capture), scaled by the voxel count; never measured inside a timed run
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "rbgs_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(tpath):
         try:
-            tj = json.load(open(tpath))
-            traffic = tj["dram_bytes_per_voxel"] * N if tj.get("kernel") == "k_rbgs_split" else None
+            traffic = json.load(open(tpath))["k_rbgs_split"]["dram_bytes_per_voxel"] * N
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_rbgs_split (one red or black half-sweep on colour-split bricks)",
@@ -324,6 +354,8 @@ def main():
                 "share_of_frame": (ms_pressure / ms_total) if solver == "rbgs" else (sweep_ms * mg_info["fine_half_sweeps_per_solve"] / ms_step),
                 "frame_algorithmic_GBps": (algorithmic_bytes_per_voxel(S, ITERATIONS, full) if solver == "rbgs" else
                                            mg_frame_bytes_per_voxel(S, full, mg_info)) * N / (ms_step * 1e-3) / 1e9}
+
+    stages = stage_breakdown(H, sim, w, S, full, peak)
 
     # ---- the other solver beside it (config 4): the same frame with the pressure stage swapped -----------------------
     other = None
@@ -397,7 +429,7 @@ def main():
                       f"multigrid: {mg_info['cycles']} V({MG_NU[0]},{MG_NU[1]}) cycles, omega {MG_OMEGA}, {mg_info['levels']} levels, "
                       f"solved to a relative Poisson residual of {mg_info['relative_residual_at_cycles']:.2e} (target 1e-4)"},
            "pressure_solver": solver, "solve_quality": solve_quality,
-           "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+           "roofline": roofline, "stages": stages, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     if solver == "mg":
         out["multigrid"] = mg_info
     if other is not None:
