@@ -97,9 +97,6 @@ struct hns_dist {
 	int32_t *d_owned = nullptr, *d_boundary = nullptr, *d_interior = nullptr;
 	int32_t *d_boundary_nbr = nullptr, *d_interior_nbr = nullptr;  // GridView::list_nbr of the two pressure work lists
 	uint32_t n_owned = 0, n_boundary = 0, n_interior = 0;
-	// interior = ring (touches a boundary leaf across a face) + deep: the three-list pressure pipeline of the peer-memory mode
-	int32_t *d_ring = nullptr, *d_deep = nullptr, *d_ring_nbr = nullptr, *d_deep_nbr = nullptr;
-	uint32_t n_ring = 0, n_deep = 0;
 	cudaStream_t comm_stream = nullptr;  // boundary sweeps + ghost exchange run here, next to the interior sweep on the caller's stream
 	cudaEvent_t ev_exchanged = nullptr;
 	cudaStream_t aux_stream = nullptr;  // the scalars' ghost exchange, hidden behind the pressure solve
@@ -135,8 +132,6 @@ struct hns_dist {
 	cudaStream_t copy_stream = nullptr;  // hns_dist_cook: host <-> device transfers overlapping the frame
 	cudaEvent_t ev_copy[6] = {};
 	bool cook_overlap = true;       // HNS_COOK_OVERLAP=0: transfers and frame one after the other on the caller's stream (A/B switch)
-	bool wait_in_kernel = false;    // HNS_WAIT_IN_KERNEL=1: the boundary sweep's own CTAs wait for the peers' flags instead of a one-warp kernel in front of it
-	                                // (A/B switch; measured at 8 GPUs: 9.81 ms per frame against 9.70 ms with the separate kernel, so off)
 };
 
 // ---- layout of one peer region: [flags 128 B][ch0 velocity 3 x 512n][ch1 advected velocity 3 x 512n][ch2 red p 256n][ch3 black p 256n]
@@ -228,7 +223,6 @@ void hns_dist_destroy(hns_dist* d) {
 	cudaFree(d->d_reduce);
 	cudaFree(d->d_elem0), cudaFree(d->d_owned), cudaFree(d->d_boundary), cudaFree(d->d_interior);
 	cudaFree(d->d_boundary_nbr), cudaFree(d->d_interior_nbr);
-	cudaFree(d->d_ring), cudaFree(d->d_deep), cudaFree(d->d_ring_nbr), cudaFree(d->d_deep_nbr);
 	for (auto& p : d->peers) {
 		if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base);
 		if (p.ipc_pbase) cudaIpcCloseMemHandle(p.ipc_pbase);
@@ -274,27 +268,6 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 		HNS_CUDA(up(bnd, &d->d_boundary));
 		d->h_boundary = bnd;
 		HNS_CUDA(up(inter, &d->d_interior));
-		// ring = interior leaves with a boundary leaf among their six face neighbours
-		std::vector<int32_t> ring, deep;
-		{
-			const uint64_t L = s->grid->num_leaves;
-			std::vector<int32_t> nbr(L * 27);
-			if (L) HNS_CUDA(cudaMemcpy(nbr.data(), s->grid->d_nbr, nbr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-			static const int face_slot[6] = {kSlotXm, kSlotXp, kSlotYm, kSlotYp, kSlotZm, kSlotZp};
-			for (int32_t leaf : inter) {
-				bool touches = false;
-				for (int f = 0; f < 6 && !touches; ++f) {
-					const int32_t nb = nbr[uint64_t(leaf) * 27 + face_slot[f]];
-					touches = nb >= 0 && is_boundary[nb];
-				}
-				(touches ? ring : deep).push_back(leaf);
-			}
-		}
-		cudaFree(d->d_ring), cudaFree(d->d_deep), cudaFree(d->d_ring_nbr), cudaFree(d->d_deep_nbr);
-		d->d_ring = d->d_deep = d->d_ring_nbr = d->d_deep_nbr = nullptr;
-		d->n_ring = uint32_t(ring.size()), d->n_deep = uint32_t(deep.size());
-		HNS_CUDA(up(ring, &d->d_ring));
-		HNS_CUDA(up(deep, &d->d_deep));
 		cudaFree(d->d_boundary_nbr), cudaFree(d->d_interior_nbr);
 		d->d_boundary_nbr = d->d_interior_nbr = nullptr;
 		const char* e = std::getenv("HNS_LIST_NBR");  // A/B switch, default on
@@ -303,10 +276,6 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 			HNS_CUDA(cudaMalloc(&d->d_interior_nbr, std::max<size_t>(inter.size(), 1) * 27 * sizeof(int32_t)));
 			launch_gather_nbr_rows(s->grid->view.nbr, d->d_boundary, d->n_boundary, d->d_boundary_nbr, nullptr);
 			launch_gather_nbr_rows(s->grid->view.nbr, d->d_interior, d->n_interior, d->d_interior_nbr, nullptr);
-			HNS_CUDA(cudaMalloc(&d->d_ring_nbr, std::max<size_t>(ring.size(), 1) * 27 * sizeof(int32_t)));
-			HNS_CUDA(cudaMalloc(&d->d_deep_nbr, std::max<size_t>(deep.size(), 1) * 27 * sizeof(int32_t)));
-			launch_gather_nbr_rows(s->grid->view.nbr, d->d_ring, d->n_ring, d->d_ring_nbr, nullptr);
-			launch_gather_nbr_rows(s->grid->view.nbr, d->d_deep, d->n_deep, d->d_deep_nbr, nullptr);
 			HNS_CUDA(cudaDeviceSynchronize());
 		}
 		s->active = d->d_owned, s->n_active = d->n_owned;
@@ -353,7 +322,6 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 	d->vel_exchanged_version = ~uint64_t(0);
 	if (const char* e = std::getenv("HNS_SIGNAL_IN_KERNEL")) d->signal_in_kernel = std::atoi(e) != 0;
 	if (const char* e = std::getenv("HNS_FUSED_PUSH")) d->fused_push = std::atoi(e) != 0;
-	if (const char* e = std::getenv("HNS_WAIT_IN_KERNEL")) d->wait_in_kernel = std::atoi(e) != 0;
 	if (const char* e = std::getenv("HNS_COOK_OVERLAP")) d->cook_overlap = std::atoi(e) != 0;
 	if (const char* e = std::getenv("HNS_AUX_BLOCKS")) d->aux_blocks = std::atoi(e);
 	if (const char* e = std::getenv("HNS_PUSH_WHOLE_LEAVES")) d->push_whole_leaves = std::atoi(e) != 0;
@@ -761,11 +729,9 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 		//   comm_stream:      B_1 x_1    B_2 x_2    B_3 x_3 ...    B_k needs B_{k-1}, x_{k-1} (in order) and I_{k-1} (event)
 		// Half-sweep k reads colour c_{k-1} and writes colour c_k, so I_k and B_k/x_k never touch the same colour of the same leaf
 		// at the same time, and the exchange latency disappears behind the interior sweep as long as B + x is the shorter chain.
-		GridView vb = s->grid->view, vi = s->grid->view, vr = s->grid->view, vd = s->grid->view;
+		GridView vb = s->grid->view, vi = s->grid->view;
 		vb.list = d->d_boundary, vb.num_list = d->n_boundary, vb.list_nbr = d->d_boundary_nbr;
 		vi.list = d->d_interior, vi.num_list = d->n_interior, vi.list_nbr = d->d_interior_nbr;
-		vr.list = d->d_ring, vr.num_list = d->n_ring, vr.list_nbr = d->d_ring_nbr;
-		vd.list = d->d_deep, vd.num_list = d->n_deep, vd.list_nbr = d->d_deep_nbr;
 		const float dx = s->grid->voxel_size;
 		cudaStream_t bs = d->comm_stream;
 		const int np = int(d->peers.size());
@@ -787,23 +753,16 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 						for (auto& e : d->dbg) cudaEventCreate(&e);
 					dbg = d->dbg, d->dbg_valid = true;
 				}
+				HNS_CUDA(cudaStreamWaitEvent(bs, d->ev_I[prev], 0));
+				if (dbg) cudaEventRecord(dbg[0], bs);
 				if (fused) {
-					// Three work lists (hns_dist_set_plan): B = boundary leaves (a peer holds a ghost copy), R = the ring of owned leaves that
-					// touch B across a face, D = everything deeper. B_k reads B, R and the ghosts; R_k reads B, R, D; D_k reads R, D. So
-					//   comm stream:  wait(peers' B_{k-1} pushed) -> B_k + push -> signal -> wait(D_{k-1}) -> R_k
-					//   caller's:     wait(R_{k-1}) -> D_k
-					// and the chain that crosses NVLink -- B_k, its push, the flag, the peers' wait -- hangs on the SMALL sweeps only: B_{k+1}
-					// needs R_k, which needs D_{k-1}, a whole half-sweep back. (With two lists, B_k waited for the whole interior sweep
-					// I_{k-1}; at 8 GPUs the boundary stream then sat 40 us per half-sweep waiting for flags the peers could not raise
-					// earlier for the same reason: 5.4 ms per solve against 4.7 ms without any exchange.)
-					if (k == 0) HNS_CUDA(cudaStreamWaitEvent(bs, d->ev_I[1], 0));  // everything before the solve (divergence, p = 0)
-					if (dbg) cudaEventRecord(dbg[0], bs);
-					const int wait_ch = k == 0 ? 5 : 2 + (color ^ 1);
-					const uint32_t wait_seq = k == 0 ? d->frame_id : d->seq_p[color ^ 1];
-					if (!d->wait_in_kernel) HNS_LAUNCH(k_wait, 1, 32, 0, bs, d->d_local_flags, np, wait_ch, wait_seq, d->d_err);
+					// ghosts of the colour this sweep reads: pushed by the peers' previous boundary sweep (first sweep: their init signal)
+					if (k == 0)
+						HNS_LAUNCH(k_wait, 1, 32, 0, bs, d->d_local_flags, np, 5, d->frame_id, d->d_err);
+					else
+						HNS_LAUNCH(k_wait, 1, 32, 0, bs, d->d_local_flags, np, 2 + (color ^ 1), d->seq_p[color ^ 1], d->d_err);
 					if (dbg) cudaEventRecord(dbg[2], bs);
 					RbgsPush push;
-					if (d->wait_in_kernel) push.wait_flags = d->d_local_flags, push.wait_ch = wait_ch, push.wait_seq = wait_seq, push.wait_err = d->d_err;
 					push.dst_off = d->d_push_off, push.dst_peer = d->d_push_peer, push.dst_leaf = d->d_push_leaf;
 					push.remote_pc = d->d_remote_p[color], push.signal_flags = d->d_remote_flags, push.n_peers = np;
 					push.signal_ch = 2 + color, push.signal_seq = ++d->seq_p[color], push.counter = d->signal_in_kernel ? d->d_counter : nullptr;
@@ -811,30 +770,19 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 					if (!d->signal_in_kernel) HNS_LAUNCH(k_signal, 1, 32, 0, bs, d->d_remote_flags, np, 2 + color, d->seq_p[color]);
 					d->bytes_sent += d->push_bytes_per_sweep;
 					++d->exchanges;
+					HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
+					if (dbg) cudaEventRecord(dbg[1], bs), cudaEventRecord(dbg[3], bs), cudaEventRecord(dbg[4], bs);
+				} else {
+					if (d->n_boundary) launch_rbgs_color(vb, s->div, s->p, dx, color, omega, color, bs);
+					HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
 					if (dbg) cudaEventRecord(dbg[1], bs);
-					HNS_CUDA(cudaStreamWaitEvent(bs, d->ev_I[prev], 0));  // D_{k-1}
-					if (d->n_ring) launch_rbgs_color(vr, s->div, s->p, dx, color, omega, color, bs);
-					HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));          // R_k (and B_k before it)
-					if (dbg) cudaEventRecord(dbg[3], bs), cudaEventRecord(dbg[4], bs);
-					HNS_CUDA(cudaStreamWaitEvent(st, d->ev_B[prev], 0));  // R_{k-1}
-					if (dbg) cudaEventRecord(dbg[5], st);
-					if (d->n_deep) launch_rbgs_color(vd, s->div, s->p, dx, color, omega, color, st);
-					HNS_CUDA(cudaEventRecord(d->ev_I[cur], st));          // D_k
-					if (dbg) cudaEventRecord(dbg[6], st);
-					continue;
 				}
-				// two lists (NCCL fallback, HNS_FUSED_PUSH=0): boundary sweep + exchange on the comm stream, the whole interior on the caller's
-				HNS_CUDA(cudaStreamWaitEvent(bs, d->ev_I[prev], 0));
-				if (dbg) cudaEventRecord(dbg[0], bs);
-				if (d->n_boundary) launch_rbgs_color(vb, s->div, s->p, dx, color, omega, color, bs);
-				HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
-				if (dbg) cudaEventRecord(dbg[1], bs);
 				HNS_CUDA(cudaStreamWaitEvent(st, d->ev_B[prev], 0));
 				if (dbg) cudaEventRecord(dbg[5], st);
 				if (d->n_interior) launch_rbgs_color(vi, s->div, s->p, dx, color, omega, color, st);
 				HNS_CUDA(cudaEventRecord(d->ev_I[cur], st));
 				if (dbg) cudaEventRecord(dbg[6], st);
-				if ((rc = exchange_channel(d, s, 2 + color, 1, color ? fblk : fred, bs, dbg))) return rc;
+				if (!fused && (rc = exchange_channel(d, s, 2 + color, 1, color ? fblk : fred, bs, dbg))) return rc;
 			}
 		if (fused) HNS_LAUNCH(k_wait, 1, 32, 0, bs, d->d_local_flags, np, 3, d->seq_p[1], d->d_err);  // the peers' last black push
 		HNS_CUDA(cudaEventRecord(d->ev_exchanged, bs));

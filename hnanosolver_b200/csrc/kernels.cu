@@ -313,23 +313,6 @@ __global__ void __launch_bounds__(256) k_rbgs_split(GridView g, const float* __r
 	RowCtx c;
 	const bool flags_stream_div = (reverse & 2) == 0;  // bit 1 of `reverse`: A/B switch, plain read-only loads of the divergence
 	reverse &= 1;
-	if (kPush && push.wait_flags) {  // the peers' pushes of the colour this sweep reads (their previous boundary sweep) must have landed
-		if (int(threadIdx.x) < push.n_peers && push.wait_flags[threadIdx.x]) {
-			const uint32_t* f = push.wait_flags[threadIdx.x] + push.wait_ch;
-			uint32_t v = 0;
-			const long long t0 = clock64();
-			for (;;) {
-				asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-				if (int32_t(v - push.wait_seq) >= 0) break;
-				if (clock64() - t0 > 8000000000ll) {
-					atomicOr(push.wait_err, 1u + uint32_t(push.wait_ch));
-					break;
-				}
-				__nanosleep(32);
-			}
-		}
-		__syncthreads();
-	}
 	uint32_t i = blockIdx.x * 4u + (threadIdx.x >> 6);
 	const bool active = i < g.count();
 	if (!active && !(kPush && push.counter)) return;

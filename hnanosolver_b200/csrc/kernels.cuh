@@ -50,13 +50,6 @@ struct RbgsPush {
 	int n_peers = 0, signal_ch = 0;
 	uint32_t signal_seq = 0;
 	uint32_t* counter = nullptr;
-	// optional: every CTA first waits until each peer has raised channel wait_ch of THIS rank's block to wait_seq (the ghosts this sweep
-	// reads have landed) -- the wait that would otherwise be a kernel of its own in front of the sweep (one launch less on the critical
-	// boundary chain of every half-sweep); a wait that exceeds ~4 s sets *wait_err instead of hanging
-	uint32_t* const* wait_flags = nullptr;
-	int wait_ch = 0;
-	uint32_t wait_seq = 0;
-	uint32_t* wait_err = nullptr;
 };
 void launch_rbgs_color_push(const GridView& g, const float* const div[2], float* const p[2], float dx, int color, float omega, int reverse,
                             const RbgsPush& push, cudaStream_t st);

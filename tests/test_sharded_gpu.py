@@ -19,7 +19,6 @@ P2P_MODES = [
     dict(),                                                       # fused boundary sweep + push, two frames (velocity-ghost reuse)
     dict(env=dict(HNS_FUSED_PUSH=0)),                             # pack / push / signal / wait / unpack kernels
     dict(env=dict(HNS_SIGNAL_IN_KERNEL=1)),                       # the boundary sweep raises the arrival flags itself
-    dict(env=dict(HNS_WAIT_IN_KERNEL=1)),                         # the boundary sweep's own CTAs wait for the peers' flags
     dict(vorticity=[0.8, 2.0]),                                   # vorticity confinement with the |curl| ghost exchange
     dict(collision=True),                                         # SDF collision path
     dict(cook=True),                                              # host-buffer entry point (hns_dist_cook), garbage in the ghost entries
