@@ -90,7 +90,7 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 	const float h = voxel_size, inv = 1.0f / h;
 	const float* sdf = s->collision_sdf();
 	if (sdf) launch_collision_boundary(g, s->vel, s->vel, sdf, inv, 0.1f, 0, st);  // enforceCollisionBoundaries, HNanoSolver.cu:153-157
-	launch_advect_vector(s->advect_view(), s->vel, s->adv, dt, inv, st, sdf, s->cold);
+	launch_advect_vector(s->view(), s->vel, s->adv, dt, inv, st, sdf, s->cold);
 	if (s->comb_enabled) {
 		const int rc = vorticity_pass(s, dt, inv, s->comb.vorticityScale, s->comb.factorScale, st);
 		if (rc) return rc;
@@ -128,7 +128,7 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 			sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i];
 			++S;
 		}
-		launch_advect_scalars(s->advect_view(), s->vel, sp, S, dt, inv, 0, s->elem0, st, sdf, s->cold);
+		launch_advect_scalars(s->view(), s->vel, sp, S, dt, inv, 0, s->elem0, st, sdf, s->cold);
 		for (int i = 0; i < s->n_scalars; ++i)
 			if (i != s->skip_scalar) std::swap(s->sc[i], s->sc_out[i]);
 	}
@@ -301,7 +301,7 @@ int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void*
 }
 int hns_state_advect_velocity(hns_state* s, float dt, void* stream) {
 	HNS_REQUIRE(s, "null state");
-	launch_advect_vector(s->advect_view(), s->vel, s->adv, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream), s->collision_sdf(), s->cold);
+	launch_advect_vector(s->view(), s->vel, s->adv, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream), s->collision_sdf(), s->cold);
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
@@ -403,7 +403,7 @@ int hns_state_advect_scalars(hns_state* s, float dt, int sampler_semantics, void
 	int S = 0;
 	for (int i = 0; i < s->n_scalars; ++i)
 		if (i != s->skip_scalar) sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i], ++S;
-	launch_advect_scalars(s->advect_view(), s->vel, sp, S, dt, 1.0f / s->grid->voxel_size, sampler_semantics, s->elem0, static_cast<cudaStream_t>(stream),
+	launch_advect_scalars(s->view(), s->vel, sp, S, dt, 1.0f / s->grid->voxel_size, sampler_semantics, s->elem0, static_cast<cudaStream_t>(stream),
 	                      s->collision_sdf(), s->cold);
 	for (int i = 0; i < s->n_scalars; ++i)
 		if (i != s->skip_scalar) std::swap(s->sc[i], s->sc_out[i]);

@@ -171,7 +171,6 @@ struct hns_grid {
 	uint8_t* d_nvdb = nullptr;
 	int4* d_origin = nullptr;
 	int32_t* d_nbr = nullptr;
-	int32_t* d_morton = nullptr;  // the leaves in Morton (Z-curve) order of their origins: the advection kernels' work list (locality in the L2)
 	hns::GridView view{};
 };
 
@@ -208,14 +207,6 @@ struct hns_state {
 	hns::GridView view() const {
 		hns::GridView v = grid->view;
 		v.list = active, v.num_list = n_active, v.far_flag = far_flag;
-		return v;
-	}
-	// The advection kernels stage a 3x3x3 leaf neighbourhood per leaf. In NanoVDB order the x-neighbour of a leaf on the face of a
-	// 128^3 lower node is ~20 k leaves away in the list and has left the L2 by the time it is needed again (ncu: DRAM reads 1.6x the
-	// algorithmic bytes). Walking the leaves along a Z-curve keeps the neighbourhood of the leaves in flight inside the L2.
-	hns::GridView advect_view() const {
-		hns::GridView v = view();
-		if (!v.list && grid->d_morton) v.list = grid->d_morton, v.num_list = uint32_t(grid->num_leaves);
 		return v;
 	}
 };

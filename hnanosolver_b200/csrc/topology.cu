@@ -220,34 +220,6 @@ static int build_grid(const int32_t* origins, uint64_t L, float voxel_size, hns_
 		if ((e = cudaMalloc(&g->d_origin, L * sizeof(int4))) != cudaSuccess) return cleanup(e, "cudaMalloc(origins)");
 		if ((e = cudaMemcpy(g->d_origin, org.data(), L * sizeof(int4), cudaMemcpyHostToDevice)) != cudaSuccess) return cleanup(e, "cudaMemcpy(origins)");
 		if ((e = cudaMalloc(&g->d_nbr, L * 27 * sizeof(int32_t))) != cudaSuccess) return cleanup(e, "cudaMalloc(neighbour table)");
-		// Z-curve order of the leaves (work list of the advection kernels, hns_state::advect_view): interleave the bits of the leaf
-		// coordinates relative to the grid's minimum corner
-		int32_t lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX};
-		for (uint64_t l = 0; l < L; ++l)
-			for (int a = 0; a < 3; ++a) lo[a] = std::min(lo[a], origins[3 * l + a]);
-		auto spread = [](uint64_t v) {  // 21 bits -> every third bit
-			v &= 0x1fffff;
-			v = (v | v << 32) & 0x1f00000000ffffull;
-			v = (v | v << 16) & 0x1f0000ff0000ffull;
-			v = (v | v << 8) & 0x100f00f00f00f00full;
-			v = (v | v << 4) & 0x10c30c30c30c30c3ull;
-			v = (v | v << 2) & 0x1249249249249249ull;
-			return v;
-		};
-		std::vector<std::pair<uint64_t, int32_t>> order(L);
-		bool fits = true;
-		for (uint64_t l = 0; l < L; ++l) {
-			uint64_t c[3];
-			for (int a = 0; a < 3; ++a) c[a] = uint64_t(int64_t(origins[3 * l + a]) - lo[a]) >> 3, fits &= c[a] < (1u << 21);
-			order[l] = {spread(c[0]) << 2 | spread(c[1]) << 1 | spread(c[2]), int32_t(l)};
-		}
-		if (fits) {
-			std::sort(order.begin(), order.end());
-			std::vector<int32_t> morton(L);
-			for (uint64_t l = 0; l < L; ++l) morton[l] = order[l].second;
-			if ((e = cudaMalloc(&g->d_morton, L * sizeof(int32_t))) != cudaSuccess) return cleanup(e, "cudaMalloc(Z-curve order)");
-			if ((e = cudaMemcpy(g->d_morton, morton.data(), L * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return cleanup(e, "cudaMemcpy(Z-curve order)");
-		}
 	}
 	g->view.nvdb = g->d_nvdb;
 	g->view.origin = g->d_origin;
@@ -309,7 +281,6 @@ void hns_grid_destroy(hns_grid* g) {
 	cudaFree(g->d_nvdb);
 	cudaFree(g->d_origin);
 	cudaFree(g->d_nbr);
-	cudaFree(g->d_morton);
 	delete g;
 }
 
