@@ -568,6 +568,7 @@ void hns_release_scratch(void) {
 	std::lock_guard<std::mutex> lk(g_scratch_mu);
 	hns_state_destroy(g_scratch);
 	g_scratch = nullptr;
+	release_grid_pool();
 }
 
 // Shared helper: a temporary grid for the stand-alone launchers + the process-wide scratch state.

@@ -24,6 +24,8 @@ int fail(int code, const std::string& msg);
 			return ::hns::fail(HNS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
 	} while (0)
 
+void release_grid_pool();  // topology.cu: device blocks of destroyed index grids kept for reuse
+
 // ---- launch accounting (hns_launch_count) ---------------------------------------------------------------
 extern std::atomic<uint64_t> g_launches;
 #define HNS_LAUNCH(kernel, grid, block, smem, stream, ...)              \
@@ -168,6 +170,8 @@ struct hns_grid {
 	float voxel_size = 0.f;
 	uint64_t num_leaves = 0, num_lower = 0, num_upper = 0;
 	uint64_t nvdb_bytes = 0;
+	uint8_t* d_block = nullptr;  // one allocation: [NanoVDB buffer | origins | neighbour table] (topology.cu)
+	uint64_t block_bytes = 0;
 	uint8_t* d_nvdb = nullptr;
 	int4* d_origin = nullptr;
 	int32_t* d_nbr = nullptr;

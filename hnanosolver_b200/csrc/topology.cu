@@ -9,6 +9,7 @@
 // walking that buffer.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -177,6 +178,53 @@ __global__ void k_get_values(GridView g, const int32_t* __restrict__ ijk, uint64
 	out[t] = sum;
 }
 
+// ---- device block pool + pinned staging of build_grid ---------------------------------------------------------------------------
+static std::mutex g_build_mu, g_pool_mu;
+static uint8_t* g_stage = nullptr;
+static uint64_t g_stage_bytes = 0;
+struct PoolBlock {
+	uint8_t* p;
+	uint64_t bytes;
+	int device;
+};
+static std::vector<PoolBlock> g_pool;  // at most kPoolMax blocks
+constexpr size_t kPoolMax = 4;
+static cudaError_t pool_take(int device, uint64_t bytes, uint8_t** p, uint64_t* got) {
+	{
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		int best = -1;
+		for (size_t i = 0; i < g_pool.size(); ++i)
+			if (g_pool[i].device == device && g_pool[i].bytes >= bytes && g_pool[i].bytes <= 2 * bytes + (1u << 20) &&
+			    (best < 0 || g_pool[i].bytes < g_pool[size_t(best)].bytes))
+				best = int(i);
+		if (best >= 0) {
+			*p = g_pool[size_t(best)].p, *got = g_pool[size_t(best)].bytes;
+			g_pool.erase(g_pool.begin() + best);
+			return cudaSuccess;
+		}
+	}
+	*got = bytes;
+	return cudaMalloc(reinterpret_cast<void**>(p), bytes);
+}
+static void pool_give(int device, uint8_t* p, uint64_t bytes) {
+	if (!p) return;
+	uint8_t* drop = nullptr;
+	{
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		g_pool.push_back(PoolBlock{p, bytes, device});
+		if (g_pool.size() > kPoolMax) drop = g_pool.front().p, g_pool.erase(g_pool.begin());
+	}
+	if (drop) cudaFree(drop);
+}
+void release_grid_pool() {
+	std::vector<PoolBlock> all;
+	{
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		all.swap(g_pool);
+	}
+	for (auto& b : all) cudaFree(b.p);
+}
+
 static int build_grid(const int32_t* origins, uint64_t L, float voxel_size, hns_grid** out) {
 	if (!out) return fail(HNS_ERR_INVALID_ARGUMENT, "out is null");
 	*out = nullptr;
@@ -204,23 +252,34 @@ static int build_grid(const int32_t* origins, uint64_t L, float voxel_size, hns_
 	g->voxel_size = voxel_size;
 	g->num_leaves = L, g->num_lower = nLower, g->num_upper = T;
 	g->nvdb_bytes = nvdb::kGrid + nvdb::kTree + nvdb::kRoot + nvdb::kTile * T + nvdb::kUpper * T + nvdb::kLower * nLower + nvdb::kLeaf * L;
-	std::vector<uint8_t> host(g->nvdb_bytes, 0);
-	emit_nanovdb(origins, L, keys, T, nLower, voxel_size, host.data(), g->nvdb_bytes);
-	std::vector<int4> org(L);
-	for (uint64_t l = 0; l < L; ++l) org[l] = make_int4(origins[3 * l], origins[3 * l + 1], origins[3 * l + 2], 0);
+	// One device block per grid: [NanoVDB buffer | leaf origins int4[L] | neighbour table int32[L][27]], taken from a small pool of
+	// blocks of destroyed grids when one fits (CreateIndexGrid runs on every cook: cudaMalloc / cudaFree of ~20 MB each time, the latter
+	// a device-wide synchronisation, were a third of its cost), filled through a pinned staging buffer that is kept as well.
+	const uint64_t off_origin = (g->nvdb_bytes + 255) & ~uint64_t(255), off_nbr = off_origin + ((L * sizeof(int4) + 255) & ~uint64_t(255));
+	const uint64_t block_bytes = off_nbr + std::max<uint64_t>(L, 1) * 27 * sizeof(int32_t);
 	auto cleanup = [&](cudaError_t e, const char* what) {
 		const std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
 		hns_grid_destroy(g);
 		return fail(HNS_ERR_CUDA, msg);
 	};
 	cudaError_t e;
-	if ((e = cudaMalloc(&g->d_nvdb, g->nvdb_bytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(nanovdb buffer)");
-	if ((e = cudaMemcpy(g->d_nvdb, host.data(), g->nvdb_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return cleanup(e, "cudaMemcpy(nanovdb buffer)");
-	if (L) {
-		if ((e = cudaMalloc(&g->d_origin, L * sizeof(int4))) != cudaSuccess) return cleanup(e, "cudaMalloc(origins)");
-		if ((e = cudaMemcpy(g->d_origin, org.data(), L * sizeof(int4), cudaMemcpyHostToDevice)) != cudaSuccess) return cleanup(e, "cudaMemcpy(origins)");
-		if ((e = cudaMalloc(&g->d_nbr, L * 27 * sizeof(int32_t))) != cudaSuccess) return cleanup(e, "cudaMalloc(neighbour table)");
+	std::lock_guard<std::mutex> lock(g_build_mu);  // the staging buffer is shared; building is host-bound anyway
+	if ((e = pool_take(g->device, block_bytes, &g->d_block, &g->block_bytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(index grid)");
+	const uint64_t stage_bytes = off_origin + L * sizeof(int4);
+	if (g_stage_bytes < stage_bytes) {
+		if (g_stage) cudaFreeHost(g_stage);
+		g_stage = nullptr, g_stage_bytes = 0;
+		if ((e = cudaMallocHost(reinterpret_cast<void**>(&g_stage), stage_bytes + stage_bytes / 4)) != cudaSuccess) return cleanup(e, "cudaMallocHost(staging)");
+		g_stage_bytes = stage_bytes + stage_bytes / 4;
 	}
+	std::memset(g_stage, 0, off_origin);
+	emit_nanovdb(origins, L, keys, T, nLower, voxel_size, g_stage, g->nvdb_bytes);
+	int4* org = reinterpret_cast<int4*>(g_stage + off_origin);
+	for (uint64_t l = 0; l < L; ++l) org[l] = make_int4(origins[3 * l], origins[3 * l + 1], origins[3 * l + 2], 0);
+	g->d_nvdb = g->d_block;
+	g->d_origin = L ? reinterpret_cast<int4*>(g->d_block + off_origin) : nullptr;
+	g->d_nbr = L ? reinterpret_cast<int32_t*>(g->d_block + off_nbr) : nullptr;
+	if ((e = cudaMemcpyAsync(g->d_block, g_stage, stage_bytes, cudaMemcpyHostToDevice, 0)) != cudaSuccess) return cleanup(e, "cudaMemcpy(index grid)");
 	g->view.nvdb = g->d_nvdb;
 	g->view.origin = g->d_origin;
 	g->view.nbr = g->d_nbr;
@@ -234,8 +293,8 @@ static int build_grid(const int32_t* origins, uint64_t L, float voxel_size, hns_
 	if (L) {
 		const uint32_t n = uint32_t(L) * 27u;
 		HNS_LAUNCH(k_neighbor_table, (n + 255) / 256, 256, 0, 0, g->view, g->d_nbr);
-		if ((e = cudaDeviceSynchronize()) != cudaSuccess) return cleanup(e, "neighbour table kernel");
 	}
+	if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return cleanup(e, "index grid upload / neighbour table kernel");  // the staging buffer is free again
 	*out = g;
 	return HNS_OK;
 }
@@ -278,9 +337,7 @@ int hns_grid_create_from_coords(const int32_t* coords, uint64_t n_voxels, float 
 
 void hns_grid_destroy(hns_grid* g) {
 	if (!g) return;
-	cudaFree(g->d_nvdb);
-	cudaFree(g->d_origin);
-	cudaFree(g->d_nbr);
+	pool_give(g->device, g->d_block, g->block_bytes);  // kept for the next grid of similar size (hns_release_scratch frees the pool)
 	delete g;
 }
 

@@ -144,7 +144,8 @@ int hns_sidecar_to_nanovdb(const int32_t* domain_origins, uint64_t n_leaves, con
  * extern "C" launchers. `stream` is a cudaStream_t passed as void* (may be NULL).
  * ------------------------------------------------------------------------------------------------------- */
 /* The one-shot launchers keep one scratch set of device buffers per process and reuse it while the problem size stays the same
- * (the reference allocates and frees everything on every call); this frees it. */
+ * (the reference allocates and frees everything on every call), and hns_grid_destroy keeps the device block of up to four destroyed
+ * index grids for the next hns_grid_create_* of similar size; this frees both. */
 void hns_release_scratch(void);
 /* Compute_Sim (src/Cuda/HNanoSolver.cu:9-372,393-396): advect velocity -> [vorticity] -> divergence -> combustion ->
  * buoyancy -> iterations x (red, black) -> gradient subtract -> advect all float fields. float_names/float_fields are
