@@ -21,16 +21,54 @@ static inline float omega_compute(float voxelSize) { return 2.0f / (1.0f + sinf(
 // ... and as pressure_projection_idx does (reference src/Cuda/PressureProjection.cu:53): double sin, narrowed at the kernel call
 static inline float omega_project(float voxelSize) { return float(2.0f / (1.0f + sin(3.14159 * voxelSize))); }
 
-static int pressure_solve(hns_state* s, int iterations, float dx, float omega, unsigned flags, cudaStream_t st) {
+static void pressure_sweeps(hns_state* s, int iterations, float dx, float omega, unsigned flags, cudaStream_t st) {
 	const GridView g = s->view();
-	HNS_CUDA(cudaMemsetAsync(s->p[0], 0, (s->n / 2) * sizeof(float), st));  // initial guess 0 (HNanoSolver.cu:113)
-	HNS_CUDA(cudaMemsetAsync(s->p[1], 0, (s->n / 2) * sizeof(float), st));
-	const L2PressureWindow window(st, s->p[0], s->n * sizeof(float));
+	cudaMemsetAsync(s->p[0], 0, (s->n / 2) * sizeof(float), st);  // initial guess 0 (HNanoSolver.cu:113)
+	cudaMemsetAsync(s->p[1], 0, (s->n / 2) * sizeof(float), st);
 	const bool alternate = !(flags & 2u);  // red sweeps walk the leaves front to back, black sweeps back to front (L2 reuse)
 	const int plain_div = (flags & 4u) ? 2 : 0;  // A/B switch: read-only instead of streaming loads of the divergence
 	for (int it = 0; it < iterations; ++it) {
 		launch_rbgs_color(g, s->div, s->p, dx, 0, omega, plain_div, st);
 		launch_rbgs_color(g, s->div, s->p, dx, 1, omega, (alternate ? 1 : 0) | plain_div, st);
+	}
+}
+
+static bool solve_graphs_enabled() {  // HNS_SOLVE_GRAPH=0: every half-sweep launched directly (A/B switch)
+	static const bool on = [] {
+		const char* e = std::getenv("HNS_SOLVE_GRAPH");
+		return !e || std::atoi(e) != 0;
+	}();
+	return on;
+}
+
+static int pressure_solve(hns_state* s, int iterations, float dx, float omega, unsigned flags, cudaStream_t st) {
+	const L2PressureWindow window(st, s->p[0], s->n * sizeof(float));
+	auto& G = s->solve_graph;
+	const bool want_graph = solve_graphs_enabled() && !window.active && iterations > 0;
+	const GridView view = s->view();
+	if (want_graph && !(G.exec && std::memcmp(&G.view, &view, sizeof(view)) == 0 && G.p == s->p[0] && G.div == s->div[0] && G.iterations == iterations &&
+	                    G.flags == flags && G.omega == omega && G.dx == dx)) {
+		if (G.exec) cudaGraphExecDestroy(G.exec), G.exec = nullptr;
+		if (!s->capture_stream && cudaStreamCreateWithFlags(&s->capture_stream, cudaStreamNonBlocking) != cudaSuccess) cudaGetLastError();
+		cudaGraph_t graph = nullptr;
+		if (s->capture_stream && cudaStreamBeginCapture(s->capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+			const uint64_t before = g_launches.load();
+			pressure_sweeps(s, iterations, dx, omega, flags, s->capture_stream);  // capture executes nothing
+			const cudaError_t e = cudaStreamEndCapture(s->capture_stream, &graph);
+			G.launches = g_launches.load() - before;
+			g_launches.fetch_sub(G.launches);  // every replay counts them
+			if (e != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess) G.exec = nullptr;
+			if (graph) cudaGraphDestroy(graph);
+		}
+		cudaGetLastError();
+		std::memcpy(&G.view, &view, sizeof(view));
+		G.p = s->p[0], G.div = s->div[0], G.iterations = iterations, G.flags = flags, G.omega = omega, G.dx = dx;
+	}
+	if (want_graph && G.exec) {
+		HNS_CUDA(cudaGraphLaunch(G.exec, st));
+		g_launches.fetch_add(G.launches, std::memory_order_relaxed);
+	} else {
+		pressure_sweeps(s, iterations, dx, omega, flags, st);
 	}
 	return HNS_OK;
 }
@@ -218,6 +256,8 @@ void hns_state_destroy(hns_state* s) {
 	cudaFree(s->aos);
 	cudaFree(s->cold);
 	cudaFree(s->d_sums);
+	if (s->solve_graph.exec) cudaGraphExecDestroy(s->solve_graph.exec);
+	if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
 	for (float* v : s->vort) cudaFree(v);
 	delete s;
 }

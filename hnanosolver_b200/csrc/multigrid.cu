@@ -15,6 +15,7 @@
 #include <array>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -51,7 +52,8 @@ struct hns_mg {
 	struct CycleGraph {
 		cudaGraphExec_t exec = nullptr;
 		const void* state = nullptr;
-		const void *p = nullptr, *rhs = nullptr, *list = nullptr;
+		hns::GridView view{};  // the fine level's view (pointers, counts, work list)
+		const void *p = nullptr, *rhs = nullptr;
 		int nu_pre = -1, nu_post = -1, coarsest_iterations = -1;
 		float omega = 0.f;
 		uint64_t launches = 0;
@@ -273,8 +275,9 @@ static void v_cycle(hns_mg* mg, hns_state* s, int nu_pre, int nu_post, float ome
 static cudaGraphExec_t cycle_graph(hns_mg* mg, hns_state* s, int nu_pre, int nu_post, float omega) {
 	if (!mg->use_graph) return nullptr;
 	auto& g = mg->graph;
-	if (g.exec && g.state == s && g.p == s->p[0] && g.rhs == s->div[0] && g.list == s->active && g.nu_pre == nu_pre && g.nu_post == nu_post &&
-	    g.omega == omega && g.coarsest_iterations == mg->coarsest_iterations)
+	const GridView view = s->view();
+	if (g.exec && g.state == s && std::memcmp(&g.view, &view, sizeof(view)) == 0 && g.p == s->p[0] && g.rhs == s->div[0] && g.nu_pre == nu_pre &&
+	    g.nu_post == nu_post && g.omega == omega && g.coarsest_iterations == mg->coarsest_iterations)
 		return g.exec;
 	if (g.exec) cudaGraphExecDestroy(g.exec), g.exec = nullptr;
 	if (!mg->capture_stream && cudaStreamCreateWithFlags(&mg->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -297,7 +300,8 @@ static cudaGraphExec_t cycle_graph(hns_mg* mg, hns_state* s, int nu_pre, int nu_
 	}
 	if (cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) g.exec = nullptr, cudaGetLastError();
 	cudaGraphDestroy(graph);
-	g.state = s, g.p = s->p[0], g.rhs = s->div[0], g.list = s->active, g.nu_pre = nu_pre, g.nu_post = nu_post, g.omega = omega;
+	std::memcpy(&g.view, &view, sizeof(view));
+	g.state = s, g.p = s->p[0], g.rhs = s->div[0], g.nu_pre = nu_pre, g.nu_post = nu_post, g.omega = omega;
 	g.coarsest_iterations = mg->coarsest_iterations, g.launches = launches;
 	return g.exec;
 }
