@@ -12,6 +12,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "kernels.cuh"
@@ -129,6 +130,7 @@ struct hns_dist {
 	uint64_t push_bytes_per_sweep = 0;
 	bool fused_push = true;         // HNS_FUSED_PUSH=0: pack / push / signal / wait / unpack kernels instead (A/B switch)
 	bool signal_in_kernel = false;  // HNS_SIGNAL_IN_KERNEL=1: the boundary sweep raises the arrival flags itself (A/B switch)
+	uint32_t* d_seq_base = nullptr;  // device [3]: sequence bases of the red pushes, black pushes, frames -- mirror seq_p[0], seq_p[1], frame_id
 	cudaStream_t copy_stream = nullptr;  // hns_dist_cook: host <-> device transfers overlapping the frame
 	cudaEvent_t ev_copy[6] = {};
 	bool cook_overlap = true;       // HNS_COOK_OVERLAP=0: transfers and frame one after the other on the caller's stream (A/B switch)
@@ -177,6 +179,34 @@ __global__ void k_wait(uint32_t* const* __restrict__ flags, int n, int ch, uint3
 			__nanosleep(64);
 		}
 	}
+}
+// The sequence numbers of the fused pressure pipeline's flags are *base + offset with the bases in device memory (base[0] red pushes,
+// base[1] black pushes, base[2] frames), advanced by the pipeline's last kernel: every frame issues identical launches.
+__global__ void k_signal_rel(uint32_t* const* __restrict__ flags, int n, int ch, const uint32_t* __restrict__ base, uint32_t offset) {
+	__threadfence_system();
+	const int t = threadIdx.x;
+	if (t < n && flags[t]) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags[t] + ch), "r"(*base + offset) : "memory");
+}
+__global__ void k_wait_rel(uint32_t* const* __restrict__ flags, int n, int ch, const uint32_t* __restrict__ base, uint32_t offset,
+                           uint32_t* __restrict__ err) {
+	const int t = threadIdx.x;
+	if (t < n && flags[t]) {
+		const uint32_t seq = *base + offset;
+		uint32_t v = 0;
+		const long long t0 = clock64();
+		for (;;) {
+			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags[t] + ch) : "memory");
+			if (int32_t(v - seq) >= 0) break;
+			if (clock64() - t0 > 8000000000ll) {
+				atomicOr(err, 1u + uint32_t(ch));
+				break;
+			}
+			__nanosleep(64);
+		}
+	}
+}
+__global__ void k_advance_bases(uint32_t* base, uint32_t iterations) {
+	if (threadIdx.x == 0) base[0] += iterations, base[1] += iterations, base[2] += 1u;
 }
 }  // namespace hns
 
@@ -234,6 +264,7 @@ void hns_dist_destroy(hns_dist* d) {
 		if (e) cudaEventDestroy(e);
 	for (auto& e : d->ev_B)
 		if (e) cudaEventDestroy(e);
+	cudaFree(d->d_seq_base);
 	if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
 	for (auto& e : d->ev_copy)
 		if (e) cudaEventDestroy(e);
@@ -323,6 +354,10 @@ int hns_dist_set_plan(hns_dist* d, hns_state* s, int n_peers, const int* peer_ra
 	if (const char* e = std::getenv("HNS_SIGNAL_IN_KERNEL")) d->signal_in_kernel = std::atoi(e) != 0;
 	if (const char* e = std::getenv("HNS_FUSED_PUSH")) d->fused_push = std::atoi(e) != 0;
 	if (const char* e = std::getenv("HNS_COOK_OVERLAP")) d->cook_overlap = std::atoi(e) != 0;
+	if (!d->d_seq_base) {
+		HNS_CUDA(cudaMalloc(&d->d_seq_base, 3 * sizeof(uint32_t)));
+		HNS_CUDA(cudaMemset(d->d_seq_base, 0, 3 * sizeof(uint32_t)));
+	}
 	if (const char* e = std::getenv("HNS_AUX_BLOCKS")) d->aux_blocks = std::atoi(e);
 	if (const char* e = std::getenv("HNS_PUSH_WHOLE_LEAVES")) d->push_whole_leaves = std::atoi(e) != 0;
 	return HNS_OK;
@@ -655,6 +690,68 @@ int hns_dist_frame_timed(hns_dist* d, hns_state* s, int iterations, float dt, vo
 	return rc ? rc : check_device_error(d);
 }
 
+// The pressure solve of the peer-memory mode: interior sweeps on `st`, boundary sweeps (which store every swept quad into the peers'
+// ghost copies) + flag signal / wait on `bs`; with `dbg_mode` the events of half-sweep 20 are recorded (timed frames).
+static int record_fused_pressure(hns_dist* d, hns_state* s, int iterations, float omega, cudaStream_t st, cudaStream_t bs, bool dbg_mode) {
+	GridView vb = s->grid->view, vi = s->grid->view;
+	vb.list = d->d_boundary, vb.num_list = d->n_boundary, vb.list_nbr = d->d_boundary_nbr;
+	vi.list = d->d_interior, vi.num_list = d->n_interior, vi.list_nbr = d->d_interior_nbr;
+	const float dx = s->grid->voxel_size;
+	const int np = int(d->peers.size());
+	const uint32_t* base = d->d_seq_base;
+	// "my pressure arrays are zeroed and nobody reads last frame's ghosts any more": peers may start pushing into them
+	HNS_LAUNCH(k_signal_rel, 1, 32, 0, st, d->d_remote_flags, np, 5, base + 2, 1u);
+	HNS_CUDA(cudaEventRecord(d->ev_I[1], st));  // "I_0": everything before the solve
+	int k = 0;
+	for (int it = 0; it < iterations; ++it)
+		for (int color = 0; color < 2; ++color, ++k) {
+			const int cur = k & 1, prev = cur ^ 1;
+			cudaEvent_t* dbg = nullptr;
+			if (dbg_mode && k == 20) {
+				if (!d->dbg[0])
+					for (auto& e : d->dbg) cudaEventCreate(&e);
+				dbg = d->dbg, d->dbg_valid = true;
+			}
+			HNS_CUDA(cudaStreamWaitEvent(bs, d->ev_I[prev], 0));
+			if (dbg) cudaEventRecord(dbg[0], bs);
+			// ghosts of the colour this sweep reads: pushed by the peers' previous boundary sweep (first sweep: their "zeroed" signal).
+			// Red sweep of iteration `it` reads black pushes up to number `it`; black reads red pushes up to `it + 1`.
+			if (k == 0) HNS_LAUNCH(k_wait_rel, 1, 32, 0, bs, d->d_local_flags, np, 5, base + 2, 1u, d->d_err);
+			else HNS_LAUNCH(k_wait_rel, 1, 32, 0, bs, d->d_local_flags, np, 2 + (color ^ 1), base + (color ^ 1), uint32_t(it + color), d->d_err);
+			if (dbg) cudaEventRecord(dbg[2], bs);
+			RbgsPush push;
+			push.dst_off = d->d_push_off, push.dst_peer = d->d_push_peer, push.dst_leaf = d->d_push_leaf;
+			push.remote_pc = d->d_remote_p[color], push.signal_flags = d->d_remote_flags, push.n_peers = np;
+			push.signal_ch = 2 + color, push.signal_seq = d->seq_p[color] + uint32_t(it) + 1u, push.counter = d->signal_in_kernel ? d->d_counter : nullptr;
+			launch_rbgs_color_push(vb, s->div, s->p, dx, color, omega, color, push, bs);
+			if (!d->signal_in_kernel) HNS_LAUNCH(k_signal_rel, 1, 32, 0, bs, d->d_remote_flags, np, 2 + color, base + color, uint32_t(it) + 1u);
+			HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
+			if (dbg) cudaEventRecord(dbg[1], bs), cudaEventRecord(dbg[3], bs), cudaEventRecord(dbg[4], bs);
+			if (k > 0) HNS_CUDA(cudaStreamWaitEvent(st, d->ev_B[prev], 0));
+			if (dbg) cudaEventRecord(dbg[5], st);
+			if (d->n_interior) launch_rbgs_color(vi, s->div, s->p, dx, color, omega, color, st);
+			HNS_CUDA(cudaEventRecord(d->ev_I[cur], st));
+			if (dbg) cudaEventRecord(dbg[6], st);
+		}
+	HNS_LAUNCH(k_wait_rel, 1, 32, 0, bs, d->d_local_flags, np, 3, base + 1, uint32_t(iterations), d->d_err);  // the peers' last black push
+	HNS_CUDA(cudaEventRecord(d->ev_exchanged, bs));
+	HNS_CUDA(cudaStreamWaitEvent(st, d->ev_exchanged, 0));
+	HNS_LAUNCH(k_advance_bases, 1, 32, 0, st, d->d_seq_base, uint32_t(iterations));
+	return HNS_OK;
+}
+
+// (Replaying this pipeline as a CUDA graph -- two captured streams, which is why the sequence numbers live in device memory -- was
+// measured at 2 GPUs: 8.75 ms per frame against 8.54 ms launched directly; the graph's two branches do not overlap the way the
+// high-priority comm stream does. Removed; profiles/r2d_tune2_dist_graph.txt.)
+static int fused_pressure(hns_dist* d, hns_state* s, int iterations, float omega, cudaStream_t st, bool timed) {
+	const int rc = record_fused_pressure(d, s, iterations, omega, st, d->comm_stream, timed);
+	if (rc) return rc;
+	d->seq_p[0] += uint32_t(iterations), d->seq_p[1] += uint32_t(iterations), ++d->frame_id;  // host mirrors of the device bases
+	d->bytes_sent += d->push_bytes_per_sweep * 2u * uint64_t(iterations);
+	d->exchanges += 2u * uint64_t(iterations);
+	return HNS_OK;
+}
+
 static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void* stream, cudaEvent_t* marks, const DistDeps* deps) {
 	if (!d || !s || iterations <= 0 || dt < 0.f) return fail(HNS_ERR_INVALID_ARGUMENT, "bad argument");
 	int rc;
@@ -734,59 +831,27 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 		vi.list = d->d_interior, vi.num_list = d->n_interior, vi.list_nbr = d->d_interior_nbr;
 		const float dx = s->grid->voxel_size;
 		cudaStream_t bs = d->comm_stream;
-		const int np = int(d->peers.size());
 		const bool fused = d->p2p && d->fused_push && d->n_boundary > 0;
 		if (fused) {
-			// "my pressure arrays are zeroed and nobody reads last frame's ghosts any more": peers may start pushing into them
-			++d->frame_id;
-			HNS_LAUNCH(k_signal, 1, 32, 0, st, d->d_remote_flags, np, 5, d->frame_id);
-		}
-		HNS_CUDA(cudaEventRecord(d->ev_I[1], st));  // "I_0": everything before the solve
-		HNS_CUDA(cudaEventRecord(d->ev_B[1], bs));  // "B_0": nothing
-		int k = 0;
-		for (int it = 0; it < iterations; ++it)
-			for (int color = 0; color < 2; ++color, ++k) {
-				const int cur = k & 1, prev = cur ^ 1;
-				cudaEvent_t* dbg = nullptr;
-				if (marks && k == 20 && d->p2p) {
-					if (!d->dbg[0])
-						for (auto& e : d->dbg) cudaEventCreate(&e);
-					dbg = d->dbg, d->dbg_valid = true;
-				}
-				HNS_CUDA(cudaStreamWaitEvent(bs, d->ev_I[prev], 0));
-				if (dbg) cudaEventRecord(dbg[0], bs);
-				if (fused) {
-					// ghosts of the colour this sweep reads: pushed by the peers' previous boundary sweep (first sweep: their init signal)
-					if (k == 0)
-						HNS_LAUNCH(k_wait, 1, 32, 0, bs, d->d_local_flags, np, 5, d->frame_id, d->d_err);
-					else
-						HNS_LAUNCH(k_wait, 1, 32, 0, bs, d->d_local_flags, np, 2 + (color ^ 1), d->seq_p[color ^ 1], d->d_err);
-					if (dbg) cudaEventRecord(dbg[2], bs);
-					RbgsPush push;
-					push.dst_off = d->d_push_off, push.dst_peer = d->d_push_peer, push.dst_leaf = d->d_push_leaf;
-					push.remote_pc = d->d_remote_p[color], push.signal_flags = d->d_remote_flags, push.n_peers = np;
-					push.signal_ch = 2 + color, push.signal_seq = ++d->seq_p[color], push.counter = d->signal_in_kernel ? d->d_counter : nullptr;
-					launch_rbgs_color_push(vb, s->div, s->p, dx, color, omega, color, push, bs);
-					if (!d->signal_in_kernel) HNS_LAUNCH(k_signal, 1, 32, 0, bs, d->d_remote_flags, np, 2 + color, d->seq_p[color]);
-					d->bytes_sent += d->push_bytes_per_sweep;
-					++d->exchanges;
-					HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
-					if (dbg) cudaEventRecord(dbg[1], bs), cudaEventRecord(dbg[3], bs), cudaEventRecord(dbg[4], bs);
-				} else {
+			if ((rc = fused_pressure(d, s, iterations, omega, st, marks != nullptr))) return rc;
+		} else {
+			HNS_CUDA(cudaEventRecord(d->ev_I[1], st));  // "I_0": everything before the solve
+			HNS_CUDA(cudaEventRecord(d->ev_B[1], bs));  // "B_0": nothing
+			int k = 0;
+			for (int it = 0; it < iterations; ++it)
+				for (int color = 0; color < 2; ++color, ++k) {
+					const int cur = k & 1, prev = cur ^ 1;
+					HNS_CUDA(cudaStreamWaitEvent(bs, d->ev_I[prev], 0));
 					if (d->n_boundary) launch_rbgs_color(vb, s->div, s->p, dx, color, omega, color, bs);
 					HNS_CUDA(cudaEventRecord(d->ev_B[cur], bs));
-					if (dbg) cudaEventRecord(dbg[1], bs);
+					HNS_CUDA(cudaStreamWaitEvent(st, d->ev_B[prev], 0));
+					if (d->n_interior) launch_rbgs_color(vi, s->div, s->p, dx, color, omega, color, st);
+					HNS_CUDA(cudaEventRecord(d->ev_I[cur], st));
+					if ((rc = exchange_channel(d, s, 2 + color, 1, color ? fblk : fred, bs))) return rc;
 				}
-				HNS_CUDA(cudaStreamWaitEvent(st, d->ev_B[prev], 0));
-				if (dbg) cudaEventRecord(dbg[5], st);
-				if (d->n_interior) launch_rbgs_color(vi, s->div, s->p, dx, color, omega, color, st);
-				HNS_CUDA(cudaEventRecord(d->ev_I[cur], st));
-				if (dbg) cudaEventRecord(dbg[6], st);
-				if (!fused && (rc = exchange_channel(d, s, 2 + color, 1, color ? fblk : fred, bs, dbg))) return rc;
-			}
-		if (fused) HNS_LAUNCH(k_wait, 1, 32, 0, bs, d->d_local_flags, np, 3, d->seq_p[1], d->d_err);  // the peers' last black push
-		HNS_CUDA(cudaEventRecord(d->ev_exchanged, bs));
-		HNS_CUDA(cudaStreamWaitEvent(st, d->ev_exchanged, 0));
+			HNS_CUDA(cudaEventRecord(d->ev_exchanged, bs));
+			HNS_CUDA(cudaStreamWaitEvent(st, d->ev_exchanged, 0));
+		}
 	}
 	mark();
 	if ((rc = hns_state_subtract_gradient(s, 1, stream))) return rc;
