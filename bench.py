@@ -178,11 +178,24 @@ def stage_breakdown(H, sim, w, S: int, full: bool, peak: float, reps: int = 5) -
             if r:
                 acc[k].append(e0.elapsed_time(e1))
     out = {}
+    measured = kernel_traffic()
     for k, b, _ in stages:
         ms = float(np.median(acc[k]))
         gbs = b * w.num_voxels / (ms * 1e-3) / 1e9
         out[k] = {"ms": ms, "algorithmic_bytes_per_voxel": b, "algorithmic_GBps": gbs, "frac_of_peak": gbs / peak}
+        key = {"advect_vector": "k_advect_vector2", f"advect_scalars({S})": f"k_advect_scalars2(S={S})"}.get(k)
+        if key in measured:   # dram bytes of the ncu capture of this kernel (profiles/kernel_traffic.json), scaled to this voxel count
+            out[k]["traffic"] = measured[key]["dram_bytes_per_voxel"] * w.num_voxels
     return out
+
+
+def kernel_traffic() -> dict:
+    """dram__bytes_read + dram__bytes_write per voxel of the committed `ncu --set full` captures (profiles/kernel_traffic.json names them);
+    measured on the config-4 workload with this round's kernels, never inside a timed run"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+    except Exception:
+        return {}
 
 
 def frame_quality(sim) -> dict:
@@ -285,7 +298,8 @@ def main():
             sweep_ms = pressure_ms / (2 * ITERATIONS)
             achieved = 8 * owned_voxels / (sweep_ms * 1e-3) / 1e9
             res["roofline"] = {"bound": "hbm", "kernel": "k_rbgs_split (interior sweep + fused boundary sweep/ghost push of one colour, per rank)",
-                               "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                               "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                               "traffic": (kernel_traffic()["k_rbgs_split"]["dram_bytes_per_voxel"] * owned_voxels) if "k_rbgs_split" in kernel_traffic() else None,
                                "algorithmic_bytes_per_launch": 8 * owned_voxels, "avg_launch_ms": sweep_ms, "launches_timed": 2 * ITERATIONS,
                                "peak_source": peak_src, "note": "max over ranks of the pressure phase incl. the pipelined ghost exchange"}
             print(json.dumps(res), flush=True)
@@ -340,13 +354,8 @@ def main():
     achieved = bytes_per_launch / (sweep_ms * 1e-3) / 1e9
     # dram__bytes_read + dram__bytes_write of the kernel per launch from the committed `ncu --set full` capture of THIS kernel on the
     # config-4 workload (profiles/kernel_traffic.json says which capture), scaled by the voxel count; never measured inside a timed run
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath))["k_rbgs_split"]["dram_bytes_per_voxel"] * N
-        except Exception:
-            traffic = None
+    kt = kernel_traffic().get("k_rbgs_split")
+    traffic = kt["dram_bytes_per_voxel"] * N if kt else None
     roofline = {"bound": "hbm", "kernel": "k_rbgs_split (one red or black half-sweep on colour-split bricks)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": sweep_ms, "launches_timed": n_sweeps,
