@@ -31,6 +31,8 @@ SIGNATURES = {
     "hns_launch_count_reset": (None, []),
     "hns_set_device": (C.c_int, [C.c_int]),
     "hns_set_l2_persist_mb": (C.c_int, [C.c_int]),
+    "hns_set_packed_advection": (C.c_int, [C.c_int]),
+    "hns_packed_advection_launches": (C.c_uint64, []),
     "hns_nvdb_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64]),
     "hns_nvdb_file_grid_bytes": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint64)]),
     "hns_nvdb_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64]),

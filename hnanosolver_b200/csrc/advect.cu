@@ -544,6 +544,328 @@ __global__ void __launch_bounds__(512) k_advect_scalars_cold(GridView g, const f
 	}
 }
 
+// =================================================================================================================================
+// Third generation: the staged region holds FOUR fields per cell (float4), fetched with one 128-bit shared-memory load.
+//
+// ncu on the second generation (profiles/r2d_advect_final_ncu.txt): 142 32-bit shared loads per voxel at S = 5, a quarter to a third of
+// their wavefronts bank conflicts between lanes that disagree about floor(y), `mio_throttle` + `short_scoreboard` the top stalls with
+// the shared pipe only 59 % busy. With the fields of a group interleaved per cell -- {u, v, w, scalar 0} and {scalar 1..4}, ... --
+//   * one LDS.128 brings the four fields of a corner: 23 loads per voxel and group instead of 92, and a corner weight is computed once
+//     per corner, not once per corner and field;
+//   * a 128-bit load is served a quarter-warp at a time, and a quarter-warp is one z-row of 8 voxels: its eight cells are 128 contiguous
+//     bytes whatever the row or plane they sit in, so lanes that disagree about floor(x) or floor(y) never conflict and no swizzle is
+//     needed (cell = rx * 224 + ry * 16 + rz; the 2x2x2 footprint is the cell + {0, 1, 16, 17, 224, 225, 240, 241}: one register);
+//   * staging is one 16-byte cp.async per cell from the packed group in global memory, with thread-constant addressing: thread t copies
+//     cell (ry, rz) = t & 255 of the planes rx = 2k + (t >> 8), so source and destination of the seven copies are immediates off three
+//     neighbour-leaf pointers.
+// The packed groups (float4[L][512], same voxel order as the brick fields) are produced by the kernel that writes the fields anyway
+// (subtractPressureGradient writes {u, v, w, scalar 0}, combustion writes {fuel, waste, temperature, flame}) or by k_pack4.
+// Arithmetic, operand order and the cold path are those of the second generation: results are bit-identical.
+// =================================================================================================================================
+constexpr int kCells = kRX * kRX * kRZ;                         // 3136 cells, 49 KB per group
+constexpr size_t kRegions4 = 2 * kCells * sizeof(float4);        // double buffer: 98 KB per CTA, two CTAs per SM
+// The regions come first in the dynamic allocation and the small tables behind them -- no static shared memory in these kernels, so a
+// region starts on a 128-byte line: with 464 bytes of static tables in front (80 bytes off a line) every 16-byte cp.async of a warp
+// straddled two lines and cost 14 shared-memory wavefronts instead of 7 (ncu source page, profiles/r2e_*).
+constexpr size_t kAdvect4Smem = kRegions4 + 3 * kMeta * sizeof(int) + 5 * sizeof(float4);
+constexpr int kCX = kRX * kRZ, kCY = kRZ;                        // cell strides: x 224, y 16, z 1
+static_assert(2 * (kAdvect4Smem + 2048) <= 233472, "two CTAs must fit one SM's shared memory");
+
+__device__ __forceinline__ void cp16v(float4* smem_dst, const float4* gsrc) {
+	const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+struct Stager4 {
+	int cell;     // ry * 16 + rz of the cells this thread copies; -1: idle (32 of 256 lanes)
+	int slot_yz;  // neighbour slot of the source leaves without its x part: (sy) * 3 + (sz)
+	int src_yz;   // voxel offset inside the source leaf without its x part
+	int xh;       // odd or even planes
+};
+__device__ __forceinline__ Stager4 make_stager4() {
+	Stager4 p;
+	const int c = threadIdx.x & 255, ry = c >> 4, rz = c & 15;
+	const int ly = ry - kHaloXY, lz = rz - kHaloZ;
+	p.cell = ry < kRX ? c : -1;
+	p.slot_yz = ((ly >> 3) + 1) * 3 + ((lz >> 3) + 1);
+	p.src_yz = ((ly & 7) << 3) | (lz & 7);
+	p.xh = threadIdx.x >> 8;
+	return p;
+}
+template <int XH>
+__device__ __forceinline__ void stage4_planes(const Stager4& p, const int* __restrict__ meta, const float4* __restrict__ src, float4* __restrict__ dst,
+                                              const float4 fill) {
+	const int l0 = meta[p.slot_yz], l1 = meta[p.slot_yz + 9], l2 = meta[p.slot_yz + 18];
+	const float4* const s[3] = {src + (uint32_t(l0) * 512u + uint32_t(p.src_yz)), src + (uint32_t(l1) * 512u + uint32_t(p.src_yz)),
+	                            src + (uint32_t(l2) * 512u + uint32_t(p.src_yz))};
+	const bool have[3] = {l0 >= 0, l1 >= 0, l2 >= 0};
+	float4* d = dst + p.cell;
+#pragma unroll
+	for (int k = 0; k < kRX / 2; ++k) {
+		const int rx = 2 * k + XH, lx = rx - kHaloXY;
+		const int sx = lx < 0 ? 0 : (lx < 8 ? 1 : 2), xoff = (lx & 7) << 6;
+		if (have[sx]) cp16v(d + rx * kCX, s[sx] + xoff);
+		else d[rx * kCX] = fill;
+	}
+}
+__device__ __forceinline__ void stage4(const Stager4& p, const int* __restrict__ meta, const float4* __restrict__ src, float4* __restrict__ dst,
+                                       const float4 fill) {
+	if (p.cell < 0) return;
+	if (p.xh) stage4_planes<1>(p, meta, src, dst, fill);
+	else stage4_planes<0>(p, meta, src, dst, fill);
+}
+// first cell of the 2x2x2 footprint of a sample; false when the footprint leaves the region
+__device__ __forceinline__ bool footprint4(int ri, int rj, int rk, int& c) {
+	const int rx = ri + kHaloXY, ry = rj + kHaloXY, rz = rk + kHaloZ;
+	c = rx * kCX + ry * kCY + rz;
+	return unsigned(rx) < unsigned(kRX - 1) && unsigned(ry) < unsigned(kRX - 1) && unsigned(rz) < unsigned(kRZ - 1);
+}
+__device__ __forceinline__ float4 lerp4(const float4 a, const float4 b, float w) {
+	return make_float4(lerpf(a.x, b.x, w), lerpf(a.y, b.y, w), lerpf(a.z, b.z, w), lerpf(a.w, b.w, w));
+}
+// TrilinearSampler on the four fields of a group: lerp z, then y, then x (Stencils.hpp:144-152)
+__device__ __forceinline__ float4 tri_lerp4(const float4* __restrict__ r, int c, float fx, float fy, float fz) {
+	const float4 y0 = lerp4(lerp4(r[c], r[c + 1], fz), lerp4(r[c + kCY], r[c + kCY + 1], fz), fy);
+	const float4 y1 = lerp4(lerp4(r[c + kCX], r[c + kCX + 1], fz), lerp4(r[c + kCX + kCY], r[c + kCX + kCY + 1], fz), fy);
+	return lerp4(y0, y1, fx);
+}
+__device__ __forceinline__ void fma4(float4& acc, const float4 v, float w) {
+	acc.x = fmaf(v.x, w, acc.x), acc.y = fmaf(v.y, w, acc.y), acc.z = fmaf(v.z, w, acc.z), acc.w = fmaf(v.w, w, acc.w);
+}
+// advect_scalars' weighted sum on the four fields of a group, corners in the reference's order (Kernel.cu:186-206, 239-243)
+__device__ __forceinline__ float4 tri_weighted4(const float4* __restrict__ r, int c, const Weights& w) {
+	float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+	fma4(acc, r[c], w.xy[0] * w.z[0]);
+	fma4(acc, r[c + kCX], w.xy[1] * w.z[0]);
+	fma4(acc, r[c + kCY], w.xy[2] * w.z[0]);
+	fma4(acc, r[c + kCX + kCY], w.xy[3] * w.z[0]);
+	fma4(acc, r[c + 1], w.xy[0] * w.z[1]);
+	fma4(acc, r[c + kCX + 1], w.xy[1] * w.z[1]);
+	fma4(acc, r[c + kCY + 1], w.xy[2] * w.z[1]);
+	fma4(acc, r[c + kCX + kCY + 1], w.xy[3] * w.z[1]);
+	return acc;
+}
+// the same two samplers on the fourth field only (32-bit loads: a 16-byte cell stride costs the four wavefronts a 128-bit load costs)
+__device__ __forceinline__ float tri_lerp_w(const float4* __restrict__ r, int c, float fx, float fy, float fz) {
+	const float z0 = lerpf(r[c].w, r[c + 1].w, fz), z1 = lerpf(r[c + kCY].w, r[c + kCY + 1].w, fz);
+	const float z2 = lerpf(r[c + kCX].w, r[c + kCX + 1].w, fz), z3 = lerpf(r[c + kCX + kCY].w, r[c + kCX + kCY + 1].w, fz);
+	return lerpf(lerpf(z0, z1, fy), lerpf(z2, z3, fy), fx);
+}
+__device__ __forceinline__ float tri_weighted_w(const float4* __restrict__ r, int c, const Weights& w) {
+	float acc = 0.f;
+	acc = fmaf(r[c].w, w.xy[0] * w.z[0], acc);
+	acc = fmaf(r[c + kCX].w, w.xy[1] * w.z[0], acc);
+	acc = fmaf(r[c + kCY].w, w.xy[2] * w.z[0], acc);
+	acc = fmaf(r[c + kCX + kCY].w, w.xy[3] * w.z[0], acc);
+	acc = fmaf(r[c + 1].w, w.xy[0] * w.z[1], acc);
+	acc = fmaf(r[c + kCX + 1].w, w.xy[1] * w.z[1], acc);
+	acc = fmaf(r[c + kCY + 1].w, w.xy[2] * w.z[1], acc);
+	acc = fmaf(r[c + kCX + kCY + 1].w, w.xy[3] * w.z[1], acc);
+	return acc;
+}
+__device__ __forceinline__ float min7(float o, float a, float b, float c, float d, float e, float f) {
+	return fminf(fminf(fminf(o, a), fminf(b, c)), fminf(fminf(d, e), f));
+}
+__device__ __forceinline__ float max7(float o, float a, float b, float c, float d, float e, float f) {
+	return fmaxf(fmaxf(fmaxf(o, a), fmaxf(b, c)), fmaxf(fmaxf(d, e), f));
+}
+// the limiter of the BFECC result (Kernel.cu:250-264, 402-429)
+__device__ __forceinline__ float limited(float mn, float mx, float first, float corrected) {
+	return fmaxf(fminf(mn, first), fminf(corrected, fmaxf(mx, first)));
+}
+
+template <bool kCollision>
+__global__ void __launch_bounds__(512, 2) k_advect_vector4(GridView g, const float4* __restrict__ vel4, float* __restrict__ ou, float* __restrict__ ov,
+                                                           float* __restrict__ ow, float sdt, const float* __restrict__ sdf,
+                                                           uint8_t* __restrict__ cold) {
+	extern __shared__ __align__(128) float4 region4[];
+	int(*meta)[kMeta] = reinterpret_cast<int(*)[kMeta]>(region4 + 2 * kCells);
+	const Items items = cta_items2(g);
+	if (!items.count) return;
+	const int tid = threadIdx.x;
+	const int x = tid >> 6, y = (tid >> 3) & 7, z = tid & 7;
+	const int oc = (x + kHaloXY) * kCX + (y + kHaloXY) * kCY + (z + kHaloZ);
+	const Stager4 stg = make_stager4();
+	const float4 fill = make_float4(0.f, 0.f, 0.f, 0.f);
+	meta_fetch(g, meta[0], items.at(0), false);
+	__syncthreads();
+	auto issue = [&](uint32_t k) {
+		stage4(stg, meta[k % 3], vel4, region4 + (k & 1) * kCells, fill);
+		if (k + 1 < items.count) meta_fetch(g, meta[(k + 1) % 3], items.at(k + 1), true);
+		cp_commit();
+	};
+	issue(0);
+	for (uint32_t k = 0; k < items.count; ++k) {
+		cp_wait_all();
+		__syncthreads();
+		if (k + 1 < items.count) issue(k + 1);
+		const float4* __restrict__ r = region4 + (k & 1) * kCells;
+		const int* m = meta[k % 3];
+		const uint32_t leaf = uint32_t(m[kMetaLeaf]);
+		const float4 c0 = r[oc];
+		const int ox = m[kMetaOx], oy = m[kMetaOx + 1], oz = m[kMetaOx + 2];
+		const float px = float(ox + x), py = float(oy + y), pz = float(oz + z);
+		float bx = fmaf(-sdt, c0.x, px), by = fmaf(-sdt, c0.y, py), bz = fmaf(-sdt, c0.z, pz);  // Kernel.cu:374
+		LeafFrame lf{ox, oy, oz, g.nbr + uint64_t(leaf) * 27u};
+		if (kCollision && trilinear_f(g, lf, sdf, bx, by, bz) < 0.0f) bx = px, by = py, bz = pz;  // :377-382
+		const int bi = __float2int_rd(bx), bj = __float2int_rd(by), bk = __float2int_rd(bz);
+		int cb;
+		if (!footprint4(bi - ox, bj - oy, bk - oz, cb)) {
+			cold[leaf] = 1;
+			continue;
+		}
+		const float4 f = tri_lerp4(r, cb, bx - float(bi), by - float(bj), bz - float(bk));
+		float fx = fmaf(sdt, f.x, bx), fy = fmaf(sdt, f.y, by), fz = fmaf(sdt, f.z, bz);  // :387
+		if (kCollision && trilinear_f(g, lf, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;  // :390-394
+		const int fi = __float2int_rd(fx), fj = __float2int_rd(fy), fk = __float2int_rd(fz);
+		int cf;
+		if (!footprint4(fi - ox, fj - oy, fk - oz, cf)) {
+			cold[leaf] = 1;
+			continue;
+		}
+		const float4 b = tri_lerp4(r, cf, fx - float(fi), fy - float(fj), fz - float(fk));
+		const float cu = fmaf(0.5f, c0.x - b.x, f.x), cv = fmaf(0.5f, c0.y - b.y, f.y), cw = fmaf(0.5f, c0.z - b.z, f.z);  // :399-400
+		const float4 n0 = r[oc - kCX], n1 = r[oc + kCX], n2 = r[oc - kCY], n3 = r[oc + kCY], n4 = r[oc - 1], n5 = r[oc + 1];
+		const uint32_t self = leaf * 512u + uint32_t(tid);
+		ou[self] = limited(min7(c0.x, n0.x, n1.x, n2.x, n3.x, n4.x, n5.x), max7(c0.x, n0.x, n1.x, n2.x, n3.x, n4.x, n5.x), f.x, cu);  // :402-429
+		ov[self] = limited(min7(c0.y, n0.y, n1.y, n2.y, n3.y, n4.y, n5.y), max7(c0.y, n0.y, n1.y, n2.y, n3.y, n4.y, n5.y), f.y, cv);
+		ow[self] = limited(min7(c0.z, n0.z, n1.z, n2.z, n3.z, n4.z, n5.z), max7(c0.z, n0.z, n1.z, n2.z, n3.z, n4.z, n5.z), f.z, cw);
+	}
+}
+
+// advect_scalars / advect_scalar on packed groups: job 0 of a leaf = group 0 {u, v, w, scalar 0} (the shared trace and the first field),
+// job j = group j {scalar 4j-3 .. 4j}
+struct GroupPtrs {
+	const float4* g[5];
+};
+struct Trace4 {
+	int cb, cf;          // first cells of the back-traced / forward-traced footprints
+	Weights wb, wf;      // kSem 0
+	float tb[3], tf[3];  // kSem 1: fractions
+};
+template <int kSem, bool kCollision>
+__global__ void __launch_bounds__(512, 2) k_advect_scalars4(GridView g, const __grid_constant__ GroupPtrs gp, const __grid_constant__ ScalarPtrs sp, int S,
+                                                            float sdt, const float* __restrict__ elem0, const float* __restrict__ sdf,
+                                                            uint8_t* __restrict__ cold) {
+	extern __shared__ __align__(128) float4 region4[];
+	int(*meta)[kMeta] = reinterpret_cast<int(*)[kMeta]>(region4 + 2 * kCells);
+	float4* fill = reinterpret_cast<float4*>(meta + 3);
+	const Items items = cta_items2(g);
+	if (!items.count) return;
+	const int tid = threadIdx.x;
+	const int x = tid >> 6, y = (tid >> 3) & 7, z = tid & 7;
+	const int oc = (x + kHaloXY) * kCX + (y + kHaloXY) * kCY + (z + kHaloZ);
+	const Stager4 stg = make_stager4();
+	const int jobs_per_leaf = 1 + (S - 1 + 3) / 4;
+	// what inactive cells hold: advect_scalars reads array element 0 (of the GLOBAL arrays: elem0 when given), advect_scalar reads 0
+	if (tid < 4 * jobs_per_leaf) {
+		float f = 0.f;
+		if (kSem == 0 && tid < 3 + S) f = elem0 ? __ldg(elem0 + tid) : __ldg(reinterpret_cast<const float*>(gp.g[tid >> 2]) + (tid & 3));
+		reinterpret_cast<float*>(fill)[tid] = f;
+	}
+	const uint32_t n_jobs = items.count * uint32_t(jobs_per_leaf);
+	meta_fetch(g, meta[0], items.at(0), false);
+	__syncthreads();
+	uint32_t issue_item = 0;
+	int issue_jj = 0;
+	auto issue = [&](uint32_t job) {
+		stage4(stg, meta[issue_item % 3], gp.g[issue_jj], region4 + (job & 1) * kCells, fill[issue_jj]);
+		if (issue_jj == 0 && issue_item + 1 < items.count) meta_fetch(g, meta[(issue_item + 1) % 3], items.at(issue_item + 1), true);
+		cp_commit();
+		if (++issue_jj == jobs_per_leaf) issue_jj = 0, ++issue_item;
+	};
+	Trace4 t;
+	bool is_cold = false;
+	uint32_t item = 0;
+	int jj = 0;
+	issue(0);
+	for (uint32_t job = 0; job < n_jobs; ++job) {
+		cp_wait_all();
+		__syncthreads();
+		if (job + 1 < n_jobs) issue(job + 1);
+		const float4* __restrict__ r = region4 + (job & 1) * kCells;
+		const int* m = meta[item % 3];
+		const uint32_t leaf = uint32_t(m[kMetaLeaf]);
+		const uint32_t self = leaf * 512u + uint32_t(tid);
+		if (jj == 0) {
+			// ---- the shared trace through the staged velocity (Kernel.cu:126-214) and, with the same loads, the first scalar field ----
+			const float4 c0 = r[oc];
+			const int ox = m[kMetaOx], oy = m[kMetaOx + 1], oz = m[kMetaOx + 2];
+			const float px = float(ox + x), py = float(oy + y), pz = float(oz + z);
+			float bx = fmaf(-sdt, c0.x, px), by = fmaf(-sdt, c0.y, py), bz = fmaf(-sdt, c0.z, pz);
+			LeafFrame lf{ox, oy, oz, g.nbr + uint64_t(leaf) * 27u};
+			// hasCollision (:142-155): the reference tests the back-traced position twice; one test decides (see the second generation)
+			if (kCollision && trilinear_f(g, lf, sdf, bx, by, bz) < 0.0f) bx = px, by = py, bz = pz;
+			const int bi = __float2int_rd(bx), bj = __float2int_rd(by), bk = __float2int_rd(bz);
+			is_cold = !footprint4(bi - ox, bj - oy, bk - oz, t.cb);
+			if (!is_cold) {
+				const float tx = bx - float(bi), ty = by - float(bj), tz = bz - float(bk);
+				float4 f;  // velocity and scalar 0 at the back-traced position
+				if (kSem == 0) {
+					t.wb = make_weights(tx, ty, tz);
+					f = tri_weighted4(r, t.cb, t.wb);  // :201-206, :239-243
+				} else {
+					t.tb[0] = tx, t.tb[1] = ty, t.tb[2] = tz;
+					f = tri_lerp4(r, t.cb, tx, ty, tz);
+				}
+				float fx = fmaf(sdt, f.x, bx), fy = fmaf(sdt, f.y, by), fz = fmaf(sdt, f.z, bz);  // :208
+				if (kCollision && trilinear_f(g, lf, sdf, fx, fy, fz) < 0.0f) fx = bx, fy = by, fz = bz;  // :211-214
+				const int fi = __float2int_rd(fx), fj = __float2int_rd(fy), fk = __float2int_rd(fz);
+				is_cold = !footprint4(fi - ox, fj - oy, fk - oz, t.cf);
+				const float sx = fx - float(fi), sy = fy - float(fj), sz = fz - float(fk);
+				if (kSem == 0) t.wf = make_weights(sx, sy, sz);
+				else t.tf[0] = sx, t.tf[1] = sy, t.tf[2] = sz;
+				if (!is_cold) {
+					const float phiB = kSem == 0 ? tri_weighted_w(r, t.cf, t.wf) : tri_lerp_w(r, t.cf, sx, sy, sz);
+					const float corr = fmaf(0.5f, c0.w - phiB, f.w);  // :246-247
+					const float a = r[oc - kCX].w, b = r[oc + kCX].w, c = r[oc - kCY].w, d = r[oc + kCY].w, e = r[oc - 1].w, h = r[oc + 1].w;
+					sp.out[0][self] = limited(min7(c0.w, a, b, c, d, e, h), max7(c0.w, a, b, c, d, e, h), f.w, corr);  // :253-264
+				}
+			}
+			if (is_cold) cold[leaf] = 1;
+		} else if (!is_cold) {
+			const int s0 = 4 * jj - 3;
+			const float4 c0 = r[oc];
+			float4 f, b;
+			if (kSem == 0) {
+				f = tri_weighted4(r, t.cb, t.wb);
+				b = tri_weighted4(r, t.cf, t.wf);
+			} else {
+				f = tri_lerp4(r, t.cb, t.tb[0], t.tb[1], t.tb[2]);
+				b = tri_lerp4(r, t.cf, t.tf[0], t.tf[1], t.tf[2]);
+			}
+			const float4 n0 = r[oc - kCX], n1 = r[oc + kCX], n2 = r[oc - kCY], n3 = r[oc + kCY], n4 = r[oc - 1], n5 = r[oc + 1];
+			sp.out[s0][self] = limited(min7(c0.x, n0.x, n1.x, n2.x, n3.x, n4.x, n5.x), max7(c0.x, n0.x, n1.x, n2.x, n3.x, n4.x, n5.x), f.x,
+			                           fmaf(0.5f, c0.x - b.x, f.x));
+			if (s0 + 1 < S)
+				sp.out[s0 + 1][self] = limited(min7(c0.y, n0.y, n1.y, n2.y, n3.y, n4.y, n5.y), max7(c0.y, n0.y, n1.y, n2.y, n3.y, n4.y, n5.y), f.y,
+				                               fmaf(0.5f, c0.y - b.y, f.y));
+			if (s0 + 2 < S)
+				sp.out[s0 + 2][self] = limited(min7(c0.z, n0.z, n1.z, n2.z, n3.z, n4.z, n5.z), max7(c0.z, n0.z, n1.z, n2.z, n3.z, n4.z, n5.z), f.z,
+				                               fmaf(0.5f, c0.z - b.z, f.z));
+			if (s0 + 3 < S)
+				sp.out[s0 + 3][self] = limited(min7(c0.w, n0.w, n1.w, n2.w, n3.w, n4.w, n5.w), max7(c0.w, n0.w, n1.w, n2.w, n3.w, n4.w, n5.w), f.w,
+				                               fmaf(0.5f, c0.w - b.w, f.w));
+		}
+		if (++jj == jobs_per_leaf) jj = 0, ++item;
+	}
+}
+
+// four brick fields -> one packed group (null field: zeros); a thread moves four consecutive voxels
+__global__ void __launch_bounds__(256) k_pack4(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                               const float* __restrict__ d, float4* __restrict__ out, uint64_t n_quads) {
+	const uint64_t q = blockIdx.x * uint64_t(256) + threadIdx.x;
+	if (q >= n_quads) return;
+	const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+	const float4 va = a ? __ldg(reinterpret_cast<const float4*>(a) + q) : zero, vb = b ? __ldg(reinterpret_cast<const float4*>(b) + q) : zero;
+	const float4 vc = c ? __ldg(reinterpret_cast<const float4*>(c) + q) : zero, vd = d ? __ldg(reinterpret_cast<const float4*>(d) + q) : zero;
+	float4* o = out + 4 * q;
+	o[0] = make_float4(va.x, vb.x, vc.x, vd.x);
+	o[1] = make_float4(va.y, vb.y, vc.y, vd.y);
+	o[2] = make_float4(va.z, vb.z, vc.z, vd.z);
+	o[3] = make_float4(va.w, vb.w, vc.w, vd.w);
+}
+
 // ---- launch plumbing -------------------------------------------------------------------------------------------------------------
 struct DeviceInfo {
 	int sms = 0;
@@ -561,8 +883,8 @@ DeviceInfo& device_info() {  // per device: function attributes and the SM count
 	return d;
 }
 template <typename K>
-void opt_in(K kernel) {
-	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAdvectSmem));
+void opt_in(K kernel, size_t smem = kAdvectSmem) {
+	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
 	cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 void ensure_attrs(DeviceInfo& d) {
@@ -570,19 +892,55 @@ void ensure_attrs(DeviceInfo& d) {
 	opt_in(k_advect_vector2<false>), opt_in(k_advect_vector2<true>);
 	opt_in(k_advect_scalars2<0, false>), opt_in(k_advect_scalars2<1, false>);
 	opt_in(k_advect_scalars2<0, true>), opt_in(k_advect_scalars2<1, true>);
+	static_assert(kAdvect4Smem >= kAdvectSmem, "opt_in asks for the second generation's size");
+	opt_in(k_advect_vector4<false>, kAdvect4Smem), opt_in(k_advect_vector4<true>, kAdvect4Smem);
+	opt_in(k_advect_scalars4<0, false>, kAdvect4Smem), opt_in(k_advect_scalars4<1, false>, kAdvect4Smem);
+	opt_in(k_advect_scalars4<0, true>, kAdvect4Smem), opt_in(k_advect_scalars4<1, true>, kAdvect4Smem);
 	d.attrs = true;
+}
+
+std::atomic<int>& packed_switch() {  // HNS_ADVECT4=0 / hns_set_packed_advection(0): the second-generation kernels on the brick fields
+	static std::atomic<int> on{[] {
+		const char* e = std::getenv("HNS_ADVECT4");
+		return (!e || std::atoi(e) != 0) ? 1 : 0;
+	}()};
+	return on;
+}
+bool packed_advection() { return packed_switch().load(std::memory_order_relaxed) != 0; }
+std::atomic<uint64_t> g_packed_launches{0};
+void pack4(const float* a, const float* b, const float* c, const float* d, float4* out, uint64_t n, cudaStream_t st) {
+	HNS_LAUNCH(k_pack4, unsigned((n / 4 + 255) / 256), 256, 0, st, a, b, c, d, out, n / 4);
 }
 
 }  // namespace
 
+void launch_pack4(const float* a, const float* b, const float* c, const float* d, float4* out, uint64_t n, cudaStream_t st) {
+	if (n) pack4(a, b, c, d, out, n, st);
+}
+bool packed_advection_enabled() { return packed_advection(); }
+int set_packed_advection(int on) { return packed_switch().exchange(on ? 1 : 0); }
+uint64_t packed_advection_launches() { return g_packed_launches.load(); }
+
 void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st, const float* sdf,
-                          uint8_t* cold) {
+                          uint8_t* cold, const AdvectGroups* grp) {
 	if (!g.count()) return;
 	DeviceInfo& d = device_info();
 	ensure_attrs(d);
 	const int grid = int(std::min<uint32_t>(uint32_t(2 * d.sms), g.count()));
 	const float sdt = dt * inv_dx;
 	const int cold_grid = int(std::min<uint32_t>(uint32_t(4 * d.sms), (g.count() + 511u) / 512u));
+	if (grp && grp->g[0] && (grp->valid & 1u) && packed_advection()) {  // group 0 holds this velocity: the third generation
+		g_packed_launches.fetch_add(1, std::memory_order_relaxed);
+		if (sdf) {
+			HNS_LAUNCH(k_advect_vector4<true>, grid, 512, kAdvect4Smem, st, g, grp->g[0], out[0], out[1], out[2], sdt, sdf, cold);
+			HNS_LAUNCH(k_advect_vector_cold<true>, cold_grid, 512, 0, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
+			launch_collision_boundary(g, out, out, sdf, inv_dx, 1.5f, 1, st);
+		} else {
+			HNS_LAUNCH(k_advect_vector4<false>, grid, 512, kAdvect4Smem, st, g, grp->g[0], out[0], out[1], out[2], sdt, sdf, cold);
+			HNS_LAUNCH(k_advect_vector_cold<false>, cold_grid, 512, 0, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
+		}
+		return;
+	}
 	if (sdf) {
 		HNS_LAUNCH(k_advect_vector2<true>, grid, 512, kAdvectSmem, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
 		HNS_LAUNCH(k_advect_vector_cold<true>, cold_grid, 512, 0, st, g, vel[0], vel[1], vel[2], out[0], out[1], out[2], sdt, sdf, cold);
@@ -594,13 +952,30 @@ void launch_advect_vector(const GridView& g, const float* const vel[3], float* c
 }
 
 void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx, int sampler_semantics,
-                           const float* elem0, cudaStream_t st, const float* sdf, uint8_t* cold) {
+                           const float* elem0, cudaStream_t st, const float* sdf, uint8_t* cold, const AdvectGroups* grp) {
 	if (!g.count() || S <= 0) return;
 	DeviceInfo& d = device_info();
 	ensure_attrs(d);
 	const int grid = int(std::min<uint32_t>(uint32_t(2 * d.sms), g.count()));
 	const float sdt = dt * inv_dx;
 	const int cold_grid = int(std::min<uint32_t>(uint32_t(4 * d.sms), (g.count() + 511u) / 512u));
+	const int n_groups = 1 + (S - 1 + 3) / 4;
+	// the third generation needs every group of this field list already packed by the kernels that wrote the fields (bit j of valid);
+	// packing here would cost more than it saves (0.2 ms per group at 40 M voxels)
+	bool packed = grp && n_groups <= 5 && packed_advection();
+	for (int j = 0; packed && j < n_groups; ++j) packed = grp->g[j] != nullptr && (grp->valid >> j & 1u);
+	if (packed) {
+		GroupPtrs gp{};
+		for (int j = 0; j < n_groups; ++j) gp.g[j] = grp->g[j];
+		g_packed_launches.fetch_add(1, std::memory_order_relaxed);
+		auto hot4 = sampler_semantics == 0 ? (sdf ? k_advect_scalars4<0, true> : k_advect_scalars4<0, false>)
+		                                   : (sdf ? k_advect_scalars4<1, true> : k_advect_scalars4<1, false>);
+		auto cold4 = sampler_semantics == 0 ? (sdf ? k_advect_scalars_cold<0, true> : k_advect_scalars_cold<0, false>)
+		                                    : (sdf ? k_advect_scalars_cold<1, true> : k_advect_scalars_cold<1, false>);
+		HNS_LAUNCH(hot4, grid, 512, kAdvect4Smem, st, g, gp, sp, S, sdt, elem0, sdf, cold);
+		HNS_LAUNCH(cold4, cold_grid, 512, 0, st, g, vel[0], vel[1], vel[2], sp, S, sdt, elem0, sdf, cold);
+		return;
+	}
 	auto hot = sampler_semantics == 0 ? (sdf ? k_advect_scalars2<0, true> : k_advect_scalars2<0, false>)
 	                                  : (sdf ? k_advect_scalars2<1, true> : k_advect_scalars2<1, false>);
 	auto cold_k = sampler_semantics == 0 ? (sdf ? k_advect_scalars_cold<0, true> : k_advect_scalars_cold<0, false>)

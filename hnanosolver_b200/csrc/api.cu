@@ -73,6 +73,110 @@ static int pressure_solve(hns_state* s, int iterations, float dx, float omega, u
 	return HNS_OK;
 }
 
+// ---- packed groups of the advection kernels (advect.cu, third generation) ------------------------------------------------------------
+// The kernels that write the velocity and the scalars right before an advection pass also write them as float4 groups:
+// subtractPressureGradient -> group 0 {u, v, w, first advected scalar}, combustion -> group 1 {fuel, waste, temperature, flame}.
+// A group is current while the version counters it was written at still match (hns_state::vel_version / sc_version, bumped by every
+// entry point that may overwrite the brick fields) and it was built from the very buffers the advection pass is about to read; otherwise
+// the advection launchers fall back to the second-generation kernels on the brick fields. Not used by sharded runs (their ghost leaves
+// are refreshed behind the groups' back) nor with collision data (the boundary pass rewrites the velocity after the gradient).
+static bool groups_allowed(const hns_state* s) { return s->n && !s->active && !s->elem0 && !s->collision_sdf() && packed_advection_enabled(); }
+static bool ensure_group(hns_state* s, int j) {
+	if (!s->grp.g[j] && cudaMalloc(&s->grp.g[j], s->n * sizeof(float4)) != cudaSuccess) {
+		cudaGetLastError();
+		s->grp.g[j] = nullptr;
+	}
+	s->grp.n = s->n;
+	return s->grp.g[j] != nullptr;
+}
+// The scalars an advection pass moves, in the order it moves them: every scalar except the one marked as not advected
+// ("collision_sdf", HNanoSolver.cu:327). When the state carries exactly one scalar besides the four combustion fields -- the
+// reference's all-in-one frame: density + fuel, waste, temperature, flame -- that one goes first and the combustion fields follow in
+// the order combustion packs them, so that they form group 1 (the fields are advected independently: the order changes no value).
+// A sharded run's elem0 table is indexed by position in the list, so there the state's own order is kept.
+static int advect_list(const hns_state* s, int* idx) {
+	int S = 0;
+	for (int i = 0; i < s->n_scalars; ++i)
+		if (i != s->skip_scalar) idx[S++] = i;
+	if (S == 5 && s->comb_enabled && groups_allowed(s)) {
+		int other = -1, n_other = 0;
+		for (int k = 0; k < S; ++k) {
+			bool comb = false;
+			for (int c : s->comb_idx) comb |= c == idx[k];
+			if (!comb) other = idx[k], ++n_other;
+		}
+		if (n_other == 1) {
+			idx[0] = other;
+			for (int c = 0; c < 4; ++c) idx[1 + c] = s->comb_idx[c];
+		}
+	}
+	return S;
+}
+static bool combustion_packs(const hns_state* s) {  // will advect_scalars find the combustion fields as its scalars 1..4?
+	int idx[16];
+	if (!s->comb_enabled || !groups_allowed(s) || advect_list(s, idx) != 5) return false;
+	for (int c = 0; c < 4; ++c)
+		if (idx[1 + c] != s->comb_idx[c]) return false;
+	return true;
+}
+
+static int stage_advect_velocity(hns_state* s, float dt, float inv, cudaStream_t st) {
+	const bool packed = groups_allowed(s) && s->grp.g[0] && s->grp0_vel_version == s->vel_version;
+	s->grp.valid = packed ? 1u : 0u;
+	launch_advect_vector(s->view(), s->vel, s->adv, dt, inv, st, s->collision_sdf(), s->cold, packed ? &s->grp : nullptr);
+	return HNS_OK;
+}
+static int stage_combustion_buoyancy(hns_state* s, float dt, cudaStream_t st) {
+	const int iF = s->comb_idx[0], iW = s->comb_idx[1], iT = s->comb_idx[2], iL = s->comb_idx[3];
+	const bool packed = combustion_packs(s) && ensure_group(s, 1);
+	if (packed) {
+		launch_combustion_buoyancy_packed(s->sc[iF], s->sc[iW], s->sc[iT], s->div, s->sc[iL], s->sc_out[iF], s->sc_out[iW], s->sc_out[iT], s->sc_out[iL],
+		                                  s->grp.g[1], s->adv, s->comb.temperatureRelease, s->comb.expansionRate, dt, s->comb.ambientTemp,
+		                                  s->comb.buoyancyStrength, s->n, st);
+	} else {
+		launch_combustion_oxygen(s->sc[iF], s->sc[iW], s->sc[iT], s->div, s->sc[iL], s->sc_out[iF], s->sc_out[iW], s->sc_out[iT], s->sc_out[iL],
+		                         s->comb.temperatureRelease, s->comb.expansionRate, s->n, st);
+		launch_buoyancy(s->adv, s->sc_out[iT], dt, s->comb.ambientTemp, s->comb.buoyancyStrength, s->n, st);
+	}
+	for (int i : {iF, iW, iT, iL}) std::swap(s->sc[i], s->sc_out[i]);  // HNanoSolver.cu:239-246
+	++s->sc_version;
+	if (packed) {
+		s->grp1_sc_version = s->sc_version;
+		for (int c = 0; c < 4; ++c) s->grp1_src[c] = s->sc[s->comb_idx[c]];
+	}
+	return HNS_OK;
+}
+// adv - grad p -> vel (from_advected), or in place on vel (the stand-alone projection; every thread reads only its own velocity row)
+static int stage_subtract_gradient(hns_state* s, bool from_advected, float inv, cudaStream_t st) {
+	int idx[16];
+	const int S = advect_list(s, idx);
+	const bool packed = from_advected && groups_allowed(s) && ensure_group(s, 0);
+	const float* s0 = packed && S > 0 ? s->sc[idx[0]] : nullptr;
+	launch_subtract_gradient(s->view(), from_advected ? s->adv : s->vel, s->p, s->vel, inv, st, packed ? s->grp.g[0] : nullptr, s0);
+	++s->vel_version;
+	if (packed) s->grp0_vel_version = s->vel_version, s->grp0_sc_version = s->sc_version, s->grp0_s0 = s0;
+	return HNS_OK;
+}
+static int stage_advect_scalars(hns_state* s, float dt, float inv, int sampler_semantics, cudaStream_t st) {
+	int idx[16];
+	const int S = advect_list(s, idx);
+	if (!S || !s->n) return HNS_OK;
+	ScalarPtrs sp{};
+	for (int k = 0; k < S; ++k) sp.in[k] = s->sc[idx[k]], sp.out[k] = s->sc_out[idx[k]];
+	unsigned valid = 0;
+	if (groups_allowed(s)) {
+		if (s->grp.g[0] && s->grp0_vel_version == s->vel_version && s->grp0_sc_version == s->sc_version && s->grp0_s0 == sp.in[0]) valid |= 1u;
+		bool g1 = S > 1 && S <= 5 && s->grp.g[1] && s->grp1_sc_version == s->sc_version;
+		for (int c = 0; g1 && c < 4; ++c) g1 = s->grp1_src[c] == sp.in[1 + c];
+		if (g1) valid |= 2u;
+	}
+	s->grp.valid = valid;
+	launch_advect_scalars(s->view(), s->vel, sp, S, dt, inv, sampler_semantics, s->elem0, st, s->collision_sdf(), s->cold, valid ? &s->grp : nullptr);
+	for (int k = 0; k < S; ++k) std::swap(s->sc[idx[k]], s->sc_out[idx[k]]);
+	++s->sc_version;
+	return HNS_OK;
+}
+
 static ScalarPtrs scalar_ptrs(const hns_state* s) {
 	ScalarPtrs sp{};
 	for (int i = 0; i < s->n_scalars; ++i) sp.in[i] = s->sc[i], sp.out[i] = s->sc_out[i];
@@ -128,27 +232,23 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 	const float h = voxel_size, inv = 1.0f / h;
 	const float* sdf = s->collision_sdf();
 	if (sdf) launch_collision_boundary(g, s->vel, s->vel, sdf, inv, 0.1f, 0, st);  // enforceCollisionBoundaries, HNanoSolver.cu:153-157
-	launch_advect_vector(s->view(), s->vel, s->adv, dt, inv, st, sdf, s->cold);
+	stage_advect_velocity(s, dt, inv, st);
 	if (s->comb_enabled) {
 		const int rc = vorticity_pass(s, dt, inv, s->comb.vorticityScale, s->comb.factorScale, st);
 		if (rc) return rc;
 	}
 	launch_divergence(g, s->adv, s->div, inv, st);
 	if (deps && deps->combustion_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->combustion_inputs, 0));
-	if (s->comb_enabled) {
-		const int iF = s->comb_idx[0], iW = s->comb_idx[1], iT = s->comb_idx[2], iL = s->comb_idx[3];
-		launch_combustion_oxygen(s->sc[iF], s->sc[iW], s->sc[iT], s->div, s->sc[iL], s->sc_out[iF], s->sc_out[iW], s->sc_out[iT], s->sc_out[iL],
-		                         s->comb.temperatureRelease, s->comb.expansionRate, s->n, st);
-		launch_buoyancy(s->adv, s->sc_out[iT], dt, s->comb.ambientTemp, s->comb.buoyancyStrength, s->n, st);
-		for (int i : {iF, iW, iT, iL}) std::swap(s->sc[i], s->sc_out[i]);  // HNanoSolver.cu:239-246
-	}
+	if (s->comb_enabled) stage_combustion_buoyancy(s, dt, st);
 	if (ev_p0) cudaEventRecord(ev_p0, st);
 	// the reference's solve, or -- opted in with hns_state_set_pressure_solver -- a fixed number of multigrid V-cycles
 	int rc = s->mg ? mg_pressure_solve(s, s->mg, s->mg_cycles, 0.0, s->mg_nu[0], s->mg_nu[1], s->mg_omega, st)
 	               : pressure_solve(s, iterations, h, omega_compute(h), flags, st);
 	if (rc) return rc;
 	if (ev_p1) cudaEventRecord(ev_p1, st);
-	launch_subtract_gradient(g, s->adv, s->p, s->vel, inv, st);
+	// with packed groups the gradient pass also reads the first advected scalar: it has to have landed by now, not only by advect_scalars
+	if (deps && deps->scalar_inputs && groups_allowed(s)) HNS_CUDA(cudaStreamWaitEvent(st, deps->scalar_inputs, 0));
+	stage_subtract_gradient(s, true, inv, st);
 	if (sdf) {
 		launch_collision_boundary(g, s->vel, s->vel, sdf, inv, 0.1f, 0, st);  // the tail of subtractPressureGradient, Kernel.cu:808-826
 		launch_collision_boundary(g, s->vel, s->vel, sdf, inv, 0.1f, 0, st);  // enforceCollisionBoundaries again, HNanoSolver.cu:292-296
@@ -158,18 +258,7 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 		HNS_CUDA(cudaEventRecord(deps->velocity_done, st));
 	}
 	if (deps && deps->scalar_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->scalar_inputs, 0));
-	if (s->n_scalars) {
-		ScalarPtrs sp{};
-		int S = 0;
-		for (int i = 0; i < s->n_scalars; ++i) {
-			if (i == s->skip_scalar) continue;  // "collision_sdf" is not advected (HNanoSolver.cu:327)
-			sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i];
-			++S;
-		}
-		launch_advect_scalars(s->view(), s->vel, sp, S, dt, inv, 0, s->elem0, st, sdf, s->cold);
-		for (int i = 0; i < s->n_scalars; ++i)
-			if (i != s->skip_scalar) std::swap(s->sc[i], s->sc_out[i]);
-	}
+	stage_advect_scalars(s, dt, inv, 0, st);
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
@@ -195,6 +284,8 @@ int hns_set_l2_persist_mb(int megabytes) {
 	cudaGetLastError();
 	return HNS_OK;
 }
+int hns_set_packed_advection(int on) { return set_packed_advection(on); }
+uint64_t hns_packed_advection_launches(void) { return packed_advection_launches(); }
 int hns_set_device(int device) {
 	HNS_CUDA(cudaSetDevice(device));
 	return HNS_OK;
@@ -255,6 +346,7 @@ void hns_state_destroy(hns_state* s) {
 	for (int i = 0; i < 16; ++i) cudaFree(s->sc[i]), cudaFree(s->sc_out[i]);
 	cudaFree(s->aos);
 	cudaFree(s->cold);
+	for (float4* q : s->grp.g) cudaFree(q);
 	cudaFree(s->d_sums);
 	if (s->solve_graph.exec) cudaGraphExecDestroy(s->solve_graph.exec);
 	if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
@@ -288,6 +380,7 @@ int hns_state_download_velocity(hns_state* s, float* host) {
 int hns_state_upload_scalar(hns_state* s, int i, const float* host) {
 	HNS_REQUIRE(s && host && i >= 0 && i < s->n_scalars, "bad argument");
 	HNS_CUDA(cudaMemcpy(s->sc[i], host, s->n * 4, cudaMemcpyHostToDevice));
+	++s->sc_version;
 	return HNS_OK;
 }
 int hns_state_download_scalar(hns_state* s, int i, float* host) {
@@ -336,12 +429,11 @@ int hns_state_step(hns_state* s, int iterations, float dt, unsigned flags, void*
 	HNS_REQUIRE(iterations > 0, "Number of pressure iterations must be positive.");
 	HNS_REQUIRE(dt >= 0.0f, "dt (time step) cannot be negative.");
 	if (!s->n) return HNS_OK;
-	++s->vel_version;
-	return frame(s, iterations, dt, s->grid->voxel_size, flags, static_cast<cudaStream_t>(stream));
+	return frame(s, iterations, dt, s->grid->voxel_size, flags, static_cast<cudaStream_t>(stream));  // bumps vel_version where it writes the velocity
 }
 int hns_state_advect_velocity(hns_state* s, float dt, void* stream) {
 	HNS_REQUIRE(s, "null state");
-	launch_advect_vector(s->view(), s->vel, s->adv, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream), s->collision_sdf(), s->cold);
+	stage_advect_velocity(s, dt, 1.0f / s->grid->voxel_size, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
@@ -390,12 +482,7 @@ int hns_state_pressure_half_sweep(hns_state* s, int color, float omega, int reve
 int hns_state_combustion_buoyancy(hns_state* s, float dt, void* stream) {
 	HNS_REQUIRE(s, "null state");
 	if (!s->comb_enabled) return fail(HNS_ERR_RUNTIME, "combustion stage not configured (hns_state_set_combustion)");
-	cudaStream_t st = static_cast<cudaStream_t>(stream);
-	const int iF = s->comb_idx[0], iW = s->comb_idx[1], iT = s->comb_idx[2], iL = s->comb_idx[3];
-	launch_combustion_oxygen(s->sc[iF], s->sc[iW], s->sc[iT], s->div, s->sc[iL], s->sc_out[iF], s->sc_out[iW], s->sc_out[iT], s->sc_out[iL],
-	                         s->comb.temperatureRelease, s->comb.expansionRate, s->n, st);
-	launch_buoyancy(s->adv, s->sc_out[iT], dt, s->comb.ambientTemp, s->comb.buoyancyStrength, s->n, st);
-	for (int i : {iF, iW, iT, iL}) std::swap(s->sc[i], s->sc_out[i]);
+	stage_combustion_buoyancy(s, dt, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
@@ -404,14 +491,8 @@ float hns_omega_project(float voxel_size) { return omega_project(voxel_size); }
 
 int hns_state_subtract_gradient(hns_state* s, int from_advected, void* stream) {
 	HNS_REQUIRE(s, "null state");
-	++s->vel_version;
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
-	if (from_advected) {
-		launch_subtract_gradient(s->view(), s->adv, s->p, s->vel, 1.0f / s->grid->voxel_size, st);
-	} else {
-		// in place is safe: every thread reads only its own velocity row (the reference does the same, PressureProjection.cu:64)
-		launch_subtract_gradient(s->view(), s->vel, s->p, s->vel, 1.0f / s->grid->voxel_size, st);
-	}
+	stage_subtract_gradient(s, from_advected != 0, 1.0f / s->grid->voxel_size, st);  // in place when !from_advected (PressureProjection.cu:64)
 	if (const float* sdf = s->collision_sdf())  // the collision tail of the kernel, Kernel.cu:808-826
 		launch_collision_boundary(s->view(), s->vel, s->vel, sdf, 1.0f / s->grid->voxel_size, 0.1f, 0, st);
 	HNS_CUDA(cudaGetLastError());
@@ -437,16 +518,9 @@ int hns_state_enforce_collision(hns_state* s, void* stream) {
 int hns_state_advect_scalars(hns_state* s, float dt, int sampler_semantics, void* stream) {
 	HNS_REQUIRE(s, "null state");
 	if (!s->n_scalars || !s->n) return HNS_OK;
-	// every scalar except the one marked as not advected ("collision_sdf", HNanoSolver.cu:327); a sharded run's elem0 table is indexed
-	// by position in this list, so there the skipped scalar has to be the last one (checked in hns_dist_frame)
-	ScalarPtrs sp{};
-	int S = 0;
-	for (int i = 0; i < s->n_scalars; ++i)
-		if (i != s->skip_scalar) sp.in[S] = s->sc[i], sp.out[S] = s->sc_out[i], ++S;
-	launch_advect_scalars(s->view(), s->vel, sp, S, dt, 1.0f / s->grid->voxel_size, sampler_semantics, s->elem0, static_cast<cudaStream_t>(stream),
-	                      s->collision_sdf(), s->cold);
-	for (int i = 0; i < s->n_scalars; ++i)
-		if (i != s->skip_scalar) std::swap(s->sc[i], s->sc_out[i]);
+	// a sharded run's elem0 table is indexed by position in the advection list (advect_list): there the skipped scalar has to be the
+	// last one (checked in hns_dist_frame)
+	stage_advect_scalars(s, dt, 1.0f / s->grid->voxel_size, sampler_semantics, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
 }
@@ -495,6 +569,14 @@ int hns_state_time_frames(hns_state* s, int frames, int iterations, float dt, un
 	for (int f = 0; f < frames && rc == HNS_OK; ++f) {
 		for (int c = 0; c < 3; ++c) cudaMemcpyAsync(s->vel[c], keep[c], fb, cudaMemcpyDeviceToDevice, st);
 		for (int i = 0; i < s->n_scalars; ++i) cudaMemcpyAsync(s->sc[i], keep[3 + i], fb, cudaMemcpyDeviceToDevice, st);
+		++s->vel_version, ++s->sc_version;
+		// A frame of a running simulation finds the velocity the previous frame's gradient pass wrote -- brick planes and packed group 0
+		// alike (every timed frame pays for that second copy in its own gradient pass). The restored input stands in for that velocity,
+		// so it is packed here, outside the events, like the restore copies themselves.
+		if (groups_allowed(s) && ensure_group(s, 0)) {
+			launch_pack4(s->vel[0], s->vel[1], s->vel[2], nullptr, s->grp.g[0], s->n, st);
+			s->grp0_vel_version = s->vel_version, s->grp0_sc_version = 0, s->grp0_s0 = nullptr;
+		}
 		cudaEventRecord(ev[4 * f + 0], st);
 		rc = frame(s, iterations, dt, s->grid->voxel_size, flags, st, ev[4 * f + 1], ev[4 * f + 2]);
 		cudaEventRecord(ev[4 * f + 3], st);
@@ -532,6 +614,7 @@ static float* field_ptr(hns_state* s, int field, int* floats_per_leaf) {
 void* hns_state_field_device_ptr(hns_state* s, int field) {
 	int fpl;
 	if (s && field >= 0 && field < 3) ++s->vel_version;  // the caller may write through the pointer
+	if (s && field >= 10) ++s->sc_version;
 	return s ? field_ptr(s, field, &fpl) : nullptr;
 }
 int hns_state_field_floats_per_leaf(int field) { return (field >= 6 && field <= 9) ? 256 : 512; }
@@ -550,6 +633,7 @@ int hns_state_unpack_leaves(hns_state* s, int field, const int32_t* ids, uint64_
 	float* f = field_ptr(s, field, &fpl);
 	HNS_REQUIRE(f, "bad field id");
 	if (field < 3) ++s->vel_version;
+	if (field >= 10) ++s->sc_version;
 	launch_unpack_leaves(f, ids, n_ids, src, fpl, static_cast<cudaStream_t>(stream));
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
@@ -582,6 +666,7 @@ int acquire_scratch(const hns_grid* g, int n_scalars, hns_state** out) {
 		g_scratch_device = dev;
 	}
 	g_scratch->grid = g;
+	++g_scratch->vel_version, ++g_scratch->sc_version;  // whatever the packed advection groups mirror belongs to an earlier call
 	g_scratch->mg = nullptr;
 	g_scratch->comb_enabled = false, g_scratch->skip_scalar = -1, g_scratch->collision = false, g_scratch->elem0 = nullptr, g_scratch->active = nullptr, g_scratch->n_active = 0;
 	*out = g_scratch;
@@ -656,6 +741,7 @@ int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char*
 	hns_state* s = sc.state;
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if ((rc = hns_state_set_combustion(s, 1, iF, iW, iT, iL, params))) return rc;
+	++s->vel_version, ++s->sc_version;  // every field is about to be overwritten from the host
 	s->skip_scalar = iSdf;
 	s->collision = has_collision && iSdf >= 0;  // hasCollisionData, HNanoSolver.cu:65-76
 	if ((rc = ensure_aos(s))) return rc;

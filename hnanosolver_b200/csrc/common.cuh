@@ -130,6 +130,13 @@ struct L2PressureWindow {
 	L2PressureWindow& operator=(const L2PressureWindow&) = delete;
 };
 
+// packed field groups of the advection kernels (kernels.cuh, advect.cu)
+struct AdvectGroups {
+	float4* g[5] = {};
+	unsigned valid = 0;
+	uint64_t n = 0;  // voxels per group
+};
+
 // slot ids of the six face neighbours
 constexpr int kSlotXm = 4, kSlotXp = 22, kSlotYm = 10, kSlotYp = 16, kSlotZm = 12, kSlotZp = 14, kSlotSelf = 13;
 
@@ -190,6 +197,12 @@ struct hns_state {
 	float* sc_out[16] = {};
 	float* aos = nullptr; // staging float[N][3] for host <-> device velocity transfers
 	uint8_t* cold = nullptr;  // [L] leaf flags of the advection kernels (advect.cu), zero between launches
+	// packed groups the advection kernels stage from, allocated on first use, and what they were built from (api.cu, "packed groups")
+	hns::AdvectGroups grp;
+	uint64_t sc_version = 1;  // bumped by every entry point that (may) overwrite a scalar field, like vel_version for the velocity
+	uint64_t grp0_vel_version = 0, grp0_sc_version = 0, grp1_sc_version = 0;  // 0 never matches: the counters start at 1
+	const float* grp0_s0 = nullptr;                                          // the scalar buffer in group 0's fourth lane
+	const float* grp1_src[4] = {nullptr, nullptr, nullptr, nullptr};         // the buffers group 1 mirrors
 	float* vort[4] = {nullptr, nullptr, nullptr, nullptr};  // vorticity confinement scratch, allocated on first use: output planes u, v, w and |curl|
 	// optional combustion + buoyancy stage of the all-in-one frame
 	bool comb_enabled = false;
@@ -199,7 +212,7 @@ struct hns_state {
 	bool collision = false;  // hasCollision with collision data: scalar `skip_scalar` is the SDF the kernels collide against
 	const float* collision_sdf() const { return collision && skip_scalar >= 0 ? sc[skip_scalar] : nullptr; }
 	const float* elem0 = nullptr;  // device float[3 + n_scalars]: element 0 of the global arrays (sharded runs), else null
-	uint64_t vel_version = 0;  // bumped by every entry point that (may) overwrite the velocity planes; lets a sharded run skip a ghost exchange of unchanged data
+	uint64_t vel_version = 1;  // bumped by every entry point that (may) overwrite the velocity planes; lets a sharded run skip a ghost exchange of unchanged data
 	const int32_t* active = nullptr;  // device list of the leaves the kernels process (sharded runs: the owned leaves), null = all
 	uint32_t n_active = 0;
 	uint32_t* far_flag = nullptr;  // GridView::far_flag

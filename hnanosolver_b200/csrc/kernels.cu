@@ -175,10 +175,14 @@ void launch_divergence(const GridView& g, const float* const vel[3], float* cons
 // =============================================================================================================
 // subtractPressureGradient  (reference Kernel.cu:765-829): u - ((p(+1) - p(-1)) * 0.5) * inv_dx, fused as in the reference SASS
 // =============================================================================================================
+// kGroup: the projected velocity also goes, together with the scalar field `s0` (or 0), into the packed group the advection kernels
+// stage from (advect.cu, third generation): float4 {u, v, w, s0} per voxel.
+template <bool kGroup>
 __global__ void __launch_bounds__(256) k_subtract_gradient(GridView g, const float* __restrict__ u, const float* __restrict__ v,
                                                            const float* __restrict__ w, const float* __restrict__ p_red,
                                                            const float* __restrict__ p_blk, float* __restrict__ ou, float* __restrict__ ov,
-                                                           float* __restrict__ ow, float inv_dx) {
+                                                           float* __restrict__ ow, float inv_dx, float4* __restrict__ grp0,
+                                                           const float* __restrict__ s0) {
 	RowCtx c;
 	if (!make_row_ctx(g, c)) return;
 	const uint64_t self = c.self();
@@ -205,11 +209,22 @@ __global__ void __launch_bounds__(256) k_subtract_gradient(GridView g, const flo
 	st_row(ou, self, a);
 	st_row(ov, self, b);
 	st_row(ow, self, d);
+	if (kGroup) {
+		const Row8 q = s0 ? ld_row(s0, self) : zero_row();
+		float4* o = grp0 + self;
+#pragma unroll
+		for (int z = 0; z < 8; ++z) o[z] = make_float4(a.v[z], b.v[z], d.v[z], q.v[z]);
+	}
 }
 void launch_subtract_gradient(const GridView& g, const float* const vel[3], const float* const p[2], float* const out[3], float inv_dx,
-                              cudaStream_t st) {
-	if (g.count())
-		HNS_LAUNCH(k_subtract_gradient, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], p[0], p[1], out[0], out[1], out[2], inv_dx);
+                              cudaStream_t st, float4* grp0, const float* s0) {
+	if (!g.count()) return;
+	if (grp0)
+		HNS_LAUNCH(k_subtract_gradient<true>, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], p[0], p[1], out[0], out[1], out[2], inv_dx,
+		           grp0, s0);
+	else
+		HNS_LAUNCH(k_subtract_gradient<false>, (g.count() + 3) / 4, 256, 0, st, g, vel[0], vel[1], vel[2], p[0], p[1], out[0], out[1], out[2], inv_dx,
+		           grp0, s0);
 }
 
 // =============================================================================================================
@@ -468,6 +483,45 @@ void launch_combustion_oxygen(const float* fuel, const float* waste, const float
 	if (n)
 		HNS_LAUNCH(k_combustion_oxygen, unsigned((n + 255) / 256), 256, 0, st, fuel, waste, temp, div[0], div[1], flame, oFuel, oWaste, oTemp,
 		           oFlame, temp_gain, expansion, n);
+}
+// combustion_oxygen + temperature_buoyancy in one pass, the four outputs also written as one float4 {fuel, waste, temperature, flame}
+// into the packed group advect_scalars stages from (advect.cu, third generation). Same expressions as the two kernels above and below;
+// the buoyancy term uses the temperature this thread just computed instead of reading it back.
+__global__ void __launch_bounds__(256) k_combustion_buoyancy_packed(const float* __restrict__ fuel, const float* __restrict__ waste,
+                                                                    const float* __restrict__ temp, float* __restrict__ div_red,
+                                                                    float* __restrict__ div_blk, const float* __restrict__ flame,
+                                                                    float* __restrict__ oFuel, float* __restrict__ oWaste, float* __restrict__ oTemp,
+                                                                    float* __restrict__ oFlame, float4* __restrict__ grp, float* __restrict__ vy,
+                                                                    float temp_gain, float expansion, float dt, float ambient, float strength,
+                                                                    uint64_t n) {
+	const uint64_t t = blockIdx.x * uint64_t(256) + threadIdx.x;
+	if (t >= n) return;
+	float f = fuel[t];
+	const float wv = waste[t], T = temp[t], fl = flame[t];
+	if (f < 0.001f) f = 0.0f;
+	const float oxygen = 1.0f - f - wv;
+	float4 o = make_float4(f, wv, T, fl);
+	if (!(oxygen < 0.0f)) {
+		const float burn = fminf(oxygen, f);
+		o.x = f - burn;
+		o.y = fmaf(burn, 2.0f, wv);
+		o.w = fmaxf(fl, fminf(1.0f, burn * 10.0f));
+		o.z = fmaf(burn, temp_gain, T);
+		const uint32_t v = uint32_t(t) & 511u;
+		const bool black = (((v >> 6) + (v >> 3) + v) & 1u) != 0;
+		float* d = (black ? div_blk : div_red) + ((t >> 3) << 2) + ((v & 7u) >> 1);
+		*d = fmaf(burn, expansion, *d);
+	}
+	oFuel[t] = o.x, oWaste[t] = o.y, oTemp[t] = o.z, oFlame[t] = o.w;
+	grp[t] = o;
+	if (o.z > ambient) vy[t] = fmaf(fmaxf(0.0f, (o.z - ambient) * strength), dt, vy[t]);
+}
+void launch_combustion_buoyancy_packed(const float* fuel, const float* waste, const float* temp, float* const div[2], const float* flame, float* oFuel,
+                                       float* oWaste, float* oTemp, float* oFlame, float4* grp, float* const vel[3], float temp_gain, float expansion,
+                                       float dt, float ambient, float strength, uint64_t n, cudaStream_t st) {
+	if (n)
+		HNS_LAUNCH(k_combustion_buoyancy_packed, unsigned((n + 255) / 256), 256, 0, st, fuel, waste, temp, div[0], div[1], flame, oFuel, oWaste, oTemp,
+		           oFlame, grp, vel[1], temp_gain, expansion, dt, ambient, strength, n);
 }
 // The reference adds Vec3f(0, b, 0) * dt to all three components (Kernel.cu:844-846); adding 0*dt only turns a -0.0 into +0.0,
 // so only the y plane is touched here (x and z stay bit-identical except for the sign of an exact zero).

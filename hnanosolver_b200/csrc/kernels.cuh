@@ -15,17 +15,27 @@ struct ScalarPtrs {
 void launch_aos_to_soa(const float* aos, float* u, float* v, float* w, uint64_t n, cudaStream_t st);
 void launch_soa_to_aos(const float* u, const float* v, const float* w, float* aos, uint64_t n, cudaStream_t st);
 
+// Packed groups of the advection kernels (advect.cu, third generation): float4[n] per group in brick voxel order, group 0 =
+// {u, v, w, first advected scalar}, group j >= 1 = {scalar 4j-3 .. 4j} of the list handed to launch_advect_scalars. Scratch owned by the
+// caller; bit j of `valid` says the producer of those fields already wrote the group, otherwise the launcher packs it first
+// (struct AdvectGroups, common.cuh).
+void launch_pack4(const float* a, const float* b, const float* c, const float* d, float4* out, uint64_t n, cudaStream_t st);
+bool packed_advection_enabled();  // HNS_ADVECT4=0 / hns_set_packed_advection(0) switch the third generation off (A/B)
+int set_packed_advection(int on);
+uint64_t packed_advection_launches();
+
 // advect_vector (reference src/Cuda/Kernel.cu:354-453)
 // cold: device uint8[num_leaves of the grid], zero between launches -- scratch in which the staged kernel flags the leaves whose samples
 // left its shared-memory region; a follow-up kernel redoes those leaves through the neighbour table and clears the flags (advect.cu)
 void launch_advect_vector(const GridView& g, const float* const vel[3], float* const out[3], float dt, float inv_dx, cudaStream_t st,
-                          const float* sdf, uint8_t* cold);  // sdf != null: the hasCollision variant incl. its boundary tail
+                          const float* sdf, uint8_t* cold, const AdvectGroups* grp = nullptr);  // sdf != null: the hasCollision variant incl. its boundary tail
 
 // advect_scalars (Kernel.cu:118-266) when sampler_semantics == 0; advect_scalar (Kernel.cu:269-352) per field when == 1
 // elem0 (device, float[3 + S], may be null): element 0 of the GLOBAL velocity / scalar arrays, the value advect_scalars reads for
 // inactive voxels; null = element 0 of the arrays passed in (single-GPU runs).
 void launch_advect_scalars(const GridView& g, const float* const vel[3], const ScalarPtrs& sp, int S, float dt, float inv_dx,
-                           int sampler_semantics, const float* elem0, cudaStream_t st, const float* sdf, uint8_t* cold);
+                           int sampler_semantics, const float* elem0, cudaStream_t st, const float* sdf, uint8_t* cold,
+                           const AdvectGroups* grp = nullptr);
 // enforceCollisionBoundaries (Kernel.cu:77-116; blend_divisor 0.1, mixed_sum 0) and the boundary tails of advect_vector (:432-450;
 // 1.5, 1) and subtractPressureGradient (:808-826; 0.1, 0): vel -> out (may alias), per voxel
 void launch_collision_boundary(const GridView& g, const float* const vel[3], float* const out[3], const float* sdf, float inv_dx,
@@ -67,8 +77,9 @@ void launch_mg_prolong(const GridView& g, float* const p[2], const float* const 
 void launch_mg_diag(const GridView& g, const uint8_t* mask, float extra, float* const diag[2], cudaStream_t st);
 void launch_mg_coarsest(float* const p[2], const float* const rhs[2], const float* const diag[2], float dx, float omega, int iterations, cudaStream_t st);
 // subtractPressureGradient (Kernel.cu:765-829)
+// grp0 != null: the result also goes into the packed advection group 0 as float4 {u, v, w, s0 (or 0)} per voxel
 void launch_subtract_gradient(const GridView& g, const float* const vel[3], const float* const p[2], float* const out[3], float inv_dx,
-                              cudaStream_t st);
+                              cudaStream_t st, float4* grp0 = nullptr, const float* s0 = nullptr);
 // vorticityConfinement (Kernel.cu:969-1025), out of place, in two launches: |curl| of every listed leaf into the plane `mag`, then
 // vel -> out using mag at the six offset positions (a sharded run exchanges the ghost leaves of `mag` in between)
 void launch_vorticity_mag(const GridView& g, const float* const vel[3], float* mag, float inv_dx, cudaStream_t st);
@@ -78,6 +89,10 @@ void launch_vorticity_force(const GridView& g, const float* const vel[3], const 
 void launch_combustion_oxygen(const float* fuel, const float* waste, const float* temp, float* const div[2], const float* flame, float* oFuel,
                               float* oWaste, float* oTemp, float* oFlame, float temp_gain, float expansion, uint64_t n, cudaStream_t st);
 void launch_buoyancy(float* const vel[3], const float* temp, float dt, float ambient, float strength, uint64_t n, cudaStream_t st);
+// both in one pass; the four outputs additionally as float4 {fuel, waste, temperature, flame} into a packed advection group
+void launch_combustion_buoyancy_packed(const float* fuel, const float* waste, const float* temp, float* const div[2], const float* flame, float* oFuel,
+                                       float* oWaste, float* oTemp, float* oFlame, float4* grp, float* const vel[3], float temp_gain, float expansion,
+                                       float dt, float ambient, float strength, uint64_t n, cudaStream_t st);
 // GridView::list_nbr for a work list: out[n][27]
 void launch_gather_nbr_rows(const int32_t* nbr, const int32_t* list, uint32_t n, int32_t* out, cudaStream_t st);
 // whole-brick gather / scatter by leaf id (ghost exchange)

@@ -65,6 +65,14 @@ int hns_set_device(int device);
  * pressure solve; default 0 = off (measured slower on B200) or the environment variable HNS_L2_PERSIST_MB, clamped to
  * the device limit. Experimental. */
 int hns_set_l2_persist_mb(int megabytes);
+/* Packed advection (default on, or the environment variable HNS_ADVECT4): the gradient and combustion passes of a resident state also
+ * write the fields they produce as float4 groups, and advect_vector / advect_scalars stage from those groups with 128-bit shared-memory
+ * loads (advect.cu, third generation). Off = the kernels that stage the brick fields directly. Results are bit-identical either way;
+ * the switch exists for A/B measurements and for the test that asserts exactly that. Returns the previous setting. */
+int hns_set_packed_advection(int on);
+/* Launches of the third-generation advection kernels so far in this process (they replace their second-generation counterparts one for
+ * one, so hns_launch_count cannot tell them apart). */
+uint64_t hns_packed_advection_launches(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Index grid -- replaces CreateIndexGrid (src/Cuda/HNanoSolver.cu:375-390), i.e.

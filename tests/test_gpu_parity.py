@@ -677,6 +677,64 @@ def test_config4_size_independent_properties(c4):
     assert np.abs(div[:, 1:7, 1:7, 1:7]).max() == 0.0
 
 
+def _three_frames(w, fields, comb, packed, iterations=6):
+    """three consecutive resident frames; returns every field and how many third-generation advection launches they took"""
+    from hnanosolver_b200 import _lib
+
+    lib = _lib.lib()
+    names = list(fields)
+    g = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    sim = H.Simulation(g, len(names))
+    sim.upload(w.velocity, list(fields.values()))
+    if comb:
+        sim.set_combustion(True, names.index("fuel"), names.index("waste"), names.index("temperature"), names.index("flame"),
+                           H.CombustionParams(*PARAMS6.tolist()))
+    prev = lib.hns_set_packed_advection(int(packed))
+    try:
+        before = lib.hns_packed_advection_launches()
+        for _ in range(3):
+            sim.step(iterations, w.dt)
+        sim.sync()
+        used = lib.hns_packed_advection_launches() - before
+    finally:
+        lib.hns_set_packed_advection(prev)
+    out = dict(vel=sim.velocity(), div=sim.aux(0), p=sim.aux(1), adv=sim.aux(2))
+    out.update({k: sim.scalar(i) for i, k in enumerate(names)})
+    return out, used
+
+
+@pytest.mark.parametrize("layout", ["density_first", "density_last", "density_only", "two_scalars"])
+def test_packed_advection_is_bit_identical_over_consecutive_frames(layout):
+    """The third-generation advection kernels stage from float4 groups that the gradient and combustion passes write (advect.cu): same
+    bits as the second generation on the brick fields, frame after frame, and the packed kernels really are the ones that ran --
+    advect_scalars in every frame, advect_vector from the second frame on (the first one finds no group yet). `two_scalars` has no
+    producer for its second group and must stay on the second generation."""
+    w = synth.random_leaves(60, 4, 9, cfl=1.2, S=2)
+    comb = _combustion_fields(w.num_voxels)
+    fields, with_comb, expect = {
+        "density_first": (dict(density=w.scalars[0], **comb), True, 5),
+        "density_last": (dict(**comb, density=w.scalars[0]), True, 5),
+        "density_only": (dict(density=w.scalars[0]), False, 5),
+        "two_scalars": (dict(density=w.scalars[0], temperature=w.scalars[1]), False, 2),   # advect_vector only, frames 2 and 3
+    }[layout]
+    got, used = _three_frames(w, fields, with_comb, True)
+    want, used_off = _three_frames(w, fields, with_comb, False)
+    assert used == expect and used_off == 0
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+
+
+def test_packed_advection_far_samples_still_take_the_tree_walk_path():
+    """a CFL far beyond the staged region: the packed kernels flag the leaves and the generic pass redoes them, as before"""
+    w = synth.random_leaves(40, 3, 5, cfl=9.0, S=1)
+    fields = dict(density=w.scalars[0])
+    got, used = _three_frames(w, fields, False, True, iterations=3)
+    want, _ = _three_frames(w, fields, False, False, iterations=3)
+    assert used == 5
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+
+
 def test_every_launch_is_counted():
     from hnanosolver_b200 import _lib
 
