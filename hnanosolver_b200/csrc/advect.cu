@@ -906,6 +906,20 @@ std::atomic<int>& packed_switch() {  // HNS_ADVECT4=0 / hns_set_packed_advection
 	}()};
 	return on;
 }
+// the same for whole leaves picked by id (sharded runs: the ghost leaves after an exchange); 128 threads per leaf
+__global__ void __launch_bounds__(128) k_pack4_leaves(const int32_t* __restrict__ ids, const float* __restrict__ a, const float* __restrict__ b,
+                                                      const float* __restrict__ c, const float* __restrict__ d, float4* __restrict__ out) {
+	const uint64_t q = uint64_t(uint32_t(__ldg(ids + blockIdx.x))) * 128u + threadIdx.x;
+	const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+	const float4 va = a ? __ldg(reinterpret_cast<const float4*>(a) + q) : zero, vb = b ? __ldg(reinterpret_cast<const float4*>(b) + q) : zero;
+	const float4 vc = c ? __ldg(reinterpret_cast<const float4*>(c) + q) : zero, vd = d ? __ldg(reinterpret_cast<const float4*>(d) + q) : zero;
+	float4* o = out + 4 * q;
+	o[0] = make_float4(va.x, vb.x, vc.x, vd.x);
+	o[1] = make_float4(va.y, vb.y, vc.y, vd.y);
+	o[2] = make_float4(va.z, vb.z, vc.z, vd.z);
+	o[3] = make_float4(va.w, vb.w, vc.w, vd.w);
+}
+
 bool packed_advection() { return packed_switch().load(std::memory_order_relaxed) != 0; }
 std::atomic<uint64_t> g_packed_launches{0};
 void pack4(const float* a, const float* b, const float* c, const float* d, float4* out, uint64_t n, cudaStream_t st) {
@@ -916,6 +930,10 @@ void pack4(const float* a, const float* b, const float* c, const float* d, float
 
 void launch_pack4(const float* a, const float* b, const float* c, const float* d, float4* out, uint64_t n, cudaStream_t st) {
 	if (n) pack4(a, b, c, d, out, n, st);
+}
+void launch_pack4_leaves(const int32_t* ids, uint64_t n_ids, const float* a, const float* b, const float* c, const float* d, float4* out,
+                         cudaStream_t st) {
+	if (n_ids) HNS_LAUNCH(k_pack4_leaves, unsigned(n_ids), 128, 0, st, ids, a, b, c, d, out);
 }
 bool packed_advection_enabled() { return packed_advection(); }
 int set_packed_advection(int on) { return packed_switch().exchange(on ? 1 : 0); }

@@ -78,9 +78,12 @@ static int pressure_solve(hns_state* s, int iterations, float dx, float omega, u
 // subtractPressureGradient -> group 0 {u, v, w, first advected scalar}, combustion -> group 1 {fuel, waste, temperature, flame}.
 // A group is current while the version counters it was written at still match (hns_state::vel_version / sc_version, bumped by every
 // entry point that may overwrite the brick fields) and it was built from the very buffers the advection pass is about to read; otherwise
-// the advection launchers fall back to the second-generation kernels on the brick fields. Not used by sharded runs (their ghost leaves
-// are refreshed behind the groups' back) nor with collision data (the boundary pass rewrites the velocity after the gradient).
-static bool groups_allowed(const hns_state* s) { return s->n && !s->active && !s->elem0 && !s->collision_sdf() && packed_advection_enabled(); }
+// the advection launchers fall back to the second-generation kernels on the brick fields. Not used with collision data (the boundary
+// pass rewrites the velocity after the gradient), nor with a work list unless it is a sharded frame's: the kernels then write the groups
+// of the owned leaves and dist.cu re-packs the ghost leaves after the exchange in front of the advection pass (groups_refresh_leaves).
+static bool groups_allowed(const hns_state* s) {
+	return s->n && (!s->active || s->grp_dist) && !s->elem0 && !s->collision_sdf() && packed_advection_enabled();
+}
 static bool ensure_group(hns_state* s, int j) {
 	if (!s->grp.g[j] && cudaMalloc(&s->grp.g[j], s->n * sizeof(float4)) != cudaSuccess) {
 		cudaGetLastError();
@@ -93,12 +96,12 @@ static bool ensure_group(hns_state* s, int j) {
 // ("collision_sdf", HNanoSolver.cu:327). When the state carries exactly one scalar besides the four combustion fields -- the
 // reference's all-in-one frame: density + fuel, waste, temperature, flame -- that one goes first and the combustion fields follow in
 // the order combustion packs them, so that they form group 1 (the fields are advected independently: the order changes no value).
-// A sharded run's elem0 table is indexed by position in the list, so there the state's own order is kept.
+// A sharded run keeps the state's own order (its exchanges and its elem0 table go by position); it packs when that order already fits.
 static int advect_list(const hns_state* s, int* idx) {
 	int S = 0;
 	for (int i = 0; i < s->n_scalars; ++i)
 		if (i != s->skip_scalar) idx[S++] = i;
-	if (S == 5 && s->comb_enabled && groups_allowed(s)) {
+	if (S == 5 && s->comb_enabled && !s->active && groups_allowed(s)) {
 		int other = -1, n_other = 0;
 		for (int k = 0; k < S; ++k) {
 			bool comb = false;
@@ -118,6 +121,24 @@ static bool combustion_packs(const hns_state* s) {  // will advect_scalars find 
 	for (int c = 0; c < 4; ++c)
 		if (idx[1 + c] != s->comb_idx[c]) return false;
 	return true;
+}
+
+GroupsCurrent groups_current(const hns_state* s) {
+	GroupsCurrent c;
+	if (!groups_allowed(s)) return c;
+	c.g0 = s->grp.g[0] && s->grp0_vel_version == s->vel_version && s->grp0_sc_version == s->sc_version;
+	c.g1 = s->grp.g[1] && s->grp1_sc_version == s->sc_version;
+	return c;
+}
+int groups_refresh_leaves(hns_state* s, const int32_t* ids, uint64_t n_ids, GroupsCurrent which, cudaStream_t st) {
+	if (which.g0) launch_pack4_leaves(ids, n_ids, s->vel[0], s->vel[1], s->vel[2], s->grp0_s0, s->grp.g[0], st);
+	if (which.g1) launch_pack4_leaves(ids, n_ids, s->grp1_src[0], s->grp1_src[1], s->grp1_src[2], s->grp1_src[3], s->grp.g[1], st);
+	HNS_CUDA(cudaGetLastError());
+	return HNS_OK;
+}
+void groups_stamp(hns_state* s, GroupsCurrent which) {
+	if (which.g0) s->grp0_vel_version = s->vel_version, s->grp0_sc_version = s->sc_version;
+	if (which.g1) s->grp1_sc_version = s->sc_version;
 }
 
 static int stage_advect_velocity(hns_state* s, float dt, float inv, cudaStream_t st) {

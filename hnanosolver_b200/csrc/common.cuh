@@ -169,6 +169,14 @@ __device__ __forceinline__ int probe_leaf(const GridView& g, int x, int y, int z
 struct hns_mg;
 struct hns_state;
 namespace hns {
+// packed advection groups in a sharded frame (api.cu): which groups the kernels of this frame have written for the owned leaves, and
+// -- after the ghost exchange that precedes the advection pass -- the same for the listed (ghost) leaves, from the brick fields
+struct GroupsCurrent {
+	bool g0 = false, g1 = false;
+};
+GroupsCurrent groups_current(const hns_state* s);
+int groups_refresh_leaves(hns_state* s, const int32_t* ids, uint64_t n_ids, GroupsCurrent which, cudaStream_t st);
+void groups_stamp(hns_state* s, GroupsCurrent which);
 int mg_pressure_solve(hns_state* s, hns_mg* mg, int max_cycles, double rel_tol, int nu_pre, int nu_post, float omega, cudaStream_t st);  // multigrid.cu
 }
 // ---- opaque handle definitions ----------------------------------------------------------------------------
@@ -203,6 +211,7 @@ struct hns_state {
 	uint64_t grp0_vel_version = 0, grp0_sc_version = 0, grp1_sc_version = 0;  // 0 never matches: the counters start at 1
 	const float* grp0_s0 = nullptr;                                          // the scalar buffer in group 0's fourth lane
 	const float* grp1_src[4] = {nullptr, nullptr, nullptr, nullptr};         // the buffers group 1 mirrors
+	bool grp_dist = false;  // a sharded frame (dist.cu) re-packs the ghost leaves of the groups after its exchanges
 	float* vort[4] = {nullptr, nullptr, nullptr, nullptr};  // vorticity confinement scratch, allocated on first use: output planes u, v, w and |curl|
 	// optional combustion + buoyancy stage of the all-in-one frame
 	bool comb_enabled = false;

@@ -660,7 +660,7 @@ int hns_dist_cook(hns_dist* d, hns_state* s, float* velocity, int n_float, float
 	HNS_CUDA(cudaEventRecord(e_all_in, cs));
 	HNS_CUDA(cudaStreamWaitEvent(st, e_vel_in, 0));
 	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
-	++s->vel_version;
+	++s->vel_version, ++s->sc_version;
 	DistDeps deps;
 	deps.combustion_inputs = e_comb_in, deps.scalar_inputs = e_all_in, deps.velocity_done = e_vel_out;
 	int rc = dist_frame(d, s, iterations, dt, stream, nullptr, &deps);
@@ -762,6 +762,7 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	mark();
 	const int fvel[3] = {0, 1, 2}, fadv[3] = {3, 4, 5}, fred[1] = {6}, fblk[1] = {7};
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	s->grp_dist = true;  // this frame re-packs the ghost leaves of the packed advection groups itself (below)
 	if (s->skip_scalar >= 0 && s->skip_scalar != s->n_scalars - 1)
 		return fail(HNS_ERR_UNSUPPORTED, "sharded frames need the non-advected scalar (collision_sdf) to be the last scalar field");
 	// collision path: enforceCollisionBoundaries and the collision tests of advect_vector read the SDF in ghost leaves (neighbour rows
@@ -805,6 +806,11 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	if ((rc = hns_state_divergence(s, 1, stream))) return rc;
 	if (deps && deps->combustion_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->combustion_inputs, 0));
 	if (s->comb_enabled && (rc = hns_state_combustion_buoyancy(s, dt, stream))) return rc;
+	// Packed advection groups (api.cu): the combustion pass has just written group 1 for every voxel, the gradient pass below writes
+	// group 0 for the owned leaves; the exchanges that follow refresh the ghost leaves of the brick fields only (and bump the version
+	// counters), so what is current now is noted here and the groups' ghost leaves are re-packed in front of advect_scalars.
+	GroupsCurrent packed;
+	packed.g1 = groups_current(s).g1;
 	if (deps && deps->scalar_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->scalar_inputs, 0));
 	// The scalars are final until advect_scalars: exchange their ghosts now, on a third stream, behind the pressure solve.
 	const bool scalars_early = d->p2p && s->n_scalars > 0;
@@ -856,6 +862,7 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 	mark();
 	if ((rc = hns_state_subtract_gradient(s, 1, stream))) return rc;
 	if (hns_state_collision_active(s) && (rc = hns_state_enforce_collision(s, stream))) return rc;  // HNanoSolver.cu:292-296
+	packed.g0 = groups_current(s).g0;
 	mark();
 	std::vector<int> last = {0, 1, 2};
 	if (!scalars_early)
@@ -866,6 +873,11 @@ static int dist_frame(hns_dist* d, hns_state* s, int iterations, float dt, void*
 		HNS_CUDA(cudaEventRecord(deps->velocity_done, st));
 	}
 	if (scalars_early) HNS_CUDA(cudaStreamWaitEvent(st, d->ev_scalars_exchanged, 0));
+	if (packed.g0 || packed.g1) {
+		for (auto& p : d->peers)
+			if (p.n_recv && (rc = groups_refresh_leaves(s, p.d_recv, p.n_recv, packed, st))) return rc;
+		groups_stamp(s, packed);
+	}
 	// advect_scalars' "inactive -> element 0" value (reference Kernel.cu:192,225) is global voxel 0's = local voxel 0's: that exchange
 	// has just refreshed it on every rank
 	mark();

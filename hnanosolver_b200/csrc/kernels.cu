@@ -209,11 +209,24 @@ __global__ void __launch_bounds__(256) k_subtract_gradient(GridView g, const flo
 	st_row(ou, self, a);
 	st_row(ov, self, b);
 	st_row(ow, self, d);
-	if (kGroup) {
+	if constexpr (kGroup) {
+		// A thread owns 8 consecutive voxels = 128 contiguous bytes of the group; stored directly, the lanes of a warp would write 16-byte
+		// pieces 128 bytes apart. The 32 rows of a warp are 256 consecutive voxels (4 of the 8 x-planes of one leaf), so they trade
+		// places through a warp-private tile and every store instruction writes 512 contiguous bytes. The tile is swizzled
+		// (z ^ row) so that both the row-wise writes and the voxel-wise reads of a quarter-warp touch eight distinct 16-byte bank groups.
+		__shared__ float4 tile[8][256];
 		const Row8 q = s0 ? ld_row(s0, self) : zero_row();
-		float4* o = grp0 + self;
+		const int lane = threadIdx.x & 31;
+		float4* t = tile[threadIdx.x >> 5];
 #pragma unroll
-		for (int z = 0; z < 8; ++z) o[z] = make_float4(a.v[z], b.v[z], d.v[z], q.v[z]);
+		for (int z = 0; z < 8; ++z) t[lane * 8 + (z ^ (lane & 7))] = make_float4(a.v[z], b.v[z], d.v[z], q.v[z]);
+		__syncwarp();
+		float4* o = grp0 + (self - uint32_t(lane) * 8u);  // first voxel of the warp's 256
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const int r = 4 * i + (lane >> 3), z = lane & 7;
+			o[32 * i + lane] = t[r * 8 + (z ^ (r & 7))];
+		}
 	}
 }
 void launch_subtract_gradient(const GridView& g, const float* const vel[3], const float* const p[2], float* const out[3], float inv_dx,

@@ -20,6 +20,8 @@ void launch_soa_to_aos(const float* u, const float* v, const float* w, float* ao
 // caller; bit j of `valid` says the producer of those fields already wrote the group, otherwise the launcher packs it first
 // (struct AdvectGroups, common.cuh).
 void launch_pack4(const float* a, const float* b, const float* c, const float* d, float4* out, uint64_t n, cudaStream_t st);
+void launch_pack4_leaves(const int32_t* ids, uint64_t n_ids, const float* a, const float* b, const float* c, const float* d, float4* out,
+                         cudaStream_t st);
 bool packed_advection_enabled();  // HNS_ADVECT4=0 / hns_set_packed_advection(0) switch the third generation off (A/B)
 int set_packed_advection(int on);
 uint64_t packed_advection_launches();

@@ -394,6 +394,7 @@ def sharded_parity_check(rank: int, world: int, device, *, box=(256, 128, 128), 
     import torch
     import torch.distributed as tdist
 
+    from . import _lib
     from . import launchers as H
 
     go = global_sparse_origins(box, fill, seed)
@@ -421,6 +422,7 @@ def sharded_parity_check(rank: int, world: int, device, *, box=(256, 128, 128), 
             sh.set_combustion(names, P)
         m = np.repeat(plan.owned_local, 512)
         lv, lf = np.ascontiguousarray(wg.velocity[lo]), [np.ascontiguousarray(f[lo]) for f in gfields]
+        packed_before = _lib.lib().hns_packed_advection_launches()
         if cook:
             # ghost entries of the host inputs are deliberately garbage: hns_dist_cook's contract says they need not be valid
             lv[~m] = np.float32(1e30)
@@ -436,6 +438,7 @@ def sharded_parity_check(rank: int, world: int, device, *, box=(256, 128, 128), 
             torch.cuda.synchronize()
             sh.check_errors()
             mine = [sh.sim.velocity()[m]] + [sh.sim.scalar(i)[m] for i in range(NS)] + [sh.sim.aux(1)[m]]
+        packed_launches = int(_lib.lib().hns_packed_advection_launches() - packed_before)   # third-generation advection launches of this rank
         gathered = [None] * world
         tdist.all_gather_object(gathered, mine)
         ok, report = None, None
@@ -463,6 +466,7 @@ def sharded_parity_check(rank: int, world: int, device, *, box=(256, 128, 128), 
                              + (f", max|diff| {np.abs(got.astype(np.float64) - ref[k]).max():.3e}, first leaves {np.unique(bad // 512)[:6].tolist()}" if bad.size else "") + ")")
             report = dict(ok=ok, leaves=int(go.shape[0]), world=world, frames=frames, iterations=iterations, p2p=bool(getattr(sh, "p2p", False)),
                           native=native, collision=collision, vorticity=list(vorticity), cook=cook, exchanges_per_frame=sh.exchanges // max(frames, 1),
+                          packed_advection_launches=packed_launches,
                           fields=lines)
             del sim
         tdist.barrier()

@@ -64,6 +64,9 @@ def test_sharded_frame_is_bitwise_the_single_gpu_frame_peer_memory(world):
     reports = _run(world, P2P_MODES, share)
     assert all(r["p2p"] for r in reports)
     assert reports[0]["exchanges_per_frame"] >= 2 * 12       # the pressure ghosts travel after every half-sweep
+    # the sharded frame runs the packed (third-generation) advection kernels too: advect_scalars in both frames, advect_vector in the
+    # second one (velocity ghosts and group 0 carried over); none with collision data
+    assert reports[0]["packed_advection_launches"] == 3 and reports[4]["packed_advection_launches"] == 0
 
 
 def test_sharded_frame_is_bitwise_the_single_gpu_frame_nccl():
