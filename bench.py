@@ -168,6 +168,8 @@ def stage_breakdown(H, sim, w, S: int, full: bool, peak: float, reps: int = 5) -
     stages += [(f"pressure_solve({ITERATIONS})", 16 * ITERATIONS, lambda: sim.pressure_solve(ITERATIONS, omega)),
                ("subtract_gradient", 28, lambda: sim.subtract_gradient(True)), (f"advect_scalars({S})", 12 + 8 * S, lambda: sim.advect_scalars(w.dt, 0))]
     acc = {k: [] for k, _, _ in stages}
+    from hnanosolver_b200 import _lib
+    packed0 = _lib.lib().hns_packed_advection_launches()
     for r in range(reps + 1):
         for k, _, fn in stages:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -179,11 +181,21 @@ def stage_breakdown(H, sim, w, S: int, full: bool, peak: float, reps: int = 5) -
                 acc[k].append(e0.elapsed_time(e1))
     out = {}
     measured = kernel_traffic()
+    # which advection kernels ran: the third generation (packed float4 groups written by the gradient / combustion passes, advect.cu)
+    # or the second (brick fields); with the packed layout the gradient and combustion passes move more bytes than the algorithm needs
+    packed = int(_lib.lib().hns_packed_advection_launches() - packed0) > 0
+    gen = "4" if packed else "2"
+    layout = {"advect_vector": 28, "combustion+buoyancy": 64, "subtract_gradient": 48} if packed and full and S == 5 else {}
     for k, b, _ in stages:
         ms = float(np.median(acc[k]))
         gbs = b * w.num_voxels / (ms * 1e-3) / 1e9
         out[k] = {"ms": ms, "algorithmic_bytes_per_voxel": b, "algorithmic_GBps": gbs, "frac_of_peak": gbs / peak}
-        key = {"advect_vector": "k_advect_vector2", f"advect_scalars({S})": f"k_advect_scalars2(S={S})"}.get(k)
+        if k in layout:       # bytes this layout actually moves (second copy of the velocity / combustion fields as packed groups)
+            out[k]["layout_bytes_per_voxel"] = layout[k]
+            out[k]["layout_frac_of_peak"] = layout[k] * w.num_voxels / (ms * 1e-3) / 1e9 / peak
+        key = {"advect_vector": f"k_advect_vector{gen}", f"advect_scalars({S})": f"k_advect_scalars{gen}(S={S})"}.get(k)
+        if key:
+            out[k]["kernel"] = key
         if key in measured:   # dram bytes of the ncu capture of this kernel (profiles/kernel_traffic.json), scaled to this voxel count
             out[k]["traffic"] = measured[key]["dram_bytes_per_voxel"] * w.num_voxels
     return out
@@ -324,12 +336,14 @@ def main():
     sampler.start()
     time.sleep(0.3)
     _lib.lib().hns_launch_count_reset()
+    packed0 = _lib.lib().hns_packed_advection_launches()
     torch.cuda.synchronize()
     tc0 = time.time()
     ms_total, ms_pressure = sim.time_frames(args.steps, ITERATIONS, w.dt, flags)   # K timed frames, CUDA events on the launch stream
     torch.cuda.synchronize()
     tc1 = time.time()
     launches = int(_lib.lib().hns_launch_count())
+    packed_launches = int(_lib.lib().hns_packed_advection_launches() - packed0)
     clocks = sampler.stop(tc0, tc1)
     ms_step = ms_total / args.steps
     value = N / (ms_step * 1e-3)
@@ -438,7 +452,9 @@ def main():
                       f"multigrid: {mg_info['cycles']} V({MG_NU[0]},{MG_NU[1]}) cycles, omega {MG_OMEGA}, {mg_info['levels']} levels, "
                       f"solved to a relative Poisson residual of {mg_info['relative_residual_at_cycles']:.2e} (target 1e-4)"},
            "pressure_solver": solver, "solve_quality": solve_quality,
-           "roofline": roofline, "stages": stages, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+           "roofline": roofline, "stages": stages, "e2e": e2e, "gpu_launches": launches,
+           "packed_advection_launches": packed_launches,   # of gpu_launches: advect_vector4 / advect_scalars4 (advect.cu, third generation)
+           "clocks": clocks}
     if solver == "mg":
         out["multigrid"] = mg_info
     if other is not None:

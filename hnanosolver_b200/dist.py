@@ -560,12 +560,14 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
     dist.barrier()
     torch.cuda.synchronize()
     t_wall0 = time.time()
+    packed0 = _lib.lib().hns_packed_advection_launches()
     e0.record()
     for _ in range(args.steps):
         sh.frame(iterations, w.dt)
     e1.record()
     torch.cuda.synchronize()
     t_wall1 = time.time()
+    packed_launches = int(_lib.lib().hns_packed_advection_launches() - packed0)   # this rank's third-generation advection launches
     dist.barrier()
     phases = sh.frame_timed(iterations, w.dt) if sh.native else {}
     sh.check_errors()
@@ -638,7 +640,7 @@ def run_sharded_bench(w, names, fields, full, args, iterations, params6, rank, w
                     "copy_floor_ms": float(floor.item()),
                     "call": "ShardedSimulation.cook (hns_dist_cook) per rank on pinned host arrays of its shard, in place, synchronous; "
                             "copy_floor_ms = the same bytes up then down on all ranks at once without any kernel"},
-            "gpu_launches": int(launches.item()),
+            "gpu_launches": int(launches.item()), "packed_advection_launches_rank0": packed_launches,
             "sharded_parity": "bitwise-ok" if parity and all(r["ok"] for r in parity) else None,
             "sharded_parity_detail": [{k: r[k] for k in ("leaves", "world", "frames", "iterations", "p2p", "collision", "vorticity", "cook")} for r in parity],
             "_timed_wall": (t_wall0, t_wall1), "_pressure": (float(slowest[0]), float(slowest[1])),
