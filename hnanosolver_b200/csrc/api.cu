@@ -147,17 +147,19 @@ static int stage_advect_velocity(hns_state* s, float dt, float inv, cudaStream_t
 	launch_advect_vector(s->view(), s->vel, s->adv, dt, inv, st, s->collision_sdf(), s->cold, packed ? &s->grp : nullptr);
 	return HNS_OK;
 }
-static int stage_combustion_buoyancy(hns_state* s, float dt, cudaStream_t st) {
+// update_div / buoyancy = false: the expansion term is already in the divergence (launch_combustion_divergence), the buoyancy force
+// already in the advected velocity (launch_buoyancy_from_inputs): frames fed over PCIe, see frame()
+static int stage_combustion_buoyancy(hns_state* s, float dt, cudaStream_t st, bool update_div = true, bool buoyancy = true) {
 	const int iF = s->comb_idx[0], iW = s->comb_idx[1], iT = s->comb_idx[2], iL = s->comb_idx[3];
 	const bool packed = combustion_packs(s) && ensure_group(s, 1);
 	if (packed) {
 		launch_combustion_buoyancy_packed(s->sc[iF], s->sc[iW], s->sc[iT], s->div, s->sc[iL], s->sc_out[iF], s->sc_out[iW], s->sc_out[iT], s->sc_out[iL],
 		                                  s->grp.g[1], s->adv, s->comb.temperatureRelease, s->comb.expansionRate, dt, s->comb.ambientTemp,
-		                                  s->comb.buoyancyStrength, s->n, st);
+		                                  s->comb.buoyancyStrength, s->n, st, update_div, buoyancy);
 	} else {
 		launch_combustion_oxygen(s->sc[iF], s->sc[iW], s->sc[iT], s->div, s->sc[iL], s->sc_out[iF], s->sc_out[iW], s->sc_out[iT], s->sc_out[iL],
-		                         s->comb.temperatureRelease, s->comb.expansionRate, s->n, st);
-		launch_buoyancy(s->adv, s->sc_out[iT], dt, s->comb.ambientTemp, s->comb.buoyancyStrength, s->n, st);
+		                         s->comb.temperatureRelease, s->comb.expansionRate, s->n, st, update_div);
+		if (buoyancy) launch_buoyancy(s->adv, s->sc_out[iT], dt, s->comb.ambientTemp, s->comb.buoyancyStrength, s->n, st);
 	}
 	for (int i : {iF, iW, iT, iL}) std::swap(s->sc[i], s->sc_out[i]);  // HNanoSolver.cu:239-246
 	++s->sc_version;
@@ -168,10 +170,10 @@ static int stage_combustion_buoyancy(hns_state* s, float dt, cudaStream_t st) {
 	return HNS_OK;
 }
 // adv - grad p -> vel (from_advected), or in place on vel (the stand-alone projection; every thread reads only its own velocity row)
-static int stage_subtract_gradient(hns_state* s, bool from_advected, float inv, cudaStream_t st) {
+static int stage_subtract_gradient(hns_state* s, bool from_advected, float inv, cudaStream_t st, bool allow_group = true) {
 	int idx[16];
 	const int S = advect_list(s, idx);
-	const bool packed = from_advected && groups_allowed(s) && ensure_group(s, 0);
+	const bool packed = allow_group && from_advected && groups_allowed(s) && ensure_group(s, 0);
 	const float* s0 = packed && S > 0 ? s->sc[idx[0]] : nullptr;
 	launch_subtract_gradient(s->view(), from_advected ? s->adv : s->vel, s->p, s->vel, inv, st, packed ? s->grp.g[0] : nullptr, s0);
 	++s->vel_version;
@@ -245,7 +247,7 @@ static int vorticity_pass(hns_state* s, float dt, float inv_dx, float scale, flo
 }
 
 struct FrameDeps {
-	cudaEvent_t combustion_inputs = nullptr, scalar_inputs = nullptr, velocity_done = nullptr;
+	cudaEvent_t fuel_waste_inputs = nullptr, temperature_input = nullptr, combustion_inputs = nullptr, scalar_inputs = nullptr, velocity_done = nullptr;
 };
 static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsigned flags, cudaStream_t st, cudaEvent_t ev_p0 = nullptr,
                  cudaEvent_t ev_p1 = nullptr, const FrameDeps* deps = nullptr) {
@@ -259,17 +261,35 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 		if (rc) return rc;
 	}
 	launch_divergence(g, s->adv, s->div, inv, st);
-	if (deps && deps->combustion_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->combustion_inputs, 0));
-	if (s->comb_enabled) stage_combustion_buoyancy(s, dt, st);
+	// Inputs still arriving (hns_compute_sim). What the projected velocity -- the first result that can leave again -- depends on:
+	// the pressure solve needs of the combustion stage only the term it adds to the divergence, i.e. fuel and waste; the gradient pass
+	// needs the buoyancy force, i.e. the temperature combustion will write, i.e. fuel, waste and temperature. So: expansion term as soon
+	// as fuel and waste have landed, solve, buoyancy from the three inputs, gradient, velocity on its way back; the field updates
+	// themselves (they need the flame field too) and advect_scalars (every scalar) follow while the velocity is already crossing PCIe in
+	// the other direction. Same arithmetic on the same values, another order of independent steps.
+	const bool split_combustion = s->comb_enabled && deps && deps->fuel_waste_inputs && deps->temperature_input;
+	if (split_combustion) {
+		HNS_CUDA(cudaStreamWaitEvent(st, deps->fuel_waste_inputs, 0));
+		launch_combustion_divergence(s->sc[s->comb_idx[0]], s->sc[s->comb_idx[1]], s->div, s->comb.expansionRate, s->n, st);
+	} else {
+		if (deps && deps->combustion_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->combustion_inputs, 0));
+		if (s->comb_enabled) stage_combustion_buoyancy(s, dt, st);
+	}
 	if (ev_p0) cudaEventRecord(ev_p0, st);
 	// the reference's solve, or -- opted in with hns_state_set_pressure_solver -- a fixed number of multigrid V-cycles
 	int rc = s->mg ? mg_pressure_solve(s, s->mg, s->mg_cycles, 0.0, s->mg_nu[0], s->mg_nu[1], s->mg_omega, st)
 	               : pressure_solve(s, iterations, h, omega_compute(h), flags, st);
 	if (rc) return rc;
 	if (ev_p1) cudaEventRecord(ev_p1, st);
-	// with packed groups the gradient pass also reads the first advected scalar: it has to have landed by now, not only by advect_scalars
-	if (deps && deps->scalar_inputs && groups_allowed(s)) HNS_CUDA(cudaStreamWaitEvent(st, deps->scalar_inputs, 0));
-	stage_subtract_gradient(s, true, inv, st);
+	if (split_combustion) {
+		HNS_CUDA(cudaStreamWaitEvent(st, deps->temperature_input, 0));
+		launch_buoyancy_from_inputs(s->sc[s->comb_idx[0]], s->sc[s->comb_idx[1]], s->sc[s->comb_idx[2]], s->adv, s->comb.temperatureRelease, dt,
+		                            s->comb.ambientTemp, s->comb.buoyancyStrength, s->n, st);
+	} else if (deps && deps->scalar_inputs && groups_allowed(s)) {
+		// with packed groups the gradient pass also reads the first advected scalar: it has to have landed by now, not only by advect_scalars
+		HNS_CUDA(cudaStreamWaitEvent(st, deps->scalar_inputs, 0));
+	}
+	stage_subtract_gradient(s, true, inv, st, !split_combustion);  // split: group 0 is packed below, once its scalar has landed
 	if (sdf) {
 		launch_collision_boundary(g, s->vel, s->vel, sdf, inv, 0.1f, 0, st);  // the tail of subtractPressureGradient, Kernel.cu:808-826
 		launch_collision_boundary(g, s->vel, s->vel, sdf, inv, 0.1f, 0, st);  // enforceCollisionBoundaries again, HNanoSolver.cu:292-296
@@ -278,7 +298,17 @@ static int frame(hns_state* s, int iterations, float dt, float voxel_size, unsig
 		launch_soa_to_aos(s->vel[0], s->vel[1], s->vel[2], s->aos, s->n, st);
 		HNS_CUDA(cudaEventRecord(deps->velocity_done, st));
 	}
+	if (split_combustion) {
+		if (deps->combustion_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->combustion_inputs, 0));
+		stage_combustion_buoyancy(s, dt, st, false, false);
+	}
 	if (deps && deps->scalar_inputs) HNS_CUDA(cudaStreamWaitEvent(st, deps->scalar_inputs, 0));
+	if (split_combustion && !sdf && groups_allowed(s) && ensure_group(s, 0)) {
+		int idx[16];
+		const float* s0 = advect_list(s, idx) > 0 ? s->sc[idx[0]] : nullptr;
+		launch_pack4(s->vel[0], s->vel[1], s->vel[2], s0, s->grp.g[0], s->n, st);  // 0.2 ms behind 40 ms of transfers
+		s->grp0_vel_version = s->vel_version, s->grp0_sc_version = s->sc_version, s->grp0_s0 = s0;
+	}
 	stage_advect_scalars(s, dt, inv, 0, st);
 	HNS_CUDA(cudaGetLastError());
 	return HNS_OK;
@@ -669,8 +699,8 @@ std::mutex g_scratch_mu;
 hns_state* g_scratch = nullptr;
 int g_scratch_device = -1;
 struct Streams {
-	cudaStream_t copy = nullptr;
-	cudaEvent_t ev[6] = {};
+	cudaStream_t copy = nullptr, copy_out = nullptr;  // uploads / downloads on streams of their own: PCIe carries both directions at once
+	cudaEvent_t ev[8] = {};
 	int device = -1;
 } g_streams;
 
@@ -699,9 +729,11 @@ int acquire_streams(Streams** out) {
 	if (g_streams.device != dev) {
 		if (g_streams.copy) {
 			cudaStreamDestroy(g_streams.copy);
+			cudaStreamDestroy(g_streams.copy_out);
 			for (auto& e : g_streams.ev) cudaEventDestroy(e);
 		}
 		HNS_CUDA(cudaStreamCreateWithFlags(&g_streams.copy, cudaStreamNonBlocking));
+		HNS_CUDA(cudaStreamCreateWithFlags(&g_streams.copy_out, cudaStreamNonBlocking));
 		for (auto& e : g_streams.ev) HNS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		g_streams.device = dev;
 	}
@@ -770,16 +802,23 @@ int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char*
 	if ((rc = acquire_streams(&ss))) return rc;
 	cudaStream_t cs = ss->copy;
 	cudaEvent_t e_start = ss->ev[0], e_vel_in = ss->ev[1], e_comb_in = ss->ev[2], e_all_in = ss->ev[3], e_vel_out = ss->ev[4], e_done = ss->ev[5];
+	cudaEvent_t e_fw_in = ss->ev[6], e_t_in = ss->ev[7];
 	// The whole state crosses PCIe in both directions (HNanoSolver.cu:120-133, 361-369; the coords are not needed on the device
 	// here). Transfers run on a copy stream and overlap the kernels: velocity first (advect_vector + divergence start as soon as
-	// it has landed), then the four combustion fields, then the remaining scalars while the pressure solve runs; the projected
-	// velocity goes back while advect_scalars runs.
+	// it has landed), then fuel and waste -- all the pressure solve needs of the combustion stage --, then the temperature (the
+	// buoyancy force the gradient pass needs), then flame and the remaining scalars; the projected velocity goes back on a second copy
+	// stream while those are still arriving and advect_scalars runs (PCIe is full duplex). See frame(). Critical path on the 512^3
+	// workload: 14.6 of the 23.5 ms of uploads, the solve, the 24 ms of downloads.
 	HNS_CUDA(cudaEventRecord(e_start, st));
 	HNS_CUDA(cudaStreamWaitEvent(cs, e_start, 0));  // everything the caller queued on `stream` before this call stays ordered
 	HNS_CUDA(cudaMemcpyAsync(s->aos, velocity, n * 12, cudaMemcpyHostToDevice, cs));
 	if (s->collision) HNS_CUDA(cudaMemcpyAsync(s->sc[iSdf], fields[iSdf], n * 4, cudaMemcpyHostToDevice, cs));  // the first kernel reads it
 	HNS_CUDA(cudaEventRecord(e_vel_in, cs));
-	for (int i : {iF, iW, iT, iL}) HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, cs));
+	for (int i : {iF, iW}) HNS_CUDA(cudaMemcpyAsync(s->sc[i], fields[i], n * 4, cudaMemcpyHostToDevice, cs));
+	HNS_CUDA(cudaEventRecord(e_fw_in, cs));
+	HNS_CUDA(cudaMemcpyAsync(s->sc[iT], fields[iT], n * 4, cudaMemcpyHostToDevice, cs));
+	HNS_CUDA(cudaEventRecord(e_t_in, cs));
+	HNS_CUDA(cudaMemcpyAsync(s->sc[iL], fields[iL], n * 4, cudaMemcpyHostToDevice, cs));
 	HNS_CUDA(cudaEventRecord(e_comb_in, cs));
 	for (int i = 0; i < n_float; ++i)
 		if (i != iF && i != iW && i != iT && i != iL && !(s->collision && i == iSdf))
@@ -788,16 +827,18 @@ int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char*
 	HNS_CUDA(cudaStreamWaitEvent(st, e_vel_in, 0));
 	launch_aos_to_soa(s->aos, s->vel[0], s->vel[1], s->vel[2], n, st);
 	FrameDeps deps;
-	deps.combustion_inputs = e_comb_in, deps.scalar_inputs = e_all_in, deps.velocity_done = e_vel_out;
+	deps.fuel_waste_inputs = e_fw_in, deps.temperature_input = e_t_in, deps.combustion_inputs = e_comb_in, deps.scalar_inputs = e_all_in, deps.velocity_done = e_vel_out;
 	if ((rc = frame(s, iterations, dt, voxel_size, 0u, st, nullptr, nullptr, &deps))) return rc;
 	// results back into the same host arrays (HNanoSolver.cu:361-369); a collision_sdf block comes back zeroed like the
 	// reference's never-written output buffer
-	HNS_CUDA(cudaStreamWaitEvent(cs, e_vel_out, 0));
-	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, cs));
+	cudaStream_t co = ss->copy_out;  // the projected velocity leaves while the last inputs are still arriving on `cs`
+	HNS_CUDA(cudaStreamWaitEvent(co, e_vel_out, 0));
+	HNS_CUDA(cudaMemcpyAsync(velocity, s->aos, n * 12, cudaMemcpyDeviceToHost, co));
 	if (iSdf >= 0) HNS_CUDA(cudaMemsetAsync(s->sc[iSdf], 0, n * 4, st));
 	HNS_CUDA(cudaEventRecord(e_done, st));
-	HNS_CUDA(cudaStreamWaitEvent(cs, e_done, 0));
-	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc[i], n * 4, cudaMemcpyDeviceToHost, cs));
+	HNS_CUDA(cudaStreamWaitEvent(co, e_done, 0));
+	for (int i = 0; i < n_float; ++i) HNS_CUDA(cudaMemcpyAsync(fields[i], s->sc[i], n * 4, cudaMemcpyDeviceToHost, co));
+	HNS_CUDA(cudaStreamSynchronize(co));
 	HNS_CUDA(cudaStreamSynchronize(cs));
 	HNS_CUDA(cudaStreamSynchronize(st));
 	HNS_CUDA(cudaGetLastError());

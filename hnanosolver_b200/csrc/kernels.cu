@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(256) k_combustion_oxygen(const float* __restri
                                                            const float* __restrict__ temp, float* __restrict__ div_red, float* __restrict__ div_blk,
                                                            const float* __restrict__ flame, float* __restrict__ oFuel,
                                                            float* __restrict__ oWaste, float* __restrict__ oTemp, float* __restrict__ oFlame,
-                                                           float temp_gain, float expansion, uint64_t n) {
+                                                           float temp_gain, float expansion, uint64_t n, bool update_div) {
 	const uint64_t t = blockIdx.x * uint64_t(256) + threadIdx.x;
 	if (t >= n) return;
 	float f = fuel[t];
@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(256) k_combustion_oxygen(const float* __restri
 	oWaste[t] = fmaf(burn, 2.0f, wv);
 	oFlame[t] = fmaxf(fl, fminf(1.0f, burn * 10.0f));
 	oTemp[t] = fmaf(burn, temp_gain, T);
+	if (!update_div) return;
 	// voxel t = leaf*512 + (x<<6 | y<<3 | z) lives in the colour-split divergence at quad (t>>3), lane z>>1 of its colour
 	const uint32_t o = uint32_t(t) & 511u;
 	const bool black = (((o >> 6) + (o >> 3) + o) & 1u) != 0;
@@ -492,10 +493,32 @@ __global__ void __launch_bounds__(256) k_combustion_oxygen(const float* __restri
 	*d = fmaf(burn, expansion, *d);
 }
 void launch_combustion_oxygen(const float* fuel, const float* waste, const float* temp, float* const div[2], const float* flame, float* oFuel,
-                              float* oWaste, float* oTemp, float* oFlame, float temp_gain, float expansion, uint64_t n, cudaStream_t st) {
+                              float* oWaste, float* oTemp, float* oFlame, float temp_gain, float expansion, uint64_t n, cudaStream_t st,
+                              bool update_div) {
 	if (n)
 		HNS_LAUNCH(k_combustion_oxygen, unsigned((n + 255) / 256), 256, 0, st, fuel, waste, temp, div[0], div[1], flame, oFuel, oWaste, oTemp,
-		           oFlame, temp_gain, expansion, n);
+		           oFlame, temp_gain, expansion, n, update_div);
+}
+// Only the expansion term combustion_oxygen adds to the divergence (Kernel.cu:963): it depends on fuel and waste alone, so a cook whose
+// inputs are still arriving over PCIe can start the pressure solve before temperature and flame have landed (hns_compute_sim); the
+// field updates follow with update_div = false. Same expressions, same rounding.
+__global__ void __launch_bounds__(256) k_combustion_divergence(const float* __restrict__ fuel, const float* __restrict__ waste,
+                                                               float* __restrict__ div_red, float* __restrict__ div_blk, float expansion, uint64_t n) {
+	const uint64_t t = blockIdx.x * uint64_t(256) + threadIdx.x;
+	if (t >= n) return;
+	float f = fuel[t];
+	const float wv = waste[t];
+	if (f < 0.001f) f = 0.0f;
+	const float oxygen = 1.0f - f - wv;
+	if (oxygen < 0.0f) return;
+	const float burn = fminf(oxygen, f);
+	const uint32_t o = uint32_t(t) & 511u;
+	const bool black = (((o >> 6) + (o >> 3) + o) & 1u) != 0;
+	float* d = (black ? div_blk : div_red) + ((t >> 3) << 2) + ((o & 7u) >> 1);
+	*d = fmaf(burn, expansion, *d);
+}
+void launch_combustion_divergence(const float* fuel, const float* waste, float* const div[2], float expansion, uint64_t n, cudaStream_t st) {
+	if (n) HNS_LAUNCH(k_combustion_divergence, unsigned((n + 255) / 256), 256, 0, st, fuel, waste, div[0], div[1], expansion, n);
 }
 // combustion_oxygen + temperature_buoyancy in one pass, the four outputs also written as one float4 {fuel, waste, temperature, flame}
 // into the packed group advect_scalars stages from (advect.cu, third generation). Same expressions as the two kernels above and below;
@@ -506,7 +529,7 @@ __global__ void __launch_bounds__(256) k_combustion_buoyancy_packed(const float*
                                                                     float* __restrict__ oFuel, float* __restrict__ oWaste, float* __restrict__ oTemp,
                                                                     float* __restrict__ oFlame, float4* __restrict__ grp, float* __restrict__ vy,
                                                                     float temp_gain, float expansion, float dt, float ambient, float strength,
-                                                                    uint64_t n) {
+                                                                    uint64_t n, bool update_div, bool buoyancy) {
 	const uint64_t t = blockIdx.x * uint64_t(256) + threadIdx.x;
 	if (t >= n) return;
 	float f = fuel[t];
@@ -520,21 +543,42 @@ __global__ void __launch_bounds__(256) k_combustion_buoyancy_packed(const float*
 		o.y = fmaf(burn, 2.0f, wv);
 		o.w = fmaxf(fl, fminf(1.0f, burn * 10.0f));
 		o.z = fmaf(burn, temp_gain, T);
-		const uint32_t v = uint32_t(t) & 511u;
-		const bool black = (((v >> 6) + (v >> 3) + v) & 1u) != 0;
-		float* d = (black ? div_blk : div_red) + ((t >> 3) << 2) + ((v & 7u) >> 1);
-		*d = fmaf(burn, expansion, *d);
+		if (update_div) {
+			const uint32_t v = uint32_t(t) & 511u;
+			const bool black = (((v >> 6) + (v >> 3) + v) & 1u) != 0;
+			float* d = (black ? div_blk : div_red) + ((t >> 3) << 2) + ((v & 7u) >> 1);
+			*d = fmaf(burn, expansion, *d);
+		}
 	}
 	oFuel[t] = o.x, oWaste[t] = o.y, oTemp[t] = o.z, oFlame[t] = o.w;
 	grp[t] = o;
-	if (o.z > ambient) vy[t] = fmaf(fmaxf(0.0f, (o.z - ambient) * strength), dt, vy[t]);
+	if (buoyancy && o.z > ambient) vy[t] = fmaf(fmaxf(0.0f, (o.z - ambient) * strength), dt, vy[t]);
 }
 void launch_combustion_buoyancy_packed(const float* fuel, const float* waste, const float* temp, float* const div[2], const float* flame, float* oFuel,
                                        float* oWaste, float* oTemp, float* oFlame, float4* grp, float* const vel[3], float temp_gain, float expansion,
-                                       float dt, float ambient, float strength, uint64_t n, cudaStream_t st) {
+                                       float dt, float ambient, float strength, uint64_t n, cudaStream_t st, bool update_div, bool buoyancy) {
 	if (n)
 		HNS_LAUNCH(k_combustion_buoyancy_packed, unsigned((n + 255) / 256), 256, 0, st, fuel, waste, temp, div[0], div[1], flame, oFuel, oWaste, oTemp,
-		           oFlame, grp, vel[1], temp_gain, expansion, dt, ambient, strength, n);
+		           oFlame, grp, vel[1], temp_gain, expansion, dt, ambient, strength, n, update_div, buoyancy);
+}
+// temperature_buoyancy (Kernel.cu:831-847) with the temperature combustion_oxygen is about to write, recomputed from its inputs
+// (Kernel.cu:941-960): lets a cook fed over PCIe project and send back its velocity before the flame field has even arrived.
+__global__ void __launch_bounds__(256) k_buoyancy_from_inputs(const float* __restrict__ fuel, const float* __restrict__ waste,
+                                                              const float* __restrict__ temp, float* __restrict__ vy, float temp_gain, float dt,
+                                                              float ambient, float strength, uint64_t n) {
+	const uint64_t t = blockIdx.x * uint64_t(256) + threadIdx.x;
+	if (t >= n) return;
+	float f = fuel[t];
+	const float wv = waste[t];
+	float T = temp[t];
+	if (f < 0.001f) f = 0.0f;
+	const float oxygen = 1.0f - f - wv;
+	if (!(oxygen < 0.0f)) T = fmaf(fminf(oxygen, f), temp_gain, T);
+	if (T > ambient) vy[t] = fmaf(fmaxf(0.0f, (T - ambient) * strength), dt, vy[t]);
+}
+void launch_buoyancy_from_inputs(const float* fuel, const float* waste, const float* temp, float* const vel[3], float temp_gain, float dt,
+                                 float ambient, float strength, uint64_t n, cudaStream_t st) {
+	if (n) HNS_LAUNCH(k_buoyancy_from_inputs, unsigned((n + 255) / 256), 256, 0, st, fuel, waste, temp, vel[1], temp_gain, dt, ambient, strength, n);
 }
 // The reference adds Vec3f(0, b, 0) * dt to all three components (Kernel.cu:844-846); adding 0*dt only turns a -0.0 into +0.0,
 // so only the y plane is touched here (x and z stay bit-identical except for the sign of an exact zero).

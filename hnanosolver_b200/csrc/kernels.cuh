@@ -88,13 +88,21 @@ void launch_vorticity_mag(const GridView& g, const float* const vel[3], float* m
 void launch_vorticity_force(const GridView& g, const float* const vel[3], const float* mag, float* const out[3], float dt, float inv_dx, float scale,
                             float factor_scale, cudaStream_t st);
 // combustion_oxygen (Kernel.cu:923-966) and temperature_buoyancy (Kernel.cu:831-847, in place on the y component)
+// update_div = false: the field updates only; the expansion term has already gone into the divergence (launch_combustion_divergence)
 void launch_combustion_oxygen(const float* fuel, const float* waste, const float* temp, float* const div[2], const float* flame, float* oFuel,
-                              float* oWaste, float* oTemp, float* oFlame, float temp_gain, float expansion, uint64_t n, cudaStream_t st);
+                              float* oWaste, float* oTemp, float* oFlame, float temp_gain, float expansion, uint64_t n, cudaStream_t st,
+                              bool update_div = true);
+// div += burn * expansion alone (Kernel.cu:963): needs only fuel and waste
+void launch_combustion_divergence(const float* fuel, const float* waste, float* const div[2], float expansion, uint64_t n, cudaStream_t st);
 void launch_buoyancy(float* const vel[3], const float* temp, float dt, float ambient, float strength, uint64_t n, cudaStream_t st);
 // both in one pass; the four outputs additionally as float4 {fuel, waste, temperature, flame} into a packed advection group
 void launch_combustion_buoyancy_packed(const float* fuel, const float* waste, const float* temp, float* const div[2], const float* flame, float* oFuel,
                                        float* oWaste, float* oTemp, float* oFlame, float4* grp, float* const vel[3], float temp_gain, float expansion,
-                                       float dt, float ambient, float strength, uint64_t n, cudaStream_t st);
+                                       float dt, float ambient, float strength, uint64_t n, cudaStream_t st, bool update_div = true,
+                                       bool buoyancy = true);
+// the buoyancy force from the temperature combustion_oxygen WILL write, recomputed from fuel, waste and temperature
+void launch_buoyancy_from_inputs(const float* fuel, const float* waste, const float* temp, float* const vel[3], float temp_gain, float dt,
+                                 float ambient, float strength, uint64_t n, cudaStream_t st);
 // GridView::list_nbr for a work list: out[n][27]
 void launch_gather_nbr_rows(const int32_t* nbr, const int32_t* list, uint32_t n, int32_t* out, cudaStream_t st);
 // whole-brick gather / scatter by leaf id (ghost exchange)
