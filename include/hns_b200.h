@@ -160,7 +160,10 @@ void hns_release_scratch(void);
  * the float blocks in insertion order (GridData.hpp:136-145); fuel, waste, temperature, flame must be among them.
  * A block named "collision_sdf" is never advected and comes back zeroed (the reference copies back an output buffer it never
  * writes, :361-369); with has_collision != 0 it is the SDF of the collision path (enforceCollisionBoundaries before the advection
- * and after the projection, collision tests of the traced positions, boundary tails of advect_vector and the gradient subtract). */
+ * and after the projection, collision tests of the traced positions, boundary tails of advect_vector and the gradient subtract).
+ * The host arrays cross PCIe on two copy streams while the kernels run: uploads in the order the projected velocity depends on them
+ * (velocity; fuel and waste -> the solve can start; temperature -> the gradient pass; flame and the other blocks), downloads as soon
+ * as a result is final. The independent steps of the combustion stage run in that order too; every value is the reference's. */
 int hns_compute_sim(const hns_grid* g, float* velocity, int n_float, const char* const* float_names, float* const* float_fields,
                     int iterations, float dt, float voxel_size, const hns_combustion_params* params, int has_collision, void* stream);
 /* AdvectIndexGrid (src/Cuda/Advection.cu:13-112,169-171): BFECC advection of every float block by the velocity block. */
