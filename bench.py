@@ -390,6 +390,13 @@ def main():
                      frame_algorithmic_GBps=mg_frame_bytes_per_voxel(S, full, mg_info) * N / (ms2 / args.steps * 1e-3) / 1e9,
                      note="same frame, pressure stage = V-cycles instead of the reference's I red-black iterations: not the reference's "
                           "arithmetic, converges further (compare relative_residual with the headline frame's)")
+        # ... and with ONE cycle: the relative Poisson residual of the reference's 40 iterations (solve_quality.relative_residual of the
+        # headline frame) is reached or beaten by a single V(2,2) cycle, in a quarter of the time
+        sim.set_pressure_solver(mg, 1, MG_NU[0], MG_NU[1], MG_OMEGA)
+        sim.time_frames(args.warmup, ITERATIONS, w.dt, flags)
+        ms1, pr1 = sim.time_frames(args.steps, ITERATIONS, w.dt, flags)
+        other["one_cycle"] = dict(cycles=1, ms_per_step=ms1 / args.steps, ms_pressure=pr1 / args.steps, value=N / (ms1 / args.steps * 1e-3),
+                                  **frame_quality(sim))
         sim.set_pressure_solver(None)
     del mg
 
