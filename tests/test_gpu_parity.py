@@ -241,6 +241,30 @@ def test_compute_sim_matches_oracle(case):
         assert_close(d.pValues(FLOAT, k), v, f"Compute_Sim {k}")
 
 
+@pytest.mark.parametrize("order", [["density", "fuel", "waste", "temperature", "flame"], ["flame", "temperature", "density", "waste", "fuel"]])
+def test_compute_sim_equals_the_resident_frame_bitwise(case, order):
+    """Compute_Sim feeds the frame while its inputs are still crossing PCIe: the term combustion adds to the divergence goes in as soon
+    as fuel and waste have landed, the buoyancy force is applied from fuel, waste and temperature after the solve, the field updates
+    follow behind the gradient pass (api.cu::frame, FrameDeps). The resident frame runs the reference's step order on fields that are
+    all there. Independent steps in another order: every bit must agree, whatever the order of the float blocks."""
+    w = case
+    comb = _combustion_fields(w.num_voxels)
+    fields = {k: (w.scalars[0] if k == "density" else comb[k]) for k in order}
+    d = _sidecar(w, {k: v.copy() for k, v in fields.items()})
+    g = H.CreateIndexGrid(d, w.voxel_size)
+    H.Compute_Sim(d, g, 7, w.dt, w.voxel_size, H.CombustionParams(*PARAMS6.tolist()), False)
+    grid = H.create_index_grid_from_origins(w.origins, w.voxel_size)
+    sim = H.Simulation(grid, len(order))
+    sim.upload(w.velocity, [fields[k] for k in order])
+    sim.set_combustion(True, order.index("fuel"), order.index("waste"), order.index("temperature"), order.index("flame"),
+                       H.CombustionParams(*PARAMS6.tolist()))
+    sim.step(7, w.dt)
+    sim.sync()
+    assert np.array_equal(d.pValues(VEC3F, "vel").reshape(-1, 3), sim.velocity().reshape(-1, 3))
+    for i, k in enumerate(order):
+        assert np.array_equal(d.pValues(FLOAT, k), sim.scalar(i)), k
+
+
 @needs_ref
 def test_compute_sim_matches_reference_compute_sim(case):
     w = case
