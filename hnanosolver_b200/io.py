@@ -160,3 +160,36 @@ def write_index_grids(directory: str, domain_origins: np.ndarray, data: GridInde
         write_nvdb(path, grid_from_sidecar(domain_origins, arr, voxel_size, name))
         paths.append(path)
     return paths
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sourcing: SOP_HNanoSolverVerb::cook adds its source grids to the fed-back state with openvdb::tools::compSum before it defines the
+# domain (reference src/SOP/HNanoSolver/SOP_HNanoSolver.cpp:159-181). compSum(A, B) leaves A with the union of both topologies and
+# A + B in every voxel (a voxel a grid does not hold counts as its background, 0). Over NanoVDB value grids and sidecar blocks that is:
+# merge the topologies in front of the domain construction, then add the source's block to the state's block over the domain.
+# ------------------------------------------------------------------------------------------------------------------
+def union_topology(*topologies):
+    """(origins (L, 3), masks (L, 8)) of the union of several (origins, masks) pairs as leaf_topology returns them: a leaf is present
+    when any grid has it, a voxel active when it is active in any of them. Sorted by (x, y, z) of the origin; build_domain orders its
+    result itself."""
+    origins = np.concatenate([np.asarray(o, np.int32).reshape(-1, 3) for o, _ in topologies] or [np.zeros((0, 3), np.int32)])
+    masks = np.concatenate([np.asarray(m, np.uint64).reshape(-1, 8) for _, m in topologies] or [np.zeros((0, 8), np.uint64)])
+    if not len(origins):
+        return origins, masks
+    uniq, inverse = np.unique(origins, axis=0, return_inverse=True)
+    out = np.zeros((uniq.shape[0], 8), np.uint64)
+    np.bitwise_or.at(out, inverse.reshape(-1), masks)
+    return np.ascontiguousarray(uniq, np.int32), out
+
+
+def comp_sum(domain_origins: np.ndarray, data: GridIndexedData, sources) -> None:
+    """sources = [(block name, NanoVDB float / Vec3f grid buffer)]: adds every source grid to the sidecar block of that name, in place,
+    over the domain's leaves (leaves the source does not have add nothing). The domain has to cover the sources' topology -- pass
+    union_topology(state, sources...) to build_domain -- or the part outside it is lost, as it would be in the reference if the source
+    were added after the domain had been defined."""
+    o = np.ascontiguousarray(np.asarray(domain_origins, np.int32).reshape(-1, 3))
+    for name, buf in sources:
+        add = sidecar_from_grid(buf, o, 0)
+        kind = VEC3F if add.ndim == 2 else FLOAT
+        block = data.pValues(kind, name)
+        block += add.reshape(block.shape)

@@ -250,3 +250,40 @@ def test_sidecar_round_trip_without_nanovdb(w, tmp_path):
     assert np.all(block[half * 512:].view(np.uint32) == 0x01010101)
     with pytest.raises(Exception):
         hio.grid_from_sidecar(w.origins[::-1] if w.num_leaves > 1 else np.array([[1, 0, 0]], np.int32), np.zeros(w.num_leaves * 512, np.float32), 0.1, "x")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sourcing (compSum, reference src/SOP/HNanoSolver/SOP_HNanoSolver.cpp:159-181) over NanoVDB value grids and sidecar blocks
+# ------------------------------------------------------------------------------------------------------------------
+def test_sourcing_adds_the_source_grids_over_the_union_topology():
+    rng = np.random.default_rng(5)
+    state_leaves = np.array([[0, 0, 0], [0, 0, 8], [8, 0, 0]], np.int32)
+    source_leaves = np.array([[16, -8, 0], [0, 0, 8]], np.int32)                  # one new leaf (another root tile: sorts first), one in common
+    assert np.array_equal(synth.nanovdb_order(state_leaves), np.arange(3)) and np.array_equal(synth.nanovdb_order(source_leaves), np.arange(2))
+    state_mask = np.full((3, 8), np.uint64(0xFFFFFFFFFFFFFFFF))
+    source_mask = np.zeros((2, 8), np.uint64)
+    source_mask[:, 0] = np.uint64(0xFF)                                           # the source only activates x = 0, y = 0
+    dens, src = rng.random(3 * 512).astype(np.float32), rng.random(2 * 512).astype(np.float32)
+    vel, vsrc = rng.random((3 * 512, 3)).astype(np.float32), rng.random((2 * 512, 3)).astype(np.float32)
+    g_dens = hio.grid_from_sidecar(state_leaves, dens, 0.1, "density", state_mask)
+    g_src = hio.grid_from_sidecar(source_leaves, src, 0.1, "density", source_mask)
+    g_vel = hio.grid_from_sidecar(state_leaves, vel, 0.1, "vel", state_mask)
+    g_vsrc = hio.grid_from_sidecar(source_leaves, vsrc, 0.1, "vel", source_mask)
+    # topology: union of leaves, masks OR-ed where the leaves coincide
+    o, m = hio.union_topology(hio.leaf_topology(g_vel), hio.leaf_topology(g_vsrc))
+    assert sorted(map(tuple, o.tolist())) == sorted({tuple(x) for x in state_leaves.tolist()} | {tuple(x) for x in source_leaves.tolist()})
+    by_leaf = {tuple(k): v for k, v in zip(o.tolist(), m)}
+    assert by_leaf[(0, 0, 8)][0] == np.uint64(0xFFFFFFFFFFFFFFFF) and by_leaf[(16, -8, 0)][0] == np.uint64(0xFF) and by_leaf[(16, -8, 0)][1] == 0
+    # values: state + source over the union domain (padding 0: the domain is the union's leaf set, in NanoVDB order)
+    domain = synth.nanovdb_order(o)
+    domain = np.ascontiguousarray(o[domain])
+    data = hio.build_sidecar(domain, [("density", g_dens, False), ("vel", g_vel, False)])
+    hio.comp_sum(domain, data, [("density", g_src), ("vel", g_vsrc)])
+    want_d, want_v = np.zeros(domain.shape[0] * 512, np.float32), np.zeros((domain.shape[0] * 512, 3), np.float32)
+    for leaves, vals, vvals in ((state_leaves, dens, vel), (source_leaves, src, vsrc)):
+        for k, leaf in enumerate(leaves.tolist()):
+            at = [tuple(x) for x in domain.tolist()].index(tuple(leaf)) * 512
+            want_d[at:at + 512] += vals[k * 512:(k + 1) * 512]
+            want_v[at:at + 512] += vvals[k * 512:(k + 1) * 512]
+    assert np.array_equal(data.pValues(FLOAT, "density"), want_d)
+    assert np.array_equal(data.pValues(VEC3F, "vel").reshape(-1, 3), want_v)
