@@ -210,6 +210,12 @@ def kernel_traffic() -> dict:
         return {}
 
 
+def workload_label(name: str, w, kind: str, S: int) -> str:
+    """config.workload of both arms (ours and --impl reference): one function, so that the two lines name the workload identically"""
+    return (f"{name}: {w.name}, {w.num_leaves} leaves = {w.num_voxels} active voxels, frame={kind}, I={ITERATIONS} red-black iterations, "
+            f"S={S} scalar fields, dt=1/24, voxel size 0.1, CFL<=2.5")
+
+
 def frame_quality(sim) -> dict:
     """of the frame the state just ran: relative Poisson residual of its pressure and ||div(u_new)||_2 (rms), both reduced on the device"""
     a, b = sim.residual_sums()
@@ -451,8 +457,7 @@ def main():
     out = {"metric": "active voxel-updates/s per advect+project frame", "value": value, "unit": "voxel-updates/s", "n_gpus": 1,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{args.workload}: {w.name}, {w.num_leaves} leaves = {N} active voxels, frame={kind}, I={ITERATIONS} red-black "
-                                  f"iterations, S={S} scalar fields, dt=1/24, voxel size 0.1, CFL<=2.5",
+           "config": {"workload": workload_label(args.workload, w, kind, S),
                       "l2": "inputs larger than L2 (per-field %.0f MB, frame working set %.1f GB); no flush" % (4 * N / 1e6, (9 + 2 * S) * 4 * N / 1e9),
                       "pressure": ("red/black half-sweeps on colour-split bricks, " + ("forward only" if args.forward_only else "alternating direction"))
                       if solver == "rbgs" else
@@ -486,7 +491,7 @@ def reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": "active voxel-updates/s per advect+project frame", "unit": "voxel-updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w.name}, {w.num_leaves} leaves = {N} active voxels, frame={kind}, I={ITERATIONS}"}}
+            "config": {"workload": workload_label(args.workload, w, kind, len(fields))}}   # the same string as our arm's: same workload
     if O.ref_gpu_available():
         rd = O.RefData(synth.dense_coords(w.origins), 2)  # AllocationType::CudaPinned
         rd.add_vec3("vel", w.velocity)
